@@ -1,0 +1,179 @@
+/* real3d_b200 — C ABI of the B200-native Real3D-Aug hot path (placement search + spherical occlusion + insertion).
+ *
+ * The reference (ctu-vras/pcl-augmentation) is pure Python with no FFI; its de-facto operator interface is the set
+ * of module-level functions `insertion.py` star-imports.  Each entry point below names the reference
+ * function(s) it replaces.  Conventions: plain pointers and sizes only; every function returns 0 on success or a
+ * negative error code (text via r3d_last_error()); outputs are caller-allocated; no ownership transfer; the
+ * "primitive" calls are re-entrant per CUDA stream and take DEVICE pointers; the "engine" calls take HOST pointers
+ * (they own the staging, the H2D/D2H copies and the device-resident state of a batch of scans).
+ *
+ * Row layouts are the reference's: a working point row is 9 float64
+ *   [x, y, z, r, azimuth, elevation, intensity, label, pix_id]      (add_space_for_spherical, od/ins:55-65)
+ * with od/ins = object_detection/Real3DAug/insertion.py, od/fs = .../tools/find_spot.py, cb = .../tools/cut_bbox.py,
+ * cl = .../tools/closing.py, ss/... = the semantic_segmentation twins.
+ */
+#ifndef REAL3D_B200_H
+#define REAL3D_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define R3D_OK 0
+#define R3D_ERR_CUDA (-1)
+#define R3D_ERR_ARG (-2)
+#define R3D_ERR_ASSERT (-3)   /* the reference would have raised AssertionError (od/ins:111-113) */
+#define R3D_ERR_INDEX (-4)    /* the reference would have raised IndexError (od/ins:410, < MAX_NUM_TRIES samples) */
+#define R3D_ERR_CAPACITY (-5)
+
+#define R3D_MAX_CLASSES 16
+#define R3D_MAX_SURFACE 8
+#define R3D_NUM_RADII 50
+#define R3D_BOX_DOUBLES 16 /* cx cy cz(bottom) m00..m22(row-major) length width height reach */
+
+typedef void* r3d_stream; /* cudaStream_t */
+
+int r3d_version(void);
+const char* r3d_last_error(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+int64_t r3d_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------ primitives */
+
+/* fill_spherical (od/ins:68-82, ss/ins:67-81): r, azimuth, elevation of n working rows written in place to columns
+ * 3..5; minmax_out[0] = max elevation, minmax_out[1] = min elevation (device, 2 doubles). */
+int r3d_fill_spherical(double* rows9, int64_t n, double* minmax_out, r3d_stream stream);
+
+/* geometrical_front_view (od/ins:85-130): spherical z-buffer.  train/label are num_row*num_col float64 (device);
+ * pix_id = row * pix_stride + col goes to column 8 (pix_stride = the reference's module global NUMCOLUMN).
+ * sample != 0 skips rows outside the elevation range (od/ins:108-109); otherwise an out-of-range bin sets
+ * *status_out (device int) to R3D_ERR_ASSERT.  zbuf_scratch: num_row*num_col uint64 (device). */
+int r3d_project_zbuffer(double* rows9, int64_t n, int num_row, int num_col, int pix_stride, double max_el,
+                        double min_el, int sample, double* train_out, double* label_out, uint64_t* zbuf_scratch,
+                        int* status_out, r3d_stream stream);
+
+/* smooth_out + class_closing (cl:9-62): 5x3 closing of the occupancy and neighbour-mean hole fill.
+ * closed_out (optional, may be NULL): the uint8 0/255 image class_closing returns. */
+int r3d_close_fill(const double* train_in, const double* label_in, int num_row, int num_col, double* train_out,
+                   double* label_out, uint8_t* closed_out, r3d_stream stream);
+
+/* cut_bounding_box (cb:7-68): mask_out[i] = 1 iff point i (x,y,z = first three doubles of a row of row_stride
+ * doubles) is strictly inside the box (R3D_BOX_DOUBLES doubles, host pointer). */
+int r3d_cut_bounding_box(const double* rows, int64_t n, int row_stride, const double* box_host, uint8_t* mask_out,
+                         r3d_stream stream);
+
+/* --------------------------------------------------------------------------------------------------- engine */
+/* Device-resident batched driver of the per-scan loop (od/ins:351-628, ss/ins:355-599): placement search
+ * (find_possible_places od/fs:227-304, ss/fs:192-273), occlusion (od/ins:468-501), accept rule and insertion
+ * (od/ins:530-561), sample scheduling (od/ins:386-428,587-614) and the output record (od/ds:76-109, ss/ds:72-106),
+ * for many scans at once with the control flow on the device. */
+
+typedef struct r3d_engine r3d_engine;
+
+typedef struct r3d_class_cfg {
+    int32_t min_points;   /* insertion.min_points[class] */
+    int32_t map_sel;      /* OD: 0 = road map ("Road"), 1 = pedestrian-area map ("Sidewalk") (od/ins:434-441) */
+    uint32_t map_ok_mask; /* semseg: bit v set iff map value v is in insertion.placement[class] (ss/fs:221,246) */
+    int32_t pedestrian;   /* OD: class == 'Pedestrian' -> only scene points >= box bottom + 0.1 collide (od/fs:123) */
+    int32_t n_surface;    /* labels the road-level search accepts: OD {labels.Road}; semseg placement_labels */
+    int32_t surface[R3D_MAX_SURFACE];
+} r3d_class_cfg;
+
+typedef struct r3d_engine_cfg {
+    int32_t task; /* 0 = object detection, 1 = semantic segmentation */
+    int32_t rows, cols; /* range image (reference constants 112 x 1440, od/ins:21-22) */
+    int32_t yaw_steps;  /* candidates per cut object (reference: 360, od/fs:263) */
+    int32_t max_tries;  /* MAX_NUM_TRIES (od/ins:24) */
+    int32_t n_classes;
+    int32_t max_scans, max_points, max_inserted, max_boxes, max_events;
+    int32_t road_label;                       /* OD: labels.Road (od/ins:354) */
+    int32_t n_road_indexes;                   /* semseg addjust_map_2: ROAD_INDEXES (ss/ins:209) */
+    int32_t road_indexes[R3D_MAX_SURFACE];
+    int32_t map_window;                       /* semseg: side of the per-scan occupied-cell window (cells) */
+    double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */
+    int32_t radii_ok[R3D_NUM_RADII];          /* 0 where the pass's "radius > 5" check already fails */
+    r3d_class_cfg classes[R3D_MAX_CLASSES];
+} r3d_engine_cfg;
+
+/* cut-object database (the role of glob(sample_path/<class>/ *.npz), sorted by name) */
+typedef struct r3d_object_db {
+    int32_t n_objects;
+    const int64_t* point_offsets; /* n_objects + 1 */
+    const double* points5;        /* total x 5 float64: x y z intensity label (object_cut_out.py:164-168) */
+    const double* boxes;          /* n_objects x 8: cx cy cz(bottom) m00 m10 length width height (read_label_line) */
+    const int32_t* class_index;   /* n_objects */
+    const int32_t* class_list_offsets; /* n_classes + 1 */
+    const int32_t* class_list;         /* object ids of each class in sorted-name order */
+} r3d_object_db;
+
+typedef struct r3d_batch {
+    int32_t n_scans;
+    const int64_t* point_offsets; /* n_scans + 1 */
+    const float* xyzi;            /* total x 4 float32, as read from velodyne/ *.bin (od/ds:62) */
+    const uint32_t* labels;       /* total, semantic label & 0xFFFF (od/ds:65) */
+    const int32_t* box_offsets;   /* n_scans + 1 */
+    const double* boxes;          /* total boxes x R3D_BOX_DOUBLES (scene annotations, extract_anno od/ins:133-157) */
+    /* OD: two uint8 maps per scan (road, pedestrian area): dims[scan][map] = {size_x, size_y, min_x, min_y} */
+    const int64_t* map_offsets;   /* (n_scans * 2) + 1, byte offsets into maps */
+    const uint8_t* maps;
+    const int32_t* map_dims;      /* n_scans x 2 x 4 */
+    /* semseg: lidar->world 4x4 per scan (ss/ds:65-70); the sequence map is set with r3d_engine_set_ss_map */
+    const double* poses;          /* n_scans x 16 */
+    /* pre-drawn randomness (generate_seed od/ins:171-187, random.shuffle od/ins:400) */
+    const int32_t* counts;        /* n_scans x n_classes */
+    const int32_t* perms;         /* n_scans x n_events x n_classes x max_tries (object ids in class-list order) */
+    int32_t n_events;
+} r3d_batch;
+
+typedef struct r3d_batch_result {
+    /* all host, caller-allocated; capacities given by the caller */
+    int64_t* out_offsets;   /* n_scans + 1: rows of scan s are out_xyzi[out_offsets[s] .. out_offsets[s+1]) */
+    float* out_xyzi;        /* capacity_points x 4: velodyne/<frame>.bin (od/ds:86-88) */
+    uint32_t* out_labels;   /* capacity_points: labels/<frame>.label (ss/ds:82-84); may be NULL */
+    int64_t capacity_points;
+    int64_t* check_offsets; /* n_scans + 1 */
+    float* check_xyzil;     /* capacity_check x 5: check/<frame>.bin rows x y z intensity label (ss/ds:76,86-88) */
+    int64_t capacity_check;
+    int32_t* n_inserted;    /* n_scans */
+    int32_t* inserted;      /* n_scans x max_events x 4: object id, rotation (yaw step index), class index, visible points */
+    double* inserted_box;   /* n_scans x max_events x 8: cx cy cz m00 m10 length width height of the placed box */
+    int32_t* status;        /* n_scans: 0 or a negative R3D_ERR_* */
+    int32_t* rounds;        /* 1: device rounds the batch took */
+} r3d_batch_result;
+
+int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out);
+int r3d_engine_destroy(r3d_engine* eng);
+int r3d_engine_set_yaw_tables(r3d_engine* eng, const double* cos_k, const double* sin_k); /* yaw_steps + 1 each */
+int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db);
+int r3d_engine_set_ss_map(r3d_engine* eng, const uint8_t* map, int32_t size_x, int32_t size_y, int64_t move_x,
+                          int64_t move_y);
+/* host -> device copy of a batch (async on the engine stream) + device-side preparation (A1/A2 spherical cache) */
+int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* batch);
+/* re-arm the already resident batch (alive flags, tails, scheduling state) without touching host memory */
+int r3d_engine_reset_batch(r3d_engine* eng);
+/* run every scan of the batch to completion on the device and compact the outputs (device-resident) */
+int r3d_engine_run(r3d_engine* eng);
+/* device -> host copy of the results of the last run */
+int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* result);
+/* blocking wait for the engine stream */
+int r3d_engine_sync(r3d_engine* eng);
+/* total output rows of the last run (valid after r3d_engine_run + r3d_engine_sync) */
+int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check);
+
+/* per-kernel device time of the runs since the last reset, measured with CUDA events on the engine stream.
+ * names_out: caller buffer receiving '\n'-separated kernel names; ms_out / launches_out: up to max_kernels entries. */
+int r3d_engine_profile_enable(r3d_engine* eng, int on);
+int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out, int64_t* launches_out,
+                            int max_kernels, int* n_kernels_out);
+
+/* debug / parity taps on the resident state of one scan (device -> host), used by the tests */
+int r3d_engine_debug_image(r3d_engine* eng, int scan, double* smooth_out /* rows*cols */);
+int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* flags_out /* yaw_steps+1 */,
+                                double* level_out /* yaw_steps+1 */, int32_t* visible_out /* yaw_steps+1 */);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REAL3D_B200_H */

@@ -1,0 +1,539 @@
+// Host side of the batched Real3D-Aug engine: device memory, H2D/D2H staging, the per-round launch sequence and
+// the C ABI declared in include/real3d_b200.h.
+#include "r3d_engine_kernels.cuh"
+#include "r3d_host.h"
+
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+using namespace r3d;
+
+namespace {
+
+enum KernelId {
+    KID_INGEST, KID_CTRL, KID_APPLY, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT1,
+    KID_HEIGHT2, KID_CANDFIN, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_COUNT
+};
+const char* kKernelNames[KID_COUNT] = {
+    "ingest_spherical", "ctrl", "apply_mask_minmax", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
+    "onmap", "height_pass1", "height_pass2", "cand_finalize", "collide_points", "collide_boxes", "feasible",
+    "occlusion_count", "select_emit", "compact_output"};
+
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    int alloc(size_t count) {
+        release();
+        n = count;
+        if (count == 0) return R3D_OK;
+        cudaError_t err = cudaMalloc((void**)&p, count * sizeof(T));
+        if (err != cudaSuccess) { p = nullptr; return r3d_fail_cuda(err, "cudaMalloc"); }
+        return R3D_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    ~DevBuf() { release(); }
+};
+
+}  // namespace
+
+struct r3d_engine {
+    r3d_engine_cfg cfg;
+    EngineDev dev;
+    cudaStream_t stream = nullptr;
+    int n_scans = 0;
+    int max_n0 = 0;
+    bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
+    int last_rounds = 0;
+    // device buffers
+    DevBuf<float4> xyzi, out_xyzi;
+    DevBuf<double> tail_x, tail_y, tail_z, r, el, smooth, poses, obj_x, obj_y, obj_z, cos_k, sin_k, radii_sq, cand_level,
+        cand_cx, cand_cy, inserted_box;
+    DevBuf<float> tail_i, obj_i, check, out_check;
+    DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, cand_zcnt, out_label;
+    DevBuf<unsigned short> col;
+    DevBuf<int> pix, gate_project, gate_try, gate_apply, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
+        class_list, radii_ok, cand_collide, cand_jmin, cand_v, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
+    DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
+    DevBuf<unsigned long long> zraw, obj_raw, cand_zsum;
+    DevBuf<long long> od_map_off, out_count, out_off, check_off;
+    DevBuf<ScanState> st;
+    DevBuf<Box> boxes;
+    DevBuf<BoxTest> box_tests, cand_bt;
+    DevBuf<ObjBox> obj;
+    DevBuf<ClassCfg> classes;
+    // host copies needed for re-arming
+    std::vector<Box> h_boxes;
+    std::vector<int> h_nbox0;
+    int* h_active = nullptr;            // pinned
+    long long* h_offsets = nullptr;     // pinned, 2 * (max_scans + 1)
+    // profiling
+    bool profile = false;
+    double prof_ms[KID_COUNT] = {0};
+    int64_t prof_launches[KID_COUNT] = {0};
+    std::vector<std::pair<int, std::pair<cudaEvent_t, cudaEvent_t>>> pending_events;
+    std::vector<cudaEvent_t> event_pool;
+};
+
+namespace {
+
+__global__ void k_box_tests(const Box* boxes, BoxTest* tests, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) tests[i] = make_box_test(boxes[i]);
+}
+__global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+struct Launcher {          // wraps every launch: launch counter + optional CUDA-event timing on the engine stream
+    r3d_engine* eng;
+    int kid;
+    cudaEvent_t a = nullptr, b = nullptr;
+    Launcher(r3d_engine* e, int k) : eng(e), kid(k) {
+        if (eng->profile) {
+            a = get_event(); b = get_event();
+            cudaEventRecord(a, eng->stream);
+        }
+    }
+    cudaEvent_t get_event() {
+        if (!eng->event_pool.empty()) { cudaEvent_t ev = eng->event_pool.back(); eng->event_pool.pop_back(); return ev; }
+        cudaEvent_t ev; cudaEventCreate(&ev); return ev;
+    }
+    ~Launcher() {
+        r3d_count_launch();
+        eng->prof_launches[kid] += 1;
+        if (eng->profile) {
+            cudaEventRecord(b, eng->stream);
+            eng->pending_events.push_back({kid, {a, b}});
+        }
+    }
+};
+
+void drain_events(r3d_engine* eng) {
+    for (auto& pe : eng->pending_events) {
+        float ms = 0.f;
+        cudaEventSynchronize(pe.second.second);
+        cudaEventElapsedTime(&ms, pe.second.first, pe.second.second);
+        eng->prof_ms[pe.first] += ms;
+        eng->event_pool.push_back(pe.second.first);
+        eng->event_pool.push_back(pe.second.second);
+    }
+    eng->pending_events.clear();
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+
+}  // namespace
+
+#define TRY(x) do { int _rc = (x); if (_rc != R3D_OK) return _rc; } while (0)
+
+extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
+    if (!cfg || !out) return r3d_fail(R3D_ERR_ARG, "r3d_engine_create: null argument");
+    if (cfg->rows <= 0 || cfg->cols <= 0 || cfg->cols > 65535 || cfg->yaw_steps <= 0 || cfg->n_classes <= 0 ||
+        cfg->n_classes > R3D_MAX_CLASSES || cfg->max_scans <= 0 || cfg->max_points <= 0 || cfg->max_inserted <= 0 ||
+        cfg->max_tries <= 0 || cfg->max_events <= 0 || cfg->max_boxes <= 0 || (cfg->task != 0 && cfg->task != 1))
+        return r3d_fail(R3D_ERR_ARG, "r3d_engine_create: bad configuration");
+    if (cfg->task == 1 && (cfg->map_window <= 0 || cfg->map_window % 32 != 0))
+        return r3d_fail(R3D_ERR_ARG, "r3d_engine_create: map_window must be a positive multiple of 32");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+        return r3d_fail(R3D_ERR_CUDA, "r3d_engine_create: no CUDA device (this library has no CPU fallback)");
+    r3d_engine* eng = new r3d_engine();
+    eng->cfg = *cfg;
+    R3D_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    EngineDev& d = eng->dev;
+    memset(&d, 0, sizeof(d));
+    d.task = cfg->task; d.rows = cfg->rows; d.cols = cfg->cols; d.hw = cfg->rows * cfg->cols; d.K = cfg->yaw_steps;
+    d.max_tries = cfg->max_tries; d.n_classes = cfg->n_classes; d.B = cfg->max_scans; d.max_points = cfg->max_points;
+    d.max_inserted = cfg->max_inserted; d.P = cfg->max_points + cfg->max_inserted; d.max_boxes = cfg->max_boxes;
+    d.max_events = cfg->max_events; d.road_label = cfg->road_label; d.n_road_indexes = cfg->n_road_indexes;
+    d.map_window = cfg->task == 1 ? cfg->map_window : 32; d.dwords = (d.hw + 31) / 32;
+    for (int i = 0; i < R3D_MAX_SURFACE; ++i) d.road_indexes[i] = cfg->road_indexes[i];
+    d.step_rad = 2.0 * 3.14159265358979323846 / (double)cfg->yaw_steps;
+    const size_t B = d.B, P = d.P, K1 = d.K + 1, HW = d.hw;
+    TRY(eng->xyzi.alloc(B * d.max_points)); TRY(eng->tail_x.alloc(B * d.max_inserted)); TRY(eng->tail_y.alloc(B * d.max_inserted));
+    TRY(eng->tail_z.alloc(B * d.max_inserted)); TRY(eng->tail_i.alloc(B * d.max_inserted)); TRY(eng->label.alloc(B * P));
+    TRY(eng->r.alloc(B * P)); TRY(eng->el.alloc(B * P)); TRY(eng->col.alloc(B * P)); TRY(eng->pix.alloc(B * P));
+    TRY(eng->alive.alloc(B * P)); TRY(eng->zraw.alloc(B * HW)); TRY(eng->obj_raw.alloc(B * HW)); TRY(eng->smooth.alloc(B * HW));
+    TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
+    TRY(eng->gate_project.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->active_count.alloc(64));
+    TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
+    TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
+    TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
+    TRY(eng->radii_sq.alloc(R3D_NUM_RADII)); TRY(eng->radii_ok.alloc(R3D_NUM_RADII)); TRY(eng->classes.alloc(R3D_MAX_CLASSES));
+    TRY(eng->cand_flags.alloc(B * K1)); TRY(eng->cand_collide.alloc(B * K1)); TRY(eng->cand_jmin.alloc(B * K1));
+    TRY(eng->cand_zsum.alloc(B * K1)); TRY(eng->cand_zcnt.alloc(B * K1)); TRY(eng->cand_level.alloc(B * K1));
+    TRY(eng->cand_cx.alloc(B * K1)); TRY(eng->cand_cy.alloc(B * K1)); TRY(eng->cand_bt.alloc(B * K1)); TRY(eng->cand_v.alloc(B * K1));
+    TRY(eng->feas.alloc(B * d.K)); TRY(eng->inserted.alloc(B * d.max_events * 4)); TRY(eng->inserted_box.alloc(B * d.max_events * 8));
+    TRY(eng->check.alloc(B * d.max_inserted * 5)); TRY(eng->out_count.alloc(B)); TRY(eng->out_off.alloc(B + 1));
+    TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
+    TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
+    TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8));
+    R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
+    R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, 2 * (B + 1) * sizeof(long long)));
+    std::vector<ClassCfg> cls(R3D_MAX_CLASSES);
+    for (int c = 0; c < R3D_MAX_CLASSES; ++c) {
+        const r3d_class_cfg& s = cfg->classes[c];
+        cls[c].min_points = s.min_points; cls[c].map_sel = s.map_sel; cls[c].map_ok_mask = s.map_ok_mask;
+        cls[c].pedestrian = s.pedestrian; cls[c].n_surface = std::min(std::max(s.n_surface, 0), R3D_MAX_SURFACE);
+        for (int i = 0; i < R3D_MAX_SURFACE; ++i) cls[c].surface[i] = s.surface[i];
+    }
+    R3D_CUDA(cudaMemcpy(eng->classes.p, cls.data(), cls.size() * sizeof(ClassCfg), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->radii_sq.p, cfg->radii_sq, sizeof(cfg->radii_sq), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->radii_ok.p, cfg->radii_ok, sizeof(cfg->radii_ok), cudaMemcpyHostToDevice));
+    k_fill_u64<<<148 * 4, 256, 0, eng->stream>>>(eng->obj_raw.p, B * HW, R3D_EMPTY_U64); r3d_count_launch();
+    R3D_CUDA(cudaMemsetAsync(eng->dmask.p, 0, B * d.dwords * sizeof(unsigned), eng->stream));
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    // wire the device view
+    d.xyzi = eng->xyzi.p; d.tail_x = eng->tail_x.p; d.tail_y = eng->tail_y.p; d.tail_z = eng->tail_z.p; d.tail_i = eng->tail_i.p;
+    d.label = eng->label.p; d.r = eng->r.p; d.el = eng->el.p; d.col = eng->col.p; d.pix = eng->pix.p; d.alive = eng->alive.p;
+    d.zraw = eng->zraw.p; d.obj_raw = eng->obj_raw.p; d.smooth = eng->smooth.p; d.dmask = eng->dmask.p; d.vmask = eng->vmask.p;
+    d.st = eng->st.p; d.gate_project = eng->gate_project.p; d.gate_try = eng->gate_try.p; d.gate_apply = eng->gate_apply.p;
+    d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
+    d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
+    d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
+    d.cand_collide = eng->cand_collide.p; d.cand_jmin = eng->cand_jmin.p; d.cand_zsum = eng->cand_zsum.p; d.cand_zcnt = eng->cand_zcnt.p;
+    d.cand_level = eng->cand_level.p; d.cand_cx = eng->cand_cx.p; d.cand_cy = eng->cand_cy.p; d.cand_bt = eng->cand_bt.p;
+    d.cand_v = eng->cand_v.p; d.feas = eng->feas.p; d.inserted = eng->inserted.p; d.inserted_box = eng->inserted_box.p;
+    d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
+    d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
+    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p;
+    *out = eng;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_destroy(r3d_engine* eng) {
+    if (!eng) return R3D_OK;
+    cudaStreamSynchronize(eng->stream);
+    drain_events(eng);
+    for (cudaEvent_t ev : eng->event_pool) cudaEventDestroy(ev);
+    if (eng->h_active) cudaFreeHost(eng->h_active);
+    if (eng->h_offsets) cudaFreeHost(eng->h_offsets);
+    cudaStreamDestroy(eng->stream);
+    delete eng;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_set_yaw_tables(r3d_engine* eng, const double* cos_k, const double* sin_k) {
+    if (!eng || !cos_k || !sin_k) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_yaw_tables: null argument");
+    const size_t n = (size_t)eng->dev.K + 1;
+    R3D_CUDA(cudaMemcpy(eng->cos_k.p, cos_k, n * sizeof(double), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->sin_k.p, sin_k, n * sizeof(double), cudaMemcpyHostToDevice));
+    eng->yaw_set = true;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) {
+    if (!eng || !db || db->n_objects <= 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_objects: bad argument");
+    EngineDev& d = eng->dev;
+    const int n = db->n_objects;
+    const int64_t total = db->point_offsets[n];
+    std::vector<double> x(total), y(total), z(total);
+    std::vector<float> in(total);
+    std::vector<unsigned> lab(total);
+    for (int64_t i = 0; i < total; ++i) {
+        const double* p = db->points5 + i * 5;
+        x[i] = p[0]; y[i] = p[1]; z[i] = p[2]; in[i] = (float)p[3]; lab[i] = (unsigned)p[4];
+    }
+    std::vector<ObjBox> ob(n);
+    int max_pts = 1;
+    for (int o = 0; o < n; ++o) {
+        const double* bx = db->boxes + (size_t)o * 8;
+        ObjBox& t = ob[o];
+        t.cx = bx[0]; t.cy = bx[1]; t.cz = bx[2]; t.a = bx[3]; t.b = bx[4];
+        t.length = bx[5]; t.width = bx[6]; t.height = bx[7];
+        t.rho = std::hypot(t.cx, t.cy); t.psi0 = std::atan2(t.cy, t.cx);
+        t.reach = 0.5 * std::hypot(t.length, t.width) + 0.05;
+        t.cls = db->class_index[o];
+        t.first = (int)db->point_offsets[o]; t.count = (int)(db->point_offsets[o + 1] - db->point_offsets[o]);
+        t.pad = 0;
+        if (t.cls < 0 || t.cls >= d.n_classes) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_objects: class index out of range");
+        max_pts = std::max(max_pts, t.count);
+    }
+    if (max_pts > 32768) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: a cut object has more than 32768 points");
+    d.max_obj_points = max_pts; d.n_objects = n;
+    TRY(eng->obj_x.alloc(total)); TRY(eng->obj_y.alloc(total)); TRY(eng->obj_z.alloc(total)); TRY(eng->obj_i.alloc(total));
+    TRY(eng->obj_label.alloc(total)); TRY(eng->obj.alloc(n)); TRY(eng->class_list_off.alloc(d.n_classes + 1));
+    const int nl = db->class_list_offsets[d.n_classes];
+    TRY(eng->class_list.alloc(std::max(nl, 1)));
+    TRY(eng->unplaceable.alloc((size_t)d.B * ((n + 31) / 32)));
+    TRY(eng->occ_pix.alloc((size_t)d.B * OCC_G * max_pts)); TRY(eng->sel_pix.alloc((size_t)d.B * max_pts));
+    R3D_CUDA(cudaMemcpy(eng->obj_x.p, x.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->obj_y.p, y.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->obj_z.p, z.data(), total * sizeof(double), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->obj_i.p, in.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->obj_label.p, lab.data(), total * sizeof(unsigned), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->obj.p, ob.data(), n * sizeof(ObjBox), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->class_list_off.p, db->class_list_offsets, (d.n_classes + 1) * sizeof(int), cudaMemcpyHostToDevice));
+    R3D_CUDA(cudaMemcpy(eng->class_list.p, db->class_list, nl * sizeof(int), cudaMemcpyHostToDevice));
+    d.obj_x = eng->obj_x.p; d.obj_y = eng->obj_y.p; d.obj_z = eng->obj_z.p; d.obj_i = eng->obj_i.p; d.obj_label = eng->obj_label.p;
+    d.obj = eng->obj.p; d.class_list_off = eng->class_list_off.p; d.class_list = eng->class_list.p;
+    d.unplaceable = eng->unplaceable.p; d.occ_pix = eng->occ_pix.p; d.sel_pix = eng->sel_pix.p;
+    const size_t sel_smem = (size_t)next_pow2(max_pts) * sizeof(unsigned long long);
+    R3D_CUDA(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sel_smem, 1024)));
+    R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d.dwords * sizeof(unsigned))));
+    eng->objects_set = true;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_set_ss_map(r3d_engine* eng, const uint8_t* map, int32_t size_x, int32_t size_y, int64_t move_x,
+                                     int64_t move_y) {
+    if (!eng || !map || size_x <= 0 || size_y <= 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_ss_map: bad argument");
+    TRY(eng->ss_map.alloc((size_t)size_x * size_y));
+    R3D_CUDA(cudaMemcpy(eng->ss_map.p, map, (size_t)size_x * size_y, cudaMemcpyHostToDevice));
+    eng->dev.ss_map = eng->ss_map.p; eng->dev.ss_sx = size_x; eng->dev.ss_sy = size_y;
+    eng->dev.ss_move_x = move_x; eng->dev.ss_move_y = move_y;
+    return R3D_OK;
+}
+
+static int arm_batch(r3d_engine* eng, bool ingest) {
+    EngineDev& d = eng->dev;
+    const int n = eng->n_scans;
+    cudaStream_t st = eng->stream;
+    k_reset_state<<<(n + 127) / 128, 128, 0, st>>>(d, n, eng->n0_arr.p, eng->nbox0_arr.p); r3d_count_launch();
+    const int chunks = (eng->max_n0 + CHUNK - 1) / CHUNK;
+    if (ingest) {
+        Launcher l(eng, KID_INGEST);
+        k_ingest<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+    } else {
+        k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
+        // scene boxes: drop the boxes appended by the previous run
+        R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, st));
+        k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, st>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
+        r3d_count_launch();
+    }
+    eng->ran = false;
+    return r3d_check_launch("arm_batch");
+}
+
+extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
+    if (!eng || !bt) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: null argument");
+    if (!eng->objects_set || !eng->yaw_set) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: set objects and yaw tables first");
+    EngineDev& d = eng->dev;
+    const int n = bt->n_scans;
+    if (n <= 0 || n > d.B) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: n_scans exceeds max_scans");
+    if (!bt->point_offsets || !bt->xyzi || !bt->labels || !bt->counts || !bt->perms || bt->n_events <= 0)
+        return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: missing arrays");
+    if (d.task == 1 && (!bt->poses || !d.ss_map)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: semseg needs poses and the map");
+    if (d.task == 0 && (!bt->maps || !bt->map_offsets || !bt->map_dims)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: OD needs maps");
+    cudaStream_t st = eng->stream;
+    std::vector<int> n0(n), nb(n);
+    eng->max_n0 = 0;
+    for (int s = 0; s < n; ++s) {
+        const int64_t cnt = bt->point_offsets[s + 1] - bt->point_offsets[s];
+        if (cnt <= 0 || cnt > d.max_points) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: scan larger than max_points (or empty)");
+        n0[s] = (int)cnt; eng->max_n0 = std::max(eng->max_n0, (int)cnt);
+        nb[s] = bt->box_offsets ? bt->box_offsets[s + 1] - bt->box_offsets[s] : 0;
+        if (nb[s] > d.max_boxes) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: too many scene boxes");
+    }
+    eng->n_scans = n;
+    // points: packed host rows -> per-scan strided device rows
+    for (int s = 0; s < n; ++s) {
+        const int64_t o = bt->point_offsets[s];
+        R3D_CUDA(cudaMemcpyAsync(eng->xyzi.p + (size_t)s * d.max_points, bt->xyzi + o * 4, (size_t)n0[s] * sizeof(float4), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->label.p + (size_t)s * d.P, bt->labels + o, (size_t)n0[s] * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+    }
+    // scene boxes
+    eng->h_boxes.assign((size_t)n * d.max_boxes, Box());
+    for (int s = 0; s < n; ++s)
+        for (int j = 0; j < nb[s]; ++j) {
+            const double* src = bt->boxes + ((size_t)bt->box_offsets[s] + j) * R3D_BOX_DOUBLES;
+            Box& b = eng->h_boxes[(size_t)s * d.max_boxes + j];
+            b.cx = src[0]; b.cy = src[1]; b.cz = src[2];
+            for (int i = 0; i < 9; ++i) b.m[i] = src[3 + i];
+            b.length = src[12]; b.width = src[13]; b.height = src[14]; b.reach = src[15];
+        }
+    eng->h_nbox0 = nb;
+    R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, st));
+    k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, st>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
+    r3d_count_launch();
+    R3D_CUDA(cudaMemcpyAsync(eng->n0_arr.p, n0.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->nbox0_arr.p, nb.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
+    if (d.task == 0) {
+        const int64_t bytes = bt->map_offsets[(size_t)n * 2];
+        if ((size_t)bytes > eng->od_maps.n) TRY(eng->od_maps.alloc((size_t)bytes));
+        R3D_CUDA(cudaMemcpyAsync(eng->od_maps.p, bt->maps, (size_t)bytes, cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->od_map_off.p, bt->map_offsets, ((size_t)n * 2 + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->od_map_dims.p, bt->map_dims, (size_t)n * 8 * sizeof(int), cudaMemcpyHostToDevice, st));
+        d.od_maps = eng->od_maps.p;
+    } else {
+        R3D_CUDA(cudaMemcpyAsync(eng->poses.p, bt->poses, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, st));
+    }
+    R3D_CUDA(cudaMemcpyAsync(eng->counts.p, bt->counts, (size_t)n * d.n_classes * sizeof(int), cudaMemcpyHostToDevice, st));
+    const size_t nperm = (size_t)n * bt->n_events * d.n_classes * d.max_tries;
+    if (nperm > eng->perms.n) TRY(eng->perms.alloc(nperm));
+    R3D_CUDA(cudaMemcpyAsync(eng->perms.p, bt->perms, nperm * sizeof(int), cudaMemcpyHostToDevice, st));
+    d.perms = eng->perms.p; d.n_perm_events = bt->n_events;
+    // the std::vectors above are pageable: the copies from them completed before cudaMemcpyAsync returned
+    eng->batch_loaded = true;
+    return arm_batch(eng, true);
+}
+
+extern "C" int r3d_engine_reset_batch(r3d_engine* eng) {
+    if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_reset_batch: no batch loaded");
+    return arm_batch(eng, false);
+}
+
+extern "C" int r3d_engine_run(r3d_engine* eng) {
+    if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: no batch loaded");
+    EngineDev d = eng->dev;
+    const int n = eng->n_scans;
+    cudaStream_t st = eng->stream;
+    const int P_live = eng->max_n0 + d.max_inserted;
+    const int chunks_all = (P_live + CHUNK - 1) / CHUNK, chunks0 = (eng->max_n0 + CHUNK - 1) / CHUNK;
+    const int kwarps = (d.K + 7) / 8;
+    const size_t sel_smem = (size_t)next_pow2(d.max_obj_points) * sizeof(unsigned long long);
+    R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * sizeof(int), st));
+    cudaEvent_t ev_ctrl[2];
+    cudaEventCreateWithFlags(&ev_ctrl[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&ev_ctrl[1], cudaEventDisableTiming);
+    const int max_rounds = d.max_events * (3 * d.max_tries + 2) + 8;
+    int round = 0;
+    bool done = false;
+    for (; round < max_rounds && !done; ++round) {
+        const int slot = round & 63;
+        d.active_count = eng->active_count.p + slot;
+        { Launcher l(eng, KID_CTRL); k_ctrl<<<n, 128, 0, st>>>(d, n); }
+        R3D_CUDA(cudaMemcpyAsync(eng->h_active + slot, eng->active_count.p + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
+        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + ((slot + 32) & 63), 0, sizeof(int), st));
+        R3D_CUDA(cudaEventRecord(ev_ctrl[round & 1], st));
+        { Launcher l(eng, KID_APPLY); k_apply_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_CLEAR); k_clear_images<<<dim3(32, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_PROJECT); k_project<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        {
+            Launcher l(eng, KID_CLOSEFILL);
+            RawImage in{d.zraw};
+            dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, n);
+            k_close_fill<RawImage><<<grid, CF_THREADS, 0, st>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
+                                                                 d.far_arr, d.gate_project);
+        }
+        if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_HEIGHT1); k_height<1><<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_HEIGHT2); k_height<2><<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_CANDFIN); k_cand_finalize<<<dim3((d.K + 255) / 256, n), 256, 0, st>>>(d, n); }
+        if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 256, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_COLLIDE_PTS); k_collide_points<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_COLLIDE_BOX); k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_FEASIBLE); k_feasible<<<n, 256, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
+        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 256, sel_smem, st>>>(d, n); }
+        // the host only looks at the counter written by the PREVIOUS round's k_ctrl, so the device never idles
+        if (round >= 1) {
+            R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));
+            if (eng->h_active[(round - 1) & 63] == 0) done = true;
+        }
+    }
+    if (!done) {
+        R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));
+        if (eng->h_active[(round - 1) & 63] != 0) {
+            cudaEventDestroy(ev_ctrl[0]); cudaEventDestroy(ev_ctrl[1]);
+            return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
+        }
+    }
+    cudaEventDestroy(ev_ctrl[0]); cudaEventDestroy(ev_ctrl[1]);
+    eng->last_rounds = round;
+    {
+        Launcher l(eng, KID_OUT);
+        k_out_count<<<n, 256, 0, st>>>(d, n);
+        k_out_offsets<<<1, 32, 0, st>>>(d, n);
+        k_out_write<<<n, 1024, 0, st>>>(d, n);
+        r3d_count_launch(2);
+    }
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets, eng->out_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets + (d.B + 1), eng->check_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    eng->ran = true;
+    return r3d_check_launch("r3d_engine_run");
+}
+
+extern "C" int r3d_engine_sync(r3d_engine* eng) {
+    if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_sync: null engine");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    drain_events(eng);
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check) {
+    if (!eng || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_output_rows: run first");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    if (total_points) *total_points = eng->h_offsets[eng->n_scans];
+    if (total_check) *total_check = eng->h_offsets[eng->dev.B + 1 + eng->n_scans];
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
+    if (!eng || !res || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_fetch: run first");
+    EngineDev& d = eng->dev;
+    const int n = eng->n_scans;
+    cudaStream_t st = eng->stream;
+    R3D_CUDA(cudaStreamSynchronize(st));
+    const long long total = eng->h_offsets[n], total_check = eng->h_offsets[d.B + 1 + n];
+    if (total > res->capacity_points || total_check > res->capacity_check)
+        return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_fetch: result buffers too small");
+    if (res->out_offsets) memcpy(res->out_offsets, eng->h_offsets, (n + 1) * sizeof(long long));
+    if (res->check_offsets) memcpy(res->check_offsets, eng->h_offsets + d.B + 1, (n + 1) * sizeof(long long));
+    if (res->out_xyzi && total) R3D_CUDA(cudaMemcpyAsync(res->out_xyzi, eng->out_xyzi.p, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    if (res->out_labels && total) R3D_CUDA(cudaMemcpyAsync(res->out_labels, eng->out_label.p, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (res->check_xyzil && total_check) R3D_CUDA(cudaMemcpyAsync(res->check_xyzil, eng->out_check.p, (size_t)total_check * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (res->inserted) R3D_CUDA(cudaMemcpyAsync(res->inserted, eng->inserted.p, (size_t)n * d.max_events * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    if (res->inserted_box) R3D_CUDA(cudaMemcpyAsync(res->inserted_box, eng->inserted_box.p, (size_t)n * d.max_events * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    std::vector<ScanState> hs(n);
+    R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p, n * sizeof(ScanState), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaStreamSynchronize(st));
+    for (int s = 0; s < n; ++s) {
+        if (res->n_inserted) res->n_inserted[s] = hs[s].n_inserted;
+        if (res->status) res->status[s] = hs[s].status;
+    }
+    if (res->rounds) *res->rounds = eng->last_rounds;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
+    if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_profile_enable: null engine");
+    cudaStreamSynchronize(eng->stream);
+    drain_events(eng);
+    eng->profile = on != 0;
+    for (int i = 0; i < KID_COUNT; ++i) { eng->prof_ms[i] = 0; eng->prof_launches[i] = 0; }
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out,
+                                       int64_t* launches_out, int max_kernels, int* n_kernels_out) {
+    if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_profile_read: null engine");
+    cudaStreamSynchronize(eng->stream);
+    drain_events(eng);
+    std::string names;
+    const int n = std::min<int>(KID_COUNT, max_kernels);
+    for (int i = 0; i < n; ++i) {
+        names += kKernelNames[i]; names += '\n';
+        if (ms_out) ms_out[i] = eng->prof_ms[i];
+        if (launches_out) launches_out[i] = eng->prof_launches[i];
+    }
+    if (names_out && names_cap > 0) { strncpy(names_out, names.c_str(), names_cap - 1); names_out[names_cap - 1] = 0; }
+    if (n_kernels_out) *n_kernels_out = n;
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_debug_image(r3d_engine* eng, int scan, double* smooth_out) {
+    if (!eng || scan < 0 || scan >= eng->n_scans || !smooth_out) return r3d_fail(R3D_ERR_ARG, "r3d_engine_debug_image: bad argument");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    R3D_CUDA(cudaMemcpy(smooth_out, eng->smooth.p + (size_t)scan * eng->dev.hw, (size_t)eng->dev.hw * sizeof(double), cudaMemcpyDeviceToHost));
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* flags_out, double* level_out, int32_t* visible_out) {
+    if (!eng || scan < 0 || scan >= eng->n_scans) return r3d_fail(R3D_ERR_ARG, "r3d_engine_debug_candidates: bad argument");
+    const size_t K1 = eng->dev.K + 1;
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    std::vector<unsigned char> f(K1);
+    std::vector<int> col(K1);
+    R3D_CUDA(cudaMemcpy(f.data(), eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost));
+    R3D_CUDA(cudaMemcpy(col.data(), eng->cand_collide.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost));
+    if (flags_out) for (size_t k = 0; k < K1; ++k) flags_out[k] = (uint8_t)(f[k] | (col[k] ? 4 : 0));
+    if (level_out) R3D_CUDA(cudaMemcpy(level_out, eng->cand_level.p + scan * K1, K1 * sizeof(double), cudaMemcpyDeviceToHost));
+    if (visible_out) R3D_CUDA(cudaMemcpy(visible_out, eng->cand_v.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost));
+    return R3D_OK;
+}

@@ -1,0 +1,145 @@
+// Device-side data model of the batched Real3D-Aug engine (one instance per GPU / process).
+//
+// HBM layout (B = scans in the batch, P = max_points + max_inserted, K = yaw_steps, HW = rows * cols):
+//   xyzi      float4 [B][max_points]   original points exactly as read from velodyne/*.bin (immutable)
+//   tail_*    double [B][max_inserted] inserted object points keep their fp64 coordinates (the reference keeps the
+//                                       working cloud in float64 until save_data casts, od/ds:86-88)
+//   label     u32    [B][P]            semantic label (original) / object label (inserted)
+//   r, el     double [B][P]            cached range / elevation (A2 is computed ONCE per point, not once per slot)
+//   col       u16    [B][P]            cached azimuth bin (depends only on the image width)
+//   pix       i32    [B][P]            pix_id of the current slot's projection
+//   alive     u8     [B][P]            0 once an occlusion removed the point (scene = scene[keep] in the reference)
+//   zraw      u64    [B][HW]           z-buffer: min range bits per pixel, all-ones = empty
+//   smooth    double [B][HW]           range image after closing + hole fill (500 = empty)
+//   obj_raw   u64    [B][HW]           scratch z-buffer of the chosen candidate (kept all-ones between uses)
+//   dmask     u32    [B][HW/32]        vis_px bit mask of the last evaluated candidate (od/ins:486)
+//   cand_*           [B][K+1]          per-candidate results of the current try (index = rotation 1..K)
+#pragma once
+#include "r3d_common.cuh"
+#include "../../include/real3d_b200.h"
+
+namespace r3d {
+
+enum : int { PH_INIT = 0, PH_AFTER_TRY = 1, PH_DONE = 2, PH_ERROR = 3 };
+enum : unsigned { CF_ONMAP = 1u, CF_HOK = 2u };
+
+struct ClassCfg {
+    int min_points, map_sel;
+    unsigned map_ok_mask;
+    int pedestrian, n_surface;
+    int surface[R3D_MAX_SURFACE];
+};
+
+struct ObjBox {          // one cut object: box from read_label_line (od/fs:175-224, ss/fs:155-189), host-prepared
+    double cx, cy, cz;   // cz = box bottom
+    double a, b;         // R0[0][0], R0[1][0]
+    double length, width, height;
+    double rho, psi0;    // range / azimuth of the box centre about the sensor (pruning only)
+    double reach;        // horizontal bounding radius (pruning only)
+    int cls, first, count, pad;
+};
+
+struct ScanState {
+    int n0, n_tail, tail_before, n_boxes;
+    int phase, status;
+    int remaining[R3D_MAX_CLASSES];
+    int inserted_class, timeout, start_idx, end_idx, s_idx, event;
+    int cur_class, cur_obj;
+    int try_active, need_project, apply_flag, dirty, scene_changed;
+    int n_feasible, found_rank, chosen_rot, accepted, chosen_v;
+    int n_inserted, n_check;
+    int far_flag;
+    int win_x0, win_y0;
+    unsigned long long min_el_bits, max_el_bits;
+    ImageGeom geom;
+    double dz_unused;
+};
+
+struct EngineDev {       // passed by value to kernels
+    int task, rows, cols, hw, K, max_tries, n_classes;
+    int B, max_points, max_inserted, P, max_boxes, max_events, max_obj_points;
+    int road_label, n_road_indexes, map_window, dwords, n_objects, n_perm_events;
+    int road_indexes[R3D_MAX_SURFACE];
+    double step_rad;
+    // per-scan resident data
+    const float4* xyzi;
+    double *tail_x, *tail_y, *tail_z;
+    float* tail_i;
+    unsigned* label;
+    double *r, *el;
+    unsigned short* col;
+    int* pix;
+    unsigned char* alive;
+    unsigned long long *zraw, *obj_raw;
+    double* smooth;
+    unsigned *dmask, *vmask;
+    ScanState* st;
+    int *gate_project, *gate_try, *gate_apply;
+    int* active_count;
+    int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
+    // scene boxes
+    Box* boxes;            // [B][max_boxes]
+    BoxTest* box_tests;    // [B][max_boxes]
+    // maps
+    const unsigned char* od_maps;     // concatenated
+    const long long* od_map_off;      // [B*2]
+    const int* od_map_dims;           // [B*2*4]
+    const unsigned char* ss_map;      // sequence map (values 0..3)
+    int ss_sx, ss_sy;
+    long long ss_move_x, ss_move_y;
+    const double* poses;              // [B][16]
+    unsigned* occ_win;                // [B][map_window*map_window/32]
+    // schedule
+    const int* counts;                // [B][C]
+    const int* perms;                 // [B][E][C][tries]
+    unsigned* unplaceable;            // [B][ceil(n_objects/32)]
+    // object DB
+    const ObjBox* obj;
+    const double *obj_x, *obj_y, *obj_z;
+    const float* obj_i;
+    const unsigned* obj_label;
+    const int* class_list_off;
+    const int* class_list;
+    const double *cos_k, *sin_k;      // [K+1]
+    const double* radii_sq;           // [50]
+    const int* radii_ok;              // [50]
+    const ClassCfg* classes;
+    // candidates of the current try
+    unsigned char* cand_flags;        // [B][K+1]
+    int* cand_collide;                // [B][K+1]
+    int* cand_jmin;                   // [B][K+1]
+    unsigned long long* cand_zsum;    // [B][K+1] fixed point 2^-40
+    unsigned* cand_zcnt;              // [B][K+1]
+    double* cand_level;               // [B][K+1]
+    double *cand_cx, *cand_cy;        // [B][K+1]
+    BoxTest* cand_bt;                 // [B][K+1]
+    int* cand_v;                      // [B][K+1]
+    int* feas;                        // [B][K]
+    int* occ_pix;                     // [B][OCC_G][max_obj_points] scratch
+    int* sel_pix;                     // [B][max_obj_points]
+    // outputs
+    int* inserted;                    // [B][E][4]
+    double* inserted_box;             // [B][E][8]
+    float* check;                     // [B][max_inserted][5]
+    long long* out_count;             // [B] rows per scan ; out_off [B+1]
+    long long* out_off;
+    long long* check_off;
+    float4* out_xyzi;
+    unsigned* out_label;
+    float* out_check;
+};
+
+constexpr int OCC_G = 16;        // CTAs per scan in the occlusion-count kernel
+constexpr double kFix = 1099511627776.0;   // 2^40 fixed point for the order-independent road-level sum
+
+__device__ __forceinline__ void load_xyz(const EngineDev& e, int b, int p, int n0, double& x, double& y, double& z) {
+    if (p < n0) {
+        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        x = (double)v.x; y = (double)v.y; z = (double)v.z;
+    } else {
+        const size_t t = (size_t)b * e.max_inserted + (p - n0);
+        x = e.tail_x[t]; y = e.tail_y[t]; z = e.tail_z[t];
+    }
+}
+
+}  // namespace r3d

@@ -1,0 +1,915 @@
+// Kernels of the batched Real3D-Aug engine.  One "round" = one tried cut object for every unfinished scan of the
+// batch; the reference's nested Python loops (od/ins:375-614) are a per-scan state machine advanced on the device
+// (k_ctrl), so the host only launches a fixed kernel sequence per round and polls one counter.
+#pragma once
+#include "r3d_engine.cuh"
+#include "r3d_closefill.cuh"
+
+namespace r3d {
+
+constexpr int CHUNK = 4096;          // points per CTA of the streaming kernels (256 threads x 16 points)
+constexpr int STREAM_THREADS = 256;
+
+__device__ __forceinline__ void set_error(ScanState& s, int code) {
+    if (s.status == 0) s.status = code;
+}
+
+// ------------------------------------------------------------------------------------------------ ingest
+// A1 + A2 (od/ins:55-82) once per original point: r, elevation and the azimuth bin are cached in HBM.
+__global__ void __launch_bounds__(STREAM_THREADS) k_ingest(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    const int n0 = s.n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n0) return;
+    const double d_az = kTwoPi / (double)e.cols;
+    const size_t base = (size_t)b * e.P;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
+        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        const double x = v.x, y = v.y, z = v.z;
+        const double r = range3(x, y, z);
+        const double el = elevation(z, r);
+        const int c = trunc_to_int(__ddiv_rn(az_mod(azimuth(x, y)), d_az));
+        if (!(r > 0.0) || c < 0 || c >= e.cols) set_error(s, R3D_ERR_ASSERT);      // od/ins:113 / nan elevation
+        e.r[base + p] = r;
+        e.el[base + p] = el;
+        e.col[base + p] = (unsigned short)max(0, min(c, e.cols - 1));
+        e.alive[base + p] = 1;
+    }
+}
+
+__global__ void k_reset_alive(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const int n0 = e.st[b].n0;
+    const size_t base = (size_t)b * e.P;
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n0; p += gridDim.x * blockDim.x) e.alive[base + p] = 1;
+}
+
+// per-scan scheduling state from the pre-drawn counts (generate_seed, od/ins:171-187)
+__global__ void k_reset_state(EngineDev e, int n_scans, const int* n0_arr, const int* nbox0_arr) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    s.n0 = n0_arr[b]; s.n_tail = 0; s.tail_before = 0; s.n_boxes = nbox0_arr[b];
+    s.phase = PH_INIT; s.status = 0;
+    s.inserted_class = -1;
+    for (int c = 0; c < R3D_MAX_CLASSES; ++c) s.remaining[c] = c < e.n_classes ? e.counts[b * e.n_classes + c] : 0;
+    for (int c = e.n_classes - 1; c >= 0; --c) if (s.remaining[c] > 0) s.inserted_class = c;
+    s.timeout = 0; s.start_idx = 0; s.end_idx = 0; s.s_idx = 0; s.event = 0;
+    s.cur_class = 0; s.cur_obj = -1;
+    s.try_active = 0; s.need_project = 0; s.apply_flag = 0; s.dirty = 0; s.scene_changed = 1;
+    s.n_feasible = 0; s.found_rank = INT_MAX; s.chosen_rot = 0; s.accepted = 0; s.chosen_v = 0;
+    s.n_inserted = 0; s.n_check = 0; s.far_flag = 0;
+    s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
+    if (e.task == 1) {     // semseg: window of map cells around the sensor for the occupied-cell overlay
+        const double* T = e.poses + (size_t)b * 16;
+        s.win_x0 = (int)(T[3] - (double)e.ss_move_x) - e.map_window / 2;
+        s.win_y0 = (int)(T[7] - (double)e.ss_move_y) - e.map_window / 2;
+    } else { s.win_x0 = 0; s.win_y0 = 0; }
+    const int uw = (e.n_objects + 31) / 32;
+    for (int w = 0; w < uw; ++w) e.unplaceable[(size_t)b * uw + w] = 0u;
+}
+
+// ------------------------------------------------------------------------------------------------- ctrl
+// A13 (od/ins:386-428, 587-614): which cut object each scan tries next.  Thread 0 advances the reference's
+// slot / window / try loops until the scan needs GPU work again; the CTA then re-arms the candidate arrays.
+__device__ int list_entry(const EngineDev& e, int b, int ev, int ci, int sidx, int len) {
+    const int* head = e.perms + (((size_t)b * e.n_perm_events + ev) * e.n_classes + ci) * e.max_tries;
+    if (sidx < e.max_tries) return head[sidx];
+    int nhead = 0;
+    while (nhead < e.max_tries && head[nhead] >= 0) ++nhead;
+    int want = sidx - nhead, seen = 0;
+    for (int j = 0; j < len; ++j) {
+        bool in_head = false;
+        for (int h = 0; h < nhead; ++h) if (head[h] == j) { in_head = true; break; }
+        if (in_head) continue;
+        if (seen == want) return j;
+        ++seen;
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    __shared__ int s_try;
+    ScanState& s = e.st[b];
+    if (threadIdx.x == 0) {
+        int apply = 0, project = 0, tryact = 0;
+        if (s.phase != PH_DONE && s.phase != PH_ERROR) {
+            const int uw = (e.n_objects + 31) / 32;
+            unsigned* unpl = e.unplaceable + (size_t)b * uw;
+            int ci = s.cur_class;
+            bool new_slot = false, new_window = false, next_try = false;
+            if (s.phase == PH_INIT) {
+                new_slot = true;
+            } else {
+                const int len = e.class_list_off[ci + 1] - e.class_list_off[ci];
+                if (s.accepted) {                                   // od/ins:536-547
+                    s.timeout = 0;
+                    s.remaining[ci] -= 1;
+                    apply = 1; s.dirty = 0; s.scene_changed = 1;
+                    new_slot = true;
+                } else {
+                    unpl[s.cur_obj >> 5] |= 1u << (s.cur_obj & 31);   // od/ins:464-466, 583-585
+                    if (s.n_feasible > 0) s.dirty = 1;                // od/ins:472,491: last failed candidate persists
+                    const int sidx = s.s_idx;
+                    if (sidx == len - 1 || sidx == 3 * e.max_tries) { s.remaining[ci] = 0; s.timeout = 1; }   // :587-591
+                    if (sidx == s.end_idx - 1) {                                                             // :595-614
+                        s.remaining[ci] -= 1;
+                        if (s.remaining[ci] <= 0) new_slot = true; else new_window = true;
+                    } else { s.s_idx = sidx + 1; next_try = true; }
+                }
+            }
+            for (int guard = 0; guard < 100000; ++guard) {
+                if (new_slot) {
+                    new_slot = false;
+                    int mx = 0;
+                    for (int c = 0; c < e.n_classes; ++c) mx = max(mx, s.remaining[c]);
+                    if (mx <= 0) {                                   // od/ins:375
+                        s.phase = PH_DONE;
+                        if (s.dirty) { apply = 1; s.dirty = 0; s.tail_before = s.n_tail; }
+                        break;
+                    }
+                    if (s.dirty) { apply = 1; s.dirty = 0; s.scene_changed = 1; s.tail_before = s.n_tail; }
+                    if (s.scene_changed) { project = 1; s.scene_changed = 0; }
+                    for (int c = 0; c < e.n_classes; ++c)
+                        if (s.remaining[c] > 0) { ci = c; break; }    // od/ins:386-391
+                    if (s.inserted_class != ci) s.timeout = 0;
+                    s.inserted_class = ci; s.cur_class = ci;
+                    new_window = true;
+                }
+                const int len = e.class_list_off[ci + 1] - e.class_list_off[ci];
+                if (new_window) {
+                    new_window = false;
+                    if (!s.timeout) {                                // od/ins:399-402 (random.shuffle = next table row)
+                        if (s.event >= e.n_perm_events) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; break; }
+                        s.event += 1;
+                        s.start_idx = 0; s.end_idx = e.max_tries;
+                    } else {                                         // od/ins:403-407
+                        s.start_idx += e.max_tries; s.end_idx += e.max_tries;
+                        if (s.end_idx > len) s.end_idx = len;
+                    }
+                    s.s_idx = s.start_idx;
+                    if (s.start_idx >= s.end_idx) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; break; }
+                    next_try = true;
+                }
+                if (next_try) {
+                    next_try = false;
+                    const int sidx = s.s_idx;
+                    if (sidx >= len) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; break; }     // od/ins:410
+                    const int idx = list_entry(e, b, s.event - 1, ci, sidx, len);
+                    if (idx < 0 || idx >= len) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; break; }
+                    const int obj = e.class_list[e.class_list_off[ci] + idx];
+                    if (unpl[obj >> 5] & (1u << (obj & 31))) {       // od/ins:422-428
+                        if (sidx == s.end_idx - 1) { s.remaining[ci] -= 1; new_slot = true; continue; }
+                        s.s_idx = sidx + 1; next_try = true; continue;
+                    }
+                    s.cur_obj = obj; tryact = 1; s.phase = PH_AFTER_TRY;
+                    break;
+                }
+            }
+            if (s.phase != PH_DONE && s.phase != PH_ERROR && !tryact) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; }
+        }
+        if (project || apply) { s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull; }
+        s.try_active = tryact; s.need_project = project; s.apply_flag = apply;
+        s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
+        e.gate_project[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply | project;
+        if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(e.active_count, 1);
+        s_try = tryact;
+    }
+    __syncthreads();
+    if (!s_try) return;
+    const ObjBox ob = e.obj[s.cur_obj];
+    const size_t cb = (size_t)b * (e.K + 1);
+    for (int k = threadIdx.x; k <= e.K; k += blockDim.x) {
+        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_jmin[cb + k] = INT_MAX;
+        e.cand_zsum[cb + k] = 0ull; e.cand_zcnt[cb + k] = 0u; e.cand_v[cb + k] = 0;
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        e.cand_cx[cb + k] = sub(mul(c, ob.cx), mul(sn, ob.cy));
+        e.cand_cy[cb + k] = add(mul(sn, ob.cx), mul(c, ob.cy));
+    }
+}
+
+// ------------------------------------------------------------------------------- apply mask + min/max el
+__device__ __forceinline__ bool pix_removed(const EngineDev& e, int b, const ScanState& s, int pix) {
+    if (pix < 0) return false;
+    if (e.dmask[(size_t)b * e.dwords + (pix >> 5)] & (1u << (pix & 31))) return true;
+    // od/ins:486: an empty object pixel holds 500, so scene pixels farther than 500 count as covered
+    return e.far_arr[b] && e.smooth[(size_t)b * e.hw + pix] > kEmptyRange;
+}
+
+// A11/A12 (od/ins:488-501, 545): scene = scene[pix_id not in vis_px]; also the elevation range of what is left (A2,
+// od/ins:79-80).  5 B/point of algorithmic traffic (pix + alive), + 8 B/point for the cached elevation.
+__global__ void __launch_bounds__(STREAM_THREADS) k_apply_minmax(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_apply[b]) return;
+    ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n) return;
+    const int limit = s.apply_flag ? s.n0 + s.tail_before : 0;
+    const size_t base = (size_t)b * e.P;
+    unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
+        unsigned char a = e.alive[base + p];
+        if (a && p < limit && pix_removed(e, b, s, e.pix[base + p])) { a = 0; e.alive[base + p] = 0; }
+        if (a) {
+            const unsigned long long bits = dbl_bits(e.el[base + p]);
+            lmin = min(lmin, bits); lmax = max(lmax, bits);
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    __shared__ unsigned long long s_min[STREAM_THREADS / 32], s_max[STREAM_THREADS / 32];
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lmin; s_max[threadIdx.x >> 5] = lmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < STREAM_THREADS / 32; ++w) { lmin = min(lmin, s_min[w]); lmax = max(lmax, s_max[w]); }
+        if (lmax >= lmin) { atomicMin(&s.min_el_bits, lmin); atomicMax(&s.max_el_bits, lmax); }
+    }
+}
+
+// clear the z-buffer (and the semseg occupied-cell window) of the scans that re-project, fix their image geometry
+__global__ void __launch_bounds__(STREAM_THREADS) k_clear_images(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_project[b]) return;
+    ScanState& s = e.st[b];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        e.far_arr[b] = 0;
+        if (s.min_el_bits == R3D_EMPTY_U64) { set_error(s, R3D_ERR_ASSERT); }
+        s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+    }
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.hw; i += gridDim.x * blockDim.x) z[i] = R3D_EMPTY_U64;
+    if (e.task == 1) {
+        const int ww = e.map_window * e.map_window / 32;
+        unsigned* o = e.occ_win + (size_t)b * ww;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ww; i += gridDim.x * blockDim.x) o[i] = 0u;
+    }
+}
+
+// A3 (od/ins:85-130): bin every live point with the reference's truncation rule, write pix_id, 64-bit atomicMin of
+// the range bits into the z-buffer.  Algorithmic traffic 20 B/point (+ 8 B/pixel for the z-buffer).
+__global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_project[b]) return;
+    ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n) return;
+    const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+    const size_t base = (size_t)b * e.P;
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
+        if (!e.alive[base + p]) continue;
+        const int row = bin_row(g, e.el[base + p]);
+        if (row < 0 || row >= g.rows) { set_error(s, R3D_ERR_ASSERT); continue; }      // od/ins:111
+        const int pix = row * g.cols + (int)e.col[base + p];
+        e.pix[base + p] = pix;
+        atomicMin(&z[pix], dbl_bits(e.r[base + p]));
+    }
+}
+
+struct RawImage {        // the engine's z-buffer as close/fill input
+    const unsigned long long* raw;
+    __device__ bool occ(int64_t i) const { return raw[i] != R3D_EMPTY_U64; }
+    __device__ bool is_one(int64_t i) const { return raw[i] != R3D_EMPTY_U64; }
+    __device__ double val(int64_t i) const { const unsigned long long b = raw[i]; return b != R3D_EMPTY_U64 ? bits_dbl(b) : kEmptyRange; }
+    __device__ double lab(int64_t i) const { return raw[i] != R3D_EMPTY_U64 ? 1.0 : -1.0; }
+};
+
+// semseg addjust_map_2 (ss/ins:202-224): map cells (value != 0) that hold a live scene point with z < 1.5 and a
+// non-ground label count as value 4 for this slot.  Kept as a per-scan bit window instead of rewriting the map.
+__global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_project[b]) return;
+    ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n) return;
+    const double* T = e.poses + (size_t)b * 16;
+    const size_t base = (size_t)b * e.P;
+    unsigned* o = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
+        if (!e.alive[base + p]) continue;
+        const unsigned lab = e.label[base + p];
+        bool ground = false;
+        for (int i = 0; i < e.n_road_indexes; ++i) ground |= lab == (unsigned)e.road_indexes[i];
+        if (ground) continue;
+        double x, y, z;
+        load_xyz(e, b, p, s.n0, x, y, z);
+        if (!(z < 1.5)) continue;
+        const double wx = add(add(add(mul(T[0], x), mul(T[1], y)), mul(T[2], z)), T[3]);
+        const double wy = add(add(add(mul(T[4], x), mul(T[5], y)), mul(T[6], z)), T[7]);
+        const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
+        const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
+        if (ix < 0 || iy < 0 || ix >= e.ss_sx || iy >= e.ss_sy) continue;   // reference: IndexError / wrap-around
+        if (e.ss_map[(size_t)ix * e.ss_sy + iy] == 0) continue;
+        const int lx = ix - s.win_x0, ly = iy - s.win_y0;
+        if (lx < 0 || ly < 0 || lx >= e.map_window || ly >= e.map_window) { set_error(s, R3D_ERR_CAPACITY); continue; }
+        const int bit = lx * e.map_window + ly;
+        atomicOr(&o[bit >> 5], 1u << (bit & 31));
+    }
+}
+
+// ------------------------------------------------------------------------------------------- placement
+// candidates (rotation indices, wrapping) whose box centre can lie within `reach` of the point (x, y)
+__device__ __forceinline__ void cand_window(const ObjBox& ob, float x, float y, float reach, float step, int K,
+                                            int& k_first, int& count) {
+    if (reach >= 0.98f * (float)ob.rho) { k_first = 1; count = K; return; }
+    const float alpha = asinf(fminf(1.f, reach / (float)ob.rho)) + 2e-4f;
+    const float w = ceilf(alpha / step) + 1.f;
+    float kc = (atan2f(y, x) - (float)ob.psi0) / step;
+    kc -= floorf(kc / (float)K) * (float)K;
+    count = min(K, 2 * (int)w + 2);
+    int k0 = (int)floorf(kc) - (int)w;
+    k0 %= K; if (k0 < 0) k0 += K;
+    k_first = k0;
+}
+__device__ __forceinline__ int cand_index(int k_first, int j, int K) {
+    int k = k_first + j;
+    if (k >= K) k -= K;
+    if (k >= K) k %= K;
+    return k == 0 ? K : k;               // rotation K*step = 360 degrees is index K
+}
+
+// A5 + A6a (od/fs:263-279): one warp per yaw candidate; every in-map object point must sit on a map cell == 1.
+__global__ void __launch_bounds__(256) k_onmap_od(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
+    if (k > e.K) return;
+    const int lane = threadIdx.x & 31;
+    const ScanState& s = e.st[b];
+    const ObjBox ob = e.obj[s.cur_obj];
+    const int msel = e.classes[ob.cls].map_sel;
+    const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
+    const int sx = dims[0], sy = dims[1];
+    const double mx = (double)dims[2], my = (double)dims[3];
+    const unsigned char* map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    bool any_in = false, bad = false;
+    for (int i0 = 0; i0 < ob.count; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < ob.count) {
+            const double x = e.obj_x[ob.first + i], y = e.obj_y[ob.first + i];
+            const double gx = sub(sub(mul(c, x), mul(sn, y)), mx);
+            const double gy = sub(add(mul(sn, x), mul(c, y)), my);
+            if (!(gx < 0.0 || gx >= (double)sx || gy < 0.0 || gy >= (double)sy)) {
+                any_in = true;
+                bad |= map[(size_t)((int)gx) * sy + (int)gy] != 1;
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) break;          // warp-ballot early-out (od/fs:277-279)
+    }
+    any_in = __any_sync(0xffffffffu, any_in);
+    bad = __any_sync(0xffffffffu, bad);
+    if (lane == 0 && any_in && !bad) e.cand_flags[(size_t)b * (e.K + 1) + k] = CF_ONMAP;
+}
+
+__device__ __forceinline__ bool surface_label(const ClassCfg& cc, unsigned lab) {
+    bool ok = false;
+    for (int i = 0; i < cc.n_surface; ++i) ok |= lab == (unsigned)cc.surface[i];
+    return ok;
+}
+
+__device__ __forceinline__ int radius_index(const double* r2, double d2) {
+    if (!(d2 <= r2[R3D_NUM_RADII - 1])) return R3D_NUM_RADII;
+    int lo = 0, hi = R3D_NUM_RADII - 1;                   // smallest j with d2 <= r2[j]
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2 <= r2[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// A7 (od/fs:138-172, ss/fs:107-152), pass 1: for every candidate the first radius (0.1, 0.2, ... accumulated) whose
+// disc holds a surface point of the ORIGINAL scan.  PASS 2 sums z of the points inside that disc in 2^-40 fixed
+// point (order independent, exact for float32 z).  Both passes stream the original points once: 20 B/point.
+template <int PASS>
+__global__ void __launch_bounds__(STREAM_THREADS) k_height(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const ScanState& s = e.st[b];
+    const int n0 = s.n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n0) return;
+    __shared__ double s_r2[R3D_NUM_RADII];
+    if (threadIdx.x < R3D_NUM_RADII) s_r2[threadIdx.x] = e.radii_sq[threadIdx.x];
+    __syncthreads();
+    const ObjBox ob = e.obj[s.cur_obj];
+    const ClassCfg& cc = e.classes[ob.cls];
+    const float reach = 5.0f;
+    const float rlo = fmaxf((float)ob.rho - reach - 0.02f, 0.f), rhi = (float)ob.rho + reach + 0.02f;
+    const float step = (float)e.step_rad;
+    const size_t cb = (size_t)b * (e.K + 1);
+    const size_t base = (size_t)b * e.P;
+    const bool need_onmap = e.task == 0;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
+        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        const float rho2 = v.x * v.x + v.y * v.y;
+        if (rho2 < rlo * rlo || rho2 > rhi * rhi) continue;
+        if (!((double)v.z > -3.0)) continue;                               // od/fs:155
+        if (!surface_label(cc, e.label[base + p])) continue;              // od/fs:154, ss/fs:125-131
+        int k_first, count;
+        cand_window(ob, v.x, v.y, reach, step, e.K, k_first, count);
+        const double x = v.x, y = v.y;
+        for (int j = 0; j < count; ++j) {
+            const int k = cand_index(k_first, j, e.K);
+            if (need_onmap && !(e.cand_flags[cb + k] & CF_ONMAP)) continue;
+            const double dx = sub(x, e.cand_cx[cb + k]), dy = sub(y, e.cand_cy[cb + k]);
+            const double d2 = add(mul(dx, dx), mul(dy, dy));               // od/fs:153
+            if (PASS == 1) {
+                const int ji = radius_index(s_r2, d2);
+                if (ji < R3D_NUM_RADII) atomicMin(&e.cand_jmin[cb + k], ji);
+            } else {
+                const int jm = e.cand_jmin[cb + k];
+                if (jm < R3D_NUM_RADII && d2 <= s_r2[jm]) {
+                    atomicAdd(&e.cand_zsum[cb + k], (unsigned long long)__double2ll_rn(mul((double)v.z, kFix)));
+                    atomicAdd(&e.cand_zcnt[cb + k], 1u);
+                }
+            }
+        }
+    }
+}
+
+// road level (od/fs:164), near_road flag (od/fs:158-160) and the candidate's box test (R_k = R0 . Rz(k*step))
+__global__ void __launch_bounds__(256) k_cand_finalize(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    if (k > e.K) return;
+    const ScanState& s = e.st[b];
+    const ObjBox ob = e.obj[s.cur_obj];
+    const size_t cb = (size_t)b * (e.K + 1);
+    const int jm = e.cand_jmin[cb + k];
+    unsigned f = e.cand_flags[cb + k];
+    if (jm < R3D_NUM_RADII && e.radii_ok[jm] && e.cand_zcnt[cb + k] > 0) {
+        const double level = __ddiv_rn(__ddiv_rn((double)(long long)e.cand_zsum[cb + k], kFix), (double)e.cand_zcnt[cb + k]);
+        e.cand_level[cb + k] = level;
+        const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, e.cos_k[k], e.sin_k[k]);
+        const Box bx = yaw_box_to_box(yb, level, ob.length, ob.width, ob.height);
+        e.cand_bt[cb + k] = make_box_test(bx);
+        f |= CF_HOK;
+    }
+    e.cand_flags[cb + k] = (unsigned char)f;
+}
+
+// A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place): candidates are visited in
+// order by one CTA; world = T . [x y z 1] - move, astype(int); every in-map cell value must be allowed.
+__global__ void __launch_bounds__(256) k_onmap_ss(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const ScanState& s = e.st[b];
+    const ObjBox ob = e.obj[s.cur_obj];
+    const unsigned okmask = e.classes[ob.cls].map_ok_mask;
+    const double* T = e.poses + (size_t)b * 16;
+    const double t00 = T[0], t01 = T[1], t02 = T[2], t03 = T[3], t10 = T[4], t11 = T[5], t12 = T[6], t13 = T[7];
+    const unsigned* o = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    const size_t cb = (size_t)b * (e.K + 1);
+    double dz = 0.0;
+    for (int k = 1; k <= e.K; ++k) {
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        int bad = 0;
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+            const double x = sub(mul(c, x0), mul(sn, y0)), y = add(mul(sn, x0), mul(c, y0));
+            const double z = add(e.obj_z[ob.first + i], dz);
+            const double wx = add(add(add(mul(t00, x), mul(t01, y)), mul(t02, z)), t03);
+            const double wy = add(add(add(mul(t10, x), mul(t11, y)), mul(t12, z)), t13);
+            const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
+            const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
+            if (ix < e.ss_sx && ix > -1 && iy < e.ss_sy && iy > -1) {
+                unsigned v = e.ss_map[(size_t)ix * e.ss_sy + iy];
+                const int lx = ix - s.win_x0, ly = iy - s.win_y0;
+                if (lx >= 0 && ly >= 0 && lx < e.map_window && ly < e.map_window) {
+                    const int bit = lx * e.map_window + ly;
+                    if (o[bit >> 5] & (1u << (bit & 31))) v = 4;
+                }
+                if (!((okmask >> v) & 1u)) bad = 1;
+            }
+        }
+        bad = __syncthreads_or(bad);
+        unsigned f = e.cand_flags[cb + k];
+        if (!bad) {
+            if (threadIdx.x == 0) e.cand_flags[cb + k] = (unsigned char)(f | CF_ONMAP);
+            if (f & CF_HOK) dz = sub(e.cand_level[cb + k], ob.cz);          // ss/fs:144-148
+        }
+    }
+}
+
+// A8 + A9 part (i) (od/fs:119-127, ss/fs:89-96): obstacle scene points strictly inside a candidate box.  One pass
+// over the live scene (20 B/point); each point only meets the candidates whose centre is within the box reach.
+__global__ void __launch_bounds__(STREAM_THREADS) k_collide_points(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n) return;
+    const ObjBox ob = e.obj[s.cur_obj];
+    const ClassCfg& cc = e.classes[ob.cls];
+    const float reach = (float)ob.reach;
+    const float rlo = fmaxf((float)ob.rho - reach - 0.02f, 0.f), rhi = (float)ob.rho + reach + 0.02f;
+    const float step = (float)e.step_rad;
+    const size_t cb = (size_t)b * (e.K + 1);
+    const size_t base = (size_t)b * e.P;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
+        if (!e.alive[base + p]) continue;
+        double x, y, z;
+        load_xyz(e, b, p, s.n0, x, y, z);
+        const float fx = (float)x, fy = (float)y;
+        const float rho2 = fx * fx + fy * fy;
+        if (rho2 < rlo * rlo || rho2 > rhi * rhi) continue;
+        const unsigned lab = e.label[base + p];
+        if (e.task == 0) { if (lab == (unsigned)e.road_label) continue; }       // od/ins:353-355 + od/fs:121
+        else if (surface_label(cc, lab)) continue;                              // ss/fs:92-93
+        if (s.dirty && pix_removed(e, b, s, e.pix[base + p])) continue;          // od/ins:472,491
+        int k_first, count;
+        cand_window(ob, fx, fy, reach, step, e.K, k_first, count);
+        for (int j = 0; j < count; ++j) {
+            const int k = cand_index(k_first, j, e.K);
+            if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK)) continue;
+            if (e.cand_collide[cb + k]) continue;
+            if (cc.pedestrian && !(z >= add(e.cand_level[cb + k], 0.1))) continue;     // od/fs:123-124
+            if (inside_box(e.cand_bt[cb + k], x, y, z)) e.cand_collide[cb + k] = 1;
+        }
+    }
+}
+
+// A9 part (ii) (od/fs:129-134): any object point strictly inside an existing / already inserted box.
+__global__ void __launch_bounds__(256) k_collide_boxes(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
+    if (k > e.K) return;
+    const int lane = threadIdx.x & 31;
+    const ScanState& s = e.st[b];
+    if (s.n_boxes == 0) return;
+    const size_t cb = (size_t)b * (e.K + 1);
+    if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK) || e.cand_collide[cb + k]) return;
+    const ObjBox ob = e.obj[s.cur_obj];
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    const double dz = sub(e.cand_level[cb + k], ob.cz);
+    const double ccx = e.cand_cx[cb + k], ccy = e.cand_cy[cb + k];
+    for (int bi = 0; bi < s.n_boxes; ++bi) {
+        const Box& bx = e.boxes[(size_t)b * e.max_boxes + bi];
+        const double ddx = ccx - bx.cx, ddy = ccy - bx.cy, rr = ob.reach + bx.reach + 0.05;
+        if (ddx * ddx + ddy * ddy > rr * rr) continue;
+        const BoxTest bt = e.box_tests[(size_t)b * e.max_boxes + bi];
+        bool hit = false;
+        for (int i0 = 0; i0 < ob.count && !hit; i0 += 32) {
+            const int i = i0 + lane;
+            bool h = false;
+            if (i < ob.count) {
+                const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+                h = inside_box(bt, sub(mul(c, x0), mul(sn, y0)), add(mul(sn, x0), mul(c, y0)),
+                               add(e.obj_z[ob.first + i], dz));
+            }
+            hit = __any_sync(0xffffffffu, h);
+        }
+        if (hit) { if (lane == 0) e.cand_collide[cb + k] = 1; return; }
+    }
+}
+
+// ordered list of the feasible rotations (the order find_possible_places returns them, od/fs:288-296)
+__global__ void __launch_bounds__(256) k_feasible(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    ScanState& s = e.st[b];
+    const size_t cb = (size_t)b * (e.K + 1);
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int k0 = 1; k0 <= e.K; k0 += 256) {
+        const int k = k0 + threadIdx.x;
+        const bool ok = k <= e.K && (e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) == (CF_ONMAP | CF_HOK) && !e.cand_collide[cb + k];
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int off = s_base;
+        for (int i = 0; i < w; ++i) off += s_warp[i];
+        if (ok) e.feas[(size_t)b * e.K + off + __popc(m & ((1u << lane) - 1u))] = k;
+        __syncthreads();
+        if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) s_base += s_warp[i]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { s.n_feasible = s_base; s.found_rank = INT_MAX; }
+}
+
+// ------------------------------------------------------------------------------------------- occlusion
+// object point i of candidate k -> (pix, r) in the CURRENT scene geometry (od/ins:474-478, sample=True)
+struct ObjProj { double x, y, z, r, el; int pix, col; };
+__device__ __forceinline__ ObjProj project_obj_point(const EngineDev& e, const ObjBox& ob, const ImageGeom& g, int i,
+                                                     double c, double sn, double dz, ScanState& s) {
+    ObjProj o;
+    const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+    o.x = sub(mul(c, x0), mul(sn, y0));
+    o.y = add(mul(sn, x0), mul(c, y0));
+    o.z = add(e.obj_z[ob.first + i], dz);
+    o.r = range3(o.x, o.y, o.z);
+    o.el = elevation(o.z, o.r);
+    const int row = bin_row(g, o.el);
+    o.col = bin_col(g, azimuth(o.x, o.y));
+    o.pix = -1;
+    if (row >= 0 && row < g.rows) {                                    // od/ins:108-109
+        if (o.col < 0 || o.col >= g.cols) set_error(s, R3D_ERR_ASSERT);  // od/ins:113
+        else o.pix = row * g.cols + o.col;
+    }
+    return o;
+}
+
+// A11 (od/ins:486-501) for every feasible candidate: V = number of object points whose pixel is visible.  A pixel
+// that holds object points keeps its own min range through smooth_out, and min_r < scene <=> some point of the pixel
+// has r < scene, so no z-buffer is needed for the count: pass 1 marks visible pixels in a shared-memory bit image,
+// pass 2 counts the points on marked pixels.  Candidates are visited in rotation order with an ordered early-out
+// (the reference stops at the first candidate that keeps >= min_points, od/ins:530-561).
+__global__ void __launch_bounds__(128) k_occl_count(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    ScanState& s = e.st[b];
+    const int nf = s.n_feasible;
+    if ((int)blockIdx.x >= nf) return;
+    extern __shared__ unsigned s_bits[];
+    __shared__ int s_cnt, s_stop;
+    for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) s_bits[i] = 0u;
+    const ObjBox ob = e.obj[s.cur_obj];
+    const int min_pts = e.classes[ob.cls].min_points;
+    const ImageGeom g = s.geom;
+    const double* smooth = e.smooth + (size_t)b * e.hw;
+    const size_t cb = (size_t)b * (e.K + 1);
+    int* pixbuf = e.occ_pix + ((size_t)b * OCC_G + blockIdx.x) * e.max_obj_points;
+    __syncthreads();
+    for (int rank = blockIdx.x; rank < nf; rank += gridDim.x) {
+        if (threadIdx.x == 0) { s_stop = *(volatile int*)&s.found_rank < rank; s_cnt = 0; }
+        __syncthreads();
+        if (s_stop) break;                                        // an earlier candidate already passed
+        const int k = e.feas[(size_t)b * e.K + rank];
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        const double dz = sub(e.cand_level[cb + k], ob.cz);
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
+            pixbuf[i] = o.pix;
+            if (o.pix >= 0 && o.r < smooth[o.pix]) atomicOr(&s_bits[o.pix >> 5], 1u << (o.pix & 31));
+        }
+        __syncthreads();
+        int cnt = 0;
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = pixbuf[i];
+            if (pix >= 0 && (s_bits[pix >> 5] & (1u << (pix & 31)))) ++cnt;
+        }
+        for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        if ((threadIdx.x & 31) == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = pixbuf[i];
+            if (pix >= 0) s_bits[pix >> 5] = 0u;
+        }
+        if (threadIdx.x == 0) {
+            e.cand_v[cb + k] = s_cnt;
+            if (s_cnt > 0 && s_cnt >= min_pts) atomicMin(&s.found_rank, rank);      // od/ins:530-536
+        }
+        __syncthreads();
+    }
+}
+
+// smoothed object range at pixel (r, c) from the scratch z-buffer: own min range, or the neighbour mean where the
+// 5x3 closing switches an empty pixel on (cl:26-62); returns false if the pixel stays empty.
+__device__ bool obj_pixel_value(const unsigned long long* raw, int H, int W, int r, int c, double& val) {
+    const unsigned long long own = raw[r * W + c];
+    if (own != R3D_EMPTY_U64) { val = bits_dbl(own); return true; }
+    for (int dr = -2; dr <= 2; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+            const int r1 = r + dr, c1 = c + dc;
+            if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;          // outside the image: ignored by the erosion
+            bool dil = false;
+            for (int er = -2; er <= 2 && !dil; ++er)
+                for (int ec = -1; ec <= 1; ++ec) {
+                    const int r2 = r1 + er, c2 = c1 + ec;
+                    if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W && raw[r2 * W + c2] != R3D_EMPTY_U64) { dil = true; break; }
+                }
+            if (!dil) return false;
+        }
+    int neighbors = 0;
+    double sum = 0.0;
+    for (int dr = -2; dr <= 2; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+            const int r1 = r + dr, c1 = c + dc;
+            if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+            const unsigned long long v = raw[r1 * W + c1];
+            if (v != R3D_EMPTY_U64) { neighbors += 1; sum = add(sum, bits_dbl(v)); }
+        }
+    if (neighbors == 0) return false;
+    val = __ddiv_rn(sum, (double)neighbors);
+    return true;
+}
+
+__device__ void bitonic_sort_u64(unsigned long long* keys, int n_pow2) {
+    for (int k = 2; k <= n_pow2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n_pow2; i += blockDim.x) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const unsigned long long a = keys[i], bb = keys[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > bb) == up) { keys[i] = bb; keys[ixj] = a; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+// A11 + A12 for the chosen candidate of each scan: the first feasible rotation that keeps >= min_points (accepted),
+// else the last feasible one (its vis_px still deletes scene points in the reference, od/ins:472-501).  Builds the
+// candidate's z-buffer in a scratch image, closes / fills it around the object, compares with the scene image
+// (strict <) into the vis_px bit mask, and on acceptance appends the visible object points in (pix_id, index) order
+// to the scene tail, the `check` record and the scene boxes.
+__global__ void __launch_bounds__(256) k_select_emit(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    ScanState& s = e.st[b];
+    const int nf = s.n_feasible;
+    if (nf == 0) return;
+    extern __shared__ unsigned long long s_keys[];
+    __shared__ int s_nvis;
+    const bool accepted = s.found_rank < nf;
+    const int rank = accepted ? s.found_rank : nf - 1;
+    const int k = e.feas[(size_t)b * e.K + rank];
+    const ObjBox ob = e.obj[s.cur_obj];
+    const ImageGeom g = s.geom;
+    const int H = g.rows, W = g.cols;
+    const size_t cb = (size_t)b * (e.K + 1);
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    const double level = e.cand_level[cb + k];
+    const double dz = sub(level, ob.cz);
+    unsigned long long* raw = e.obj_raw + (size_t)b * e.hw;
+    unsigned* dm = e.dmask + (size_t)b * e.dwords;
+    unsigned* vm = e.vmask + (size_t)b * e.dwords;
+    const double* smooth = e.smooth + (size_t)b * e.hw;
+    int* pixbuf = e.sel_pix + (size_t)b * e.max_obj_points;
+    const int t0 = s.n_tail, chk0 = s.n_check, nbox0 = s.n_boxes, nins0 = s.n_inserted, n0 = s.n0;
+    if (threadIdx.x == 0) s_nvis = 0;
+    for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) { dm[i] = 0u; vm[i] = 0u; }
+    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+        const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
+        pixbuf[i] = o.pix;
+        if (o.pix >= 0) atomicMin(&raw[o.pix], dbl_bits(o.r));
+    }
+    __threadfence_block();
+    __syncthreads();
+    // every pixel within the 5x3 neighbourhood of an object pixel may be switched on by the closing
+    for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
+        const int i = t / 15, o = t % 15;
+        const int pix = pixbuf[i];
+        if (pix < 0) continue;
+        const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
+        if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
+        const int q = r * W + cc;
+        const unsigned bit = 1u << (q & 31);
+        if (atomicOr(&vm[q >> 5], bit) & bit) continue;                  // already evaluated by another thread
+        double val;
+        if (obj_pixel_value(raw, H, W, r, cc, val) && val < smooth[q]) atomicOr(&dm[q >> 5], bit);   // od/ins:486
+    }
+    __threadfence_block();
+    __syncthreads();
+    // visible object points, ordered by (pix_id, original index) as the reference's per-pixel loop emits them
+    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+        const int pix = pixbuf[i];
+        if (pix >= 0 && (dm[pix >> 5] & (1u << (pix & 31)))) {
+            const int slot = atomicAdd(&s_nvis, 1);
+            s_keys[slot] = ((unsigned long long)(unsigned)pix << 32) | (unsigned)i;
+        }
+    }
+    __syncthreads();
+    const int nvis = s_nvis;
+    if (accepted) {
+        int np2 = 1;
+        while (np2 < nvis) np2 <<= 1;
+        for (int i = nvis + threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = R3D_EMPTY_U64;
+        __syncthreads();
+        bitonic_sort_u64(s_keys, np2);
+        if (t0 + nvis > e.max_inserted || nbox0 + 1 > e.max_boxes || nins0 + 1 > e.max_events) {
+            __syncthreads();
+            if (threadIdx.x == 0) { set_error(s, R3D_ERR_CAPACITY); s.phase = PH_ERROR; }
+        } else {
+            const size_t base = (size_t)b * e.P + n0 + t0;
+            const size_t tb = (size_t)b * e.max_inserted + t0;
+            const size_t chk = ((size_t)b * e.max_inserted + chk0) * 5;
+            for (int j = threadIdx.x; j < nvis; j += blockDim.x) {
+                const int i = (int)(s_keys[j] & 0xffffffffull);
+                const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
+                e.tail_x[tb + j] = o.x; e.tail_y[tb + j] = o.y; e.tail_z[tb + j] = o.z;
+                const float inten = e.obj_i[ob.first + i];
+                const unsigned lab = e.obj_label[ob.first + i];
+                e.tail_i[tb + j] = inten;
+                e.label[base + j] = lab;
+                e.r[base + j] = o.r; e.el[base + j] = o.el;
+                e.col[base + j] = (unsigned short)o.col;
+                e.pix[base + j] = o.pix;
+                e.alive[base + j] = 1;
+                float* ck = e.check + chk + (size_t)j * 5;
+                ck[0] = (float)o.x; ck[1] = (float)o.y; ck[2] = (float)o.z; ck[3] = inten; ck[4] = (float)lab;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                int* rec = e.inserted + ((size_t)b * e.max_events + nins0) * 4;
+                rec[0] = s.cur_obj; rec[1] = k; rec[2] = ob.cls; rec[3] = nvis;
+                const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
+                double* ib = e.inserted_box + ((size_t)b * e.max_events + nins0) * 8;
+                ib[0] = yb.cx; ib[1] = yb.cy; ib[2] = level; ib[3] = yb.m00; ib[4] = yb.m10;
+                ib[5] = ob.length; ib[6] = ob.width; ib[7] = ob.height;
+                Box bx = yaw_box_to_box(yb, level, ob.length, ob.width, ob.height);      // od/ins:555
+                bx.reach = ob.reach;
+                e.boxes[(size_t)b * e.max_boxes + nbox0] = bx;
+                e.box_tests[(size_t)b * e.max_boxes + nbox0] = make_box_test(bx);
+                s.n_boxes = nbox0 + 1; s.n_inserted = nins0 + 1;
+                s.tail_before = t0; s.n_tail = t0 + nvis; s.n_check = chk0 + nvis;
+            }
+        }
+    }
+    if (threadIdx.x == 0) { s.accepted = accepted ? 1 : 0; s.chosen_rot = k; s.chosen_v = nvis; }
+    // leave the scratch z-buffer empty for the next use
+    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+        const int pix = pixbuf[i];
+        if (pix >= 0) raw[pix] = R3D_EMPTY_U64;
+    }
+}
+
+// --------------------------------------------------------------------------------------------- outputs
+// A14 (od/ds:76-109, ss/ds:72-106): surviving rows in order (original points, then inserted points), cast to
+// float32 / uint32.  40 B/point of algorithmic traffic.
+__global__ void __launch_bounds__(256) k_out_count(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    const ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const size_t base = (size_t)b * e.P;
+    int cnt = 0;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) cnt += e.alive[base + p] ? 1 : 0;
+    __shared__ int s_w[8];
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += s_w[w];
+        e.out_count[b] = t;
+    }
+}
+
+__global__ void k_out_offsets(EngineDev e, int n_scans) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long acc = 0, cacc = 0;
+        for (int b = 0; b < n_scans; ++b) {
+            e.out_off[b] = acc; acc += e.out_count[b];
+            e.check_off[b] = cacc; cacc += e.st[b].n_check;
+        }
+        e.out_off[n_scans] = acc; e.check_off[n_scans] = cacc;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_out_write(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    const ScanState& s = e.st[b];
+    const int n = s.n0 + s.n_tail;
+    const size_t base = (size_t)b * e.P;
+    const long long o0 = e.out_off[b];
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int p0 = 0; p0 < n; p0 += 1024) {
+        const int p = p0 + threadIdx.x;
+        const bool a = p < n && e.alive[base + p];
+        const unsigned m = __ballot_sync(0xffffffffu, a);
+        if (lane == 0) s_w[w] = __popc(m);
+        __syncthreads();
+        int off = s_run;
+        for (int i = 0; i < w; ++i) off += s_w[i];
+        if (a) {
+            const long long o = o0 + off + __popc(m & ((1u << lane) - 1u));
+            float4 v;
+            if (p < s.n0) v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+            else {
+                const size_t t = (size_t)b * e.max_inserted + (p - s.n0);
+                v = make_float4((float)e.tail_x[t], (float)e.tail_y[t], (float)e.tail_z[t], e.tail_i[t]);
+            }
+            e.out_xyzi[o] = v;
+            e.out_label[o] = e.label[base + p];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int i = 0; i < 32; ++i) t += s_w[i]; s_run += t; }
+        __syncthreads();
+    }
+    const long long c0 = e.check_off[b];
+    const float* ck = e.check + (size_t)b * e.max_inserted * 5;
+    for (int i = threadIdx.x; i < s.n_check * 5; i += blockDim.x) e.out_check[c0 * 5 + i] = ck[i];
+}
+
+}  // namespace r3d

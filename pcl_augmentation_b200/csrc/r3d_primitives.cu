@@ -1,0 +1,153 @@
+// Primitive operators of the Real3D-Aug hot path on the reference's own float64 working-row layout (N x 9).
+// These back the drop-in Python functions (fill_spherical, geometrical_front_view, smooth_out, cut_bounding_box).
+#include "r3d_common.cuh"
+#include "r3d_host.h"
+#include "../../include/real3d_b200.h"
+
+using namespace r3d;
+
+// ------------------------------------------------------------------------------------ A1/A2 fill_spherical
+__global__ void __launch_bounds__(256) k_fill_spherical_rows(double* __restrict__ rows, int64_t n,
+                                                              unsigned long long* __restrict__ minmax_bits) {
+    __shared__ unsigned long long s_min[8], s_max[8];
+    unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double* p = rows + i * 9;
+        const double x = p[0], y = p[1], z = p[2];
+        const double r = range3(x, y, z);
+        const double az = azimuth(x, y);
+        const double el = elevation(z, r);
+        p[3] = r; p[4] = az; p[5] = el;
+        const unsigned long long b = dbl_bits(el);
+        lmin = min(lmin, b); lmax = max(lmax, b);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lmin; s_max[threadIdx.x >> 5] = lmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lmin = min(lmin, s_min[w]); lmax = max(lmax, s_max[w]); }
+        atomicMax(&minmax_bits[0], lmax);
+        atomicMin(&minmax_bits[1], lmin);
+    }
+}
+
+__global__ void k_init_minmax(unsigned long long* mm) { mm[0] = 0ull; mm[1] = R3D_EMPTY_U64; }
+
+extern "C" int r3d_fill_spherical(double* rows9, int64_t n, double* minmax_out, r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || !minmax_out || (n > 0 && !rows9)) return r3d_fail(R3D_ERR_ARG, "r3d_fill_spherical: bad argument");
+    unsigned long long* mm = reinterpret_cast<unsigned long long*>(minmax_out);
+    k_init_minmax<<<1, 1, 0, stream>>>(mm); r3d_count_launch();
+    if (n > 0) {
+        int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        k_fill_spherical_rows<<<grid, 256, 0, stream>>>(rows9, n, mm); r3d_count_launch();
+    }
+    return r3d_check_launch("r3d_fill_spherical");
+}
+
+// ----------------------------------------------------------------------------- A3 geometrical_front_view
+__global__ void __launch_bounds__(256) k_zbuf_fill(unsigned long long* __restrict__ zbuf, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        zbuf[i] = R3D_EMPTY_U64;
+}
+
+__global__ void __launch_bounds__(256) k_project_rows(double* __restrict__ rows, int64_t n, ImageGeom g, int sample,
+                                                       unsigned long long* __restrict__ zbuf, int* __restrict__ status) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double* p = rows + i * 9;
+        const int row = bin_row(g, p[5]);
+        const int col = bin_col(g, p[4]);
+        const bool row_ok = row >= 0 && row < g.rows;
+        if (!row_ok) {
+            if (!sample) *status = R3D_ERR_ASSERT;          // od/ins:111
+            continue;                                       // od/ins:108-109
+        }
+        if (!(col >= 0 && col < g.cols)) { *status = R3D_ERR_ASSERT; continue; }     // od/ins:113
+        p[8] = (double)(row * g.pix_stride + col);                                  // od/ins:117,128
+        atomicMin(&zbuf[row * g.cols + col], dbl_bits(p[3]));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_zbuf_to_images(const unsigned long long* __restrict__ zbuf, int64_t n,
+                                                         double* __restrict__ train, double* __restrict__ label) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long b = zbuf[i];
+        const bool hit = b != R3D_EMPTY_U64;
+        train[i] = hit ? bits_dbl(b) : kEmptyRange;
+        label[i] = hit ? 1.0 : -1.0;
+    }
+}
+
+extern "C" int r3d_project_zbuffer(double* rows9, int64_t n, int num_row, int num_col, int pix_stride, double max_el,
+                                   double min_el, int sample, double* train_out, double* label_out,
+                                   uint64_t* zbuf_scratch, int* status_out, r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (num_row <= 0 || num_col <= 0 || !train_out || !label_out || !zbuf_scratch || !status_out)
+        return r3d_fail(R3D_ERR_ARG, "r3d_project_zbuffer: bad argument");
+    const int64_t px = (int64_t)num_row * num_col;
+    const int gpx = (int)std::min<int64_t>((px + 255) / 256, 148 * 8);
+    cudaMemsetAsync(status_out, 0, sizeof(int), stream);
+    k_zbuf_fill<<<gpx, 256, 0, stream>>>((unsigned long long*)zbuf_scratch, px); r3d_count_launch();
+    if (n > 0) {
+        ImageGeom g = make_geom(num_row, num_col, pix_stride, max_el, min_el);
+        int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+        k_project_rows<<<grid, 256, 0, stream>>>(rows9, n, g, sample, (unsigned long long*)zbuf_scratch, status_out);
+        r3d_count_launch();
+    }
+    k_zbuf_to_images<<<gpx, 256, 0, stream>>>((const unsigned long long*)zbuf_scratch, px, train_out, label_out);
+    r3d_count_launch();
+    return r3d_check_launch("r3d_project_zbuffer");
+}
+
+// ------------------------------------------------------------------------------------ A4 close + fill
+// Input adaptor for the float64 train/label pair the reference passes to smooth_out.
+struct F64Image {
+    const double* train; const double* label;
+    __device__ bool occ(int64_t i) const { return label[i] > 0.0; }            // np.clip(label, 0, 1) -> 0/255 (cl:16-19)
+    __device__ double val(int64_t i) const { return train[i]; }
+    __device__ bool is_one(int64_t i) const { return label[i] == 1.0; }    // cl:41, cl:48
+    __device__ double lab(int64_t i) const { return label[i]; }
+};
+
+#include "r3d_closefill.cuh"
+
+extern "C" int r3d_close_fill(const double* train_in, const double* label_in, int num_row, int num_col,
+                              double* train_out, double* label_out, uint8_t* closed_out, r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!train_in || !label_in || !train_out || !label_out || num_row <= 0 || num_col <= 0)
+        return r3d_fail(R3D_ERR_ARG, "r3d_close_fill: bad argument");
+    F64Image in{train_in, label_in};
+    dim3 grid((num_col + CF_TW - 1) / CF_TW, (num_row + CF_TH - 1) / CF_TH, 1);
+    k_close_fill<F64Image><<<grid, CF_THREADS, 0, stream>>>(in, num_row, num_col, 0, train_out, label_out, closed_out,
+                                                            nullptr, nullptr);
+    r3d_count_launch();
+    return r3d_check_launch("r3d_close_fill");
+}
+
+// ------------------------------------------------------------------------------------ A8 cut_bounding_box
+__global__ void __launch_bounds__(256) k_cut_box(const double* __restrict__ rows, int64_t n, int stride, Box box,
+                                                  uint8_t* __restrict__ mask) {
+    const BoxTest t = make_box_test(box);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* p = rows + i * stride;
+        mask[i] = inside_box(t, p[0], p[1], p[2]) ? 1 : 0;
+    }
+}
+
+extern "C" int r3d_cut_bounding_box(const double* rows, int64_t n, int row_stride, const double* box_host,
+                                    uint8_t* mask_out, r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || row_stride < 3 || !box_host || (n > 0 && (!rows || !mask_out)))
+        return r3d_fail(R3D_ERR_ARG, "r3d_cut_bounding_box: bad argument");
+    if (n == 0) return R3D_OK;
+    Box b;
+    b.cx = box_host[0]; b.cy = box_host[1]; b.cz = box_host[2];
+    for (int i = 0; i < 9; ++i) b.m[i] = box_host[3 + i];
+    b.length = box_host[12]; b.width = box_host[13]; b.height = box_host[14]; b.reach = box_host[15];
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_cut_box<<<grid, 256, 0, stream>>>(rows, n, row_stride, b, mask_out); r3d_count_launch();
+    return r3d_check_launch("r3d_cut_bounding_box");
+}

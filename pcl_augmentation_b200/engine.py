@@ -1,0 +1,355 @@
+"""Batched, device-resident driver of the Real3D-Aug per-scan loop (``augment_batch``).
+
+The reference runs one scan at a time through nested Python loops (od/ins:321-628, ss/ins:317-599).  Here a whole
+batch of scans is resident in HBM and advanced in lock-step rounds by ``libreal3d_b200.so``; this module only
+prepares the host-side tables (class configuration from the YAML, parsed boxes, yaw and radius tables, the cut-object
+database, the pre-drawn schedules) and unpacks the results into the reference's output records
+(``save_data`` od/ds:76-95, ss/ds:72-91; ``create_annotation_line`` od/ins:227-265; ``added_objects/<frame>.txt``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+from . import boxes as bx
+
+ROAD_INDEXES = [40, 44, 48]          # od/fs:14, used by the semseg addjust_map_2 (ss/ins:209)
+MAX_NUM_TRIES = 100                  # od/ins:24
+
+
+@dataclass
+class ScanInput:
+    """One scan in the layouts the reference's dataset adapters hand to insertion.py."""
+    xyzi: np.ndarray                  # N x 4 float32 (velodyne/*.bin)
+    labels: np.ndarray                # N uint32 (semantic label & 0xFFFF)
+    box_lines: list                   # scene annotation lines (label_2/*.txt or bbox/*.txt)
+    counts: np.ndarray                # objects to insert per class (generate_seed)
+    perms: np.ndarray                 # int32 [events, classes, tries]: pre-drawn random.shuffle results
+    maps: dict | None = None          # OD: {'Road': {...}, 'Sidewalk': {...}} (npz payloads)
+    pose: np.ndarray | None = None    # semseg: 4x4 lidar->world
+
+
+@dataclass
+class ScanResult:
+    velodyne: np.ndarray              # N' x 4 float32  (velodyne/<frame>.bin)
+    labels: np.ndarray                # N' uint32       (labels/<frame>.label, semseg)
+    check: np.ndarray                 # V x 4 (OD) / V x 5 (semseg) float32 (check/<frame>.bin)
+    inserted: list                    # [(object name, rotation, class)]  -> added_objects/<frame>.txt
+    lines: list                       # OD: KITTI annotation lines of the inserted objects
+    boxes: list                       # box dictionaries of the inserted objects
+    visible: list                     # visible points per inserted object
+    status: int = 0
+    extra: dict = field(default_factory=dict)
+
+
+def _pinned(shape, dtype):
+    """numpy array backed by page-locked host memory (owned by a torch tensor kept alive on the array)."""
+    import torch
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64,
+           np.uint8: torch.uint8}[np.dtype(dtype).type]
+    pin = torch.cuda.is_available()
+    t = torch.empty(tuple(int(s) for s in np.atleast_1d(shape)), dtype=tdt, pin_memory=pin)
+    return t.numpy()
+
+
+class Real3DEngine:
+    """One engine per process / GPU.  ``task`` is 'od' (KITTI) or 'ss' (SemanticKITTI)."""
+
+    def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
+                 max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
+                 map_window=512, road_indexes=ROAD_INDEXES):
+        _lib.require_cuda()
+        self.lib = _lib.load()
+        self.task = task
+        self.config = config
+        self.classes = list(config['insertion']['classes'])
+        self.rows, self.cols, self.yaw_steps, self.max_tries = rows, cols, yaw_steps, max_tries
+        self.max_scans, self.max_points = int(max_scans), int(max_points)
+        nobj = int(config['insertion'].get('number_of_object', 10))
+        self.max_events = int(max_events if max_events is not None else nobj + 1)
+        self._prepare_db(db)
+        if max_inserted is None:
+            max_inserted = max(4096, self.max_events * self.max_obj_points)
+        self.max_inserted, self.max_boxes = int(max_inserted), int(max_boxes)
+        cfg = _lib.EngineCfg()
+        cfg.task = 0 if task == 'od' else 1
+        cfg.rows, cfg.cols, cfg.yaw_steps, cfg.max_tries = rows, cols, yaw_steps, max_tries
+        cfg.n_classes = len(self.classes)
+        cfg.max_scans, cfg.max_points, cfg.max_inserted = self.max_scans, self.max_points, self.max_inserted
+        cfg.max_boxes, cfg.max_events = self.max_boxes, self.max_events
+        cfg.road_label = int(config['labels']['Road']) if task == 'od' else 0
+        cfg.n_road_indexes = len(road_indexes)
+        for i, v in enumerate(road_indexes):
+            cfg.road_indexes[i] = int(v)
+        cfg.map_window = int(map_window)
+        r2, ok = bx.search_radii()
+        for i in range(50):
+            cfg.radii_sq[i] = float(r2[i])
+            cfg.radii_ok[i] = int(ok[i])
+        for ci, cls in enumerate(self.classes):
+            cc = cfg.classes[ci]
+            cc.min_points = int(config['insertion']['min_points'][cls])
+            if task == 'od':
+                placement = config['insertion']['placement'][cls]
+                assert placement in ('Road', 'Sidewalk'), f'unrecognized placement area for {cls}'    # od/ins:443
+                cc.map_sel = 0 if placement == 'Road' else 1
+                cc.pedestrian = 1 if cls == 'Pedestrian' else 0
+                cc.n_surface = 1
+                cc.surface[0] = int(config['labels']['Road'])                                        # od/fs:154
+            else:
+                ok_map_surface = config['insertion']['placement'][cls]                               # ss/fs:221
+                mask = 0
+                surf = []
+                for v in ok_map_surface:
+                    mask |= 1 << int(v)
+                    surf += list(config['insertion']['placement_labels'][v])                         # ss/fs:223-226
+                cc.map_ok_mask = mask
+                cc.n_surface = len(surf)
+                assert len(surf) <= _lib.R3D_MAX_SURFACE
+                for i, v in enumerate(surf):
+                    cc.surface[i] = int(v)
+        handle = C.c_void_p()
+        _lib.check(self.lib.r3d_engine_create(C.byref(cfg), C.byref(handle)), "r3d_engine_create")
+        self.handle = handle
+        cos_k, sin_k = bx.yaw_tables(yaw_steps)
+        _lib.check(self.lib.r3d_engine_set_yaw_tables(handle, cos_k.ctypes.data, sin_k.ctypes.data), "set_yaw_tables")
+        self._upload_db()
+        if task == 'ss':
+            assert map_data is not None, "semseg needs the sequence rich map {'map', 'move'}"
+            m = np.ascontiguousarray(np.asarray(map_data['map']).astype(np.uint8))
+            mv = np.asarray(map_data['move']).reshape(-1)
+            _lib.check(self.lib.r3d_engine_set_ss_map(handle, m.ctypes.data, m.shape[0], m.shape[1], int(mv[0]),
+                                                      int(mv[1])), "set_ss_map")
+        self._keep = []
+        self._n_scans = 0
+
+    # ------------------------------------------------------------------------------------------ database
+    def _prepare_db(self, db):
+        read = bx.read_label_line_ss if self.task == 'ss' else bx.read_label_line_od
+        names, pts, offs, box_rows, cls_idx, lists, list_off, annos, strings = [], [], [0], [], [], [], [0], [], []
+        for ci, cls in enumerate(self.classes):
+            for name, sample in db[cls]:
+                pcl = np.array(sample['pcl'], dtype=np.float64, copy=True)
+                if self.task == 'od':
+                    pcl[:, 4] = 1                                     # od/fs:251
+                anno = read(str(sample['anno'].item() if hasattr(sample['anno'], 'item') else sample['anno']))
+                lists.append(len(names))
+                names.append(name)
+                pts.append(pcl[:, :5])
+                offs.append(offs[-1] + len(pcl))
+                box_rows.append(bx.object_box_record(anno))
+                cls_idx.append(ci)
+                annos.append(anno)
+                strings.append(sample['anno'])
+            list_off.append(len(lists))
+        self.obj_names, self.obj_annos, self.obj_strings = names, annos, strings
+        self._db_points = np.ascontiguousarray(np.concatenate(pts, axis=0))
+        self._db_offsets = np.array(offs, dtype=np.int64)
+        self._db_boxes = np.ascontiguousarray(np.array(box_rows, dtype=np.float64))
+        self._db_cls = np.array(cls_idx, dtype=np.int32)
+        self._db_list_off = np.array(list_off, dtype=np.int32)
+        self._db_list = np.array(lists, dtype=np.int32)
+        self.max_obj_points = int(np.diff(self._db_offsets).max())
+
+    def _upload_db(self):
+        db = _lib.ObjectDb()
+        db.n_objects = len(self.obj_names)
+        db.point_offsets = self._db_offsets.ctypes.data
+        db.points5 = self._db_points.ctypes.data
+        db.boxes = self._db_boxes.ctypes.data
+        db.class_index = self._db_cls.ctypes.data
+        db.class_list_offsets = self._db_list_off.ctypes.data
+        db.class_list = self._db_list.ctypes.data
+        _lib.check(self.lib.r3d_engine_set_objects(self.handle, C.byref(db)), "set_objects")
+
+    # --------------------------------------------------------------------------------------------- batch
+    def stage(self, scans):
+        """Pack a list of ScanInput into pinned host buffers (not part of the timed e2e path's GPU work; this is the
+        role of the dataset reader).  Returns an opaque staged batch for ``load``."""
+        n = len(scans)
+        assert 0 < n <= self.max_scans
+        read = bx.read_label_line_ss if self.task == 'ss' else bx.read_label_line_od
+        pt_off = np.zeros(n + 1, dtype=np.int64)
+        for i, s in enumerate(scans):
+            pt_off[i + 1] = pt_off[i] + len(s.xyzi)
+        total = int(pt_off[-1])
+        xyzi = _pinned((total, 4), np.float32)
+        labels = _pinned((total,), np.int32)
+        box_off = np.zeros(n + 1, dtype=np.int32)
+        box_rows = []
+        n_events = max(int(np.asarray(s.perms).shape[0]) for s in scans)
+        nc = len(self.classes)
+        counts = np.zeros((n, nc), dtype=np.int32)
+        perms = np.full((n, n_events, nc, self.max_tries), -1, dtype=np.int32)
+        for i, s in enumerate(scans):
+            xyzi[pt_off[i]:pt_off[i + 1]] = s.xyzi
+            labels[pt_off[i]:pt_off[i + 1]] = np.asarray(s.labels).astype(np.uint32).view(np.int32)
+            for line in s.box_lines:
+                box_rows.append(bx.box_record(read(line)))
+            box_off[i + 1] = len(box_rows)
+            counts[i] = np.asarray(s.counts, dtype=np.int32)
+            p = np.asarray(s.perms, dtype=np.int32)
+            perms[i, :p.shape[0], :, :p.shape[2]] = p
+        staged = {'n': n, 'pt_off': pt_off, 'xyzi': xyzi, 'labels': labels, 'box_off': box_off,
+                  'boxes': np.ascontiguousarray(np.array(box_rows, dtype=np.float64).reshape(-1, 16)),
+                  'counts': counts, 'perms': perms, 'n_events': n_events, 'total': total}
+        if self.task == 'od':
+            blobs, moff, dims = [], [0], np.zeros((n, 2, 4), dtype=np.int32)
+            for i, s in enumerate(scans):
+                for j, key in enumerate(('Road', 'Sidewalk')):
+                    md = s.maps[key]
+                    m = np.ascontiguousarray(np.asarray(md['map']).astype(np.uint8))
+                    blobs.append(m.reshape(-1))
+                    moff.append(moff[-1] + m.size)
+                    dims[i, j] = (m.shape[0], m.shape[1], int(md['min_x']), int(md['min_y']))
+            staged.update(maps=np.ascontiguousarray(np.concatenate(blobs)), map_off=np.array(moff, dtype=np.int64),
+                          map_dims=dims)
+        else:
+            staged['poses'] = np.ascontiguousarray(np.stack([np.asarray(s.pose, dtype=np.float64) for s in scans]))
+        return staged
+
+    def load(self, staged):
+        """Host -> device copy of a staged batch + the one-off spherical cache (A1/A2)."""
+        b = _lib.Batch()
+        b.n_scans = staged['n']
+        b.point_offsets = staged['pt_off'].ctypes.data
+        b.xyzi = staged['xyzi'].ctypes.data
+        b.labels = staged['labels'].ctypes.data
+        b.box_offsets = staged['box_off'].ctypes.data
+        b.boxes = staged['boxes'].ctypes.data if staged['boxes'].size else None
+        if self.task == 'od':
+            b.map_offsets = staged['map_off'].ctypes.data
+            b.maps = staged['maps'].ctypes.data
+            b.map_dims = staged['map_dims'].ctypes.data
+        else:
+            b.poses = staged['poses'].ctypes.data
+        b.counts = staged['counts'].ctypes.data
+        b.perms = staged['perms'].ctypes.data
+        b.n_events = staged['n_events']
+        self._keep = [staged, b]
+        self._n_scans = staged['n']
+        self._in_bytes = staged['total'] * 20
+        _lib.check(self.lib.r3d_engine_load_batch(self.handle, C.byref(b)), "load_batch")
+
+    def reset(self):
+        _lib.check(self.lib.r3d_engine_reset_batch(self.handle), "reset_batch")
+
+    def run(self):
+        _lib.check(self.lib.r3d_engine_run(self.handle), "run")
+
+    def sync(self):
+        _lib.check(self.lib.r3d_engine_sync(self.handle), "sync")
+
+    def output_rows(self):
+        a, b = C.c_int64(), C.c_int64()
+        _lib.check(self.lib.r3d_engine_output_rows(self.handle, C.byref(a), C.byref(b)), "output_rows")
+        return a.value, b.value
+
+    def fetch_raw(self, buffers=None):
+        """Device -> host copy of the last run's outputs into (reusable, pinned) buffers."""
+        n = self._n_scans
+        rows, chk = self.output_rows()
+        if buffers is None or buffers['cap_points'] < rows or buffers['cap_check'] < chk:
+            cap_p, cap_c = max(rows, 1), max(chk, 1)
+            buffers = {'cap_points': cap_p, 'cap_check': cap_c, 'xyzi': _pinned((cap_p, 4), np.float32),
+                       'labels': _pinned((cap_p,), np.int32), 'check': _pinned((cap_c, 5), np.float32)}
+        buffers.update(out_off=np.zeros(n + 1, dtype=np.int64), check_off=np.zeros(n + 1, dtype=np.int64),
+                       n_inserted=np.zeros(n, dtype=np.int32), inserted=np.zeros((n, self.max_events, 4), dtype=np.int32),
+                       inserted_box=np.zeros((n, self.max_events, 8), dtype=np.float64),
+                       status=np.zeros(n, dtype=np.int32), rounds=np.zeros(1, dtype=np.int32))
+        r = _lib.BatchResult()
+        r.out_offsets = buffers['out_off'].ctypes.data
+        r.out_xyzi = buffers['xyzi'].ctypes.data
+        r.out_labels = buffers['labels'].ctypes.data
+        r.capacity_points = buffers['cap_points']
+        r.check_offsets = buffers['check_off'].ctypes.data
+        r.check_xyzil = buffers['check'].ctypes.data
+        r.capacity_check = buffers['cap_check']
+        r.n_inserted = buffers['n_inserted'].ctypes.data
+        r.inserted = buffers['inserted'].ctypes.data
+        r.inserted_box = buffers['inserted_box'].ctypes.data
+        r.status = buffers['status'].ctypes.data
+        r.rounds = buffers['rounds'].ctypes.data
+        _lib.check(self.lib.r3d_engine_fetch(self.handle, C.byref(r)), "fetch")
+        buffers['out_bytes'] = rows * 20 + chk * 20
+        return buffers
+
+    def unpack(self, buffers, raise_on_error=True):
+        """Per-scan output records in the reference's formats."""
+        out = []
+        ss = self.task == 'ss'
+        for s in range(self._n_scans):
+            st = int(buffers['status'][s])
+            if st != 0 and raise_on_error:
+                _lib.check(st, f"scan {s}")
+            a, b = buffers['out_off'][s], buffers['out_off'][s + 1]
+            ca, cb = buffers['check_off'][s], buffers['check_off'][s + 1]
+            inserted, lines, boxes, visible = [], [], [], []
+            for j in range(int(buffers['n_inserted'][s])):
+                obj, rot, ci, nvis = (int(v) for v in buffers['inserted'][s, j])
+                cls = self.classes[ci]
+                box = bx.placed_box_dictionary(buffers['inserted_box'][s, j], str(cls) if ss else cls, ss)
+                inserted.append((self.obj_names[obj], rot, cls))
+                boxes.append(box)
+                visible.append(nvis)
+                if not ss:
+                    lines.append(bx.create_annotation_line(self.obj_strings[obj], box, rot * (360.0 / self.yaw_steps)))
+            chk = np.array(buffers['check'][ca:cb])
+            out.append(ScanResult(velodyne=np.array(buffers['xyzi'][a:b]),
+                                  labels=np.array(buffers['labels'][a:b]).view(np.uint32),
+                                  check=chk if ss else chk[:, :4], inserted=inserted, lines=lines, boxes=boxes,
+                                  visible=visible, status=st, extra={'rounds': int(buffers['rounds'][0])}))
+        return out
+
+    def augment_batch(self, scans):
+        """Load, run and fetch one batch of ScanInput; returns a list of ScanResult."""
+        self.load(self.stage(scans))
+        self.run()
+        return self.unpack(self.fetch_raw())
+
+    # ------------------------------------------------------------------------------------------ profiling
+    def profile(self, on=True):
+        _lib.check(self.lib.r3d_engine_profile_enable(self.handle, 1 if on else 0), "profile_enable")
+
+    def profile_read(self):
+        names = C.create_string_buffer(4096)
+        ms = (C.c_double * 64)()
+        launches = (C.c_int64 * 64)()
+        n = C.c_int()
+        _lib.check(self.lib.r3d_engine_profile_read(self.handle, names, 4096, ms, launches, 64, C.byref(n)), "profile_read")
+        ks = names.value.decode().split('\n')
+        return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
+
+    def debug_image(self, scan):
+        out = np.zeros((self.rows, self.cols), dtype=np.float64)
+        _lib.check(self.lib.r3d_engine_debug_image(self.handle, scan, out.ctypes.data), "debug_image")
+        return out
+
+    def debug_candidates(self, scan):
+        k1 = self.yaw_steps + 1
+        flags, level, vis = np.zeros(k1, np.uint8), np.zeros(k1, np.float64), np.zeros(k1, np.int32)
+        _lib.check(self.lib.r3d_engine_debug_candidates(self.handle, scan, flags.ctypes.data, level.ctypes.data,
+                                                        vis.ctypes.data), "debug_candidates")
+        return flags, level, vis
+
+    def close(self):
+        if getattr(self, 'handle', None):
+            self.lib.r3d_engine_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def scan_input_from_case(case, pose=None):
+    """ScanInput from a ``synth.Case`` (used by tests, smoke and bench)."""
+    return ScanInput(xyzi=np.ascontiguousarray(case.pcl5[:, :4].astype(np.float32)),
+                     labels=case.pcl5[:, 4].astype(np.uint32), box_lines=list(case.box_lines),
+                     counts=case.schedule.counts, perms=case.schedule.perms, maps=case.maps,
+                     pose=case.pose if pose is None else pose)
