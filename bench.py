@@ -1,0 +1,350 @@
+"""bench.py — augmented scans/sec of the Real3D-Aug hot path on B200 (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the one the metric is quoted on): a batch of 256 synthetic KITTI-shape HDL-64
+scans (120 000 points each, 112 x 1440 range image), 10 cut pedestrians / cyclists to insert per scan, 1024 yaw
+candidates per cut object, sharded by scan: every rank owns its own batch of 256 (weak scaling, no collective on
+the data path).  One step = one pass of the whole hot path (placement search + occlusion + insertion + output
+compaction) over the rank's batch.
+
+  value  : scans/s with the batch already resident in HBM (device re-arm + run, CUDA events on the engine stream)
+  e2e    : scans/s through the public API with HOST (pinned) buffers: H2D of every scan + run + D2H of the results
+  roofline: the kernel with the largest share of device time; achieved = algorithmic bytes / measured time
+  cpu_baseline: the numpy oracle port of the reference timed on one host core on a bounded sample (rank 0, N = 1)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SCANS_PER_GPU = 256
+DISTINCT_SCANS = 32
+N_OBJECTS = 10
+YAW_STEPS = 1024
+ROWS, COLS = 112, 1440
+METRIC = "augmented scans/sec (120k-pt KITTI scan, placement + occlusion + insertion)"
+
+
+def workload_config(n_gpus):
+    return {"workload": "batch of 256 KITTI-shape scans per GPU (120000 pts, 112x1440 range image), 10 cut "
+                        "pedestrians/cyclists per scan, 1024 yaw candidates per object, sharded by scan",
+            "scans_per_gpu": SCANS_PER_GPU, "points_per_scan": 120000, "objects_per_scan": N_OBJECTS,
+            "yaw_candidates": YAW_STEPS, "range_image": [ROWS, COLS], "parallelism": f"scan-sharded x{n_gpus}",
+            "l2": "inputs larger than L2 (614 MB of points per batch, no flush needed)",
+            "distinct_scans": DISTINCT_SCANS}
+
+
+def build_cases(rank, n_scans=SCANS_PER_GPU, distinct=DISTINCT_SCANS):
+    """`distinct` different synthetic scans per rank, tiled to `n_scans` with different schedules / object draws."""
+    from pcl_augmentation_b200 import synth
+    base = [synth.make_case("od", 9000 + rank * 1000 + i, number_of_object=N_OBJECTS) for i in range(distinct)]
+    cases = []
+    for j in range(n_scans):
+        c = base[j % distinct]
+        sched = synth.make_schedule(50000 + rank * 10000 + j, len(c.config["insertion"]["classes"]), N_OBJECTS,
+                                    [len(c.db[k]) for k in c.config["insertion"]["classes"]])
+        cases.append(synth.Case(c.task, c.config, c.pcl5, c.box_lines, c.db, sched, maps=c.maps, cars=c.cars))
+    return cases
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# algorithmic bytes per unit: N points, HW pixels, 20 B point record
+def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
+    per_project = stats["projected_scans"]
+    per_try = stats["tried_objects"]
+    per_mask = stats["masked_scans"]
+    table = {
+        "project_zbuffer": (20 * n_points + 8 * hw, per_project),      # z-buffer pass
+        "clear_images": (8 * hw, per_project),
+        "close_fill": (16 * hw, per_project),
+        "apply_mask_minmax": (5 * n_points, per_mask),                 # occlusion mask
+        "height_pass1": (20 * n_points, per_try),                      # placement pass over the scene
+        "height_pass2": (20 * n_points, per_try),
+        "collide_points": (20 * n_points, per_try),
+        "compact_output": (40 * n_points, n_scans * steps),
+        "ingest_spherical": (20 * n_points, 0),
+    }
+    per_unit, units = table.get(kernel, (0, 0))
+    return per_unit, units
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def cpu_baseline_sample(yaw_steps=YAW_STEPS, budget_s=25.0):
+    """The numpy oracle port of the reference (oracle/real3d_oracle.py) on ONE host core on whole scans of the same
+    workload until ~budget_s of CPU work is spent (at least one scan)."""
+    from oracle import real3d_oracle as orc            # checker / baseline only
+    from pcl_augmentation_b200 import synth
+    t_total, n = 0.0, 0
+    while t_total < budget_s and n < 4:
+        case = synth.make_case("od", 9000 + n, number_of_object=N_OBJECTS)
+        t0 = time.perf_counter()
+        orc.augment_scan("od", case.pcl5, case.box_lines, case.db, case.schedule.counts, case.schedule.perms,
+                         case.config, maps=case.maps, mode="closed", yaw_steps=yaw_steps, num_row=ROWS, num_column=COLS)
+        t_total += time.perf_counter() - t0
+        n += 1
+    return n / t_total, n, t_total
+
+
+def _ref_worker(seed):
+    from oracle import real3d_oracle as orc
+    from pcl_augmentation_b200 import synth
+    case = synth.make_case("od", seed, number_of_object=N_OBJECTS)
+    t0 = time.perf_counter()
+    orc.augment_scan("od", case.pcl5, case.box_lines, case.db, case.schedule.counts, case.schedule.perms, case.config,
+                     maps=case.maps, mode="closed", yaw_steps=YAW_STEPS, num_row=ROWS, num_column=COLS)
+    return time.perf_counter() - t0
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (the oracle port: the Python reference itself cannot
+    travel to the GPU box) on all host cores, one scan per worker process per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = max(1, min(os.cpu_count() or 1, 32))
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        for w in range(args.warmup):
+            pool.map(_ref_worker, [9000 + i for i in range(cores)])
+            break                                            # one warm-up wave is enough for a CPU path
+        t0 = time.perf_counter()
+        done = 0
+        for s in range(args.steps):
+            pool.map(_ref_worker, [9100 + s * cores + i for i in range(cores)])
+            done += cores
+        dt = time.perf_counter() - t0
+    value = done / dt
+    sample = f"{cores} whole scans per step (one per worker process), {args.steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    from pcl_augmentation_b200.engine import Real3DEngine, scan_input_from_case
+    n_scans = args.scans
+    cases = build_cases(rank, n_scans, min(DISTINCT_SCANS, n_scans))
+    n_points = len(cases[0].pcl5)
+    eng = Real3DEngine("od", cases[0].config, cases[0].db, max_scans=n_scans, max_points=n_points, rows=ROWS, cols=COLS,
+                       yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1)
+    staged = eng.stage([scan_input_from_case(c) for c in cases])
+    stream = eng.cuda_stream()
+
+    # ---- device-resident throughput ("value") --------------------------------------------------------
+    eng.load(staged)
+    eng.sync()
+    for _ in range(args.warmup):
+        eng.reset(); eng.run(); eng.sync()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        eng.reset()
+        eng.run()
+    ev1.record(stream)
+    eng.sync()
+    barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    prof = eng.profile_read()
+    stats = eng.stats()
+    eng.profile(False)
+    dev_ms = max_over_ranks(dev_ms)
+    value = world * n_scans * args.steps / (dev_ms / 1000.0)
+
+    # ---- end to end through the public API with host buffers ("e2e") -----------------------------------
+    buffers = None
+    for _ in range(2):
+        eng.load(staged); eng.run(); buffers = eng.fetch_raw(buffers)
+    barrier()
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(args.steps):
+        eng.load(staged)
+        eng.run()
+        buffers = eng.fetch_raw(buffers)
+        d2h += buffers["out_bytes"]
+    eng.sync()
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = world * n_scans * args.steps / e2e_s
+    h2d = staged["total"] * 20 + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
+    results = eng.unpack(buffers)
+    inserted_total = sum(len(r.inserted) for r in results)
+
+    # ---- roofline of the dominant kernel ------------------------------------------------------------------
+    peak, peak_src = peaks()
+    hw = ROWS * COLS
+    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
+    roofline = None
+    ranked = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
+    kernel_table = {}
+    total_kernel_ms = sum(v["ms"] for v in prof.values())
+    for name, v in ranked:
+        per_unit, units = algorithmic_bytes(name, n_points, hw, stats, n_scans, args.steps)
+        entry = {"ms": round(v["ms"], 3), "launches": v["launches"], "share": round(v["ms"] / max(total_kernel_ms, 1e-9), 4)}
+        if per_unit and units and v["ms"] > 0:
+            gbs = per_unit * units / (v["ms"] / 1000.0) / 1e9
+            entry.update(algorithmic_bytes_per_unit=per_unit, units=units, achieved_gbs=round(gbs, 1),
+                         frac=round(gbs / peak, 4))
+        kernel_table[name] = entry
+    for name, v in ranked:                      # dominant kernel that has a bytes model
+        e = kernel_table[name]
+        if "achieved_gbs" in e:
+            roofline = {"kernel": name, "bound": "hbm", "achieved": e["achieved_gbs"], "peak": peak, "unit": "GB/s",
+                        "frac": e["frac"], "traffic": None, "peak_source": peak_src,
+                        "bytes_per_launch": e["algorithmic_bytes_per_unit"] * e["units"] / max(e["launches"], 1),
+                        "avg_launch_ms": e["ms"] / max(e["launches"], 1), "share_of_kernel_time": e["share"]}
+            break
+    b_scan = N_OBJECTS * (45 * n_points + 24 * hw) + 40 * n_points
+    step_roofline = {"algorithmic_bytes_per_scan": b_scan, "achieved_gbs": round(value / world * b_scan / 1e9, 1),
+                     "frac_of_peak": round(value / world * b_scan / 1e9 / peak, 4)}
+
+    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, n_done, secs = cpu_baseline_sample()
+        cpu = {"value": v, "unit": "scans/s", "cores": 1, "kind": "port",
+               "sample": f"{n_done} whole scan(s) of the same workload through oracle/real3d_oracle.py, {secs:.1f} s",
+               "host_cpus": os.cpu_count()}
+    inserted_all = sum_over_ranks(inserted_total)
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h / args.steps)},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "step_roofline": step_roofline, "kernels": kernel_table,
+            "rounds_per_step": results[0].extra["rounds"], "objects_inserted_per_scan": inserted_all / (world * n_scans),
+            "engine_stats": stats}))
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

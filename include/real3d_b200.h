@@ -168,6 +168,12 @@ int r3d_engine_profile_enable(r3d_engine* eng, int on);
 int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out, int64_t* launches_out,
                             int max_kernels, int* n_kernels_out);
 
+/* gated scan-launch counters since the last r3d_engine_profile_enable: out4 = {scans projected, cut objects tried,
+ * scans masked/re-ranged, 0} — the "units one launch processes" of the roofline arithmetic */
+int r3d_engine_stats(r3d_engine* eng, uint64_t* out4);
+/* the engine's cudaStream_t (so callers can bracket work with their own CUDA events) */
+void* r3d_engine_stream(r3d_engine* eng);
+
 /* debug / parity taps on the resident state of one scan (device -> host), used by the tests */
 int r3d_engine_debug_image(r3d_engine* eng, int scan, double* smooth_out /* rows*cols */);
 int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* flags_out /* yaw_steps+1 */,

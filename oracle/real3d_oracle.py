@@ -621,7 +621,9 @@ def augment_scan(task, scene_pcl5, scene_box_lines, db, counts, perms, config, *
                         remaining[ci] -= 1
                         all_visible_parts = np.append(all_visible_parts, visible_sample, axis=0)
                         if not ss:
-                            lines.append(create_annotation_line(sample_data['anno'], sample_annotation, sample_rotation))
+                            # the reference's step is 1 degree, so its rotation index IS the angle (od/ins:553)
+                            lines.append(create_annotation_line(sample_data['anno'], sample_annotation,
+                                                                sample_rotation * (360.0 / yaw_steps)))
                         if np.max(remaining) > 0:
                             scene_annotation = scene_annotation + [sample_annotation]
                         break

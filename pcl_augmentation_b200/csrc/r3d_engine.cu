@@ -58,7 +58,7 @@ struct r3d_engine {
     DevBuf<int> pix, gate_project, gate_try, gate_apply, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_collide, cand_jmin, cand_v, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
-    DevBuf<unsigned long long> zraw, obj_raw, cand_zsum;
+    DevBuf<unsigned long long> zraw, obj_raw, cand_zsum, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
     DevBuf<ScanState> st;
     DevBuf<Box> boxes;
@@ -171,7 +171,8 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->check.alloc(B * d.max_inserted * 5)); TRY(eng->out_count.alloc(B)); TRY(eng->out_off.alloc(B + 1));
     TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
     TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
-    TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8));
+    TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
+    R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, 2 * (B + 1) * sizeof(long long)));
     std::vector<ClassCfg> cls(R3D_MAX_CLASSES);
@@ -200,7 +201,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.cand_v = eng->cand_v.p; d.feas = eng->feas.p; d.inserted = eng->inserted.p; d.inserted_box = eng->inserted_box.p;
     d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
-    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p;
+    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
     *out = eng;
     return R3D_OK;
 }
@@ -497,8 +498,18 @@ extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
     drain_events(eng);
     eng->profile = on != 0;
     for (int i = 0; i < KID_COUNT; ++i) { eng->prof_ms[i] = 0; eng->prof_launches[i] = 0; }
+    R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     return R3D_OK;
 }
+
+extern "C" int r3d_engine_stats(r3d_engine* eng, uint64_t* out4) {
+    if (!eng || !out4) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats: null argument");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    R3D_CUDA(cudaMemcpy(out4, eng->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return R3D_OK;
+}
+
+extern "C" void* r3d_engine_stream(r3d_engine* eng) { return eng ? (void*)eng->stream : nullptr; }
 
 extern "C" int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out,
                                        int64_t* launches_out, int max_kernels, int* n_kernels_out) {

@@ -76,6 +76,7 @@ struct EngineDev {       // passed by value to kernels
     ScanState* st;
     int *gate_project, *gate_try, *gate_apply;
     int* active_count;
+    unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
     // scene boxes
     Box* boxes;            // [B][max_boxes]

@@ -178,6 +178,9 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
         s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
         e.gate_project[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply | project;
         if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(e.active_count, 1);
+        if (project) atomicAdd(&e.stats[0], 1ull);
+        if (tryact) atomicAdd(&e.stats[1], 1ull);
+        if (apply | project) atomicAdd(&e.stats[2], 1ull);
         s_try = tryact;
     }
     __syncthreads();

@@ -323,6 +323,18 @@ class Real3DEngine:
         ks = names.value.decode().split('\n')
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
+    def stats(self):
+        out = np.zeros(4, dtype=np.uint64)
+        _lib.check(self.lib.r3d_engine_stats(self.handle, out.ctypes.data), "stats")
+        return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2])}
+
+    def cuda_stream(self):
+        import torch
+        return torch.cuda.ExternalStream(int(self.lib.r3d_engine_stream(self.handle)))
+
+    def launch_count(self):
+        return int(self.lib.r3d_launch_count())
+
     def debug_image(self, scan):
         out = np.zeros((self.rows, self.cols), dtype=np.float64)
         _lib.check(self.lib.r3d_engine_debug_image(self.handle, scan, out.ctypes.data), "debug_image")

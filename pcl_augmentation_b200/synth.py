@@ -363,7 +363,7 @@ def make_case(task, seed, shape: ScanShape = KITTI_SHAPE, n_cars=None, n_per_cla
         _DB_CACHE[key] = make_object_db(1000 + db_seed, classes, n_per_class, semseg, shape, obj_range)
     db = _DB_CACHE[key]
     if number_of_object is None:
-        number_of_object = cfg["insertion"]["number_of_object"]
+        number_of_object = int(np.sum(counts)) if counts is not None else cfg["insertion"]["number_of_object"]
     cfg["insertion"]["number_of_object"] = number_of_object
     sched = make_schedule(seed, len(classes), number_of_object, [len(db[c]) for c in classes], tries=tries,
                           random_counts=counts is None, fixed_counts=counts)
