@@ -3,14 +3,18 @@
 //   ignored, no azimuth wrap; pixels switched on by the closing that hold no point get the mean of their occupied
 //   neighbours' ORIGINAL ranges, summed in the reference's (drow, dcol) order in fp64 (cl:46-51,57).
 // Templated on the input adaptor so the same code serves the float64 train/label pair of the drop-in smooth_out and
-// the engine's raw uint64 z-buffer.  HBM traffic: one read of the input tile (+halo from L2) and one write of the
-// output -> 16 B/pixel for the engine variant.
+// the engine's raw uint64 z-buffer.  The tile (+ a 4-row / 2-col halo) is staged once in shared memory with
+// coalesced row reads; dilation, erosion and the hole fill then run out of shared memory, so HBM sees one read of
+// the input (x1.33 for the halo, mostly L2 hits) and one write of the output: 16 B/pixel for the engine variant.
 #pragma once
 #include "r3d_common.cuh"
 
-constexpr int CF_TH = 16;       // output rows per CTA
+constexpr int CF_TH = 32;       // output rows per CTA
 constexpr int CF_TW = 64;       // output cols per CTA
 constexpr int CF_THREADS = 256;
+constexpr int CF_HR = 4, CF_HC = 2;                    // halo: two 5x3 passes
+constexpr int CF_SH = CF_TH + 2 * CF_HR;               // staged rows
+constexpr int CF_SW = CF_TW + 2 * CF_HC;               // staged cols
 
 template <class In>
 __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, int64_t img_stride,
@@ -19,14 +23,19 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, 
                                                             const int* __restrict__ gate) {
     const int z = blockIdx.z;
     if (gate && !gate[z]) return;
-    __shared__ uint8_t s_occ[CF_TH + 8][CF_TW + 4];
+    __shared__ double s_val[CF_SH][CF_SW];
+    __shared__ uint8_t s_occ[CF_SH][CF_SW];            // bit0: occupancy (clip(label,0,1) > 0), bit1: label == 1
     __shared__ uint8_t s_dil[CF_TH + 4][CF_TW + 2];
     const int r0 = blockIdx.y * CF_TH, c0 = blockIdx.x * CF_TW;
     const int64_t base = (int64_t)z * img_stride;
-    for (int i = threadIdx.x; i < (CF_TH + 8) * (CF_TW + 4); i += CF_THREADS) {
-        const int lr = i / (CF_TW + 4), lc = i % (CF_TW + 4);
-        const int r = r0 - 4 + lr, c = c0 - 2 + lc;
-        s_occ[lr][lc] = (r >= 0 && r < H && c >= 0 && c < W) ? (in.occ(base + (int64_t)r * W + c) ? 1 : 0) : 0;
+    for (int i = threadIdx.x; i < CF_SH * CF_SW; i += CF_THREADS) {
+        const int lr = i / CF_SW, lc = i % CF_SW;
+        const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
+        uint8_t o = 0;
+        double v = 0.0;
+        if (r >= 0 && r < H && c >= 0 && c < W) in.load(base + (int64_t)r * W + c, v, o);
+        s_val[lr][lc] = v;
+        s_occ[lr][lc] = o;
     }
     __syncthreads();
     for (int i = threadIdx.x; i < (CF_TH + 4) * (CF_TW + 2); i += CF_THREADS) {
@@ -38,7 +47,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, 
 #pragma unroll
             for (int dr = 0; dr < 5; ++dr)
 #pragma unroll
-                for (int dc = 0; dc < 3; ++dc) d |= s_occ[lr + dr][lc + dc];
+                for (int dc = 0; dc < 3; ++dc) d |= s_occ[lr + dr][lc + dc + 0] & 1;
         }
         s_dil[lr][lc] = d;
     }
@@ -53,26 +62,24 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, 
         for (int dr = 0; dr < 5; ++dr)
 #pragma unroll
             for (int dc = 0; dc < 3; ++dc) e &= s_dil[lr + dr][lc + dc];
-        const int64_t idx = base + (int64_t)r * W + c;
-        double t = in.val(idx);
-        bool one = in.is_one(idx);
-        double lab = in.lab(idx);
+        const int sr = lr + CF_HR, sc = lc + CF_HC;
+        double t = s_val[sr][sc];
+        const bool one = (s_occ[sr][sc] & 2) != 0;
+        bool filled = false;
         if (e && !one) {                                  // cl:41-43: closed == 255 and label != 1
             int neighbors = 0;
             double sum = 0.0;
+#pragma unroll
             for (int dr = -2; dr <= 2; ++dr)
-                for (int dc = -1; dc <= 1; ++dc) {
-                    const int rr = r + dr, cc = c + dc;
-                    if (rr >= 0 && rr < H && cc >= 0 && cc < W) {
-                        const int64_t j = base + (int64_t)rr * W + cc;
-                        if (in.is_one(j)) { neighbors += 1; sum = r3d::add(sum, in.val(j)); }
-                    }
-                }
+#pragma unroll
+                for (int dc = -1; dc <= 1; ++dc)           // out-of-image neighbours were staged as "not 1"
+                    if (s_occ[sr + dr][sc + dc] & 2) { neighbors += 1; sum = r3d::add(sum, s_val[sr + dr][sc + dc]); }
             if (neighbors > 0) t = __ddiv_rn(sum, (double)neighbors);        // cl:57
-            lab = 1.0;                                                       // cl:55,58
+            filled = true;                                                   // cl:55,58: label = 1
         }
+        const int64_t idx = base + (int64_t)r * W + c;
         out_train[idx] = t;
-        if (out_label) out_label[idx] = lab;
+        if (out_label) out_label[idx] = filled ? 1.0 : in.lab(idx);
         if (closed_out) closed_out[idx] = e ? 255 : 0;
         far |= t > r3d::kEmptyRange;
     }

@@ -14,12 +14,12 @@ using namespace r3d;
 namespace {
 
 enum KernelId {
-    KID_INGEST, KID_CTRL, KID_APPLY, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT1,
-    KID_HEIGHT2, KID_CANDFIN, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_COUNT
+    KID_INGEST, KID_CTRL, KID_APPLY, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT,
+    KID_GRID, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
     "ingest_spherical", "ctrl", "apply_mask_minmax", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
-    "onmap", "height_pass1", "height_pass2", "cand_finalize", "collide_points", "collide_boxes", "feasible",
+    "onmap", "height_grid", "grid_build", "collide_points", "collide_boxes", "feasible",
     "occlusion_count", "select_emit", "compact_output"};
 
 template <class T>
@@ -49,16 +49,16 @@ struct r3d_engine {
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
     int last_rounds = 0;
     // device buffers
-    DevBuf<float4> xyzi, out_xyzi;
+    DevBuf<float4> xyzi, out_xyzi, gpts;
     DevBuf<double> tail_x, tail_y, tail_z, r, el, smooth, poses, obj_x, obj_y, obj_z, cos_k, sin_k, radii_sq, cand_level,
         cand_cx, cand_cy, inserted_box;
     DevBuf<float> tail_i, obj_i, check, out_check;
-    DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, cand_zcnt, out_label;
+    DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label;
     DevBuf<unsigned short> col;
     DevBuf<int> pix, gate_project, gate_try, gate_apply, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
-        class_list, radii_ok, cand_collide, cand_jmin, cand_v, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
+        class_list, radii_ok, cand_collide, cand_v, gcell, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
-    DevBuf<unsigned long long> zraw, obj_raw, cand_zsum, stats;
+    DevBuf<unsigned long long> zraw, obj_raw, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
     DevBuf<ScanState> st;
     DevBuf<Box> boxes;
@@ -153,6 +153,9 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.map_window = cfg->task == 1 ? cfg->map_window : 32; d.dwords = (d.hw + 31) / 32;
     for (int i = 0; i < R3D_MAX_SURFACE; ++i) d.road_indexes[i] = cfg->road_indexes[i];
     d.step_rad = 2.0 * 3.14159265358979323846 / (double)cfg->yaw_steps;
+    d.grid_cell = cfg->grid_cell > 0 ? cfg->grid_cell : 0.5;
+    d.grid_inv_cell = (float)(1.0 / d.grid_cell);
+    d.G = 2 * (cfg->grid_half > 0 ? cfg->grid_half : 200);
     const size_t B = d.B, P = d.P, K1 = d.K + 1, HW = d.hw;
     TRY(eng->xyzi.alloc(B * d.max_points)); TRY(eng->tail_x.alloc(B * d.max_inserted)); TRY(eng->tail_y.alloc(B * d.max_inserted));
     TRY(eng->tail_z.alloc(B * d.max_inserted)); TRY(eng->tail_i.alloc(B * d.max_inserted)); TRY(eng->label.alloc(B * P));
@@ -164,13 +167,14 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
     TRY(eng->radii_sq.alloc(R3D_NUM_RADII)); TRY(eng->radii_ok.alloc(R3D_NUM_RADII)); TRY(eng->classes.alloc(R3D_MAX_CLASSES));
-    TRY(eng->cand_flags.alloc(B * K1)); TRY(eng->cand_collide.alloc(B * K1)); TRY(eng->cand_jmin.alloc(B * K1));
-    TRY(eng->cand_zsum.alloc(B * K1)); TRY(eng->cand_zcnt.alloc(B * K1)); TRY(eng->cand_level.alloc(B * K1));
+    TRY(eng->cand_flags.alloc(B * K1)); TRY(eng->cand_collide.alloc(B * K1));
+    TRY(eng->cand_level.alloc(B * K1));
     TRY(eng->cand_cx.alloc(B * K1)); TRY(eng->cand_cy.alloc(B * K1)); TRY(eng->cand_bt.alloc(B * K1)); TRY(eng->cand_v.alloc(B * K1));
     TRY(eng->feas.alloc(B * d.K)); TRY(eng->inserted.alloc(B * d.max_events * 4)); TRY(eng->inserted_box.alloc(B * d.max_events * 8));
     TRY(eng->check.alloc(B * d.max_inserted * 5)); TRY(eng->out_count.alloc(B)); TRY(eng->out_off.alloc(B + 1));
     TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
     TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
+    TRY(eng->gcell.alloc(B * (size_t)d.G * d.G)); TRY(eng->gpts.alloc(B * d.max_points));
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
@@ -196,11 +200,12 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
     d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
     d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
-    d.cand_collide = eng->cand_collide.p; d.cand_jmin = eng->cand_jmin.p; d.cand_zsum = eng->cand_zsum.p; d.cand_zcnt = eng->cand_zcnt.p;
+    d.cand_collide = eng->cand_collide.p;
     d.cand_level = eng->cand_level.p; d.cand_cx = eng->cand_cx.p; d.cand_cy = eng->cand_cy.p; d.cand_bt = eng->cand_bt.p;
     d.cand_v = eng->cand_v.p; d.feas = eng->feas.p; d.inserted = eng->inserted.p; d.inserted_box = eng->inserted_box.p;
     d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
+    d.gcell = eng->gcell.p; d.gpts = eng->gpts.p;
     d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
     *out = eng;
     return R3D_OK;
@@ -297,8 +302,13 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
     k_reset_state<<<(n + 127) / 128, 128, 0, st>>>(d, n, eng->n0_arr.p, eng->nbox0_arr.p); r3d_count_launch();
     const int chunks = (eng->max_n0 + CHUNK - 1) / CHUNK;
     if (ingest) {
-        Launcher l(eng, KID_INGEST);
-        k_ingest<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+        { Launcher l(eng, KID_INGEST); k_ingest<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
+        Launcher l(eng, KID_GRID);
+        R3D_CUDA(cudaMemsetAsync(eng->gcell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
+        k_grid_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+        k_grid_scan<<<n, 1024, 0, st>>>(d, n);
+        k_grid_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+        r3d_count_launch(2);
     } else {
         k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
         // scene boxes: drop the boxes appended by the previous run
@@ -384,7 +394,7 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
     const int P_live = eng->max_n0 + d.max_inserted;
-    const int chunks_all = (P_live + CHUNK - 1) / CHUNK, chunks0 = (eng->max_n0 + CHUNK - 1) / CHUNK;
+    const int chunks_all = (P_live + CHUNK - 1) / CHUNK;
     const int kwarps = (d.K + 7) / 8;
     const size_t sel_smem = (size_t)next_pow2(d.max_obj_points) * sizeof(unsigned long long);
     R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * sizeof(int), st));
@@ -413,15 +423,13 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_HEIGHT1); k_height<1><<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_HEIGHT2); k_height<2><<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_CANDFIN); k_cand_finalize<<<dim3((d.K + 255) / 256, n), 256, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_HEIGHT); k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
         if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_COLLIDE_PTS); k_collide_points<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_COLLIDE_BOX); k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_FEASIBLE); k_feasible<<<n, 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
-        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 256, sel_smem, st>>>(d, n); }
+        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n); }
         // the host only looks at the counter written by the PREVIOUS round's k_ctrl, so the device never idles
         if (round >= 1) {
             R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));

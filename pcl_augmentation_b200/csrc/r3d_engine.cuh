@@ -61,6 +61,11 @@ struct EngineDev {       // passed by value to kernels
     int road_label, n_road_indexes, map_window, dwords, n_objects, n_perm_events;
     int road_indexes[R3D_MAX_SURFACE];
     double step_rad;
+    int G;                            // road-level grid side in cells
+    float grid_inv_cell;
+    double grid_cell;
+    int* gcell;                       // [B][G*G]   CSR end offsets (cell c holds gpts[gcell[c-1] .. gcell[c]) )
+    float4* gpts;                     // [B][max_points]  surface points sorted by cell: x, y, z, label bits
     // per-scan resident data
     const float4* xyzi;
     double *tail_x, *tail_y, *tail_z;
@@ -108,9 +113,6 @@ struct EngineDev {       // passed by value to kernels
     // candidates of the current try
     unsigned char* cand_flags;        // [B][K+1]
     int* cand_collide;                // [B][K+1]
-    int* cand_jmin;                   // [B][K+1]
-    unsigned long long* cand_zsum;    // [B][K+1] fixed point 2^-40
-    unsigned* cand_zcnt;              // [B][K+1]
     double* cand_level;               // [B][K+1]
     double *cand_cx, *cand_cy;        // [B][K+1]
     BoxTest* cand_bt;                 // [B][K+1]

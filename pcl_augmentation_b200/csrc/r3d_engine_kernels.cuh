@@ -188,8 +188,7 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
     const ObjBox ob = e.obj[s.cur_obj];
     const size_t cb = (size_t)b * (e.K + 1);
     for (int k = threadIdx.x; k <= e.K; k += blockDim.x) {
-        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_jmin[cb + k] = INT_MAX;
-        e.cand_zsum[cb + k] = 0ull; e.cand_zcnt[cb + k] = 0u; e.cand_v[cb + k] = 0;
+        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_v[cb + k] = 0;
         const double c = e.cos_k[k], sn = e.sin_k[k];
         e.cand_cx[cb + k] = sub(mul(c, ob.cx), mul(sn, ob.cy));
         e.cand_cy[cb + k] = add(mul(sn, ob.cx), mul(c, ob.cy));
@@ -280,9 +279,12 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_s
 
 struct RawImage {        // the engine's z-buffer as close/fill input
     const unsigned long long* raw;
-    __device__ bool occ(int64_t i) const { return raw[i] != R3D_EMPTY_U64; }
-    __device__ bool is_one(int64_t i) const { return raw[i] != R3D_EMPTY_U64; }
-    __device__ double val(int64_t i) const { const unsigned long long b = raw[i]; return b != R3D_EMPTY_U64 ? bits_dbl(b) : kEmptyRange; }
+    __device__ void load(int64_t i, double& v, uint8_t& o) const {
+        const unsigned long long b = raw[i];
+        const bool hit = b != R3D_EMPTY_U64;
+        v = hit ? bits_dbl(b) : kEmptyRange;            // od/ins:100: empty = 500
+        o = hit ? 3 : 0;
+    }
     __device__ double lab(int64_t i) const { return raw[i] != R3D_EMPTY_U64 ? 1.0 : -1.0; }
 };
 
@@ -388,76 +390,138 @@ __device__ __forceinline__ int radius_index(const double* r2, double d2) {
     return lo;
 }
 
-// A7 (od/fs:138-172, ss/fs:107-152), pass 1: for every candidate the first radius (0.1, 0.2, ... accumulated) whose
-// disc holds a surface point of the ORIGINAL scan.  PASS 2 sums z of the points inside that disc in 2^-40 fixed
-// point (order independent, exact for float32 z).  Both passes stream the original points once: 20 B/point.
-template <int PASS>
-__global__ void __launch_bounds__(STREAM_THREADS) k_height(EngineDev e, int n_scans) {
+// ------------------------------------------------------------------------------- road-level search grid
+// The ORIGINAL scan never changes (correct_height reads original_pcl, od/fs:282), so its surface points (any label a
+// class may stand on, z > -3) are bucketed ONCE per scan into a uniform grid (CSR by cell, rows contiguous in x).
+// Points outside the grid extent are clamped into border cells: distances are always computed from the coordinates,
+// and clamping never increases a cell-index difference, so the square searches below stay exact.
+__device__ __forceinline__ bool any_surface_label(const EngineDev& e, unsigned lab) {
+    for (int c = 0; c < e.n_classes; ++c) {
+        const ClassCfg& cc = e.classes[c];
+        for (int i = 0; i < cc.n_surface; ++i) if (lab == (unsigned)cc.surface[i]) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ int grid_coord(const EngineDev& e, float v) {
+    const int i = (int)floorf(v * e.grid_inv_cell) + (e.G >> 1);
+    return max(0, min(i, e.G - 1));
+}
+
+template <int PASS>     // 1: count per cell, 2: scatter (after the prefix scan)
+__global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    const ScanState& s = e.st[b];
-    const int n0 = s.n0;
+    if (b >= n_scans) return;
+    const int n0 = e.st[b].n0;
     const int p0 = blockIdx.x * CHUNK;
     if (p0 >= n0) return;
-    __shared__ double s_r2[R3D_NUM_RADII];
-    if (threadIdx.x < R3D_NUM_RADII) s_r2[threadIdx.x] = e.radii_sq[threadIdx.x];
-    __syncthreads();
-    const ObjBox ob = e.obj[s.cur_obj];
-    const ClassCfg& cc = e.classes[ob.cls];
-    const float reach = 5.0f;
-    const float rlo = fmaxf((float)ob.rho - reach - 0.02f, 0.f), rhi = (float)ob.rho + reach + 0.02f;
-    const float step = (float)e.step_rad;
-    const size_t cb = (size_t)b * (e.K + 1);
     const size_t base = (size_t)b * e.P;
-    const bool need_onmap = e.task == 0;
+    int* cell = e.gcell + (size_t)b * e.G * e.G;
+    float4* out = e.gpts + (size_t)b * e.max_points;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
         const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
-        const float rho2 = v.x * v.x + v.y * v.y;
-        if (rho2 < rlo * rlo || rho2 > rhi * rhi) continue;
-        if (!((double)v.z > -3.0)) continue;                               // od/fs:155
-        if (!surface_label(cc, e.label[base + p])) continue;              // od/fs:154, ss/fs:125-131
-        int k_first, count;
-        cand_window(ob, v.x, v.y, reach, step, e.K, k_first, count);
-        const double x = v.x, y = v.y;
-        for (int j = 0; j < count; ++j) {
-            const int k = cand_index(k_first, j, e.K);
-            if (need_onmap && !(e.cand_flags[cb + k] & CF_ONMAP)) continue;
-            const double dx = sub(x, e.cand_cx[cb + k]), dy = sub(y, e.cand_cy[cb + k]);
-            const double d2 = add(mul(dx, dx), mul(dy, dy));               // od/fs:153
-            if (PASS == 1) {
-                const int ji = radius_index(s_r2, d2);
-                if (ji < R3D_NUM_RADII) atomicMin(&e.cand_jmin[cb + k], ji);
-            } else {
-                const int jm = e.cand_jmin[cb + k];
-                if (jm < R3D_NUM_RADII && d2 <= s_r2[jm]) {
-                    atomicAdd(&e.cand_zsum[cb + k], (unsigned long long)__double2ll_rn(mul((double)v.z, kFix)));
-                    atomicAdd(&e.cand_zcnt[cb + k], 1u);
-                }
-            }
-        }
+        const unsigned lab = e.label[base + p];
+        if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
+        const int c = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
+        if (PASS == 1) atomicAdd(&cell[c], 1);
+        else out[atomicAdd(&cell[c], 1)] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
     }
 }
 
-// road level (od/fs:164), near_road flag (od/fs:158-160) and the candidate's box test (R_k = R0 . Rz(k*step))
-__global__ void __launch_bounds__(256) k_cand_finalize(EngineDev e, int n_scans) {
+// exclusive prefix sum of the per-cell counts (one CTA per scan); after the scatter pass cell[c] = END of cell c
+__global__ void __launch_bounds__(1024) k_grid_scan(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    int* cell = e.gcell + (size_t)b * e.G * e.G;
+    const int n = e.G * e.G;
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < n ? cell[i] : 0;
+        int inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        int off = s_run;
+        for (int j = 0; j < w; ++j) off += s_w[j];
+        if (i < n) cell[i] = off + inc - v;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int j = 0; j < 32; ++j) t += s_w[j]; s_run += t; }
+        __syncthreads();
+    }
+}
+
+// A7 (od/fs:138-172, ss/fs:107-152): road level under every candidate that needs it, one warp per candidate.
+// "first radius 0.1, 0.2, ... whose disc holds a surface point" == radius index of the NEAREST surface point, found
+// by scanning growing squares of grid cells; the level is the mean z of the points inside that disc, summed in
+// 2^-40 fixed point (order independent; exact for float32 z, so equal to numpy's sequential float64 sum).  Also
+// builds the candidate's box test (R_k = R0 . Rz(k * step)).
+__global__ void __launch_bounds__(256) k_height_grid(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_try[b]) return;
-    const int k = blockIdx.x * blockDim.x + threadIdx.x + 1;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
     if (k > e.K) return;
+    const int lane = threadIdx.x & 31;
     const ScanState& s = e.st[b];
-    const ObjBox ob = e.obj[s.cur_obj];
     const size_t cb = (size_t)b * (e.K + 1);
-    const int jm = e.cand_jmin[cb + k];
     unsigned f = e.cand_flags[cb + k];
-    if (jm < R3D_NUM_RADII && e.radii_ok[jm] && e.cand_zcnt[cb + k] > 0) {
-        const double level = __ddiv_rn(__ddiv_rn((double)(long long)e.cand_zsum[cb + k], kFix), (double)e.cand_zcnt[cb + k]);
+    if (e.task == 0 && !(f & CF_ONMAP)) return;                       // OD: only on-map candidates (od/fs:281)
+    const ObjBox ob = e.obj[s.cur_obj];
+    const ClassCfg& cc = e.classes[ob.cls];
+    const int G = e.G;
+    const int* cell = e.gcell + (size_t)b * G * G;
+    const float4* pts = e.gpts + (size_t)b * e.max_points;
+    const double cx = e.cand_cx[cb + k], cy = e.cand_cy[cb + k];
+    const int icx = grid_coord(e, (float)cx), icy = grid_coord(e, (float)cy);
+    const int t_max = (int)ceil(5.0 / e.grid_cell) + 1;
+    double best = 1e300;
+    for (int T = 1;; T = min(2 * T, t_max)) {
+        const int x0 = max(icx - T, 0), x1 = min(icx + T, G - 1);
+        for (int iy = max(icy - T, 0); iy <= min(icy + T, G - 1); ++iy) {
+            const int c0 = iy * G + x0, c1 = iy * G + x1;
+            const int beg = c0 > 0 ? cell[c0 - 1] : 0, end = cell[c1];
+            for (int i = beg + lane; i < end; i += 32) {
+                const float4 v = pts[i];
+                if (!surface_label(cc, __float_as_uint(v.w))) continue;
+                const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+                best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                       // od/fs:153
+            }
+        }
+        for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+        const double safe = (double)T * e.grid_cell * 0.999;          // every point outside the square is farther
+        if (best <= safe * safe || T >= t_max) break;
+    }
+    const int j = best < 1e299 ? radius_index(e.radii_sq, best) : R3D_NUM_RADII;
+    if (j >= R3D_NUM_RADII || !e.radii_ok[j]) return;                 // od/fs:156-160: no surface within reach
+    const double r2 = e.radii_sq[j];
+    const int T = min(t_max, (int)ceil(sqrt(r2) / e.grid_cell) + 1);
+    long long zsum = 0;
+    int cnt = 0;
+    const int x0 = max(icx - T, 0), x1 = min(icx + T, G - 1);
+    for (int iy = max(icy - T, 0); iy <= min(icy + T, G - 1); ++iy) {
+        const int c0 = iy * G + x0, c1 = iy * G + x1;
+        const int beg = c0 > 0 ? cell[c0 - 1] : 0, end = cell[c1];
+        for (int i = beg + lane; i < end; i += 32) {
+            const float4 v = pts[i];
+            if (!surface_label(cc, __float_as_uint(v.w))) continue;
+            const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+            if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    }
+    if (lane == 0 && cnt > 0) {
+        const double level = __ddiv_rn(__ddiv_rn((double)zsum, kFix), (double)cnt);       // od/fs:164 np.mean
         e.cand_level[cb + k] = level;
         const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, e.cos_k[k], e.sin_k[k]);
-        const Box bx = yaw_box_to_box(yb, level, ob.length, ob.width, ob.height);
-        e.cand_bt[cb + k] = make_box_test(bx);
-        f |= CF_HOK;
+        e.cand_bt[cb + k] = make_box_test(yaw_box_to_box(yb, level, ob.length, ob.width, ob.height));
+        e.cand_flags[cb + k] = (unsigned char)(f | CF_HOK);
     }
-    e.cand_flags[cb + k] = (unsigned char)f;
 }
 
 // A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place): candidates are visited in
@@ -680,22 +744,18 @@ __global__ void __launch_bounds__(128) k_occl_count(EngineDev e, int n_scans) {
     }
 }
 
-// smoothed object range at pixel (r, c) from the scratch z-buffer: own min range, or the neighbour mean where the
-// 5x3 closing switches an empty pixel on (cl:26-62); returns false if the pixel stays empty.
-__device__ bool obj_pixel_value(const unsigned long long* raw, int H, int W, int r, int c, double& val) {
+// smoothed object range at pixel (r, c): own min range, or the neighbour mean where the 5x3 closing switches an
+// empty pixel on (cl:26-62).  `dil` is the bit image of the dilated occupancy (union of the 5x3 neighbourhoods of the
+// object's pixels), so closed(q) = AND of dil over the in-image 5x3 neighbourhood of q.
+__device__ bool obj_pixel_value(const unsigned long long* raw, const unsigned* dil, int H, int W, int r, int c, double& val) {
     const unsigned long long own = raw[r * W + c];
     if (own != R3D_EMPTY_U64) { val = bits_dbl(own); return true; }
     for (int dr = -2; dr <= 2; ++dr)
         for (int dc = -1; dc <= 1; ++dc) {
             const int r1 = r + dr, c1 = c + dc;
             if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;          // outside the image: ignored by the erosion
-            bool dil = false;
-            for (int er = -2; er <= 2 && !dil; ++er)
-                for (int ec = -1; ec <= 1; ++ec) {
-                    const int r2 = r1 + er, c2 = c1 + ec;
-                    if (r2 >= 0 && r2 < H && c2 >= 0 && c2 < W && raw[r2 * W + c2] != R3D_EMPTY_U64) { dil = true; break; }
-                }
-            if (!dil) return false;
+            const int q = r1 * W + c1;
+            if (!(dil[q >> 5] & (1u << (q & 31)))) return false;
         }
     int neighbors = 0;
     double sum = 0.0;
@@ -731,7 +791,7 @@ __device__ void bitonic_sort_u64(unsigned long long* keys, int n_pow2) {
 // candidate's z-buffer in a scratch image, closes / fills it around the object, compares with the scene image
 // (strict <) into the vis_px bit mask, and on acceptance appends the visible object points in (pix_id, index) order
 // to the scene tail, the `check` record and the scene boxes.
-__global__ void __launch_bounds__(256) k_select_emit(EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans || !e.gate_try[b]) return;
     ScanState& s = e.st[b];
@@ -757,10 +817,20 @@ __global__ void __launch_bounds__(256) k_select_emit(EngineDev e, int n_scans) {
     const int t0 = s.n_tail, chk0 = s.n_check, nbox0 = s.n_boxes, nins0 = s.n_inserted, n0 = s.n0;
     if (threadIdx.x == 0) s_nvis = 0;
     for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) { dm[i] = 0u; vm[i] = 0u; }
+    __syncthreads();
     for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
         const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
         pixbuf[i] = o.pix;
-        if (o.pix >= 0) atomicMin(&raw[o.pix], dbl_bits(o.r));
+        if (o.pix < 0) continue;
+        atomicMin(&raw[o.pix], dbl_bits(o.r));
+        const int pr = o.pix / W, pc = o.pix % W;                        // dilated occupancy (5 rows x 3 cols)
+        for (int dr = -2; dr <= 2; ++dr)
+            for (int dc = -1; dc <= 1; ++dc) {
+                const int r1 = pr + dr, c1 = pc + dc;
+                if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+                const int q = r1 * W + c1;
+                atomicOr(&vm[q >> 5], 1u << (q & 31));
+            }
     }
     __threadfence_block();
     __syncthreads();
@@ -772,10 +842,8 @@ __global__ void __launch_bounds__(256) k_select_emit(EngineDev e, int n_scans) {
         const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
         if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
         const int q = r * W + cc;
-        const unsigned bit = 1u << (q & 31);
-        if (atomicOr(&vm[q >> 5], bit) & bit) continue;                  // already evaluated by another thread
         double val;
-        if (obj_pixel_value(raw, H, W, r, cc, val) && val < smooth[q]) atomicOr(&dm[q >> 5], bit);   // od/ins:486
+        if (obj_pixel_value(raw, vm, H, W, r, cc, val) && val < smooth[q]) atomicOr(&dm[q >> 5], 1u << (q & 31));   // od/ins:486
     }
     __threadfence_block();
     __syncthreads();

@@ -106,9 +106,11 @@ extern "C" int r3d_project_zbuffer(double* rows9, int64_t n, int num_row, int nu
 // Input adaptor for the float64 train/label pair the reference passes to smooth_out.
 struct F64Image {
     const double* train; const double* label;
-    __device__ bool occ(int64_t i) const { return label[i] > 0.0; }            // np.clip(label, 0, 1) -> 0/255 (cl:16-19)
-    __device__ double val(int64_t i) const { return train[i]; }
-    __device__ bool is_one(int64_t i) const { return label[i] == 1.0; }    // cl:41, cl:48
+    __device__ void load(int64_t i, double& v, uint8_t& o) const {
+        const double l = label[i];
+        v = train[i];
+        o = (l > 0.0 ? 1 : 0) | (l == 1.0 ? 2 : 0);     // np.clip(label, 0, 1) -> 0/255 (cl:16-19); label == 1 (cl:41,48)
+    }
     __device__ double lab(int64_t i) const { return label[i]; }
 };
 

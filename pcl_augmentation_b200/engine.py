@@ -60,7 +60,7 @@ class Real3DEngine:
 
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
-                 map_window=512, road_indexes=ROAD_INDEXES):
+                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -85,6 +85,7 @@ class Real3DEngine:
         for i, v in enumerate(road_indexes):
             cfg.road_indexes[i] = int(v)
         cfg.map_window = int(map_window)
+        cfg.grid_half, cfg.grid_cell = int(grid_half), float(grid_cell)
         r2, ok = bx.search_radii()
         for i in range(50):
             cfg.radii_sq[i] = float(r2[i])
