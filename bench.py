@@ -220,19 +220,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    from pcl_augmentation_b200 import sharding
+
     def max_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return sharding.all_reduce_scalar(x, "max", "cuda")
 
     def sum_over_ranks(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+        return sharding.all_reduce_scalar(x, "sum", "cuda")
 
     from pcl_augmentation_b200.engine import Real3DEngine, scan_input_from_case
     n_scans = args.scans

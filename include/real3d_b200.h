@@ -64,6 +64,24 @@ int r3d_close_fill(const double* train_in, const double* label_in, int num_row, 
 int r3d_cut_bounding_box(const double* rows, int64_t n, int row_stride, const double* box_host, uint8_t* mask_out,
                          r3d_stream stream);
 
+/* rotate_bounding_box (od/fs:97-102, ss/fs:72) + the z move of correct_height (od/fs:167): in place on rows of
+ * row_stride doubles (device): x' = c x - s y, y' = s x + c y, z' = z + dz. */
+int r3d_transform_points(double* rows, int64_t n, int row_stride, double cos_t, double sin_t, double dz,
+                         r3d_stream stream);
+
+/* correct_height's growing-radius road-level search (od/fs:149-164, ss/fs:118-144) around (cx, cy) over rows whose
+ * column label_col is one of labels[] and whose z > -3.  rows: device; labels, radii tables, outputs: host;
+ * scratch3: 3 uint64 on the device.  Blocks until the result is on the host. */
+int r3d_road_level(const double* rows, int64_t n, int row_stride, int label_col, const int32_t* labels, int n_labels,
+                   double cx, double cy, const double* radii_sq, const int32_t* radii_ok, uint64_t* scratch3,
+                   double* level_out, int32_t* ok_out, r3d_stream stream);
+
+/* addjust_map_2 (ss/ins:202-224): map cells (value != 0) holding a working row with z < 1.5 and a label outside
+ * ground_labels become 4.  rows9, map_dev (size_x * size_y float64): device; pose (4x4 row-major), labels: host. */
+int r3d_adjust_map(const double* rows9, int64_t n, const double* pose16_host, int64_t move_x, int64_t move_y,
+                   const int32_t* ground_labels, int n_ground, double* map_dev, int size_x, int size_y,
+                   r3d_stream stream);
+
 /* --------------------------------------------------------------------------------------------------- engine */
 /* Device-resident batched driver of the per-scan loop (od/ins:351-628, ss/ins:355-599): placement search
  * (find_possible_places od/fs:227-304, ss/fs:192-273), occlusion (od/ins:468-501), accept rule and insertion
@@ -169,6 +187,17 @@ int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* tota
 int r3d_engine_profile_enable(r3d_engine* eng, int on);
 int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out, int64_t* launches_out,
                             int max_kernels, int* n_kernels_out);
+
+/* find_possible_places (od/fs:227-304, ss/fs:192-273) for ONE cut object against an arbitrary current scene.
+ * scene_rows9: host n_rows x 9 float64 working rows of the CURRENT scene (collision test, od/fs:120-127; semseg also
+ * the occupied map cells of addjust_map_2); the scan's ORIGINAL points (road level), boxes, maps and pose come from
+ * the loaded batch.  flags_out[k] (yaw_steps+1): bit0 on map, bit1 road level found, bit2 collision;
+ * box_out[k] (yaw_steps+1 x 5): cx cy road-level m00 m10 of candidate k; xyz_out (optional): for the feasible
+ * candidates in rotation order, n_points x 3 float64 each (capacity xyz_capacity candidates); *n_feasible_out.
+ * Re-arms the batch state (run r3d_engine_reset_batch before the next r3d_engine_run). */
+int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const double* scene_rows9, int64_t n_rows,
+                            uint8_t* flags_out, double* box_out, double* xyz_out, int xyz_capacity,
+                            int32_t* n_feasible_out);
 
 /* gated scan-launch counters since the last r3d_engine_profile_enable: out4 = {scans projected, cut objects tried,
  * scans masked/re-ranged, 0} — the "units one launch processes" of the roofline arithmetic */

@@ -556,3 +556,123 @@ extern "C" int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* f
     if (visible_out) R3D_CUDA(cudaMemcpy(visible_out, eng->cand_v.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost));
     return R3D_OK;
 }
+
+// ------------------------------------------------------------------------------- find_possible_places probe
+namespace {
+
+// the probed scan: originals stay resident for the road level but are not part of the "current scene"; the caller's
+// rows become the (fp64) tail; one try is armed for `obj`
+__global__ void k_probe_setup(EngineDev e, int n_scans, int scan, int obj, int n_rows) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    const bool me = b == scan;
+    if (threadIdx.x == 0) {
+        s.try_active = me; s.need_project = 0; s.apply_flag = 0; s.dirty = 0;
+        e.gate_try[b] = me; e.gate_project[b] = me; e.gate_apply[b] = 0;
+        if (me) { s.n_tail = n_rows; s.cur_obj = obj; s.cur_class = e.obj[obj].cls; s.n_feasible = 0; s.found_rank = INT_MAX; }
+    }
+    if (!me) return;
+    const ObjBox ob = e.obj[obj];
+    const size_t cb = (size_t)b * (e.K + 1);
+    for (int k = threadIdx.x; k <= e.K; k += blockDim.x) {
+        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_v[cb + k] = 0; e.cand_level[cb + k] = 0.0;
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        e.cand_cx[cb + k] = sub(mul(c, ob.cx), mul(sn, ob.cy));
+        e.cand_cy[cb + k] = add(mul(sn, ob.cx), mul(c, ob.cy));
+    }
+    const int ww = e.map_window * e.map_window / 32;
+    if (e.task == 1) for (int i = threadIdx.x; i < ww; i += blockDim.x) e.occ_win[(size_t)b * ww + i] = 0u;
+}
+
+__global__ void k_probe_points(EngineDev e, int scan, int obj, int n_feasible, double* xyz_out, double* box_out) {
+    const ObjBox ob = e.obj[obj];
+    const size_t cb = (size_t)scan * (e.K + 1);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k <= e.K; k += gridDim.x * blockDim.x) {
+        const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, e.cos_k[k], e.sin_k[k]);
+        double* bo = box_out + (size_t)k * 5;
+        bo[0] = yb.cx; bo[1] = yb.cy; bo[2] = e.cand_level[cb + k]; bo[3] = yb.m00; bo[4] = yb.m10;
+    }
+    if (!xyz_out) return;
+    const long long total = (long long)n_feasible * ob.count;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const int f = (int)(t / ob.count), i = (int)(t % ob.count);
+        const int k = e.feas[(size_t)scan * e.K + f];
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+        double* o = xyz_out + t * 3;
+        o[0] = sub(mul(c, x0), mul(sn, y0));
+        o[1] = add(mul(sn, x0), mul(c, y0));
+        o[2] = add(e.obj_z[ob.first + i], sub(e.cand_level[cb + k], ob.cz));
+    }
+}
+
+}  // namespace
+
+extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const double* scene_rows9, int64_t n_rows,
+                                       uint8_t* flags_out, double* box_out, double* xyz_out, int xyz_capacity,
+                                       int32_t* n_feasible_out) {
+    if (!eng || !eng->batch_loaded || scan < 0 || scan >= eng->n_scans || object_id < 0 || object_id >= eng->dev.n_objects ||
+        n_rows < 0 || (n_rows > 0 && !scene_rows9) || !flags_out || !box_out || !n_feasible_out)
+        return r3d_fail(R3D_ERR_ARG, "r3d_engine_probe_places: bad argument");
+    EngineDev d = eng->dev;
+    if (n_rows > d.max_inserted) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_probe_places: scene larger than max_inserted");
+    const int n = eng->n_scans;
+    cudaStream_t st = eng->stream;
+    TRY(arm_batch(eng, false));
+    // current scene -> fp64 tail of the probed scan; the original rows are not part of it
+    std::vector<double> x(n_rows), y(n_rows), z(n_rows);
+    std::vector<float> in(n_rows);
+    std::vector<unsigned> lab(n_rows);
+    for (int64_t i = 0; i < n_rows; ++i) {
+        const double* p = scene_rows9 + i * 9;
+        x[i] = p[0]; y[i] = p[1]; z[i] = p[2]; in[i] = (float)p[6]; lab[i] = (unsigned)(long long)p[7];
+    }
+    R3D_CUDA(cudaStreamSynchronize(st));
+    std::vector<int> n0v(n);
+    R3D_CUDA(cudaMemcpy(n0v.data(), eng->n0_arr.p, n * sizeof(int), cudaMemcpyDeviceToHost));
+    const int n0 = n0v[scan];
+    const size_t tb = (size_t)scan * d.max_inserted, pb = (size_t)scan * d.P;
+    R3D_CUDA(cudaMemsetAsync(eng->alive.p + pb, 0, n0, st));
+    if (n_rows) {
+        R3D_CUDA(cudaMemcpyAsync(eng->tail_x.p + tb, x.data(), n_rows * sizeof(double), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->tail_y.p + tb, y.data(), n_rows * sizeof(double), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->tail_z.p + tb, z.data(), n_rows * sizeof(double), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->tail_i.p + tb, in.data(), n_rows * sizeof(float), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->label.p + pb + n0, lab.data(), n_rows * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemsetAsync(eng->alive.p + pb + n0, 1, n_rows, st));
+    }
+    k_probe_setup<<<n, 128, 0, st>>>(d, n, scan, object_id, (int)n_rows); r3d_count_launch();
+    const int chunks_all = (n0 + (int)n_rows + CHUNK - 1) / CHUNK, kwarps = (d.K + 7) / 8;
+    if (d.task == 1) { k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch(); }
+    if (d.task == 0) { k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch(); }
+    k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
+    if (d.task == 1) { k_onmap_ss<<<n, 256, 0, st>>>(d, n); r3d_count_launch(); }
+    k_collide_points<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch();
+    k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
+    k_feasible<<<n, 256, 0, st>>>(d, n); r3d_count_launch();
+    std::vector<ScanState> hs(1);
+    R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p + scan, sizeof(ScanState), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaStreamSynchronize(st));
+    const int nf = hs[0].n_feasible;
+    *n_feasible_out = nf;
+    if (hs[0].status != 0) return r3d_fail(hs[0].status, "r3d_engine_probe_places: scan status");
+    if (xyz_out && nf > xyz_capacity) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_probe_places: xyz_capacity too small");
+    const size_t K1 = d.K + 1;
+    DevBuf<double> dbox, dxyz;
+    TRY(dbox.alloc(K1 * 5));
+    std::vector<ObjBox> hob(1);
+    R3D_CUDA(cudaMemcpy(hob.data(), eng->obj.p + object_id, sizeof(ObjBox), cudaMemcpyDeviceToHost));
+    const size_t nxyz = xyz_out ? (size_t)nf * hob[0].count * 3 : 0;
+    if (nxyz) TRY(dxyz.alloc(nxyz));
+    k_probe_points<<<148, 256, 0, st>>>(d, scan, object_id, nf, nxyz ? dxyz.p : nullptr, dbox.p); r3d_count_launch();
+    std::vector<unsigned char> f(K1);
+    std::vector<int> col(K1);
+    R3D_CUDA(cudaMemcpyAsync(f.data(), eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(col.data(), eng->cand_collide.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(box_out, dbox.p, K1 * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
+    if (nxyz) R3D_CUDA(cudaMemcpyAsync(xyz_out, dxyz.p, nxyz * sizeof(double), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaStreamSynchronize(st));
+    for (size_t k = 0; k < K1; ++k) flags_out[k] = (uint8_t)(f[k] | (col[k] ? 4 : 0));
+    return r3d_check_launch("r3d_engine_probe_places");
+}

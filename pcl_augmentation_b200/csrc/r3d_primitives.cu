@@ -3,6 +3,7 @@
 #include "r3d_common.cuh"
 #include "r3d_host.h"
 #include "../../include/real3d_b200.h"
+#include <cstring>
 
 using namespace r3d;
 
@@ -152,4 +153,120 @@ extern "C" int r3d_cut_bounding_box(const double* rows, int64_t n, int row_strid
     int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
     k_cut_box<<<grid, 256, 0, stream>>>(rows, n, row_stride, b, mask_out); r3d_count_launch();
     return r3d_check_launch("r3d_cut_bounding_box");
+}
+
+// --------------------------------------------------------- A5 / A7 helper: rotate about the sensor z-axis, shift z
+// rotate_bounding_box (od/fs:97-102, ss/fs:72) and the z move of correct_height (od/fs:167) on rows of `stride` doubles
+__global__ void __launch_bounds__(256) k_transform_rows(double* __restrict__ rows, int64_t n, int stride, double c, double s,
+                                                         double dz) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double* p = rows + i * stride;
+        const double x = p[0], y = p[1];
+        p[0] = sub(mul(c, x), mul(s, y));
+        p[1] = add(mul(s, x), mul(c, y));
+        p[2] = add(p[2], dz);
+    }
+}
+
+extern "C" int r3d_transform_points(double* rows, int64_t n, int row_stride, double cos_t, double sin_t, double dz,
+                                    r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (n < 0 || row_stride < 3 || (n > 0 && !rows)) return r3d_fail(R3D_ERR_ARG, "r3d_transform_points: bad argument");
+    if (n == 0) return R3D_OK;
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_transform_rows<<<grid, 256, 0, stream>>>(rows, n, row_stride, cos_t, sin_t, dz); r3d_count_launch();
+    return r3d_check_launch("r3d_transform_points");
+}
+
+// ------------------------------------------------------------------------------ A7 correct_height (single query)
+struct LabelSet { int n; int v[R3D_MAX_SURFACE]; };
+struct RadiiTable { double r2[R3D_NUM_RADII]; int ok[R3D_NUM_RADII]; };
+
+template <int PASS>
+__global__ void __launch_bounds__(256) k_road_level(const double* __restrict__ rows, int64_t n, int stride, int label_col,
+                                                     LabelSet labels, double cx, double cy, double r2_limit,
+                                                     unsigned long long* __restrict__ acc) {
+    // acc[0] = min d2 bits, acc[1] = fixed-point z sum, acc[2] = count
+    unsigned long long lmin = R3D_EMPTY_U64;
+    long long zsum = 0; unsigned long long cnt = 0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* p = rows + i * stride;
+        bool ok = false;
+        for (int j = 0; j < labels.n; ++j) ok |= p[label_col] == (double)labels.v[j];
+        if (!ok || !(p[2] > -3.0)) continue;
+        const double dx = sub(p[0], cx), dy = sub(p[1], cy);
+        const double d2 = add(mul(dx, dx), mul(dy, dy));
+        if (PASS == 1) lmin = min(lmin, dbl_bits(d2));
+        else if (d2 <= r2_limit) { zsum += __double2ll_rn(mul(p[2], 1099511627776.0)); ++cnt; }
+    }
+    if (PASS == 1) { if (lmin != R3D_EMPTY_U64) atomicMin(&acc[0], lmin); }
+    else if (cnt) { atomicAdd(&acc[1], (unsigned long long)zsum); atomicAdd(&acc[2], cnt); }
+}
+
+extern "C" int r3d_road_level(const double* rows, int64_t n, int row_stride, int label_col, const int32_t* labels,
+                              int n_labels, double cx, double cy, const double* radii_sq, const int32_t* radii_ok,
+                              uint64_t* scratch3, double* level_out, int32_t* ok_out, r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!level_out || !ok_out || !scratch3 || !radii_sq || !radii_ok || n_labels < 0 || n_labels > R3D_MAX_SURFACE ||
+        row_stride <= label_col || label_col < 3)
+        return r3d_fail(R3D_ERR_ARG, "r3d_road_level: bad argument");
+    *ok_out = 0; *level_out = 0.0;
+    if (n <= 0) return R3D_OK;
+    LabelSet ls; ls.n = n_labels;
+    for (int i = 0; i < n_labels; ++i) ls.v[i] = labels[i];
+    unsigned long long h[3] = {R3D_EMPTY_U64, 0ull, 0ull};
+    R3D_CUDA(cudaMemcpyAsync(scratch3, h, sizeof(h), cudaMemcpyHostToDevice, stream));
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_road_level<1><<<grid, 256, 0, stream>>>(rows, n, row_stride, label_col, ls, cx, cy, 0.0, (unsigned long long*)scratch3);
+    r3d_count_launch();
+    R3D_CUDA(cudaMemcpyAsync(h, scratch3, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    R3D_CUDA(cudaStreamSynchronize(stream));
+    if (h[0] == R3D_EMPTY_U64) return R3D_OK;
+    double d2; memcpy(&d2, &h[0], sizeof(double));
+    int j = 0;
+    while (j < R3D_NUM_RADII && !(d2 <= radii_sq[j])) ++j;                 // od/fs:152-160
+    if (j >= R3D_NUM_RADII || !radii_ok[j]) return R3D_OK;
+    k_road_level<2><<<grid, 256, 0, stream>>>(rows, n, row_stride, label_col, ls, cx, cy, radii_sq[j], (unsigned long long*)scratch3);
+    r3d_count_launch();
+    R3D_CUDA(cudaMemcpyAsync(h, scratch3, sizeof(h), cudaMemcpyDeviceToHost, stream));
+    R3D_CUDA(cudaStreamSynchronize(stream));
+    if (h[2] == 0) return R3D_OK;
+    *level_out = ((double)(long long)h[1] / 1099511627776.0) / (double)h[2];    // od/fs:164 np.mean
+    *ok_out = 1;
+    return r3d_check_launch("r3d_road_level");
+}
+
+// --------------------------------------------------------------------------------- semseg addjust_map_2
+struct Pose34 { double t[12]; };
+__global__ void __launch_bounds__(256) k_adjust_map_rows(const double* __restrict__ rows, int64_t n, Pose34 T, double move_x,
+                                                          double move_y, LabelSet ground, double* __restrict__ map, int sx,
+                                                          int sy) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double* p = rows + i * 9;
+        if (!(p[2] < 1.5)) continue;                                   // ss/ins:207
+        bool g = false;
+        for (int j = 0; j < ground.n; ++j) g |= p[7] == (double)ground.v[j];
+        if (g) continue;                                               // ss/ins:209-210
+        const double wx = add(add(add(mul(T.t[0], p[0]), mul(T.t[1], p[1])), mul(T.t[2], p[2])), T.t[3]);
+        const double wy = add(add(add(mul(T.t[4], p[0]), mul(T.t[5], p[1])), mul(T.t[6], p[2])), T.t[7]);
+        const int ix = trunc_to_int(sub(wx, move_x)), iy = trunc_to_int(sub(wy, move_y));
+        if (ix < 0 || iy < 0 || ix >= sx || iy >= sy) continue;        // reference: IndexError / negative wrap
+        double* cell = map + (size_t)ix * sy + iy;
+        if (*cell != 0.0) *cell = 4.0;                                 // ss/ins:221-222
+    }
+}
+
+extern "C" int r3d_adjust_map(const double* rows9, int64_t n, const double* pose16_host, int64_t move_x, int64_t move_y,
+                              const int32_t* ground_labels, int n_ground, double* map_dev, int size_x, int size_y,
+                              r3d_stream stream_) {
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!pose16_host || !map_dev || size_x <= 0 || size_y <= 0 || n_ground < 0 || n_ground > R3D_MAX_SURFACE)
+        return r3d_fail(R3D_ERR_ARG, "r3d_adjust_map: bad argument");
+    if (n <= 0) return R3D_OK;
+    Pose34 T; for (int i = 0; i < 12; ++i) T.t[i] = pose16_host[i];
+    LabelSet g; g.n = n_ground; for (int i = 0; i < n_ground; ++i) g.v[i] = ground_labels[i];
+    int grid = (int)std::min<int64_t>((n + 255) / 256, 148 * 8);
+    k_adjust_map_rows<<<grid, 256, 0, stream>>>(rows9, n, T, (double)move_x, (double)move_y, g, map_dev, size_x, size_y);
+    r3d_count_launch();
+    return r3d_check_launch("r3d_adjust_map");
 }

@@ -30,6 +30,7 @@ class ScanInput:
     perms: np.ndarray                 # int32 [events, classes, tries]: pre-drawn random.shuffle results
     maps: dict | None = None          # OD: {'Road': {...}, 'Sidewalk': {...}} (npz payloads)
     pose: np.ndarray | None = None    # semseg: 4x4 lidar->world
+    box_dicts: list | None = None     # scene annotations already parsed to box dictionaries (instead of box_lines)
 
 
 @dataclass
@@ -132,7 +133,7 @@ class Real3DEngine:
         read = bx.read_label_line_ss if self.task == 'ss' else bx.read_label_line_od
         names, pts, offs, box_rows, cls_idx, lists, list_off, annos, strings = [], [], [0], [], [], [], [0], [], []
         for ci, cls in enumerate(self.classes):
-            for name, sample in db[cls]:
+            for name, sample in db.get(cls, []):
                 pcl = np.array(sample['pcl'], dtype=np.float64, copy=True)
                 if self.task == 'od':
                     pcl[:, 4] = 1                                     # od/fs:251
@@ -188,8 +189,8 @@ class Real3DEngine:
         for i, s in enumerate(scans):
             xyzi[pt_off[i]:pt_off[i + 1]] = s.xyzi
             labels[pt_off[i]:pt_off[i + 1]] = np.asarray(s.labels).astype(np.uint32).view(np.int32)
-            for line in s.box_lines:
-                box_rows.append(bx.box_record(read(line)))
+            for anno in (s.box_dicts if s.box_dicts is not None else [read(line) for line in s.box_lines]):
+                box_rows.append(bx.box_record(anno))
             box_off[i + 1] = len(box_rows)
             counts[i] = np.asarray(s.counts, dtype=np.int32)
             p = np.asarray(s.perms, dtype=np.int32)
@@ -310,6 +311,25 @@ class Real3DEngine:
         self.load(self.stage(scans))
         self.run()
         return self.unpack(self.fetch_raw())
+
+    def probe_places(self, scan, object_id, scene_rows9, want_points=True):
+        """find_possible_places of ONE cut object against the given current scene (N' x 9 float64 working rows);
+        the scan's original points / boxes / maps come from the loaded batch.  Returns (flags[K+1], boxes[K+1, 5],
+        xyz [n_feasible, M, 3] or None, rotations of the feasible candidates)."""
+        k1 = self.yaw_steps + 1
+        rows = np.ascontiguousarray(scene_rows9, dtype=np.float64)
+        flags = np.zeros(k1, dtype=np.uint8)
+        boxes = np.zeros((k1, 5), dtype=np.float64)
+        m = int(self._db_offsets[object_id + 1] - self._db_offsets[object_id])
+        xyz = np.zeros((self.yaw_steps, m, 3), dtype=np.float64) if want_points else None
+        nf = C.c_int32()
+        _lib.check(self.lib.r3d_engine_probe_places(self.handle, scan, object_id, rows.ctypes.data, len(rows),
+                                                    flags.ctypes.data, boxes.ctypes.data,
+                                                    xyz.ctypes.data if want_points else None, self.yaw_steps,
+                                                    C.byref(nf)), "probe_places")
+        rots = [k for k in range(1, k1) if flags[k] == 3]
+        assert len(rots) == nf.value
+        return flags, boxes, (xyz[:nf.value] if want_points else None), rots
 
     # ------------------------------------------------------------------------------------------ profiling
     def profile(self, on=True):

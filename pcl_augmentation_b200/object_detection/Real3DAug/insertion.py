@@ -1,0 +1,46 @@
+"""Drop-in for the function layer of the reference's object-detection ``insertion.py``.
+
+The projection functions (add_space_for_spherical :55, fill_spherical :68, geometrical_front_view :85) run in CUDA;
+``generate_seed`` (:171), ``extract_anno`` (:133) and ``create_annotation_line`` (:227) are the reference's tiny host
+helpers.  The script part of the reference (its ``while len(dataset_functions) > 0`` loop, :321-628) is replaced by
+``pcl_augmentation_b200.engine.Real3DEngine.augment_batch`` — see INTEGRATION.md.
+"""
+import numpy as np
+
+from ... import ops as _ops
+from ...boxes import create_annotation_line                      # noqa: F401
+from ...ops import add_space_for_spherical, fill_spherical       # noqa: F401
+from .tools.closing import class_closing, smooth_out             # noqa: F401
+from .tools.find_spot import *                                   # noqa: F401,F403
+from .tools.find_spot import read_label_line
+
+NUMROW = 112
+NUMCOLUMN = 360 * 4
+MAX_NUM_TRIES = 100
+
+
+def geometrical_front_view(point_cloud, num_row, num_column, max_elevation_angle, min_elevation_angle, sample=False):
+    _ops.NUMCOLUMN = NUMCOLUMN          # pix_id uses this module's global, like the reference (:117)
+    return _ops.geometrical_front_view(point_cloud, num_row, num_column, max_elevation_angle, min_elevation_angle, sample)
+
+
+def extract_anno(anno_path):
+    """List of box dictionaries from a KITTI label_2 file (:133-157)."""
+    with open(anno_path, 'r') as f:
+        return np.array([read_label_line(line) for line in f if len(line) > 0])
+
+
+def generate_seed(config):
+    """Objects to insert per class and the first class to insert (:171-187)."""
+    if config['insertion']['random']:
+        seed = np.zeros(len(config['insertion']['classes']))
+        for i in np.random.randint(len(config['insertion']['classes']), size=config['insertion']['number_of_object']):
+            seed[i] += 1
+    else:
+        seed = np.array(config['insertion']['number_of_classes'])
+    inserted_class = None
+    for i in range(len(seed)):
+        if seed[i] > 0:
+            inserted_class = config['insertion']['classes'][i]
+            break
+    return seed, inserted_class

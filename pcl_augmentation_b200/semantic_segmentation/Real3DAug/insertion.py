@@ -1,0 +1,49 @@
+"""Drop-in for the function layer of the reference's semantic-segmentation ``insertion.py`` (projection functions
+:54-129, ``addjust_map_2`` :202, ``generate_seed`` :171); CUDA inside.  The script loop (:317-599) is replaced by
+``Real3DEngine('ss', ...).augment_batch`` — see INTEGRATION.md."""
+import numpy as np
+
+from ... import _lib
+from ... import ops as _ops
+from ...object_detection.Real3DAug.insertion import generate_seed                   # noqa: F401
+from ...ops import _dev, _stream, add_space_for_spherical, fill_spherical           # noqa: F401
+from .tools.closing import class_closing, smooth_out                                # noqa: F401
+from .tools.find_spot import *                                                      # noqa: F401,F403
+from .tools.find_spot import read_label_line
+
+NUMROW = 112
+NUMCOLUMN = 360 * 4
+MAX_NUM_TRIES = 100
+ROAD_INDEXES = [40, 44, 48]     # undefined in the reference's semseg insertion.py (:209); value of od/fs:14
+
+
+def geometrical_front_view(point_cloud, num_row, num_column, max_elevation_angle, min_elevation_angle, sample=False):
+    _ops.NUMCOLUMN = NUMCOLUMN
+    return _ops.geometrical_front_view(point_cloud, num_row, num_column, max_elevation_angle, min_elevation_angle, sample)
+
+
+def extract_anno(anno_path):
+    with open(anno_path, 'r') as f:
+        return np.array([read_label_line(line) for line in f if len(line) > 0])
+
+
+def addjust_map_2(map_data, point_cloud, transformation_matrix):
+    """Mark the rich-map cells occupied by non-ground scene points below z < 1.5 with 4 (:202-224).  Returns
+    (map, map_move) like the reference; cells outside the map are skipped (the reference would raise / wrap)."""
+    lib = _lib.load()
+    map_arr = map_data['map']
+    map_move = map_data['move']
+    d_map = _dev(map_arr, np.float64)
+    if len(point_cloud):
+        d_pts = _dev(point_cloud, np.float64)
+        pose = np.ascontiguousarray(transformation_matrix, dtype=np.float64)
+        ground = np.asarray(ROAD_INDEXES, dtype=np.int32)
+        mv = np.asarray(map_move).reshape(-1)
+        _lib.check(lib.r3d_adjust_map(d_pts.data_ptr(), len(point_cloud), pose.ctypes.data, int(mv[0]), int(mv[1]),
+                                      ground.ctypes.data, len(ground), d_map.data_ptr(), map_arr.shape[0],
+                                      map_arr.shape[1], _stream()), "addjust_map_2")
+    out = d_map.cpu().numpy()
+    if isinstance(map_arr, np.ndarray) and map_arr.flags.writeable:
+        map_arr[...] = out                   # the reference edits the array it was handed in place
+        out = map_arr
+    return out, map_move
