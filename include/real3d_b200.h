@@ -112,6 +112,7 @@ typedef struct r3d_engine_cfg {
     int32_t map_window;                       /* semseg: side of the per-scan occupied-cell window (cells) */
     int32_t grid_half;                        /* road-level search grid: cells per half side (grid covers +-grid_half*grid_cell m) */
     double grid_cell;                         /* road-level search grid: cell size in metres (0 -> 0.5) */
+    int32_t flags;                            /* bit0: re-project every slot in full (disable the in-place image patch) */
     double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */
     int32_t radii_ok[R3D_NUM_RADII];          /* 0 where the pass's "radius > 5" check already fails */
     r3d_class_cfg classes[R3D_MAX_CLASSES];

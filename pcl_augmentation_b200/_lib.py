@@ -32,7 +32,7 @@ class EngineCfg(C.Structure):
                 ("max_points", C.c_int32), ("max_inserted", C.c_int32), ("max_boxes", C.c_int32),
                 ("max_events", C.c_int32), ("road_label", C.c_int32), ("n_road_indexes", C.c_int32),
                 ("road_indexes", C.c_int32 * R3D_MAX_SURFACE), ("map_window", C.c_int32),
-                ("grid_half", C.c_int32), ("grid_cell", C.c_double),
+                ("grid_half", C.c_int32), ("grid_cell", C.c_double), ("flags", C.c_int32),
                 ("radii_sq", C.c_double * R3D_NUM_RADII), ("radii_ok", C.c_int32 * R3D_NUM_RADII),
                 ("classes", ClassCfg * R3D_MAX_CLASSES)]
 

@@ -20,9 +20,13 @@ template <class In>
 __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, int64_t img_stride,
                                                             double* __restrict__ out_train, double* __restrict__ out_label,
                                                             uint8_t* __restrict__ closed_out, int* __restrict__ far_flag,
-                                                            const int* __restrict__ gate) {
+                                                            const int* __restrict__ rect) {
     const int z = blockIdx.z;
-    if (gate && !gate[z]) return;
+    if (rect) {          // per-image rectangle (rows r0..r1, cols c0..c1) that needs recomputing; tiles outside skip
+        const int* q = rect + (size_t)z * 4;
+        const int tr0 = blockIdx.y * CF_TH, tc0 = blockIdx.x * CF_TW;
+        if (q[1] < q[0] || tr0 > q[1] || tr0 + CF_TH - 1 < q[0] || tc0 > q[3] || tc0 + CF_TW - 1 < q[2]) return;
+    }
     __shared__ double s_val[CF_SH][CF_SW];
     __shared__ uint8_t s_occ[CF_SH][CF_SW];            // bit0: occupancy (clip(label,0,1) > 0), bit1: label == 1
     __shared__ uint8_t s_dil[CF_TH + 4][CF_TW + 2];

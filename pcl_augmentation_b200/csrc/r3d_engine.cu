@@ -15,12 +15,13 @@ namespace {
 
 enum KernelId {
     KID_INGEST, KID_CTRL, KID_APPLY, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT,
-    KID_GRID, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_COUNT
+    KID_GRID, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_DECIDE, KID_MINMAX,
+    KID_PATCH, KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
-    "ingest_spherical", "ctrl", "apply_mask_minmax", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
-    "onmap", "height_grid", "grid_build", "collide_points", "collide_boxes", "feasible",
-    "occlusion_count", "select_emit", "compact_output"};
+    "ingest_spherical", "ctrl", "apply_mask_window", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
+    "onmap", "height_grid", "index_build", "collide_points", "collide_boxes", "feasible",
+    "occlusion_count", "select_emit", "compact_output", "decide", "minmax_elevation", "patch_zbuffer"};
 
 template <class T>
 struct DevBuf {
@@ -55,7 +56,7 @@ struct r3d_engine {
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label;
     DevBuf<unsigned short> col;
-    DevBuf<int> pix, gate_project, gate_try, gate_apply, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
+    DevBuf<int> pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, rad_off, rad_idx, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_collide, cand_v, gcell, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -156,13 +157,16 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.grid_cell = cfg->grid_cell > 0 ? cfg->grid_cell : 0.5;
     d.grid_inv_cell = (float)(1.0 / d.grid_cell);
     d.G = 2 * (cfg->grid_half > 0 ? cfg->grid_half : 200);
+    d.RB = 512; d.rad_inv_cell = 4.0f;                 // 0.25 m radial bins up to 128 m (farther points share the last bin)
+    d.force_full = (cfg->flags & 1) ? 1 : 0;
     const size_t B = d.B, P = d.P, K1 = d.K + 1, HW = d.hw;
     TRY(eng->xyzi.alloc(B * d.max_points)); TRY(eng->tail_x.alloc(B * d.max_inserted)); TRY(eng->tail_y.alloc(B * d.max_inserted));
     TRY(eng->tail_z.alloc(B * d.max_inserted)); TRY(eng->tail_i.alloc(B * d.max_inserted)); TRY(eng->label.alloc(B * P));
     TRY(eng->r.alloc(B * P)); TRY(eng->el.alloc(B * P)); TRY(eng->col.alloc(B * P)); TRY(eng->pix.alloc(B * P));
     TRY(eng->alive.alloc(B * P)); TRY(eng->zraw.alloc(B * HW)); TRY(eng->obj_raw.alloc(B * HW)); TRY(eng->smooth.alloc(B * HW));
     TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
-    TRY(eng->gate_project.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->active_count.alloc(64));
+    TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
+    TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(64));
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -175,6 +179,8 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
     TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
     TRY(eng->gcell.alloc(B * (size_t)d.G * d.G)); TRY(eng->gpts.alloc(B * d.max_points));
+    TRY(eng->col_off.alloc(B * (size_t)(d.cols + 1))); TRY(eng->col_idx.alloc(B * d.max_points));
+    TRY(eng->rad_off.alloc(B * (size_t)(d.RB + 1))); TRY(eng->rad_idx.alloc(B * d.max_points));
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
@@ -196,7 +202,8 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.xyzi = eng->xyzi.p; d.tail_x = eng->tail_x.p; d.tail_y = eng->tail_y.p; d.tail_z = eng->tail_z.p; d.tail_i = eng->tail_i.p;
     d.label = eng->label.p; d.r = eng->r.p; d.el = eng->el.p; d.col = eng->col.p; d.pix = eng->pix.p; d.alive = eng->alive.p;
     d.zraw = eng->zraw.p; d.obj_raw = eng->obj_raw.p; d.smooth = eng->smooth.p; d.dmask = eng->dmask.p; d.vmask = eng->vmask.p;
-    d.st = eng->st.p; d.gate_project = eng->gate_project.p; d.gate_try = eng->gate_try.p; d.gate_apply = eng->gate_apply.p;
+    d.st = eng->st.p; d.gate_update = eng->gate_update.p; d.gate_try = eng->gate_try.p; d.gate_apply = eng->gate_apply.p;
+    d.gate_full = eng->gate_full.p; d.gate_patch = eng->gate_patch.p; d.cf_rect = eng->cf_rect.p;
     d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
     d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
     d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
@@ -206,6 +213,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
     d.gcell = eng->gcell.p; d.gpts = eng->gpts.p;
+    d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.rad_off = eng->rad_off.p; d.rad_idx = eng->rad_idx.p;
     d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
     *out = eng;
     return R3D_OK;
@@ -305,10 +313,16 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
         { Launcher l(eng, KID_INGEST); k_ingest<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
         Launcher l(eng, KID_GRID);
         R3D_CUDA(cudaMemsetAsync(eng->gcell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
+        R3D_CUDA(cudaMemsetAsync(eng->col_off.p, 0, (size_t)n * (d.cols + 1) * sizeof(int), st));
+        R3D_CUDA(cudaMemsetAsync(eng->rad_off.p, 0, (size_t)n * (d.RB + 1) * sizeof(int), st));
         k_grid_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        k_grid_scan<<<n, 1024, 0, st>>>(d, n);
+        k_index_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+        k_bucket_scan<<<n, 1024, 0, st>>>(eng->gcell.p, (size_t)d.G * d.G, d.G * d.G, n);
+        k_bucket_scan<<<n, 1024, 0, st>>>(eng->col_off.p, (size_t)d.cols + 1, d.cols, n);
+        k_bucket_scan<<<n, 1024, 0, st>>>(eng->rad_off.p, (size_t)d.RB + 1, d.RB, n);
         k_grid_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        r3d_count_launch(2);
+        k_index_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
+        r3d_count_launch(6);
     } else {
         k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
         // scene boxes: drop the boxes appended by the previous run
@@ -411,21 +425,24 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         R3D_CUDA(cudaMemcpyAsync(eng->h_active + slot, eng->active_count.p + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
         R3D_CUDA(cudaMemsetAsync(eng->active_count.p + ((slot + 32) & 63), 0, sizeof(int), st));
         R3D_CUDA(cudaEventRecord(ev_ctrl[round & 1], st));
-        { Launcher l(eng, KID_APPLY); k_apply_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_APPLY); k_apply_window<<<dim3(APPLY_G, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_DECIDE); k_decide<<<n, 128, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_MINMAX); k_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_CLEAR); k_clear_images<<<dim3(32, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_PROJECT); k_project<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_PATCH); k_patch_raw<<<n, 256, 0, st>>>(d, n); }
         {
             Launcher l(eng, KID_CLOSEFILL);
             RawImage in{d.zraw};
             dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, n);
             k_close_fill<RawImage><<<grid, CF_THREADS, 0, st>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
-                                                                 d.far_arr, d.gate_project);
+                                                                 d.far_arr, d.cf_rect);
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_HEIGHT); k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
         if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 256, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_COLLIDE_PTS); k_collide_points<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_COLLIDE_PTS); k_collide_points<<<dim3(COLL_G, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_COLLIDE_BOX); k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_FEASIBLE); k_feasible<<<n, 256, 0, st>>>(d, n); }
         { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
@@ -569,7 +586,7 @@ __global__ void k_probe_setup(EngineDev e, int n_scans, int scan, int obj, int n
     const bool me = b == scan;
     if (threadIdx.x == 0) {
         s.try_active = me; s.need_project = 0; s.apply_flag = 0; s.dirty = 0;
-        e.gate_try[b] = me; e.gate_project[b] = me; e.gate_apply[b] = 0;
+        e.gate_try[b] = me; e.gate_update[b] = me; e.gate_apply[b] = 0; e.gate_full[b] = 0; e.gate_patch[b] = 0;
         if (me) { s.n_tail = n_rows; s.cur_obj = obj; s.cur_class = e.obj[obj].cls; s.n_feasible = 0; s.found_rank = INT_MAX; }
     }
     if (!me) return;
@@ -648,7 +665,7 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
     if (d.task == 0) { k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch(); }
     k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
     if (d.task == 1) { k_onmap_ss<<<n, 256, 0, st>>>(d, n); r3d_count_launch(); }
-    k_collide_points<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch();
+    k_collide_points<<<dim3(COLL_G, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch();
     k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
     k_feasible<<<n, 256, 0, st>>>(d, n); r3d_count_launch();
     std::vector<ScanState> hs(1);

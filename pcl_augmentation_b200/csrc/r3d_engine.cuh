@@ -49,6 +49,9 @@ struct ScanState {
     int n_feasible, found_rank, chosen_rot, accepted, chosen_v;
     int n_inserted, n_check;
     int far_flag;
+    int first, extreme_removed;          // first slot of the scan / a removed point held the min or max elevation
+    int d_r0, d_r1, d_c0, d_c1;          // pixel rectangle (inclusive) that contains every bit of dmask
+    unsigned long long new_min_bits, new_max_bits;   // elevation range of the points the last accept appended
     int win_x0, win_y0;
     unsigned long long min_el_bits, max_el_bits;
     ImageGeom geom;
@@ -79,7 +82,13 @@ struct EngineDev {       // passed by value to kernels
     double* smooth;
     unsigned *dmask, *vmask;
     ScanState* st;
-    int *gate_project, *gate_try, *gate_apply;
+    int *gate_update, *gate_try, *gate_apply, *gate_full, *gate_patch;
+    int* cf_rect;                     // [B][4] rows r0..r1, cols c0..c1 (inclusive) close/fill must recompute
+    int force_full;                   // debug / test: always take the full re-projection path
+    int RB;                           // radial bins of the obstacle index
+    float rad_inv_cell;
+    int *col_off, *col_idx;           // [B][cols+1], [B][max_points]: original points bucketed by azimuth bin
+    int *rad_off, *rad_idx;           // [B][RB+1],   [B][max_points]: original points bucketed by horizontal range
     int* active_count;
     unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)

@@ -62,6 +62,8 @@ __global__ void k_reset_state(EngineDev e, int n_scans, const int* n0_arr, const
     s.try_active = 0; s.need_project = 0; s.apply_flag = 0; s.dirty = 0; s.scene_changed = 1;
     s.n_feasible = 0; s.found_rank = INT_MAX; s.chosen_rot = 0; s.accepted = 0; s.chosen_v = 0;
     s.n_inserted = 0; s.n_check = 0; s.far_flag = 0;
+    s.first = 1; s.extreme_removed = 0; s.d_r0 = 0; s.d_r1 = -1; s.d_c0 = 0; s.d_c1 = -1;
+    s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull;
     s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
     if (e.task == 1) {     // semseg: window of map cells around the sensor for the occupied-cell overlay
         const double* T = e.poses + (size_t)b * 16;
@@ -173,14 +175,13 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
             }
             if (s.phase != PH_DONE && s.phase != PH_ERROR && !tryact) { set_error(s, R3D_ERR_INDEX); s.phase = PH_ERROR; }
         }
-        if (project || apply) { s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull; }
         s.try_active = tryact; s.need_project = project; s.apply_flag = apply;
         s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
-        e.gate_project[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply | project;
+        if (apply) s.extreme_removed = 0;
+        e.gate_update[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply;
         if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(e.active_count, 1);
-        if (project) atomicAdd(&e.stats[0], 1ull);
         if (tryact) atomicAdd(&e.stats[1], 1ull);
-        if (apply | project) atomicAdd(&e.stats[2], 1ull);
+        if (apply) atomicAdd(&e.stats[2], 1ull);
         s_try = tryact;
     }
     __syncthreads();
@@ -203,22 +204,94 @@ __device__ __forceinline__ bool pix_removed(const EngineDev& e, int b, const Sca
     return e.far_arr[b] && e.smooth[(size_t)b * e.hw + pix] > kEmptyRange;
 }
 
-// A11/A12 (od/ins:488-501, 545): scene = scene[pix_id not in vis_px]; also the elevation range of what is left (A2,
-// od/ins:79-80).  5 B/point of algorithmic traffic (pix + alive), + 8 B/point for the cached elevation.
-__global__ void __launch_bounds__(STREAM_THREADS) k_apply_minmax(EngineDev e, int n_scans) {
+// A11/A12 (od/ins:488-501, 545): scene = scene[pix_id not in vis_px].  vis_px lies inside the pixel rectangle
+// select_emit recorded, so only the points whose azimuth bin falls in that column range are visited (CSR by column,
+// built once per scan) plus the inserted tail: O(window) instead of O(N).  Also notes whether a removed point held
+// the scene's min / max elevation (then the image geometry changes and the slot is re-projected in full).
+constexpr int APPLY_G = 8;
+__global__ void __launch_bounds__(STREAM_THREADS) k_apply_window(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_apply[b]) return;
+    ScanState& s = e.st[b];
+    const size_t base = (size_t)b * e.P;
+    const int* off = e.col_off + (size_t)b * (e.cols + 1);
+    const int* idx = e.col_idx + (size_t)b * e.max_points;
+    int c0 = s.d_c0, c1 = s.d_c1;
+    if (e.far_arr[b]) { c0 = 0; c1 = e.cols - 1; }          // od/ins:486 quirk: covered pixels can be anywhere
+    bool extreme = false;
+    const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
+    if (c1 >= c0) {
+        const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
+        for (int i = beg + blockIdx.x * STREAM_THREADS + threadIdx.x; i < end; i += APPLY_G * STREAM_THREADS) {
+            const int p = idx[i];
+            if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
+                e.alive[base + p] = 0;
+                const unsigned long long bits = dbl_bits(e.el[base + p]);
+                extreme |= bits == lo || bits == hi;
+            }
+        }
+    }
+    for (int t = blockIdx.x * STREAM_THREADS + threadIdx.x; t < s.tail_before; t += APPLY_G * STREAM_THREADS) {
+        const int p = s.n0 + t;
+        if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
+            e.alive[base + p] = 0;
+            const unsigned long long bits = dbl_bits(e.el[base + p]);
+            extreme |= bits == lo || bits == hi;
+        }
+    }
+    if (__syncthreads_or(extreme) && threadIdx.x == 0) atomicOr(&s.extreme_removed, 1);
+}
+
+// full re-projection or in-place patch?  The image geometry (od/ins:97-98) depends only on the scene's min / max
+// elevation; if neither moved, every surviving point keeps its pixel and only the pixels of vis_px change.
+__global__ void __launch_bounds__(128) k_decide(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    __shared__ int s_upd;
+    if (threadIdx.x == 0) {
+        const int upd = e.gate_update[b];
+        int full = 0, patch = 0;
+        int* rect = e.cf_rect + (size_t)b * 4;
+        rect[0] = 0; rect[1] = -1; rect[2] = 0; rect[3] = -1;
+        if (upd) {
+            const bool extended = s.new_min_bits < s.min_el_bits || s.new_max_bits > s.max_el_bits;
+            full = s.first || s.extreme_removed || extended || e.far_arr[b] || e.force_full;
+            patch = !full;
+            if (full) {
+                s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
+                rect[0] = 0; rect[1] = e.rows - 1; rect[2] = 0; rect[3] = e.cols - 1;
+            } else {
+                rect[0] = max(s.d_r0 - 4, 0); rect[1] = min(s.d_r1 + 4, e.rows - 1);
+                rect[2] = max(s.d_c0 - 2, 0); rect[3] = min(s.d_c1 + 2, e.cols - 1);
+            }
+            s.first = 0; s.extreme_removed = 0;
+            s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull;
+            atomicAdd(&e.stats[full ? 0 : 3], 1ull);
+        }
+        e.gate_full[b] = full; e.gate_patch[b] = patch;
+        s_upd = upd;
+    }
+    __syncthreads();
+    if (s_upd && e.task == 1) {
+        const int ww = e.map_window * e.map_window / 32;
+        unsigned* o = e.occ_win + (size_t)b * ww;
+        for (int i = threadIdx.x; i < ww; i += blockDim.x) o[i] = 0u;
+    }
+}
+
+// A2 (od/ins:79-80) on the cached elevations: min / max over the live points (full path only)
+__global__ void __launch_bounds__(STREAM_THREADS) k_minmax(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_full[b]) return;
     ScanState& s = e.st[b];
     const int n = s.n0 + s.n_tail;
     const int p0 = blockIdx.x * CHUNK;
     if (p0 >= n) return;
-    const int limit = s.apply_flag ? s.n0 + s.tail_before : 0;
     const size_t base = (size_t)b * e.P;
     unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
-        unsigned char a = e.alive[base + p];
-        if (a && p < limit && pix_removed(e, b, s, e.pix[base + p])) { a = 0; e.alive[base + p] = 0; }
-        if (a) {
+        if (e.alive[base + p]) {
             const unsigned long long bits = dbl_bits(e.el[base + p]);
             lmin = min(lmin, bits); lmax = max(lmax, bits);
         }
@@ -236,10 +309,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_apply_minmax(EngineDev e, in
     }
 }
 
-// clear the z-buffer (and the semseg occupied-cell window) of the scans that re-project, fix their image geometry
+// clear the z-buffer of the scans that re-project in full and fix their image geometry
 __global__ void __launch_bounds__(STREAM_THREADS) k_clear_images(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_project[b]) return;
+    if (b >= n_scans || !e.gate_full[b]) return;
     ScanState& s = e.st[b];
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         e.far_arr[b] = 0;
@@ -248,18 +321,13 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_clear_images(EngineDev e, in
     }
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.hw; i += gridDim.x * blockDim.x) z[i] = R3D_EMPTY_U64;
-    if (e.task == 1) {
-        const int ww = e.map_window * e.map_window / 32;
-        unsigned* o = e.occ_win + (size_t)b * ww;
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < ww; i += gridDim.x * blockDim.x) o[i] = 0u;
-    }
 }
 
 // A3 (od/ins:85-130): bin every live point with the reference's truncation rule, write pix_id, 64-bit atomicMin of
 // the range bits into the z-buffer.  Algorithmic traffic 20 B/point (+ 8 B/pixel for the z-buffer).
 __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_project[b]) return;
+    if (b >= n_scans || !e.gate_full[b]) return;
     ScanState& s = e.st[b];
     const int n = s.n0 + s.n_tail;
     const int p0 = blockIdx.x * CHUNK;
@@ -277,6 +345,28 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_s
     }
 }
 
+// patch path: the z-buffer changes only at the pixels of vis_px — all their scene points were removed
+// (od/ins:491) and the visible object points were appended there (od/ins:545).
+__global__ void __launch_bounds__(256) k_patch_raw(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_patch[b]) return;
+    const ScanState& s = e.st[b];
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    const unsigned* dm = e.dmask + (size_t)b * e.dwords;
+    if (s.d_r1 >= s.d_r0) {
+        const int w0 = (s.d_r0 * e.cols) >> 5, w1 = ((s.d_r1 + 1) * e.cols - 1) >> 5;
+        for (int w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
+            unsigned m = dm[w];
+            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; z[(w << 5) + bit] = R3D_EMPTY_U64; }
+        }
+    }
+    __syncthreads();
+    const size_t base = (size_t)b * e.P;
+    if (s.apply_flag)                                        // points appended by the accept being applied
+        for (int p = s.n0 + s.tail_before + threadIdx.x; p < s.n0 + s.n_tail; p += blockDim.x)
+            if (e.alive[base + p]) atomicMin(&z[e.pix[base + p]], dbl_bits(e.r[base + p]));
+}
+
 struct RawImage {        // the engine's z-buffer as close/fill input
     const unsigned long long* raw;
     __device__ void load(int64_t i, double& v, uint8_t& o) const {
@@ -292,7 +382,7 @@ struct RawImage {        // the engine's z-buffer as close/fill input
 // non-ground label count as value 4 for this slot.  Kept as a per-scan bit window instead of rewriting the map.
 __global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_project[b]) return;
+    if (b >= n_scans || !e.gate_update[b]) return;
     ScanState& s = e.st[b];
     const int n = s.n0 + s.n_tail;
     const int p0 = blockIdx.x * CHUNK;
@@ -427,12 +517,36 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int 
     }
 }
 
+// Two more once-per-scan CSR indexes over the ORIGINAL points (their azimuth bin and horizontal range never change):
+// by image column (for k_apply_window) and by 0.25 m radial bin (for k_collide_points).
+__device__ __forceinline__ int radial_bin(const EngineDev& e, float x, float y) {
+    return min(e.RB - 1, (int)(sqrtf(x * x + y * y) * e.rad_inv_cell));
+}
+template <int PASS>     // 1: count, 2: scatter point indices
+__global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const int n0 = e.st[b].n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n0) return;
+    const size_t base = (size_t)b * e.P;
+    int* coff = e.col_off + (size_t)b * (e.cols + 1);
+    int* roff = e.rad_off + (size_t)b * (e.RB + 1);
+    int* cidx = e.col_idx + (size_t)b * e.max_points;
+    int* ridx = e.rad_idx + (size_t)b * e.max_points;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
+        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        const int c = e.col[base + p], rb = radial_bin(e, v.x, v.y);
+        if (PASS == 1) { atomicAdd(&coff[c], 1); atomicAdd(&roff[rb], 1); }
+        else { cidx[atomicAdd(&coff[c], 1)] = p; ridx[atomicAdd(&roff[rb], 1)] = p; }
+    }
+}
+
 // exclusive prefix sum of the per-cell counts (one CTA per scan); after the scatter pass cell[c] = END of cell c
-__global__ void __launch_bounds__(1024) k_grid_scan(EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans) return;
-    int* cell = e.gcell + (size_t)b * e.G * e.G;
-    const int n = e.G * e.G;
+    int* cell = arr + (size_t)b * stride;
     __shared__ int s_w[32];
     __shared__ int s_run;
     if (threadIdx.x == 0) s_run = 0;
@@ -567,15 +681,38 @@ __global__ void __launch_bounds__(256) k_onmap_ss(EngineDev e, int n_scans) {
     }
 }
 
-// A8 + A9 part (i) (od/fs:119-127, ss/fs:89-96): obstacle scene points strictly inside a candidate box.  One pass
-// over the live scene (20 B/point); each point only meets the candidates whose centre is within the box reach.
+// A8 + A9 part (i) (od/fs:119-127, ss/fs:89-96): obstacle scene points strictly inside a candidate box.  Every
+// candidate box centre lies on the circle of radius rho about the sensor, so only the points of the radial bins
+// covering [rho - reach, rho + reach] (CSR built once per scan) plus the inserted tail are visited; each point then
+// only meets the candidates whose centre is within the box reach (azimuth window) with the exact cut_bounding_box test.
+constexpr int COLL_G = 8;
+__device__ __forceinline__ void collide_one(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
+                                            int p, float rlo, float rhi, float reach, float step, size_t cb, size_t base) {
+    if (!e.alive[base + p]) return;
+    double x, y, z;
+    load_xyz(e, b, p, s.n0, x, y, z);
+    const float fx = (float)x, fy = (float)y;
+    const float rho2 = fx * fx + fy * fy;
+    if (rho2 < rlo * rlo || rho2 > rhi * rhi) return;
+    const unsigned lab = e.label[base + p];
+    if (e.task == 0) { if (lab == (unsigned)e.road_label) return; }         // od/ins:353-355 + od/fs:121
+    else if (surface_label(cc, lab)) return;                                // ss/fs:92-93
+    if (s.dirty && pix_removed(e, b, s, e.pix[base + p])) return;            // od/ins:472,491
+    int k_first, count;
+    cand_window(ob, fx, fy, reach, step, e.K, k_first, count);
+    for (int j = 0; j < count; ++j) {
+        const int k = cand_index(k_first, j, e.K);
+        if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK)) continue;
+        if (e.cand_collide[cb + k]) continue;
+        if (cc.pedestrian && !(z >= add(e.cand_level[cb + k], 0.1))) continue;     // od/fs:123-124
+        if (inside_box(e.cand_bt[cb + k], x, y, z)) e.cand_collide[cb + k] = 1;
+    }
+}
+
 __global__ void __launch_bounds__(STREAM_THREADS) k_collide_points(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_try[b]) return;
     const ScanState& s = e.st[b];
-    const int n = s.n0 + s.n_tail;
-    const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n) return;
     const ObjBox ob = e.obj[s.cur_obj];
     const ClassCfg& cc = e.classes[ob.cls];
     const float reach = (float)ob.reach;
@@ -583,27 +720,14 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_collide_points(EngineDev e, 
     const float step = (float)e.step_rad;
     const size_t cb = (size_t)b * (e.K + 1);
     const size_t base = (size_t)b * e.P;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
-        if (!e.alive[base + p]) continue;
-        double x, y, z;
-        load_xyz(e, b, p, s.n0, x, y, z);
-        const float fx = (float)x, fy = (float)y;
-        const float rho2 = fx * fx + fy * fy;
-        if (rho2 < rlo * rlo || rho2 > rhi * rhi) continue;
-        const unsigned lab = e.label[base + p];
-        if (e.task == 0) { if (lab == (unsigned)e.road_label) continue; }       // od/ins:353-355 + od/fs:121
-        else if (surface_label(cc, lab)) continue;                              // ss/fs:92-93
-        if (s.dirty && pix_removed(e, b, s, e.pix[base + p])) continue;          // od/ins:472,491
-        int k_first, count;
-        cand_window(ob, fx, fy, reach, step, e.K, k_first, count);
-        for (int j = 0; j < count; ++j) {
-            const int k = cand_index(k_first, j, e.K);
-            if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK)) continue;
-            if (e.cand_collide[cb + k]) continue;
-            if (cc.pedestrian && !(z >= add(e.cand_level[cb + k], 0.1))) continue;     // od/fs:123-124
-            if (inside_box(e.cand_bt[cb + k], x, y, z)) e.cand_collide[cb + k] = 1;
-        }
-    }
+    const int* off = e.rad_off + (size_t)b * (e.RB + 1);
+    const int* idx = e.rad_idx + (size_t)b * e.max_points;
+    const int b0 = max(0, (int)(rlo * e.rad_inv_cell) - 1), b1 = min(e.RB - 1, (int)(rhi * e.rad_inv_cell) + 1);
+    const int beg = b0 > 0 ? off[b0 - 1] : 0, end = off[b1];
+    for (int i = beg + blockIdx.x * STREAM_THREADS + threadIdx.x; i < end; i += COLL_G * STREAM_THREADS)
+        collide_one(e, b, s, ob, cc, idx[i], rlo, rhi, reach, step, cb, base);
+    for (int t = blockIdx.x * STREAM_THREADS + threadIdx.x; t < s.n_tail; t += COLL_G * STREAM_THREADS)
+        collide_one(e, b, s, ob, cc, s.n0 + t, rlo, rhi, reach, step, cb, base);
 }
 
 // A9 part (ii) (od/fs:129-134): any object point strictly inside an existing / already inserted box.
@@ -799,6 +923,9 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
     if (nf == 0) return;
     extern __shared__ unsigned long long s_keys[];
     __shared__ int s_nvis;
+    __shared__ int s_rect[4];
+    __shared__ unsigned long long s_el[2];
+    if (threadIdx.x == 0) { s_rect[0] = INT_MAX; s_rect[1] = -1; s_rect[2] = INT_MAX; s_rect[3] = -1; s_el[0] = R3D_EMPTY_U64; s_el[1] = 0ull; }
     const bool accepted = s.found_rank < nf;
     const int rank = accepted ? s.found_rank : nf - 1;
     const int k = e.feas[(size_t)b * e.K + rank];
@@ -834,6 +961,22 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
     }
     __threadfence_block();
     __syncthreads();
+    {   // pixel rectangle that contains vis_px: the object's pixels grown by the 5x3 window
+        int r_lo = INT_MAX, r_hi = -1, c_lo = INT_MAX, c_hi = -1;
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = pixbuf[i];
+            if (pix < 0) continue;
+            const int pr = pix / W, pc = pix % W;
+            r_lo = min(r_lo, pr); r_hi = max(r_hi, pr); c_lo = min(c_lo, pc); c_hi = max(c_hi, pc);
+        }
+        for (int o = 16; o > 0; o >>= 1) {
+            r_lo = min(r_lo, __shfl_xor_sync(0xffffffffu, r_lo, o)); r_hi = max(r_hi, __shfl_xor_sync(0xffffffffu, r_hi, o));
+            c_lo = min(c_lo, __shfl_xor_sync(0xffffffffu, c_lo, o)); c_hi = max(c_hi, __shfl_xor_sync(0xffffffffu, c_hi, o));
+        }
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&s_rect[0], r_lo); atomicMax(&s_rect[1], r_hi); atomicMin(&s_rect[2], c_lo); atomicMax(&s_rect[3], c_hi);
+        }
+    }
     // every pixel within the 5x3 neighbourhood of an object pixel may be switched on by the closing
     for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
         const int i = t / 15, o = t % 15;
@@ -879,6 +1022,7 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
                 e.tail_i[tb + j] = inten;
                 e.label[base + j] = lab;
                 e.r[base + j] = o.r; e.el[base + j] = o.el;
+                atomicMin(&s_el[0], dbl_bits(o.el)); atomicMax(&s_el[1], dbl_bits(o.el));
                 e.col[base + j] = (unsigned short)o.col;
                 e.pix[base + j] = o.pix;
                 e.alive[base + j] = 1;
@@ -899,10 +1043,18 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
                 e.box_tests[(size_t)b * e.max_boxes + nbox0] = make_box_test(bx);
                 s.n_boxes = nbox0 + 1; s.n_inserted = nins0 + 1;
                 s.tail_before = t0; s.n_tail = t0 + nvis; s.n_check = chk0 + nvis;
+                s.new_min_bits = s_el[0]; s.new_max_bits = s_el[1];
             }
         }
     }
-    if (threadIdx.x == 0) { s.accepted = accepted ? 1 : 0; s.chosen_rot = k; s.chosen_v = nvis; }
+    if (threadIdx.x == 0) {
+        s.accepted = accepted ? 1 : 0; s.chosen_rot = k; s.chosen_v = nvis;
+        if (s_rect[1] >= 0) {
+            s.d_r0 = max(s_rect[0] - 2, 0); s.d_r1 = min(s_rect[1] + 2, H - 1);
+            s.d_c0 = max(s_rect[2] - 1, 0); s.d_c1 = min(s_rect[3] + 1, W - 1);
+        } else { s.d_r0 = 0; s.d_r1 = -1; s.d_c0 = 0; s.d_c1 = -1; }
+        if (!accepted) { s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull; }
+    }
     // leave the scratch z-buffer empty for the next use
     for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
         const int pix = pixbuf[i];

@@ -61,7 +61,7 @@ class Real3DEngine:
 
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
-                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200):
+                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200, force_full_projection=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -87,6 +87,7 @@ class Real3DEngine:
             cfg.road_indexes[i] = int(v)
         cfg.map_window = int(map_window)
         cfg.grid_half, cfg.grid_cell = int(grid_half), float(grid_cell)
+        cfg.flags = 1 if force_full_projection else 0
         r2, ok = bx.search_radii()
         for i in range(50):
             cfg.radii_sq[i] = float(r2[i])
@@ -347,7 +348,8 @@ class Real3DEngine:
     def stats(self):
         out = np.zeros(4, dtype=np.uint64)
         _lib.check(self.lib.r3d_engine_stats(self.handle, out.ctypes.data), "stats")
-        return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2])}
+        return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
+                'patched_scans': int(out[3])}
 
     def cuda_stream(self):
         import torch

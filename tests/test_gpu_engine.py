@@ -140,3 +140,22 @@ def test_candidate_flags_match_oracle_first_try():
         last = tries[-1]
         feasible = [k for k in range(1, 361) if flags[k] == 3]
         assert feasible == last[2]
+
+
+@pytest.mark.parametrize("task,seed,counts", [("od", 701, [2, 2]), ("ss", 702, [1, 1, 1, 1, 0, 0])])
+def test_in_place_image_patch_equals_full_reprojection(task, seed, counts):
+    """The incremental slot update (window mask + z-buffer patch + windowed close/fill) must give exactly what a full
+    re-projection of every slot gives."""
+    case = synth.make_case(task, seed, shape=GOLDEN_SHAPE, counts=counts, obj_range=(4.0, 16.0))
+    outs = []
+    for force in (False, True):
+        eng = make_engine(case, force_full_projection=force)
+        outs.append(eng.augment_batch([scan_input_from_case(case)])[0])
+        st = eng.stats()
+        assert (st["patched_scans"] == 0) == force
+        eng.close()
+    a, b = outs
+    assert a.inserted == b.inserted and len(a.inserted) >= 2
+    np.testing.assert_array_equal(a.velodyne, b.velodyne)
+    np.testing.assert_array_equal(a.labels, b.labels)
+    np.testing.assert_array_equal(a.check, b.check)
