@@ -118,7 +118,7 @@ def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
         "project_zbuffer": (20 * n_points + 8 * hw, per_project),      # z-buffer pass
         "clear_images": (8 * hw, per_project),
         "close_fill": (16 * hw, per_project),
-        "apply_mask_window": (5 * n_points, per_mask),                 # occlusion mask
+        "update_mask_patch": (5 * n_points, per_mask),                 # occlusion mask
         "collide_points": (20 * n_points, per_try),                    # placement pass over the scene
         "compact_output": (40 * n_points, n_scans * steps),
         "ingest_spherical": (20 * n_points, 0),

@@ -200,9 +200,10 @@ int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const doub
                             uint8_t* flags_out, double* box_out, double* xyz_out, int xyz_capacity,
                             int32_t* n_feasible_out);
 
-/* gated scan-launch counters since the last r3d_engine_profile_enable: out4 = {scans projected, cut objects tried,
- * scans masked/re-ranged, 0} — the "units one launch processes" of the roofline arithmetic */
-int r3d_engine_stats(r3d_engine* eng, uint64_t* out4);
+/* gated scan-launch counters since the last r3d_engine_profile_enable: out8 = {scans re-projected in full, cut
+ * objects tried, vis_px masks applied, scans patched in place, selections in the shared-memory tile, selections in
+ * the global scratch image, 0, 0} — the "units one launch processes" of the roofline arithmetic */
+int r3d_engine_stats(r3d_engine* eng, uint64_t* out8);
 /* the engine's cudaStream_t (so callers can bracket work with their own CUDA events) */
 void* r3d_engine_stream(r3d_engine* eng);
 

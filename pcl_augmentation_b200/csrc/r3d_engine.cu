@@ -14,14 +14,12 @@ using namespace r3d;
 namespace {
 
 enum KernelId {
-    KID_INGEST, KID_CTRL, KID_APPLY, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT,
-    KID_GRID, KID_COLLIDE_PTS, KID_COLLIDE_BOX, KID_FEASIBLE, KID_OCCL, KID_SELECT, KID_OUT, KID_DECIDE, KID_MINMAX,
-    KID_PATCH, KID_COUNT
+    KID_INGEST, KID_CTRL, KID_UPDATE, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT, KID_COLLIDE,
+    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
-    "ingest_spherical", "ctrl", "apply_mask_window", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
-    "onmap", "height_grid", "index_build", "collide_points", "collide_boxes", "feasible",
-    "occlusion_count", "select_emit", "compact_output", "decide", "minmax_elevation", "patch_zbuffer"};
+    "ingest_spherical", "ctrl", "update_mask_patch", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
+    "onmap", "road_level", "collide", "index_build", "occlusion_count", "select_emit", "compact_output", "minmax_elevation"};
 
 template <class T>
 struct DevBuf {
@@ -50,20 +48,20 @@ struct r3d_engine {
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
     int last_rounds = 0;
     // device buffers
-    DevBuf<float4> xyzi, out_xyzi, gpts;
+    DevBuf<float4> xyzi, out_xyzi, gpts, apts;
     DevBuf<double> tail_x, tail_y, tail_z, r, el, smooth, poses, obj_x, obj_y, obj_z, cos_k, sin_k, radii_sq, cand_level,
-        cand_cx, cand_cy, inserted_box;
+        inserted_box;
     DevBuf<float> tail_i, obj_i, check, out_check;
-    DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label;
-    DevBuf<unsigned short> col;
-    DevBuf<int> pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, rad_off, rad_idx, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
-        class_list, radii_ok, cand_collide, cand_v, gcell, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
+    DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
+    DevBuf<unsigned short> col, cand_list;
+    DevBuf<int> pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
+        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
     DevBuf<ScanState> st;
     DevBuf<Box> boxes;
-    DevBuf<BoxTest> box_tests, cand_bt;
+    DevBuf<BoxTest> box_tests;
     DevBuf<ObjBox> obj;
     DevBuf<ClassCfg> classes;
     // host copies needed for re-arming
@@ -126,6 +124,11 @@ void drain_events(r3d_engine* eng) {
 }
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+// dynamic shared memory of k_select_emit: sort keys, ranges, object tile, pixel ids, dilation + visibility bits
+size_t select_smem_bytes(int max_pts) {
+    return (size_t)next_pow2(max_pts) * 8 + (size_t)max_pts * 8 + (size_t)SEL_TILE_PX * 8 + (size_t)max_pts * 4 +
+           2 * (size_t)(SEL_TILE_PX / 32) * 4 + 16;
+}
 
 }  // namespace
 
@@ -157,7 +160,6 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.grid_cell = cfg->grid_cell > 0 ? cfg->grid_cell : 0.5;
     d.grid_inv_cell = (float)(1.0 / d.grid_cell);
     d.G = 2 * (cfg->grid_half > 0 ? cfg->grid_half : 200);
-    d.RB = 512; d.rad_inv_cell = 4.0f;                 // 0.25 m radial bins up to 128 m (farther points share the last bin)
     d.force_full = (cfg->flags & 1) ? 1 : 0;
     const size_t B = d.B, P = d.P, K1 = d.K + 1, HW = d.hw;
     TRY(eng->xyzi.alloc(B * d.max_points)); TRY(eng->tail_x.alloc(B * d.max_inserted)); TRY(eng->tail_y.alloc(B * d.max_inserted));
@@ -171,16 +173,16 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
     TRY(eng->radii_sq.alloc(R3D_NUM_RADII)); TRY(eng->radii_ok.alloc(R3D_NUM_RADII)); TRY(eng->classes.alloc(R3D_MAX_CLASSES));
-    TRY(eng->cand_flags.alloc(B * K1)); TRY(eng->cand_collide.alloc(B * K1));
-    TRY(eng->cand_level.alloc(B * K1));
-    TRY(eng->cand_cx.alloc(B * K1)); TRY(eng->cand_cy.alloc(B * K1)); TRY(eng->cand_bt.alloc(B * K1)); TRY(eng->cand_v.alloc(B * K1));
+    TRY(eng->cand_flags.alloc(B * K1)); TRY(eng->cand_level.alloc(B * K1)); TRY(eng->cand_v.alloc(B * K1));
+    TRY(eng->cand_list.alloc(B * K1)); TRY(eng->n_list.alloc(B)); TRY(eng->tickets.alloc(B * 4));
+    R3D_CUDA(cudaMemset(eng->tickets.p, 0, B * 4 * sizeof(unsigned)));
     TRY(eng->feas.alloc(B * d.K)); TRY(eng->inserted.alloc(B * d.max_events * 4)); TRY(eng->inserted_box.alloc(B * d.max_events * 8));
     TRY(eng->check.alloc(B * d.max_inserted * 5)); TRY(eng->out_count.alloc(B)); TRY(eng->out_off.alloc(B + 1));
     TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
     TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
     TRY(eng->gcell.alloc(B * (size_t)d.G * d.G)); TRY(eng->gpts.alloc(B * d.max_points));
     TRY(eng->col_off.alloc(B * (size_t)(d.cols + 1))); TRY(eng->col_idx.alloc(B * d.max_points));
-    TRY(eng->rad_off.alloc(B * (size_t)(d.RB + 1))); TRY(eng->rad_idx.alloc(B * d.max_points));
+    TRY(eng->acell.alloc(B * (size_t)d.G * d.G)); TRY(eng->apts.alloc(B * d.max_points));
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
@@ -207,13 +209,12 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
     d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
     d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
-    d.cand_collide = eng->cand_collide.p;
-    d.cand_level = eng->cand_level.p; d.cand_cx = eng->cand_cx.p; d.cand_cy = eng->cand_cy.p; d.cand_bt = eng->cand_bt.p;
+    d.cand_level = eng->cand_level.p; d.cand_list = eng->cand_list.p; d.n_list = eng->n_list.p; d.tickets = eng->tickets.p;
     d.cand_v = eng->cand_v.p; d.feas = eng->feas.p; d.inserted = eng->inserted.p; d.inserted_box = eng->inserted_box.p;
     d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
     d.gcell = eng->gcell.p; d.gpts = eng->gpts.p;
-    d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.rad_off = eng->rad_off.p; d.rad_idx = eng->rad_idx.p;
+    d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.acell = eng->acell.p; d.apts = eng->apts.p;
     d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
     *out = eng;
     return R3D_OK;
@@ -286,8 +287,9 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     d.obj_x = eng->obj_x.p; d.obj_y = eng->obj_y.p; d.obj_z = eng->obj_z.p; d.obj_i = eng->obj_i.p; d.obj_label = eng->obj_label.p;
     d.obj = eng->obj.p; d.class_list_off = eng->class_list_off.p; d.class_list = eng->class_list.p;
     d.unplaceable = eng->unplaceable.p; d.occ_pix = eng->occ_pix.p; d.sel_pix = eng->sel_pix.p;
-    const size_t sel_smem = (size_t)next_pow2(max_pts) * sizeof(unsigned long long);
-    R3D_CUDA(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(sel_smem, 1024)));
+    const size_t sel_smem = select_smem_bytes(max_pts);
+    if (sel_smem > 200 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: a cut object is too large for the selection kernel's shared memory");
+    R3D_CUDA(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d.dwords * sizeof(unsigned))));
     eng->objects_set = true;
     return R3D_OK;
@@ -314,12 +316,12 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
         Launcher l(eng, KID_GRID);
         R3D_CUDA(cudaMemsetAsync(eng->gcell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
         R3D_CUDA(cudaMemsetAsync(eng->col_off.p, 0, (size_t)n * (d.cols + 1) * sizeof(int), st));
-        R3D_CUDA(cudaMemsetAsync(eng->rad_off.p, 0, (size_t)n * (d.RB + 1) * sizeof(int), st));
+        R3D_CUDA(cudaMemsetAsync(eng->acell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
         k_grid_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
         k_index_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
         k_bucket_scan<<<n, 1024, 0, st>>>(eng->gcell.p, (size_t)d.G * d.G, d.G * d.G, n);
         k_bucket_scan<<<n, 1024, 0, st>>>(eng->col_off.p, (size_t)d.cols + 1, d.cols, n);
-        k_bucket_scan<<<n, 1024, 0, st>>>(eng->rad_off.p, (size_t)d.RB + 1, d.RB, n);
+        k_bucket_scan<<<n, 1024, 0, st>>>(eng->acell.p, (size_t)d.G * d.G, d.G * d.G, n);
         k_grid_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
         k_index_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
         r3d_count_launch(6);
@@ -410,7 +412,8 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     const int P_live = eng->max_n0 + d.max_inserted;
     const int chunks_all = (P_live + CHUNK - 1) / CHUNK;
     const int kwarps = (d.K + 7) / 8;
-    const size_t sel_smem = (size_t)next_pow2(d.max_obj_points) * sizeof(unsigned long long);
+    const size_t sel_smem = select_smem_bytes(d.max_obj_points);
+    const int key_cap = next_pow2(d.max_obj_points);
     R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * sizeof(int), st));
     cudaEvent_t ev_ctrl[2];
     cudaEventCreateWithFlags(&ev_ctrl[0], cudaEventDisableTiming);
@@ -425,12 +428,10 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         R3D_CUDA(cudaMemcpyAsync(eng->h_active + slot, eng->active_count.p + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
         R3D_CUDA(cudaMemsetAsync(eng->active_count.p + ((slot + 32) & 63), 0, sizeof(int), st));
         R3D_CUDA(cudaEventRecord(ev_ctrl[round & 1], st));
-        { Launcher l(eng, KID_APPLY); k_apply_window<<<dim3(APPLY_G, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_DECIDE); k_decide<<<n, 128, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_UPDATE); k_update<<<dim3(UPDATE_G, n), UPDATE_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_MINMAX); k_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_CLEAR); k_clear_images<<<dim3(32, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_PROJECT); k_project<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_PATCH); k_patch_raw<<<n, 256, 0, st>>>(d, n); }
         {
             Launcher l(eng, KID_CLOSEFILL);
             RawImage in{d.zraw};
@@ -439,14 +440,12 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
                                                                  d.far_arr, d.cf_rect);
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_HEIGHT); k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
-        if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 256, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_COLLIDE_PTS); k_collide_points<<<dim3(COLL_G, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_COLLIDE_BOX); k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_FEASIBLE); k_feasible<<<n, 256, 0, st>>>(d, n); }
+        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), PLACE_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_HEIGHT); k_height<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); }
+        if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 1024, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_COLLIDE); k_collide<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
-        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n); }
+        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n, key_cap); }
         // the host only looks at the counter written by the PREVIOUS round's k_ctrl, so the device never idles
         if (round >= 1) {
             R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));
@@ -527,10 +526,10 @@ extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
     return R3D_OK;
 }
 
-extern "C" int r3d_engine_stats(r3d_engine* eng, uint64_t* out4) {
-    if (!eng || !out4) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats: null argument");
+extern "C" int r3d_engine_stats(r3d_engine* eng, uint64_t* out8) {
+    if (!eng || !out8) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats: null argument");
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
-    R3D_CUDA(cudaMemcpy(out4, eng->stats.p, 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    R3D_CUDA(cudaMemcpy(out8, eng->stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return R3D_OK;
 }
 
@@ -564,11 +563,7 @@ extern "C" int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* f
     if (!eng || scan < 0 || scan >= eng->n_scans) return r3d_fail(R3D_ERR_ARG, "r3d_engine_debug_candidates: bad argument");
     const size_t K1 = eng->dev.K + 1;
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
-    std::vector<unsigned char> f(K1);
-    std::vector<int> col(K1);
-    R3D_CUDA(cudaMemcpy(f.data(), eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost));
-    R3D_CUDA(cudaMemcpy(col.data(), eng->cand_collide.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost));
-    if (flags_out) for (size_t k = 0; k < K1; ++k) flags_out[k] = (uint8_t)(f[k] | (col[k] ? 4 : 0));
+    if (flags_out) R3D_CUDA(cudaMemcpy(flags_out, eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost));
     if (level_out) R3D_CUDA(cudaMemcpy(level_out, eng->cand_level.p + scan * K1, K1 * sizeof(double), cudaMemcpyDeviceToHost));
     if (visible_out) R3D_CUDA(cudaMemcpy(visible_out, eng->cand_v.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost));
     return R3D_OK;
@@ -587,17 +582,22 @@ __global__ void k_probe_setup(EngineDev e, int n_scans, int scan, int obj, int n
     if (threadIdx.x == 0) {
         s.try_active = me; s.need_project = 0; s.apply_flag = 0; s.dirty = 0;
         e.gate_try[b] = me; e.gate_update[b] = me; e.gate_apply[b] = 0; e.gate_full[b] = 0; e.gate_patch[b] = 0;
-        if (me) { s.n_tail = n_rows; s.cur_obj = obj; s.cur_class = e.obj[obj].cls; s.n_feasible = 0; s.found_rank = INT_MAX; }
+        for (int i = 0; i < 4; ++i) e.tickets[(size_t)b * 4 + i] = 0u;
+        if (me) {
+            s.n_tail = n_rows; s.cur_obj = obj; s.cur_class = e.obj[obj].cls; s.n_feasible = 0; s.found_rank = INT_MAX;
+            // the whole probed scene is one "inserted object" with an all-covering, zero-size box, so that k_collide
+            // visits every tail point and no object point can ever be inside that box
+            Box dummy;
+            dummy.cx = dummy.cy = dummy.cz = 0.0;
+            for (int i = 0; i < 9; ++i) dummy.m[i] = (i % 4 == 0) ? 1.0 : 0.0;
+            dummy.length = dummy.width = dummy.height = 0.0; dummy.reach = 1e9;
+            e.boxes[(size_t)b * e.max_boxes + s.n_boxes] = dummy;
+            e.box_tests[(size_t)b * e.max_boxes + s.n_boxes] = make_box_test(dummy);
+            e.inserted[((size_t)b * e.max_events + 0) * 4 + 3] = n_rows;
+            s.n_boxes += 1; s.n_inserted = 1;
+        }
     }
     if (!me) return;
-    const ObjBox ob = e.obj[obj];
-    const size_t cb = (size_t)b * (e.K + 1);
-    for (int k = threadIdx.x; k <= e.K; k += blockDim.x) {
-        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_v[cb + k] = 0; e.cand_level[cb + k] = 0.0;
-        const double c = e.cos_k[k], sn = e.sin_k[k];
-        e.cand_cx[cb + k] = sub(mul(c, ob.cx), mul(sn, ob.cy));
-        e.cand_cy[cb + k] = add(mul(sn, ob.cx), mul(c, ob.cy));
-    }
     const int ww = e.map_window * e.map_window / 32;
     if (e.task == 1) for (int i = threadIdx.x; i < ww; i += blockDim.x) e.occ_win[(size_t)b * ww + i] = 0u;
 }
@@ -634,6 +634,7 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
         return r3d_fail(R3D_ERR_ARG, "r3d_engine_probe_places: bad argument");
     EngineDev d = eng->dev;
     if (n_rows > d.max_inserted) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_probe_places: scene larger than max_inserted");
+    if (eng->h_nbox0[scan] + 1 > d.max_boxes) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_probe_places: max_boxes too small");
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
     TRY(arm_batch(eng, false));
@@ -660,14 +661,13 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
         R3D_CUDA(cudaMemsetAsync(eng->alive.p + pb + n0, 1, n_rows, st));
     }
     k_probe_setup<<<n, 128, 0, st>>>(d, n, scan, object_id, (int)n_rows); r3d_count_launch();
-    const int chunks_all = (n0 + (int)n_rows + CHUNK - 1) / CHUNK, kwarps = (d.K + 7) / 8;
+    const int chunks_all = (n0 + (int)n_rows + CHUNK - 1) / CHUNK;
     if (d.task == 1) { k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch(); }
-    if (d.task == 0) { k_onmap_od<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch(); }
-    k_height_grid<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
-    if (d.task == 1) { k_onmap_ss<<<n, 256, 0, st>>>(d, n); r3d_count_launch(); }
-    k_collide_points<<<dim3(COLL_G, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch();
-    k_collide_boxes<<<dim3(kwarps, n), 256, 0, st>>>(d, n); r3d_count_launch();
-    k_feasible<<<n, 256, 0, st>>>(d, n); r3d_count_launch();
+    const int kwarps = (d.K + 7) / 8;
+    if (d.task == 0) { k_onmap_od<<<dim3(kwarps, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch(); }
+    k_height<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch();
+    if (d.task == 1) { k_onmap_ss<<<n, 1024, 0, st>>>(d, n); r3d_count_launch(); }
+    k_collide<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch();
     std::vector<ScanState> hs(1);
     R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p + scan, sizeof(ScanState), cudaMemcpyDeviceToHost, st));
     R3D_CUDA(cudaStreamSynchronize(st));
@@ -683,13 +683,9 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
     const size_t nxyz = xyz_out ? (size_t)nf * hob[0].count * 3 : 0;
     if (nxyz) TRY(dxyz.alloc(nxyz));
     k_probe_points<<<148, 256, 0, st>>>(d, scan, object_id, nf, nxyz ? dxyz.p : nullptr, dbox.p); r3d_count_launch();
-    std::vector<unsigned char> f(K1);
-    std::vector<int> col(K1);
-    R3D_CUDA(cudaMemcpyAsync(f.data(), eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost, st));
-    R3D_CUDA(cudaMemcpyAsync(col.data(), eng->cand_collide.p + scan * K1, K1 * sizeof(int), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(flags_out, eng->cand_flags.p + scan * K1, K1, cudaMemcpyDeviceToHost, st));
     R3D_CUDA(cudaMemcpyAsync(box_out, dbox.p, K1 * 5 * sizeof(double), cudaMemcpyDeviceToHost, st));
     if (nxyz) R3D_CUDA(cudaMemcpyAsync(xyz_out, dxyz.p, nxyz * sizeof(double), cudaMemcpyDeviceToHost, st));
     R3D_CUDA(cudaStreamSynchronize(st));
-    for (size_t k = 0; k < K1; ++k) flags_out[k] = (uint8_t)(f[k] | (col[k] ? 4 : 0));
     return r3d_check_launch("r3d_engine_probe_places");
 }

@@ -69,6 +69,8 @@ struct EngineDev {       // passed by value to kernels
     double grid_cell;
     int* gcell;                       // [B][G*G]   CSR end offsets (cell c holds gpts[gcell[c-1] .. gcell[c]) )
     float4* gpts;                     // [B][max_points]  surface points sorted by cell: x, y, z, label bits
+    int* acell;                       // [B][G*G]   same grid over ALL original points (collision test)
+    float4* apts;                     // [B][max_points]  x, y, z, point index bits
     // per-scan resident data
     const float4* xyzi;
     double *tail_x, *tail_y, *tail_z;
@@ -85,10 +87,7 @@ struct EngineDev {       // passed by value to kernels
     int *gate_update, *gate_try, *gate_apply, *gate_full, *gate_patch;
     int* cf_rect;                     // [B][4] rows r0..r1, cols c0..c1 (inclusive) close/fill must recompute
     int force_full;                   // debug / test: always take the full re-projection path
-    int RB;                           // radial bins of the obstacle index
-    float rad_inv_cell;
     int *col_off, *col_idx;           // [B][cols+1], [B][max_points]: original points bucketed by azimuth bin
-    int *rad_off, *rad_idx;           // [B][RB+1],   [B][max_points]: original points bucketed by horizontal range
     int* active_count;
     unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
@@ -120,12 +119,12 @@ struct EngineDev {       // passed by value to kernels
     const int* radii_ok;              // [50]
     const ClassCfg* classes;
     // candidates of the current try
-    unsigned char* cand_flags;        // [B][K+1]
-    int* cand_collide;                // [B][K+1]
+    unsigned char* cand_flags;        // [B][K+1]  bit0 on map, bit1 road level found, bit2 collision
     double* cand_level;               // [B][K+1]
-    double *cand_cx, *cand_cy;        // [B][K+1]
-    BoxTest* cand_bt;                 // [B][K+1]
     int* cand_v;                      // [B][K+1]
+    unsigned short* cand_list;        // [B][K+1] compacted rotations the next placement stage works on
+    int* n_list;                      // [B]
+    unsigned* tickets;                // [B][4]  "last CTA done" counters of the staged kernels (zeroed by k_ctrl)
     int* feas;                        // [B][K]
     int* occ_pix;                     // [B][OCC_G][max_obj_points] scratch
     int* sel_pix;                     // [B][max_obj_points]

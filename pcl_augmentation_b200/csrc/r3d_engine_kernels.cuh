@@ -96,7 +96,6 @@ __device__ int list_entry(const EngineDev& e, int b, int ev, int ci, int sidx, i
 __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans) return;
-    __shared__ int s_try;
     ScanState& s = e.st[b];
     if (threadIdx.x == 0) {
         int apply = 0, project = 0, tryact = 0;
@@ -177,22 +176,11 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
         }
         s.try_active = tryact; s.need_project = project; s.apply_flag = apply;
         s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
-        if (apply) s.extreme_removed = 0;
         e.gate_update[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply;
+        for (int i = 0; i < 4; ++i) e.tickets[(size_t)b * 4 + i] = 0u;
         if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(e.active_count, 1);
         if (tryact) atomicAdd(&e.stats[1], 1ull);
         if (apply) atomicAdd(&e.stats[2], 1ull);
-        s_try = tryact;
-    }
-    __syncthreads();
-    if (!s_try) return;
-    const ObjBox ob = e.obj[s.cur_obj];
-    const size_t cb = (size_t)b * (e.K + 1);
-    for (int k = threadIdx.x; k <= e.K; k += blockDim.x) {
-        e.cand_flags[cb + k] = 0; e.cand_collide[cb + k] = 0; e.cand_v[cb + k] = 0;
-        const double c = e.cos_k[k], sn = e.sin_k[k];
-        e.cand_cx[cb + k] = sub(mul(c, ob.cx), mul(sn, ob.cy));
-        e.cand_cy[cb + k] = add(mul(sn, ob.cx), mul(c, ob.cy));
     }
 }
 
@@ -204,26 +192,61 @@ __device__ __forceinline__ bool pix_removed(const EngineDev& e, int b, const Sca
     return e.far_arr[b] && e.smooth[(size_t)b * e.hw + pix] > kEmptyRange;
 }
 
-// A11/A12 (od/ins:488-501, 545): scene = scene[pix_id not in vis_px].  vis_px lies inside the pixel rectangle
-// select_emit recorded, so only the points whose azimuth bin falls in that column range are visited (CSR by column,
-// built once per scan) plus the inserted tail: O(window) instead of O(N).  Also notes whether a removed point held
-// the scene's min / max elevation (then the image geometry changes and the slot is re-projected in full).
-constexpr int APPLY_G = 8;
-__global__ void __launch_bounds__(STREAM_THREADS) k_apply_window(EngineDev e, int n_scans) {
+// Slot update, one CTA per scan (A11/A12 + the decision how the range image is refreshed):
+//  1. scene = scene[pix_id not in vis_px] (od/ins:488-501, 545).  vis_px lies inside the pixel rectangle select_emit
+//     recorded, so only the points whose azimuth bin falls in that column range are visited (CSR by column, built once
+//     per scan) plus the inserted tail: O(window) instead of O(N).  Notes whether a removed point held the scene's
+//     min / max elevation.
+//  2. full re-projection or in-place patch?  The image geometry (od/ins:97-98) depends only on the scene's min / max
+//     elevation; if neither moved, every surviving point keeps its pixel and only the pixels of vis_px change.
+//  3. patch: the z-buffer changes only at the pixels of vis_px — all their scene points were removed (od/ins:491)
+//     and the visible object points were appended there (od/ins:545).
+constexpr int UPDATE_THREADS = 256;
+constexpr int UPDATE_G = 8;          // CTAs per scan; the last one to finish takes the decision and patches
+__device__ __forceinline__ bool last_block_done(unsigned* ticket, unsigned n_blocks) {
+    __shared__ bool s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(ticket, 1u) == n_blocks - 1;
+    __syncthreads();
+    if (s_last) __threadfence();
+    return s_last;
+}
+
+__global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_apply[b]) return;
+    if (b >= n_scans) return;
+    const int do_apply = e.gate_apply[b], do_update = e.gate_update[b];
+    if (!do_apply && !do_update) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            e.gate_full[b] = 0; e.gate_patch[b] = 0;
+            int* r = e.cf_rect + (size_t)b * 4; r[0] = 0; r[1] = -1; r[2] = 0; r[3] = -1;
+        }
+        return;
+    }
     ScanState& s = e.st[b];
     const size_t base = (size_t)b * e.P;
-    const int* off = e.col_off + (size_t)b * (e.cols + 1);
-    const int* idx = e.col_idx + (size_t)b * e.max_points;
-    int c0 = s.d_c0, c1 = s.d_c1;
-    if (e.far_arr[b]) { c0 = 0; c1 = e.cols - 1; }          // od/ins:486 quirk: covered pixels can be anywhere
+    const int tid = blockIdx.x * UPDATE_THREADS + threadIdx.x, nthr = UPDATE_G * UPDATE_THREADS;
     bool extreme = false;
-    const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
-    if (c1 >= c0) {
-        const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
-        for (int i = beg + blockIdx.x * STREAM_THREADS + threadIdx.x; i < end; i += APPLY_G * STREAM_THREADS) {
-            const int p = idx[i];
+    if (do_apply) {
+        const int* off = e.col_off + (size_t)b * (e.cols + 1);
+        const int* idx = e.col_idx + (size_t)b * e.max_points;
+        int c0 = s.d_c0, c1 = s.d_c1;
+        if (e.far_arr[b]) { c0 = 0; c1 = e.cols - 1; }          // od/ins:486 quirk: covered pixels can be anywhere
+        const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
+        if (c1 >= c0) {
+            const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
+            for (int i = beg + tid; i < end; i += nthr) {
+                const int p = idx[i];
+                if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
+                    e.alive[base + p] = 0;
+                    const unsigned long long bits = dbl_bits(e.el[base + p]);
+                    extreme |= bits == lo || bits == hi;
+                }
+            }
+        }
+        for (int t = tid; t < s.tail_before; t += nthr) {
+            const int p = s.n0 + t;
             if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
                 e.alive[base + p] = 0;
                 const unsigned long long bits = dbl_bits(e.el[base + p]);
@@ -231,32 +254,16 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_apply_window(EngineDev e, in
             }
         }
     }
-    for (int t = blockIdx.x * STREAM_THREADS + threadIdx.x; t < s.tail_before; t += APPLY_G * STREAM_THREADS) {
-        const int p = s.n0 + t;
-        if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
-            e.alive[base + p] = 0;
-            const unsigned long long bits = dbl_bits(e.el[base + p]);
-            extreme |= bits == lo || bits == hi;
-        }
-    }
     if (__syncthreads_or(extreme) && threadIdx.x == 0) atomicOr(&s.extreme_removed, 1);
-}
-
-// full re-projection or in-place patch?  The image geometry (od/ins:97-98) depends only on the scene's min / max
-// elevation; if neither moved, every surviving point keeps its pixel and only the pixels of vis_px change.
-__global__ void __launch_bounds__(128) k_decide(EngineDev e, int n_scans) {
-    const int b = blockIdx.x;
-    if (b >= n_scans) return;
-    ScanState& s = e.st[b];
-    __shared__ int s_upd;
+    if (!last_block_done(&e.tickets[(size_t)b * 4 + 0], UPDATE_G)) return;
+    __shared__ int s_patch;
     if (threadIdx.x == 0) {
-        const int upd = e.gate_update[b];
         int full = 0, patch = 0;
         int* rect = e.cf_rect + (size_t)b * 4;
         rect[0] = 0; rect[1] = -1; rect[2] = 0; rect[3] = -1;
-        if (upd) {
+        if (do_update) {
             const bool extended = s.new_min_bits < s.min_el_bits || s.new_max_bits > s.max_el_bits;
-            full = s.first || s.extreme_removed || extended || e.far_arr[b] || e.force_full;
+            full = s.first || *(volatile int*)&s.extreme_removed || extended || e.far_arr[b] || e.force_full;
             patch = !full;
             if (full) {
                 s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
@@ -265,19 +272,34 @@ __global__ void __launch_bounds__(128) k_decide(EngineDev e, int n_scans) {
                 rect[0] = max(s.d_r0 - 4, 0); rect[1] = min(s.d_r1 + 4, e.rows - 1);
                 rect[2] = max(s.d_c0 - 2, 0); rect[3] = min(s.d_c1 + 2, e.cols - 1);
             }
-            s.first = 0; s.extreme_removed = 0;
+            s.first = 0;
             s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull;
             atomicAdd(&e.stats[full ? 0 : 3], 1ull);
         }
+        s.extreme_removed = 0;
         e.gate_full[b] = full; e.gate_patch[b] = patch;
-        s_upd = upd;
+        s_patch = patch;
     }
     __syncthreads();
-    if (s_upd && e.task == 1) {
+    if (do_update && e.task == 1) {
         const int ww = e.map_window * e.map_window / 32;
         unsigned* o = e.occ_win + (size_t)b * ww;
-        for (int i = threadIdx.x; i < ww; i += blockDim.x) o[i] = 0u;
+        for (int i = threadIdx.x; i < ww; i += UPDATE_THREADS) o[i] = 0u;
     }
+    if (!s_patch) return;
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    const unsigned* dm = e.dmask + (size_t)b * e.dwords;
+    if (s.d_r1 >= s.d_r0) {
+        const int w0 = (s.d_r0 * e.cols) >> 5, w1 = ((s.d_r1 + 1) * e.cols - 1) >> 5;
+        for (int w = w0 + threadIdx.x; w <= w1; w += UPDATE_THREADS) {
+            unsigned m = dm[w];
+            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; z[(w << 5) + bit] = R3D_EMPTY_U64; }
+        }
+    }
+    __syncthreads();
+    if (s.apply_flag)                                        // points appended by the accept being applied
+        for (int p = s.n0 + s.tail_before + threadIdx.x; p < s.n0 + s.n_tail; p += UPDATE_THREADS)
+            if (e.alive[base + p]) atomicMin(&z[e.pix[base + p]], dbl_bits(e.r[base + p]));
 }
 
 // A2 (od/ins:79-80) on the cached elevations: min / max over the live points (full path only)
@@ -345,28 +367,6 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_s
     }
 }
 
-// patch path: the z-buffer changes only at the pixels of vis_px — all their scene points were removed
-// (od/ins:491) and the visible object points were appended there (od/ins:545).
-__global__ void __launch_bounds__(256) k_patch_raw(EngineDev e, int n_scans) {
-    const int b = blockIdx.x;
-    if (b >= n_scans || !e.gate_patch[b]) return;
-    const ScanState& s = e.st[b];
-    unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    const unsigned* dm = e.dmask + (size_t)b * e.dwords;
-    if (s.d_r1 >= s.d_r0) {
-        const int w0 = (s.d_r0 * e.cols) >> 5, w1 = ((s.d_r1 + 1) * e.cols - 1) >> 5;
-        for (int w = w0 + threadIdx.x; w <= w1; w += blockDim.x) {
-            unsigned m = dm[w];
-            while (m) { const int bit = __ffs(m) - 1; m &= m - 1; z[(w << 5) + bit] = R3D_EMPTY_U64; }
-        }
-    }
-    __syncthreads();
-    const size_t base = (size_t)b * e.P;
-    if (s.apply_flag)                                        // points appended by the accept being applied
-        for (int p = s.n0 + s.tail_before + threadIdx.x; p < s.n0 + s.n_tail; p += blockDim.x)
-            if (e.alive[base + p]) atomicMin(&z[e.pix[base + p]], dbl_bits(e.r[base + p]));
-}
-
 struct RawImage {        // the engine's z-buffer as close/fill input
     const unsigned long long* raw;
     __device__ void load(int64_t i, double& v, uint8_t& o) const {
@@ -413,60 +413,6 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int 
 }
 
 // ------------------------------------------------------------------------------------------- placement
-// candidates (rotation indices, wrapping) whose box centre can lie within `reach` of the point (x, y)
-__device__ __forceinline__ void cand_window(const ObjBox& ob, float x, float y, float reach, float step, int K,
-                                            int& k_first, int& count) {
-    if (reach >= 0.98f * (float)ob.rho) { k_first = 1; count = K; return; }
-    const float alpha = asinf(fminf(1.f, reach / (float)ob.rho)) + 2e-4f;
-    const float w = ceilf(alpha / step) + 1.f;
-    float kc = (atan2f(y, x) - (float)ob.psi0) / step;
-    kc -= floorf(kc / (float)K) * (float)K;
-    count = min(K, 2 * (int)w + 2);
-    int k0 = (int)floorf(kc) - (int)w;
-    k0 %= K; if (k0 < 0) k0 += K;
-    k_first = k0;
-}
-__device__ __forceinline__ int cand_index(int k_first, int j, int K) {
-    int k = k_first + j;
-    if (k >= K) k -= K;
-    if (k >= K) k %= K;
-    return k == 0 ? K : k;               // rotation K*step = 360 degrees is index K
-}
-
-// A5 + A6a (od/fs:263-279): one warp per yaw candidate; every in-map object point must sit on a map cell == 1.
-__global__ void __launch_bounds__(256) k_onmap_od(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
-    if (k > e.K) return;
-    const int lane = threadIdx.x & 31;
-    const ScanState& s = e.st[b];
-    const ObjBox ob = e.obj[s.cur_obj];
-    const int msel = e.classes[ob.cls].map_sel;
-    const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
-    const int sx = dims[0], sy = dims[1];
-    const double mx = (double)dims[2], my = (double)dims[3];
-    const unsigned char* map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
-    const double c = e.cos_k[k], sn = e.sin_k[k];
-    bool any_in = false, bad = false;
-    for (int i0 = 0; i0 < ob.count; i0 += 32) {
-        const int i = i0 + lane;
-        if (i < ob.count) {
-            const double x = e.obj_x[ob.first + i], y = e.obj_y[ob.first + i];
-            const double gx = sub(sub(mul(c, x), mul(sn, y)), mx);
-            const double gy = sub(add(mul(sn, x), mul(c, y)), my);
-            if (!(gx < 0.0 || gx >= (double)sx || gy < 0.0 || gy >= (double)sy)) {
-                any_in = true;
-                bad |= map[(size_t)((int)gx) * sy + (int)gy] != 1;
-            }
-        }
-        if (__any_sync(0xffffffffu, bad)) break;          // warp-ballot early-out (od/fs:277-279)
-    }
-    any_in = __any_sync(0xffffffffu, any_in);
-    bad = __any_sync(0xffffffffu, bad);
-    if (lane == 0 && any_in && !bad) e.cand_flags[(size_t)b * (e.K + 1) + k] = CF_ONMAP;
-}
-
 __device__ __forceinline__ bool surface_label(const ClassCfg& cc, unsigned lab) {
     bool ok = false;
     for (int i = 0; i < cc.n_surface; ++i) ok |= lab == (unsigned)cc.surface[i];
@@ -506,22 +452,25 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int 
     if (p0 >= n0) return;
     const size_t base = (size_t)b * e.P;
     int* cell = e.gcell + (size_t)b * e.G * e.G;
+    int* acell = e.acell + (size_t)b * e.G * e.G;
     float4* out = e.gpts + (size_t)b * e.max_points;
+    float4* aout = e.apts + (size_t)b * e.max_points;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
         const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
         const unsigned lab = e.label[base + p];
-        if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
         const int c = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
+        if (!(e.task == 0 && lab == (unsigned)e.road_label)) {      // OD: Road points are never obstacles (od/ins:353-355)
+            if (PASS == 1) atomicAdd(&acell[c], 1);
+            else aout[atomicAdd(&acell[c], 1)] = make_float4(v.x, v.y, v.z, __int_as_float(p));
+        }
+        if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
         if (PASS == 1) atomicAdd(&cell[c], 1);
         else out[atomicAdd(&cell[c], 1)] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
     }
 }
 
-// Two more once-per-scan CSR indexes over the ORIGINAL points (their azimuth bin and horizontal range never change):
-// by image column (for k_apply_window) and by 0.25 m radial bin (for k_collide_points).
-__device__ __forceinline__ int radial_bin(const EngineDev& e, float x, float y) {
-    return min(e.RB - 1, (int)(sqrtf(x * x + y * y) * e.rad_inv_cell));
-}
+// One more once-per-scan CSR index over the ORIGINAL points (their azimuth bin never changes): by image column,
+// for k_apply_window.
 template <int PASS>     // 1: count, 2: scatter point indices
 __global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
@@ -531,15 +480,51 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int
     if (p0 >= n0) return;
     const size_t base = (size_t)b * e.P;
     int* coff = e.col_off + (size_t)b * (e.cols + 1);
-    int* roff = e.rad_off + (size_t)b * (e.RB + 1);
     int* cidx = e.col_idx + (size_t)b * e.max_points;
-    int* ridx = e.rad_idx + (size_t)b * e.max_points;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
-        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
-        const int c = e.col[base + p], rb = radial_bin(e, v.x, v.y);
-        if (PASS == 1) { atomicAdd(&coff[c], 1); atomicAdd(&roff[rb], 1); }
-        else { cidx[atomicAdd(&coff[c], 1)] = p; ridx[atomicAdd(&roff[rb], 1)] = p; }
+        const int c = e.col[base + p];
+        if (PASS == 1) atomicAdd(&coff[c], 1);
+        else cidx[atomicAdd(&coff[c], 1)] = p;
     }
+}
+
+// Warp-cooperative visit of every point stored in the grid cells [icx-T, icx+T] x [icy-T, icy+T]: lane r fetches
+// the CSR range of row r (a row of cells is contiguous), an inclusive scan flattens the rows, and the lanes then
+// stride over the flattened points — balanced and with independent loads instead of one dependent chain per row.
+template <class F>
+__device__ __forceinline__ void warp_visit_rect(const int* __restrict__ cell, const float4* __restrict__ pts, int G, int x0,
+                                                int x1, int y0, int y1, int lane, F f) {
+    for (int yb = y0; yb <= y1; yb += 32) {
+        const int nrows = min(32, y1 - yb + 1);
+        int beg = 0, cnt = 0;
+        if (lane < nrows) {
+            const int c0 = (yb + lane) * G + x0, c1 = (yb + lane) * G + x1;
+            beg = c0 > 0 ? cell[c0 - 1] : 0;
+            cnt = cell[c1] - beg;
+        }
+        int inc = cnt;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        const int total = __shfl_sync(0xffffffffu, inc, 31);
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            const int t = t0 + lane;
+            int lo = 0, hi = 31;
+#pragma unroll
+            for (int it = 0; it < 5; ++it) {
+                const int mid = (lo + hi) >> 1;
+                const int v = __shfl_sync(0xffffffffu, inc, mid);
+                if (v > t) hi = mid; else lo = mid + 1;
+            }
+            const int r = min(lo, 31);
+            const int start = __shfl_sync(0xffffffffu, inc - cnt, r);
+            const int rb = __shfl_sync(0xffffffffu, beg, r);
+            if (t < total) f(pts[rb + (t - start)]);
+        }
+    }
+}
+template <class F>
+__device__ __forceinline__ void warp_visit_cells(const int* __restrict__ cell, const float4* __restrict__ pts, int G, int icx,
+                                                 int icy, int T, int lane, F f) {
+    warp_visit_rect(cell, pts, G, max(icx - T, 0), min(icx + T, G - 1), max(icy - T, 0), min(icy + T, G - 1), lane, f);
 }
 
 // exclusive prefix sum of the per-cell counts (one CTA per scan); after the scatter pass cell[c] = END of cell c
@@ -568,79 +553,240 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, i
     }
 }
 
-// A7 (od/fs:138-172, ss/fs:107-152): road level under every candidate that needs it, one warp per candidate.
+// A7 (od/fs:138-172, ss/fs:107-152): road level under a candidate centre (cx, cy), one warp.
 // "first radius 0.1, 0.2, ... whose disc holds a surface point" == radius index of the NEAREST surface point, found
 // by scanning growing squares of grid cells; the level is the mean z of the points inside that disc, summed in
-// 2^-40 fixed point (order independent; exact for float32 z, so equal to numpy's sequential float64 sum).  Also
-// builds the candidate's box test (R_k = R0 . Rz(k * step)).
-__global__ void __launch_bounds__(256) k_height_grid(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
-    if (k > e.K) return;
-    const int lane = threadIdx.x & 31;
-    const ScanState& s = e.st[b];
-    const size_t cb = (size_t)b * (e.K + 1);
-    unsigned f = e.cand_flags[cb + k];
-    if (e.task == 0 && !(f & CF_ONMAP)) return;                       // OD: only on-map candidates (od/fs:281)
-    const ObjBox ob = e.obj[s.cur_obj];
-    const ClassCfg& cc = e.classes[ob.cls];
+// 2^-40 fixed point (order independent; exact for float32 z, so equal to numpy's sequential float64 sum).
+__device__ bool warp_road_level(const EngineDev& e, int b, const ClassCfg& cc, double cx, double cy, int lane, double& level) {
     const int G = e.G;
     const int* cell = e.gcell + (size_t)b * G * G;
     const float4* pts = e.gpts + (size_t)b * e.max_points;
-    const double cx = e.cand_cx[cb + k], cy = e.cand_cy[cb + k];
     const int icx = grid_coord(e, (float)cx), icy = grid_coord(e, (float)cy);
     const int t_max = (int)ceil(5.0 / e.grid_cell) + 1;
     double best = 1e300;
     for (int T = 1;; T = min(2 * T, t_max)) {
-        const int x0 = max(icx - T, 0), x1 = min(icx + T, G - 1);
-        for (int iy = max(icy - T, 0); iy <= min(icy + T, G - 1); ++iy) {
-            const int c0 = iy * G + x0, c1 = iy * G + x1;
-            const int beg = c0 > 0 ? cell[c0 - 1] : 0, end = cell[c1];
-            for (int i = beg + lane; i < end; i += 32) {
-                const float4 v = pts[i];
-                if (!surface_label(cc, __float_as_uint(v.w))) continue;
-                const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
-                best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                       // od/fs:153
-            }
-        }
+        warp_visit_cells(cell, pts, G, icx, icy, T, lane, [&](const float4 v) {
+            if (!surface_label(cc, __float_as_uint(v.w))) return;
+            const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+            best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                           // od/fs:153
+        });
         for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
         const double safe = (double)T * e.grid_cell * 0.999;          // every point outside the square is farther
         if (best <= safe * safe || T >= t_max) break;
     }
     const int j = best < 1e299 ? radius_index(e.radii_sq, best) : R3D_NUM_RADII;
-    if (j >= R3D_NUM_RADII || !e.radii_ok[j]) return;                 // od/fs:156-160: no surface within reach
+    if (j >= R3D_NUM_RADII || !e.radii_ok[j]) return false;           // od/fs:156-160: no surface within reach
     const double r2 = e.radii_sq[j];
     const int T = min(t_max, (int)ceil(sqrt(r2) / e.grid_cell) + 1);
     long long zsum = 0;
     int cnt = 0;
-    const int x0 = max(icx - T, 0), x1 = min(icx + T, G - 1);
-    for (int iy = max(icy - T, 0); iy <= min(icy + T, G - 1); ++iy) {
-        const int c0 = iy * G + x0, c1 = iy * G + x1;
-        const int beg = c0 > 0 ? cell[c0 - 1] : 0, end = cell[c1];
-        for (int i = beg + lane; i < end; i += 32) {
-            const float4 v = pts[i];
-            if (!surface_label(cc, __float_as_uint(v.w))) continue;
-            const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
-            if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
-        }
-    }
+    warp_visit_cells(cell, pts, G, icx, icy, T, lane, [&](const float4 v) {
+        if (!surface_label(cc, __float_as_uint(v.w))) return;
+        const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+        if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
+    });
     for (int o = 16; o > 0; o >>= 1) {
         zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
         cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
-    if (lane == 0 && cnt > 0) {
-        const double level = __ddiv_rn(__ddiv_rn((double)zsum, kFix), (double)cnt);       // od/fs:164 np.mean
-        e.cand_level[cb + k] = level;
-        const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, e.cos_k[k], e.sin_k[k]);
-        e.cand_bt[cb + k] = make_box_test(yaw_box_to_box(yb, level, ob.length, ob.width, ob.height));
-        e.cand_flags[cb + k] = (unsigned char)(f | CF_HOK);
-    }
+    if (cnt == 0) return false;
+    level = __ddiv_rn(__ddiv_rn((double)zsum, kFix), (double)cnt);    // od/fs:164 np.mean
+    return true;
 }
 
-// A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place): candidates are visited in
-// order by one CTA; world = T . [x y z 1] - move, astype(int); every in-map cell value must be allowed.
-__global__ void __launch_bounds__(256) k_onmap_ss(EngineDev e, int n_scans) {
+// A5 + A6a (od/fs:263-279), one warp: every in-map object point of yaw candidate k must sit on a map cell == 1.
+__device__ bool warp_onmap_od(const EngineDev& e, int b, const ObjBox& ob, int k, int lane) {
+    const int msel = e.classes[ob.cls].map_sel;
+    const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
+    const int sx = dims[0], sy = dims[1];
+    const double mx = (double)dims[2], my = (double)dims[3];
+    const unsigned char* map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    bool any_in = false, bad = false;
+    for (int i0 = 0; i0 < ob.count; i0 += 32) {
+        const int i = i0 + lane;
+        if (i < ob.count) {
+            const double x = e.obj_x[ob.first + i], y = e.obj_y[ob.first + i];
+            const double gx = sub(sub(mul(c, x), mul(sn, y)), mx);
+            const double gy = sub(add(mul(sn, x), mul(c, y)), my);
+            if (!(gx < 0.0 || gx >= (double)sx || gy < 0.0 || gy >= (double)sy)) {
+                any_in = true;
+                bad |= map[(size_t)((int)gx) * sy + (int)gy] != 1;
+            }
+        }
+        if (__any_sync(0xffffffffu, bad)) break;          // warp-ballot early-out (od/fs:277-279)
+    }
+    any_in = __any_sync(0xffffffffu, any_in);
+    bad = __any_sync(0xffffffffu, bad);
+    return any_in && !bad;
+}
+
+__device__ __forceinline__ bool obstacle_point(const EngineDev& e, int b, const ScanState& s, const ClassCfg& cc, size_t base,
+                                               int p) {
+    if (!e.alive[base + p]) return false;
+    const unsigned lab = e.label[base + p];
+    if (e.task == 0) { if (lab == (unsigned)e.road_label) return false; }         // od/ins:353-355 + od/fs:121
+    else if (surface_label(cc, lab)) return false;                                // ss/fs:92-93
+    if (s.dirty && pix_removed(e, b, s, e.pix[base + p])) return false;            // od/ins:472,491
+    return true;
+}
+
+// A8 + A9 (od/fs:109-135, ss/fs:79-104) for candidate k with road level `level`, one warp:
+//  (i)  obstacle scene points strictly inside the candidate box: the ORIGINAL points come from the all-points grid
+//       (only the cells within the box reach of the candidate centre), the INSERTED points from the tails of the
+//       already placed objects whose box is close enough;
+//  (ii) object points strictly inside an existing / already inserted box.
+// The exact cut_bounding_box test (six strict inequalities in the reference's expression order) decides; grid cells
+// and bounding circles only prune.  Warp-ballot early-out on the first hit.
+__device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, int k,
+                              double level, int lane) {
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
+    const BoxTest bt = make_box_test(yaw_box_to_box(yb, level, ob.length, ob.width, ob.height));
+    const double ccx = yb.cx, ccy = yb.cy;
+    const double zmin_ped = add(level, 0.1);                                      // od/fs:123-124
+    const size_t base = (size_t)b * e.P;
+    bool hit = false;
+    {
+        const int G = e.G;
+        const float fcx = (float)ccx, fcy = (float)ccy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
+        const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
+        warp_visit_rect(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, grid_coord(e, fcx - fr),
+                        grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr), lane, [&](const float4 v) {
+            if (hit) return;
+            const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
+            if (dx * dx + dy * dy > fr2 || v.z < zlo || v.z > zhi) return;
+            const double x = v.x, y = v.y, z = v.z;
+            if (cc.pedestrian && !(z >= zmin_ped)) return;
+            if (!inside_box(bt, x, y, z)) return;                        // exact test (cb:30-66)
+            if (obstacle_point(e, b, s, cc, base, __float_as_int(v.w))) hit = true;
+        });
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    const int nbox0 = s.n_boxes - s.n_inserted;
+    int t0 = 0;
+    for (int j = 0; j < s.n_inserted; ++j) {                             // the tail of placed object j lies inside its box
+        const int cnt = e.inserted[((size_t)b * e.max_events + j) * 4 + 3];
+        const Box& bx = e.boxes[(size_t)b * e.max_boxes + nbox0 + j];
+        const double ddx = ccx - bx.cx, ddy = ccy - bx.cy, rr = ob.reach + bx.reach + 0.05;
+        if (ddx * ddx + ddy * ddy <= rr * rr) {
+            for (int i0 = 0; i0 < cnt && !hit; i0 += 32) {
+                const int i = i0 + lane;
+                bool h = false;
+                if (i < cnt) {
+                    const int p = s.n0 + t0 + i;
+                    const size_t t = (size_t)b * e.max_inserted + t0 + i;
+                    const double x = e.tail_x[t], y = e.tail_y[t], z = e.tail_z[t];
+                    h = (!cc.pedestrian || z >= zmin_ped) && inside_box(bt, x, y, z) && obstacle_point(e, b, s, cc, base, p);
+                }
+                hit = __any_sync(0xffffffffu, h);
+            }
+            if (hit) return true;
+        }
+        t0 += cnt;
+    }
+    const double dz = sub(level, ob.cz);
+    for (int bi = 0; bi < s.n_boxes; ++bi) {                             // (ii) od/fs:129-134
+        const Box& bx = e.boxes[(size_t)b * e.max_boxes + bi];
+        const double ddx = ccx - bx.cx, ddy = ccy - bx.cy, rr = ob.reach + bx.reach + 0.05;
+        if (ddx * ddx + ddy * ddy > rr * rr) continue;
+        const BoxTest sbt = e.box_tests[(size_t)b * e.max_boxes + bi];
+        for (int i0 = 0; i0 < ob.count && !hit; i0 += 32) {
+            const int i = i0 + lane;
+            bool h = false;
+            if (i < ob.count) {
+                const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+                h = inside_box(sbt, sub(mul(c, x0), mul(sn, y0)), add(mul(sn, x0), mul(c, y0)), add(e.obj_z[ob.first + i], dz));
+            }
+            hit = __any_sync(0xffffffffu, h);
+        }
+        if (hit) return true;
+    }
+    return false;
+}
+
+// ordered compaction of the rotations 1..K whose flag byte satisfies (f & mask) == want (all threads of the CTA)
+__device__ int block_compact(const unsigned char* flags, int K, unsigned mask, unsigned want, unsigned short* list, int* s_warp) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int base = 0;
+    for (int k0 = 1; k0 <= K; k0 += blockDim.x) {
+        const int k = k0 + threadIdx.x;
+        const bool ok = k <= K && (flags[k] & mask) == want;
+        const unsigned m = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) s_warp[w] = __popc(m);
+        __syncthreads();
+        int off = base, tot = 0;
+        for (int i = 0; i < nw; ++i) { if (i < w) off += s_warp[i]; tot += s_warp[i]; }
+        if (ok) list[off + __popc(m & ((1u << lane) - 1u))] = (unsigned short)k;
+        base += tot;
+        __syncthreads();
+    }
+    return base;
+}
+
+// find_possible_places (od/fs:227-304, ss/fs:192-273) for the cut object each scan is trying, as three staged
+// kernels with MANY warps in flight (every stage is a chain of dependent L2 loads per candidate, so throughput comes
+// from concurrency): on-map test -> road level -> collision.  The last CTA of each stage to finish ("ticket") compacts
+// the surviving rotations, in order, into the list the next stage strides over, so no stage launches empty warps.
+constexpr unsigned CF_COLLIDE = 4u;
+constexpr int PLACE_THREADS = 256;
+constexpr int PLACE_G = 32;          // CTAs per scan of the road-level and collision stages
+
+__device__ void compact_stage(const EngineDev& e, int b, unsigned mask, unsigned want, bool final_stage) {
+    __shared__ int s_warp[PLACE_THREADS / 32];
+    const size_t cb = (size_t)b * (e.K + 1);
+    unsigned short* list = e.cand_list + cb;
+    const int n = block_compact(e.cand_flags + cb, e.K, mask, want, list, s_warp);
+    if (final_stage) {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) e.feas[(size_t)b * e.K + i] = list[i];
+        if (threadIdx.x == 0) { e.st[b].n_feasible = n; e.st[b].found_rank = INT_MAX; }
+    }
+    if (threadIdx.x == 0) e.n_list[b] = n;
+}
+
+// stage 1 (OD): A5 + A6a for all K yaws, one warp each
+__global__ void __launch_bounds__(PLACE_THREADS) k_onmap_od(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
+    const int lane = threadIdx.x & 31;
+    const size_t cb = (size_t)b * (e.K + 1);
+    if (k <= e.K) {
+        const ObjBox ob = e.obj[e.st[b].cur_obj];
+        const bool on = warp_onmap_od(e, b, ob, k, lane);
+        if (lane == 0) { e.cand_flags[cb + k] = on ? CF_ONMAP : 0; e.cand_level[cb + k] = 0.0; e.cand_v[cb + k] = 0; }
+    }
+    if (last_block_done(&e.tickets[(size_t)b * 4 + 1], gridDim.x)) compact_stage(e, b, CF_ONMAP, CF_ONMAP, false);
+}
+
+// stage 2: A7 for the listed yaws (OD: the on-map ones, od/fs:281; semseg: all, the map test comes after)
+__global__ void __launch_bounds__(PLACE_THREADS) k_height(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const ScanState& s = e.st[b];
+    const ObjBox ob = e.obj[s.cur_obj];
+    const ClassCfg& cc = e.classes[ob.cls];
+    const int lane = threadIdx.x & 31;
+    const size_t cb = (size_t)b * (e.K + 1);
+    const int n = e.task == 0 ? e.n_list[b] : e.K;
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += PLACE_G * 8) {
+        const int k = e.task == 0 ? (int)e.cand_list[cb + i] : i + 1;
+        const double c = e.cos_k[k], sn = e.sin_k[k];
+        double level = 0.0;
+        const bool ok = warp_road_level(e, b, cc, sub(mul(c, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(c, ob.cy)), lane, level);
+        if (lane == 0) {
+            if (e.task == 1) { e.cand_flags[cb + k] = ok ? CF_HOK : 0; e.cand_v[cb + k] = 0; }
+            else if (ok) e.cand_flags[cb + k] = CF_ONMAP | CF_HOK;
+            e.cand_level[cb + k] = ok ? level : 0.0;
+        }
+    }
+    if (e.task == 0 && last_block_done(&e.tickets[(size_t)b * 4 + 2], PLACE_G))
+        compact_stage(e, b, CF_ONMAP | CF_HOK, CF_ONMAP | CF_HOK, false);
+}
+
+// stage 2b (semseg): A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place): the yaws
+// are visited in order by one CTA; world = T . [x y z 1] - move, astype(int); every in-map cell value must be allowed.
+__global__ void __launch_bounds__(1024) k_onmap_ss(EngineDev e, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans || !e.gate_try[b]) return;
     const ScanState& s = e.st[b];
@@ -673,123 +819,38 @@ __global__ void __launch_bounds__(256) k_onmap_ss(EngineDev e, int n_scans) {
             }
         }
         bad = __syncthreads_or(bad);
-        unsigned f = e.cand_flags[cb + k];
         if (!bad) {
+            const unsigned f = e.cand_flags[cb + k];
+            if (f & CF_HOK) dz = sub(e.cand_level[cb + k], ob.cz);              // ss/fs:144-148
+            __syncthreads();
             if (threadIdx.x == 0) e.cand_flags[cb + k] = (unsigned char)(f | CF_ONMAP);
-            if (f & CF_HOK) dz = sub(e.cand_level[cb + k], ob.cz);          // ss/fs:144-148
         }
     }
+    __threadfence_block();
+    __syncthreads();
+    __shared__ int s_warp[32];
+    const int n = block_compact(e.cand_flags + cb, e.K, CF_ONMAP | CF_HOK, CF_ONMAP | CF_HOK, e.cand_list + cb, s_warp);
+    if (threadIdx.x == 0) e.n_list[b] = n;
 }
 
-// A8 + A9 part (i) (od/fs:119-127, ss/fs:89-96): obstacle scene points strictly inside a candidate box.  Every
-// candidate box centre lies on the circle of radius rho about the sensor, so only the points of the radial bins
-// covering [rho - reach, rho + reach] (CSR built once per scan) plus the inserted tail are visited; each point then
-// only meets the candidates whose centre is within the box reach (azimuth window) with the exact cut_bounding_box test.
-constexpr int COLL_G = 8;
-__device__ __forceinline__ void collide_one(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
-                                            int p, float rlo, float rhi, float reach, float step, size_t cb, size_t base) {
-    if (!e.alive[base + p]) return;
-    double x, y, z;
-    load_xyz(e, b, p, s.n0, x, y, z);
-    const float fx = (float)x, fy = (float)y;
-    const float rho2 = fx * fx + fy * fy;
-    if (rho2 < rlo * rlo || rho2 > rhi * rhi) return;
-    const unsigned lab = e.label[base + p];
-    if (e.task == 0) { if (lab == (unsigned)e.road_label) return; }         // od/ins:353-355 + od/fs:121
-    else if (surface_label(cc, lab)) return;                                // ss/fs:92-93
-    if (s.dirty && pix_removed(e, b, s, e.pix[base + p])) return;            // od/ins:472,491
-    int k_first, count;
-    cand_window(ob, fx, fy, reach, step, e.K, k_first, count);
-    for (int j = 0; j < count; ++j) {
-        const int k = cand_index(k_first, j, e.K);
-        if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK)) continue;
-        if (e.cand_collide[cb + k]) continue;
-        if (cc.pedestrian && !(z >= add(e.cand_level[cb + k], 0.1))) continue;     // od/fs:123-124
-        if (inside_box(e.cand_bt[cb + k], x, y, z)) e.cand_collide[cb + k] = 1;
-    }
-}
-
-__global__ void __launch_bounds__(STREAM_THREADS) k_collide_points(EngineDev e, int n_scans) {
+// stage 3: A8 + A9 for the yaws that are on the map and have a road level; the last CTA builds the ordered list of
+// feasible rotations (the order find_possible_places returns them, od/fs:288-296)
+__global__ void __launch_bounds__(PLACE_THREADS) k_collide(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_try[b]) return;
     const ScanState& s = e.st[b];
     const ObjBox ob = e.obj[s.cur_obj];
     const ClassCfg& cc = e.classes[ob.cls];
-    const float reach = (float)ob.reach;
-    const float rlo = fmaxf((float)ob.rho - reach - 0.02f, 0.f), rhi = (float)ob.rho + reach + 0.02f;
-    const float step = (float)e.step_rad;
-    const size_t cb = (size_t)b * (e.K + 1);
-    const size_t base = (size_t)b * e.P;
-    const int* off = e.rad_off + (size_t)b * (e.RB + 1);
-    const int* idx = e.rad_idx + (size_t)b * e.max_points;
-    const int b0 = max(0, (int)(rlo * e.rad_inv_cell) - 1), b1 = min(e.RB - 1, (int)(rhi * e.rad_inv_cell) + 1);
-    const int beg = b0 > 0 ? off[b0 - 1] : 0, end = off[b1];
-    for (int i = beg + blockIdx.x * STREAM_THREADS + threadIdx.x; i < end; i += COLL_G * STREAM_THREADS)
-        collide_one(e, b, s, ob, cc, idx[i], rlo, rhi, reach, step, cb, base);
-    for (int t = blockIdx.x * STREAM_THREADS + threadIdx.x; t < s.n_tail; t += COLL_G * STREAM_THREADS)
-        collide_one(e, b, s, ob, cc, s.n0 + t, rlo, rhi, reach, step, cb, base);
-}
-
-// A9 part (ii) (od/fs:129-134): any object point strictly inside an existing / already inserted box.
-__global__ void __launch_bounds__(256) k_collide_boxes(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5) + 1;
-    if (k > e.K) return;
     const int lane = threadIdx.x & 31;
-    const ScanState& s = e.st[b];
-    if (s.n_boxes == 0) return;
     const size_t cb = (size_t)b * (e.K + 1);
-    if ((e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) != (CF_ONMAP | CF_HOK) || e.cand_collide[cb + k]) return;
-    const ObjBox ob = e.obj[s.cur_obj];
-    const double c = e.cos_k[k], sn = e.sin_k[k];
-    const double dz = sub(e.cand_level[cb + k], ob.cz);
-    const double ccx = e.cand_cx[cb + k], ccy = e.cand_cy[cb + k];
-    for (int bi = 0; bi < s.n_boxes; ++bi) {
-        const Box& bx = e.boxes[(size_t)b * e.max_boxes + bi];
-        const double ddx = ccx - bx.cx, ddy = ccy - bx.cy, rr = ob.reach + bx.reach + 0.05;
-        if (ddx * ddx + ddy * ddy > rr * rr) continue;
-        const BoxTest bt = e.box_tests[(size_t)b * e.max_boxes + bi];
-        bool hit = false;
-        for (int i0 = 0; i0 < ob.count && !hit; i0 += 32) {
-            const int i = i0 + lane;
-            bool h = false;
-            if (i < ob.count) {
-                const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
-                h = inside_box(bt, sub(mul(c, x0), mul(sn, y0)), add(mul(sn, x0), mul(c, y0)),
-                               add(e.obj_z[ob.first + i], dz));
-            }
-            hit = __any_sync(0xffffffffu, h);
-        }
-        if (hit) { if (lane == 0) e.cand_collide[cb + k] = 1; return; }
+    const int n = e.n_list[b];
+    for (int i = blockIdx.x * 8 + (threadIdx.x >> 5); i < n; i += PLACE_G * 8) {
+        const int k = e.cand_list[cb + i];
+        if (warp_collides(e, b, s, ob, cc, k, e.cand_level[cb + k], lane) && lane == 0)
+            e.cand_flags[cb + k] = CF_ONMAP | CF_HOK | CF_COLLIDE;
     }
-}
-
-// ordered list of the feasible rotations (the order find_possible_places returns them, od/fs:288-296)
-__global__ void __launch_bounds__(256) k_feasible(EngineDev e, int n_scans) {
-    const int b = blockIdx.x;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    ScanState& s = e.st[b];
-    const size_t cb = (size_t)b * (e.K + 1);
-    __shared__ int s_warp[8];
-    __shared__ int s_base;
-    if (threadIdx.x == 0) s_base = 0;
-    __syncthreads();
-    for (int k0 = 1; k0 <= e.K; k0 += 256) {
-        const int k = k0 + threadIdx.x;
-        const bool ok = k <= e.K && (e.cand_flags[cb + k] & (CF_ONMAP | CF_HOK)) == (CF_ONMAP | CF_HOK) && !e.cand_collide[cb + k];
-        const unsigned m = __ballot_sync(0xffffffffu, ok);
-        const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-        if (lane == 0) s_warp[w] = __popc(m);
-        __syncthreads();
-        int off = s_base;
-        for (int i = 0; i < w; ++i) off += s_warp[i];
-        if (ok) e.feas[(size_t)b * e.K + off + __popc(m & ((1u << lane) - 1u))] = k;
-        __syncthreads();
-        if (threadIdx.x == 0) { for (int i = 0; i < 8; ++i) s_base += s_warp[i]; }
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) { s.n_feasible = s_base; s.found_rank = INT_MAX; }
+    if (last_block_done(&e.tickets[(size_t)b * 4 + 3], PLACE_G))
+        compact_stage(e, b, CF_ONMAP | CF_HOK | CF_COLLIDE, CF_ONMAP | CF_HOK, true);
 }
 
 // ------------------------------------------------------------------------------------------- occlusion
@@ -915,17 +976,63 @@ __device__ void bitonic_sort_u64(unsigned long long* keys, int n_pow2) {
 // candidate's z-buffer in a scratch image, closes / fills it around the object, compares with the scene image
 // (strict <) into the vis_px bit mask, and on acceptance appends the visible object points in (pix_id, index) order
 // to the scene tail, the `check` record and the scene boxes.
-__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
+constexpr int SEL_TILE_PX = 8192;      // pixels of the shared-memory object tile (64 KB of fp64 ranges)
+
+// local variant of obj_pixel_value on the shared-memory tile (rows r_lo.., cols c_lo.., nr x nc).  Pixels outside the
+// tile but inside the image hold no object point and are farther than the 5x3 window from every object pixel, so
+// their occupancy and dilation are 0; pixels outside the image are ignored by the erosion.
+__device__ __forceinline__ bool tile_pixel_value(const unsigned long long* tile, const unsigned* dil, int H, int W, int r_lo,
+                                                 int c_lo, int nr, int nc, int r, int c, double& val) {
+    const unsigned long long own = tile[(r - r_lo) * nc + (c - c_lo)];
+    if (own != R3D_EMPTY_U64) { val = bits_dbl(own); return true; }
+    for (int dr = -2; dr <= 2; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+            const int r1 = r + dr, c1 = c + dc;
+            if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+            const int lr = r1 - r_lo, lc = c1 - c_lo;
+            if (lr < 0 || lr >= nr || lc < 0 || lc >= nc) return false;
+            const int q = lr * nc + lc;
+            if (!(dil[q >> 5] & (1u << (q & 31)))) return false;
+        }
+    int neighbors = 0;
+    double sum = 0.0;
+    for (int dr = -2; dr <= 2; ++dr)
+        for (int dc = -1; dc <= 1; ++dc) {
+            const int lr = r + dr - r_lo, lc = c + dc - c_lo;
+            if (lr < 0 || lr >= nr || lc < 0 || lc >= nc) continue;
+            const unsigned long long v = tile[lr * nc + lc];
+            if (v != R3D_EMPTY_U64) { neighbors += 1; sum = add(sum, bits_dbl(v)); }
+        }
+    if (neighbors == 0) return false;
+    val = __ddiv_rn(sum, (double)neighbors);
+    return true;
+}
+
+// A11 + A12 for the chosen candidate of each scan: the first feasible rotation that keeps >= min_points (accepted),
+// else the last feasible one (its vis_px still deletes scene points in the reference, od/ins:472-501).  Builds the
+// candidate's z-buffer (in a shared-memory tile around the object when it fits, else in a global scratch image),
+// closes / fills it, compares with the scene image (strict <) into the vis_px bit mask, and on acceptance appends the
+// visible object points in (pix_id, index) order to the scene tail, the `check` record and the scene boxes.
+__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, int key_cap) {
     const int b = blockIdx.x;
     if (b >= n_scans || !e.gate_try[b]) return;
     ScanState& s = e.st[b];
     const int nf = s.n_feasible;
     if (nf == 0) return;
-    extern __shared__ unsigned long long s_keys[];
+    extern __shared__ unsigned long long s_dyn[];
+    unsigned long long* s_keys = s_dyn;                                   // [key_cap]
+    double* s_r = reinterpret_cast<double*>(s_dyn + key_cap);            // [max_obj_points]
+    unsigned long long* s_tile = s_dyn + key_cap + e.max_obj_points;     // [SEL_TILE_PX]
+    int* s_pix = reinterpret_cast<int*>(s_tile + SEL_TILE_PX);           // [max_obj_points]
+    unsigned* s_dil = reinterpret_cast<unsigned*>(s_pix + e.max_obj_points);   // [SEL_TILE_PX / 32]
+    unsigned* s_vis = s_dil + SEL_TILE_PX / 32;                          // [SEL_TILE_PX / 32]
     __shared__ int s_nvis;
     __shared__ int s_rect[4];
     __shared__ unsigned long long s_el[2];
-    if (threadIdx.x == 0) { s_rect[0] = INT_MAX; s_rect[1] = -1; s_rect[2] = INT_MAX; s_rect[3] = -1; s_el[0] = R3D_EMPTY_U64; s_el[1] = 0ull; }
+    if (threadIdx.x == 0) {
+        s_rect[0] = INT_MAX; s_rect[1] = -1; s_rect[2] = INT_MAX; s_rect[3] = -1; s_el[0] = R3D_EMPTY_U64; s_el[1] = 0ull;
+        s_nvis = 0;
+    }
     const bool accepted = s.found_rank < nf;
     const int rank = accepted ? s.found_rank : nf - 1;
     const int k = e.feas[(size_t)b * e.K + rank];
@@ -936,37 +1043,19 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
     const double c = e.cos_k[k], sn = e.sin_k[k];
     const double level = e.cand_level[cb + k];
     const double dz = sub(level, ob.cz);
-    unsigned long long* raw = e.obj_raw + (size_t)b * e.hw;
     unsigned* dm = e.dmask + (size_t)b * e.dwords;
-    unsigned* vm = e.vmask + (size_t)b * e.dwords;
     const double* smooth = e.smooth + (size_t)b * e.hw;
-    int* pixbuf = e.sel_pix + (size_t)b * e.max_obj_points;
     const int t0 = s.n_tail, chk0 = s.n_check, nbox0 = s.n_boxes, nins0 = s.n_inserted, n0 = s.n0;
-    if (threadIdx.x == 0) s_nvis = 0;
-    for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) { dm[i] = 0u; vm[i] = 0u; }
+    for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) dm[i] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
-        const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
-        pixbuf[i] = o.pix;
-        if (o.pix < 0) continue;
-        atomicMin(&raw[o.pix], dbl_bits(o.r));
-        const int pr = o.pix / W, pc = o.pix % W;                        // dilated occupancy (5 rows x 3 cols)
-        for (int dr = -2; dr <= 2; ++dr)
-            for (int dc = -1; dc <= 1; ++dc) {
-                const int r1 = pr + dr, c1 = pc + dc;
-                if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
-                const int q = r1 * W + c1;
-                atomicOr(&vm[q >> 5], 1u << (q & 31));
-            }
-    }
-    __threadfence_block();
-    __syncthreads();
-    {   // pixel rectangle that contains vis_px: the object's pixels grown by the 5x3 window
+    // project every object point once (od/ins:474-478); pixel rectangle of the object
+    {
         int r_lo = INT_MAX, r_hi = -1, c_lo = INT_MAX, c_hi = -1;
         for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
-            const int pix = pixbuf[i];
-            if (pix < 0) continue;
-            const int pr = pix / W, pc = pix % W;
+            const ObjProj o = project_obj_point(e, ob, g, i, c, sn, dz, s);
+            s_pix[i] = o.pix; s_r[i] = o.r;
+            if (o.pix < 0) continue;
+            const int pr = o.pix / W, pc = o.pix % W;
             r_lo = min(r_lo, pr); r_hi = max(r_hi, pr); c_lo = min(c_lo, pc); c_hi = max(c_hi, pc);
         }
         for (int o = 16; o > 0; o >>= 1) {
@@ -977,28 +1066,103 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
             atomicMin(&s_rect[0], r_lo); atomicMax(&s_rect[1], r_hi); atomicMin(&s_rect[2], c_lo); atomicMax(&s_rect[3], c_hi);
         }
     }
-    // every pixel within the 5x3 neighbourhood of an object pixel may be switched on by the closing
-    for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
-        const int i = t / 15, o = t % 15;
-        const int pix = pixbuf[i];
-        if (pix < 0) continue;
-        const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
-        if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
-        const int q = r * W + cc;
-        double val;
-        if (obj_pixel_value(raw, vm, H, W, r, cc, val) && val < smooth[q]) atomicOr(&dm[q >> 5], 1u << (q & 31));   // od/ins:486
-    }
-    __threadfence_block();
     __syncthreads();
-    // visible object points, ordered by (pix_id, original index) as the reference's per-pixel loop emits them
-    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
-        const int pix = pixbuf[i];
-        if (pix >= 0 && (dm[pix >> 5] & (1u << (pix & 31)))) {
-            const int slot = atomicAdd(&s_nvis, 1);
-            s_keys[slot] = ((unsigned long long)(unsigned)pix << 32) | (unsigned)i;
+    const bool any_px = s_rect[1] >= 0;
+    // vis_px can only lie within the object's pixels grown by the 5x3 window
+    const int wr0 = any_px ? max(s_rect[0] - 2, 0) : 0, wr1 = any_px ? min(s_rect[1] + 2, H - 1) : -1;
+    const int wc0 = any_px ? max(s_rect[2] - 1, 0) : 0, wc1 = any_px ? min(s_rect[3] + 1, W - 1) : -1;
+    const int nr = wr1 - wr0 + 1, nc = wc1 - wc0 + 1;
+    const bool in_smem = any_px && nr * nc <= SEL_TILE_PX;
+    if (threadIdx.x == 0 && any_px) atomicAdd(&e.stats[in_smem ? 4 : 5], 1ull);
+    if (in_smem) {
+        const int npx = nr * nc;
+        for (int i = threadIdx.x; i < npx; i += blockDim.x) s_tile[i] = R3D_EMPTY_U64;
+        for (int i = threadIdx.x; i < (npx + 31) / 32; i += blockDim.x) { s_dil[i] = 0u; s_vis[i] = 0u; }
+        __syncthreads();
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = s_pix[i];
+            if (pix < 0) continue;
+            const int pr = pix / W, pc = pix % W;
+            atomicMin(&s_tile[(pr - wr0) * nc + (pc - wc0)], dbl_bits(s_r[i]));
+            for (int dr = -2; dr <= 2; ++dr)                             // dilated occupancy (5 rows x 3 cols)
+                for (int dc = -1; dc <= 1; ++dc) {
+                    const int r1 = pr + dr, c1 = pc + dc;
+                    if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+                    const int q = (r1 - wr0) * nc + (c1 - wc0);
+                    atomicOr(&s_dil[q >> 5], 1u << (q & 31));
+                }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
+            const int i = t / 15, o = t % 15;
+            const int pix = s_pix[i];
+            if (pix < 0) continue;
+            const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
+            if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
+            const int lq = (r - wr0) * nc + (cc - wc0);
+            if (s_vis[lq >> 5] & (1u << (lq & 31))) continue;
+            double val;
+            if (tile_pixel_value(s_tile, s_dil, H, W, wr0, wc0, nr, nc, r, cc, val) && val < smooth[r * W + cc]) {   // od/ins:486
+                if (!(atomicOr(&s_vis[lq >> 5], 1u << (lq & 31)) & (1u << (lq & 31)))) {
+                    const int q = r * W + cc;
+                    atomicOr(&dm[q >> 5], 1u << (q & 31));
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = s_pix[i];
+            if (pix < 0) continue;
+            const int lq = (pix / W - wr0) * nc + (pix % W - wc0);
+            if (s_vis[lq >> 5] & (1u << (lq & 31))) {
+                const int slot = atomicAdd(&s_nvis, 1);
+                s_keys[slot] = ((unsigned long long)(unsigned)pix << 32) | (unsigned)i;
+            }
+        }
+    } else if (any_px) {
+        // object too wide for the tile (very close / very large): global scratch image + global dilation mask
+        unsigned long long* raw = e.obj_raw + (size_t)b * e.hw;
+        unsigned* vm = e.vmask + (size_t)b * e.dwords;
+        for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) vm[i] = 0u;
+        __syncthreads();
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = s_pix[i];
+            if (pix < 0) continue;
+            atomicMin(&raw[pix], dbl_bits(s_r[i]));
+            const int pr = pix / W, pc = pix % W;
+            for (int dr = -2; dr <= 2; ++dr)
+                for (int dc = -1; dc <= 1; ++dc) {
+                    const int r1 = pr + dr, c1 = pc + dc;
+                    if (r1 < 0 || r1 >= H || c1 < 0 || c1 >= W) continue;
+                    const int q = r1 * W + c1;
+                    atomicOr(&vm[q >> 5], 1u << (q & 31));
+                }
+        }
+        __threadfence_block();
+        __syncthreads();
+        for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
+            const int i = t / 15, o = t % 15;
+            const int pix = s_pix[i];
+            if (pix < 0) continue;
+            const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
+            if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
+            const int q = r * W + cc;
+            double val;
+            if (obj_pixel_value(raw, vm, H, W, r, cc, val) && val < smooth[q]) atomicOr(&dm[q >> 5], 1u << (q & 31));   // od/ins:486
+        }
+        __threadfence_block();
+        __syncthreads();
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
+            const int pix = s_pix[i];
+            if (pix >= 0 && (dm[pix >> 5] & (1u << (pix & 31)))) {
+                const int slot = atomicAdd(&s_nvis, 1);
+                s_keys[slot] = ((unsigned long long)(unsigned)pix << 32) | (unsigned)i;
+            }
+            if (pix >= 0) raw[pix] = R3D_EMPTY_U64;                      // leave the scratch z-buffer empty
         }
     }
     __syncthreads();
+    // visible object points, ordered by (pix_id, original index) as the reference's per-pixel loop emits them
     const int nvis = s_nvis;
     if (accepted) {
         int np2 = 1;
@@ -1049,16 +1213,8 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans) {
     }
     if (threadIdx.x == 0) {
         s.accepted = accepted ? 1 : 0; s.chosen_rot = k; s.chosen_v = nvis;
-        if (s_rect[1] >= 0) {
-            s.d_r0 = max(s_rect[0] - 2, 0); s.d_r1 = min(s_rect[1] + 2, H - 1);
-            s.d_c0 = max(s_rect[2] - 1, 0); s.d_c1 = min(s_rect[3] + 1, W - 1);
-        } else { s.d_r0 = 0; s.d_r1 = -1; s.d_c0 = 0; s.d_c1 = -1; }
+        s.d_r0 = wr0; s.d_r1 = wr1; s.d_c0 = wc0; s.d_c1 = wc1;
         if (!accepted) { s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull; }
-    }
-    // leave the scratch z-buffer empty for the next use
-    for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
-        const int pix = pixbuf[i];
-        if (pix >= 0) raw[pix] = R3D_EMPTY_U64;
     }
 }
 

@@ -346,10 +346,10 @@ class Real3DEngine:
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
     def stats(self):
-        out = np.zeros(4, dtype=np.uint64)
+        out = np.zeros(8, dtype=np.uint64)
         _lib.check(self.lib.r3d_engine_stats(self.handle, out.ctypes.data), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
-                'patched_scans': int(out[3])}
+                'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5])}
 
     def cuda_stream(self):
         import torch
