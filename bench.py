@@ -10,7 +10,8 @@ the data path).  One step = one pass of the whole hot path (placement search + o
 compaction) over the rank's batch.
 
   value  : scans/s with the batch already resident in HBM (device re-arm + run, CUDA events on the engine stream)
-  e2e    : scans/s through the public API with HOST (pinned) buffers: H2D of every scan + run + D2H of the results
+  e2e    : scans/s through the public API (ScanPipeline) with HOST (pinned) buffers: H2D of every scan + run + D2H of
+           the results, consecutive batches overlapped on 3 engines / streams
   roofline: the kernel with the largest share of device time; achieved = algorithmic bytes / measured time
   cpu_baseline: the numpy oracle port of the reference timed on one host core on a bounded sample (rank 0, N = 1)
 """
@@ -200,6 +201,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
@@ -228,12 +230,16 @@ def main():
     def sum_over_ranks(x):
         return sharding.all_reduce_scalar(x, "sum", "cuda")
 
-    from pcl_augmentation_b200.engine import Real3DEngine, scan_input_from_case
+    from pcl_augmentation_b200.engine import scan_input_from_case
+    from pcl_augmentation_b200.pipeline import ScanPipeline
     n_scans = args.scans
     cases = build_cases(rank, n_scans, min(DISTINCT_SCANS, n_scans))
     n_points = len(cases[0].pcl5)
-    eng = Real3DEngine("od", cases[0].config, cases[0].db, max_scans=n_scans, max_points=n_points, rows=ROWS, cols=COLS,
-                       yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1)
+    # PIPE_DEPTH engines (own stream, own device-resident batch, own host thread): the e2e leg streams batches through
+    # all of them so H2D, compute and D2H of consecutive batches overlap; the device-resident leg uses the first one
+    pipe = ScanPipeline("od", cases[0].config, cases[0].db, depth=args.depth, max_scans=n_scans, max_points=n_points,
+                        rows=ROWS, cols=COLS, yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1)
+    eng = pipe.engines[0]
     staged = eng.stage([scan_input_from_case(c) for c in cases])
     stream = eng.cuda_stream()
 
@@ -266,23 +272,19 @@ def main():
     value = world * n_scans * args.steps / (dev_ms / 1000.0)
 
     # ---- end to end through the public API with host buffers ("e2e") -----------------------------------
-    buffers = None
-    for _ in range(2):
-        eng.load(staged); eng.run(); buffers = eng.fetch_raw(buffers)
+    # every step = one staged batch in pinned host memory: H2D of all points / labels / maps / schedules, the
+    # spherical ingest, the augmentation rounds, D2H of the augmented clouds into pinned host buffers
+    pipe.warmup(staged)
+    pipe.warmup(staged)
     barrier()
     t0 = time.perf_counter()
-    d2h = 0
-    for _ in range(args.steps):
-        eng.load(staged)
-        eng.run()
-        buffers = eng.fetch_raw(buffers)
-        d2h += buffers["out_bytes"]
-    eng.sync()
+    out_bytes = pipe.process([staged] * args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    d2h = sum(out_bytes)
     e2e_value = world * n_scans * args.steps / e2e_s
     h2d = staged["total"] * 20 + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
-    results = eng.unpack(buffers)
+    results = eng.unpack(pipe._buffers[0])
     inserted_total = sum(len(r.inserted) for r in results)
 
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
@@ -328,12 +330,13 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h / args.steps)},
+                    "d2h_bytes_per_step": int(d2h / args.steps), "pipeline_depth": args.depth,
+                    "ms_per_step": 1000.0 * e2e_s / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
             "step_roofline": step_roofline, "kernels": kernel_table,
             "rounds_per_step": results[0].extra["rounds"], "objects_inserted_per_scan": inserted_all / (world * n_scans),
             "engine_stats": stats}))
-    eng.close()
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 

@@ -67,7 +67,9 @@ struct r3d_engine {
     // host copies needed for re-arming
     std::vector<Box> h_boxes;
     std::vector<int> h_nbox0;
-    int* h_active = nullptr;            // pinned
+    unsigned long long* h_words = nullptr;   // mapped pinned: one word per round slot, written by k_ctrl
+    unsigned long long* d_words = nullptr;   // device alias of h_words
+    unsigned seq = 0;
     long long* h_offsets = nullptr;     // pinned, 2 * (max_scans + 1)
     // profiling
     bool profile = false;
@@ -168,7 +170,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->alive.alloc(B * P)); TRY(eng->zraw.alloc(B * HW)); TRY(eng->obj_raw.alloc(B * HW)); TRY(eng->smooth.alloc(B * HW));
     TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
     TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
-    TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(64));
+    TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(64 * 2));
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -185,7 +187,9 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->acell.alloc(B * (size_t)d.G * d.G)); TRY(eng->apts.alloc(B * d.max_points));
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
-    R3D_CUDA(cudaMallocHost((void**)&eng->h_active, 64 * sizeof(int)));
+    R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(eng->h_words, 0, 64 * sizeof(unsigned long long));
+    R3D_CUDA(cudaHostGetDevicePointer((void**)&eng->d_words, eng->h_words, 0));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, 2 * (B + 1) * sizeof(long long)));
     std::vector<ClassCfg> cls(R3D_MAX_CLASSES);
     for (int c = 0; c < R3D_MAX_CLASSES; ++c) {
@@ -225,7 +229,7 @@ extern "C" int r3d_engine_destroy(r3d_engine* eng) {
     cudaStreamSynchronize(eng->stream);
     drain_events(eng);
     for (cudaEvent_t ev : eng->event_pool) cudaEventDestroy(ev);
-    if (eng->h_active) cudaFreeHost(eng->h_active);
+    if (eng->h_words) cudaFreeHost(eng->h_words);
     if (eng->h_offsets) cudaFreeHost(eng->h_offsets);
     cudaStreamDestroy(eng->stream);
     delete eng;
@@ -357,12 +361,6 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
         if (nb[s] > d.max_boxes) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: too many scene boxes");
     }
     eng->n_scans = n;
-    // points: packed host rows -> per-scan strided device rows
-    for (int s = 0; s < n; ++s) {
-        const int64_t o = bt->point_offsets[s];
-        R3D_CUDA(cudaMemcpyAsync(eng->xyzi.p + (size_t)s * d.max_points, bt->xyzi + o * 4, (size_t)n0[s] * sizeof(float4), cudaMemcpyHostToDevice, st));
-        R3D_CUDA(cudaMemcpyAsync(eng->label.p + (size_t)s * d.P, bt->labels + o, (size_t)n0[s] * sizeof(unsigned), cudaMemcpyHostToDevice, st));
-    }
     // scene boxes
     eng->h_boxes.assign((size_t)n * d.max_boxes, Box());
     for (int s = 0; s < n; ++s)
@@ -394,6 +392,21 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     if (nperm > eng->perms.n) TRY(eng->perms.alloc(nperm));
     R3D_CUDA(cudaMemcpyAsync(eng->perms.p, bt->perms, nperm * sizeof(int), cudaMemcpyHostToDevice, st));
     d.perms = eng->perms.p; d.n_perm_events = bt->n_events;
+    // points: packed host rows -> per-scan strided device rows (one pitched copy when every scan has the same size)
+    bool uniform = true;
+    for (int s = 1; s < n; ++s) uniform &= n0[s] == n0[0];
+    if (uniform) {
+        R3D_CUDA(cudaMemcpy2DAsync(eng->xyzi.p, (size_t)d.max_points * sizeof(float4), bt->xyzi + bt->point_offsets[0] * 4,
+                                   (size_t)n0[0] * sizeof(float4), (size_t)n0[0] * sizeof(float4), n, cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpy2DAsync(eng->label.p, (size_t)d.P * sizeof(unsigned), bt->labels + bt->point_offsets[0],
+                                   (size_t)n0[0] * sizeof(unsigned), (size_t)n0[0] * sizeof(unsigned), n, cudaMemcpyHostToDevice, st));
+    } else {
+        for (int s = 0; s < n; ++s) {
+            const int64_t o = bt->point_offsets[s];
+            R3D_CUDA(cudaMemcpyAsync(eng->xyzi.p + (size_t)s * d.max_points, bt->xyzi + o * 4, (size_t)n0[s] * sizeof(float4), cudaMemcpyHostToDevice, st));
+            R3D_CUDA(cudaMemcpyAsync(eng->label.p + (size_t)s * d.P, bt->labels + o, (size_t)n0[s] * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+        }
+    }
     // the std::vectors above are pageable: the copies from them completed before cudaMemcpyAsync returned
     eng->batch_loaded = true;
     return arm_batch(eng, true);
@@ -414,20 +427,33 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     const int kwarps = (d.K + 7) / 8;
     const size_t sel_smem = select_smem_bytes(d.max_obj_points);
     const int key_cap = next_pow2(d.max_obj_points);
-    R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * sizeof(int), st));
-    cudaEvent_t ev_ctrl[2];
-    cudaEventCreateWithFlags(&ev_ctrl[0], cudaEventDisableTiming);
-    cudaEventCreateWithFlags(&ev_ctrl[1], cudaEventDisableTiming);
+    R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * 2 * sizeof(int), st));
     const int max_rounds = d.max_events * (3 * d.max_tries + 2) + 8;
+    // wait until the k_ctrl of `round` has published its word; returns the number of unfinished scans (< 0: error)
+    auto wait_round = [&](int round, unsigned seq) -> long long {
+        volatile unsigned long long* w = eng->h_words + (round & 63);
+        for (unsigned spins = 0;; ++spins) {
+            const unsigned long long v = *w;
+            if ((unsigned)(v >> 32) == seq) return (long long)(v & 0xffffffffull);
+            if ((spins & 0xfff) == 0xfff) {
+                const cudaError_t q = cudaStreamQuery(st);
+                if (q != cudaSuccess && q != cudaErrorNotReady) return -1;
+                if (q == cudaSuccess && (unsigned)(*w >> 32) != seq) return -1;      // stream drained without the word
+            }
+        }
+    };
     int round = 0;
     bool done = false;
+    unsigned seq_prev = 0;
     for (; round < max_rounds && !done; ++round) {
         const int slot = round & 63;
-        d.active_count = eng->active_count.p + slot;
+        d.active_count = eng->active_count.p + 2 * slot;
+        d.host_word = eng->d_words + slot;
+        if (++eng->seq == 0) ++eng->seq;
+        d.ctrl_seq = eng->seq;
+        const unsigned seq_now = eng->seq;
         { Launcher l(eng, KID_CTRL); k_ctrl<<<n, 128, 0, st>>>(d, n); }
-        R3D_CUDA(cudaMemcpyAsync(eng->h_active + slot, eng->active_count.p + slot, sizeof(int), cudaMemcpyDeviceToHost, st));
-        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + ((slot + 32) & 63), 0, sizeof(int), st));
-        R3D_CUDA(cudaEventRecord(ev_ctrl[round & 1], st));
+        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + 2 * ((slot + 32) & 63), 0, 2 * sizeof(int), st));
         { Launcher l(eng, KID_UPDATE); k_update<<<dim3(UPDATE_G, n), UPDATE_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_MINMAX); k_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_CLEAR); k_clear_images<<<dim3(32, n), STREAM_THREADS, 0, st>>>(d, n); }
@@ -446,20 +472,19 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         { Launcher l(eng, KID_COLLIDE); k_collide<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
         { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n, key_cap); }
-        // the host only looks at the counter written by the PREVIOUS round's k_ctrl, so the device never idles
+        // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
         if (round >= 1) {
-            R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));
-            if (eng->h_active[(round - 1) & 63] == 0) done = true;
+            const long long left = wait_round(round - 1, seq_prev);
+            if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
+            if (left == 0) done = true;
         }
+        seq_prev = seq_now;
     }
     if (!done) {
-        R3D_CUDA(cudaEventSynchronize(ev_ctrl[(round - 1) & 1]));
-        if (eng->h_active[(round - 1) & 63] != 0) {
-            cudaEventDestroy(ev_ctrl[0]); cudaEventDestroy(ev_ctrl[1]);
-            return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
-        }
+        const long long left = wait_round(round - 1, seq_prev);
+        if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
+        if (left != 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
     }
-    cudaEventDestroy(ev_ctrl[0]); cudaEventDestroy(ev_ctrl[1]);
     eng->last_rounds = round;
     {
         Launcher l(eng, KID_OUT);

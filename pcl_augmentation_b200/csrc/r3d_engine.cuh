@@ -88,7 +88,9 @@ struct EngineDev {       // passed by value to kernels
     int* cf_rect;                     // [B][4] rows r0..r1, cols c0..c1 (inclusive) close/fill must recompute
     int force_full;                   // debug / test: always take the full re-projection path
     int *col_off, *col_idx;           // [B][cols+1], [B][max_points]: original points bucketed by azimuth bin
-    int* active_count;
+    int* active_count;                // [2] device counters of the current round: unfinished scans, finished k_ctrl CTAs
+    unsigned long long* host_word;    // mapped pinned host word the last k_ctrl CTA publishes (seq << 32 | unfinished scans)
+    unsigned ctrl_seq;
     unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
     // scene boxes

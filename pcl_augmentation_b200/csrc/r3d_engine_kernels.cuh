@@ -178,7 +178,15 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
         s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
         e.gate_update[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply;
         for (int i = 0; i < 4; ++i) e.tickets[(size_t)b * 4 + i] = 0u;
-        if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(e.active_count, 1);
+        if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(&e.active_count[0], 1);
+        // the last CTA publishes the number of unfinished scans straight into mapped host memory: the host polls this
+        // word instead of waiting for a D2H copy (which would queue behind another engine's bulk transfers)
+        __threadfence();
+        if (atomicAdd(&e.active_count[1], 1) == n_scans - 1) {
+            const unsigned left = (unsigned)atomicAdd(&e.active_count[0], 0);
+            *(volatile unsigned long long*)e.host_word = ((unsigned long long)e.ctrl_seq << 32) | left;
+            __threadfence_system();
+        }
         if (tryact) atomicAdd(&e.stats[1], 1ull);
         if (apply) atomicAdd(&e.stats[2], 1ull);
     }

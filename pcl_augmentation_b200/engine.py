@@ -185,8 +185,10 @@ class Real3DEngine:
         box_rows = []
         n_events = max(int(np.asarray(s.perms).shape[0]) for s in scans)
         nc = len(self.classes)
-        counts = np.zeros((n, nc), dtype=np.int32)
-        perms = np.full((n, n_events, nc, self.max_tries), -1, dtype=np.int32)
+        counts = _pinned((n, nc), np.int32)
+        counts[:] = 0
+        perms = _pinned((n, n_events, nc, self.max_tries), np.int32)
+        perms[:] = -1
         for i, s in enumerate(scans):
             xyzi[pt_off[i]:pt_off[i + 1]] = s.xyzi
             labels[pt_off[i]:pt_off[i + 1]] = np.asarray(s.labels).astype(np.uint32).view(np.int32)
@@ -196,8 +198,10 @@ class Real3DEngine:
             counts[i] = np.asarray(s.counts, dtype=np.int32)
             p = np.asarray(s.perms, dtype=np.int32)
             perms[i, :p.shape[0], :, :p.shape[2]] = p
-        staged = {'n': n, 'pt_off': pt_off, 'xyzi': xyzi, 'labels': labels, 'box_off': box_off,
-                  'boxes': np.ascontiguousarray(np.array(box_rows, dtype=np.float64).reshape(-1, 16)),
+        boxes = _pinned((max(len(box_rows), 1), 16), np.float64)[:len(box_rows)]
+        if box_rows:
+            boxes[:] = np.array(box_rows, dtype=np.float64).reshape(-1, 16)
+        staged = {'n': n, 'pt_off': pt_off, 'xyzi': xyzi, 'labels': labels, 'box_off': box_off, 'boxes': boxes,
                   'counts': counts, 'perms': perms, 'n_events': n_events, 'total': total}
         if self.task == 'od':
             blobs, moff, dims = [], [0], np.zeros((n, 2, 4), dtype=np.int32)
@@ -208,8 +212,9 @@ class Real3DEngine:
                     blobs.append(m.reshape(-1))
                     moff.append(moff[-1] + m.size)
                     dims[i, j] = (m.shape[0], m.shape[1], int(md['min_x']), int(md['min_y']))
-            staged.update(maps=np.ascontiguousarray(np.concatenate(blobs)), map_off=np.array(moff, dtype=np.int64),
-                          map_dims=dims)
+            maps = _pinned((moff[-1],), np.uint8)
+            maps[:] = np.concatenate(blobs)
+            staged.update(maps=maps, map_off=np.array(moff, dtype=np.int64), map_dims=dims)
         else:
             staged['poses'] = np.ascontiguousarray(np.stack([np.asarray(s.pose, dtype=np.float64) for s in scans]))
         return staged
