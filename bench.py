@@ -63,54 +63,81 @@ def build_cases(rank, n_scans=SCANS_PER_GPU, distinct=DISTINCT_SCANS):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    """SM clock / throttle reasons of this rank's GPU, sampled through NVML every 10 ms from a background thread
+    while the timed regions run (the quantities of the profiling recipe's nvidia-smi line: clocks.sm, clocks.max.sm,
+    power.draw, clocks_event_reasons.*).  `mark(True/False)` brackets the timed regions; only samples taken inside
+    them are summarised."""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", "nvmlClocksEventReasonHwSlowdown"), ("hw_thermal_slowdown", "nvmlClocksEventReasonHwThermalSlowdown"),
+               ("sw_thermal_slowdown", "nvmlClocksEventReasonSwThermalSlowdown"), ("sw_power_cap", "nvmlClocksEventReasonSwPowerCap"),
+               ("hw_power_brake", "nvmlClocksEventReasonHwPowerBrakeSlowdown"))
 
-    def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+    def __init__(self, cuda_index, period_s=0.01):
+        self.period, self.samples, self.inside, self.stop_flag, self.thread = period_s, [], False, False, None
+        self.nv, self.handle, self.error = None, None, None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            uuid = str(torch.cuda.get_device_properties(cuda_index).uuid)
+            self.handle = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            self.nv = pynvml
+        except Exception as exc:                      # reported in the JSON line, never silently dropped
+            self.error = f"NVML unavailable: {exc!r}"
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
-            self.thread.start()
-        except Exception:
-            self.proc = None
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._loop, daemon=True)
+        self.thread.start()
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def mark(self, inside):
+        self.inside = inside
+
+    def _loop(self):
+        nv, h = self.nv, self.handle
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                pw = nv.nvmlDeviceGetPowerUsage(h) / 1000.0
+                self.samples.append((self.inside, sm, mask, pw))
+            except Exception as exc:
+                self.error = f"NVML sample failed: {exc!r}"
+                return
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [self.error or "NVML unavailable"], "samples": 0}
+        self.stop_flag = True
+        self.thread.join(timeout=2)
+        nv = self.nv
+        mx = nv.nvmlDeviceGetMaxClockInfo(self.handle, nv.NVML_CLOCK_SM)
+        timed = [s for s in self.samples if s[0]]
+        reasons = set()
+        for _, _, mask, _ in timed:
+            for name, attr in self.REASONS:
+                if mask & getattr(nv, attr, 0):
                     reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        out = {"sm_mhz": statistics.median(s[1] for s in timed) if timed else None, "sm_max_mhz": float(mx),
+               "sm_min_mhz": min(s[1] for s in timed) if timed else None,
+               "power_w_max": round(max(s[3] for s in timed), 1) if timed else None,
+               "reasons": sorted(reasons), "samples": len(timed), "samples_total": len(self.samples),
+               "source": "NVML, 10 ms period, samples inside the two timed regions (device-resident + e2e)"}
+        if self.error:
+            out["error"] = self.error
+        return out
 
 
-# algorithmic bytes per unit (SURVEY.md §8d): N points, HW pixels, 20 B point record
+# algorithmic bytes per unit (SURVEY.md §8d): N points, HW pixels, 20 B point record.  "units" = how many scans /
+# tries the kernel really processed in the timed region (engine counters), so gated-off launches add time but no bytes.
+PLACEMENT_STAGES = ("onmap", "road_level", "collide", "place_try")
+
+
 def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
     per_project = stats["projected_scans"]
     per_try = stats["tried_objects"]
@@ -120,12 +147,22 @@ def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
         "clear_images": (8 * hw, per_project),
         "close_fill": (16 * hw, per_project),
         "update_mask_patch": (5 * n_points, per_mask),                 # occlusion mask
-        "collide_points": (20 * n_points, per_try),                    # placement pass over the scene
+        "placement": (20 * n_points, per_try),                         # placement pass over the scene, all stages
         "compact_output": (40 * n_points, n_scans * steps),
         "ingest_spherical": (20 * n_points, 0),
     }
     per_unit, units = table.get(kernel, (0, 0))
     return per_unit, units
+
+
+def measured_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(kernel)
 
 
 def peaks():
@@ -196,7 +233,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
@@ -250,21 +287,22 @@ def main():
         eng.reset(); eng.run(); eng.sync()
     eng.profile(True)
     sampler = ClockSampler(local_rank)
-    barrier()
     sampler.start()
+    barrier()
     launches0 = eng.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark(True)
     ev0.record(stream)
     for _ in range(args.steps):
         eng.reset()
         eng.run()
     ev1.record(stream)
     eng.sync()
+    sampler.mark(False)
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
-    clocks = sampler.stop()
     prof = eng.profile_read()
     stats = eng.stats()
     eng.profile(False)
@@ -277,10 +315,13 @@ def main():
     pipe.warmup(staged)
     pipe.warmup(staged)
     barrier()
+    sampler.mark(True)
     t0 = time.perf_counter()
     out_bytes = pipe.process([staged] * args.steps)
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    sampler.mark(False)
+    clocks = sampler.stop()
     d2h = sum(out_bytes)
     e2e_value = world * n_scans * args.steps / e2e_s
     h2d = staged["total"] * 20 + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
@@ -290,24 +331,30 @@ def main():
     # ---- roofline of the dominant kernel ------------------------------------------------------------------
     peak, peak_src = peaks()
     hw = ROWS * COLS
-    top = max(prof.items(), key=lambda kv: kv[1]["ms"])
-    roofline = None
-    ranked = sorted(prof.items(), key=lambda kv: -kv[1]["ms"])
-    kernel_table = {}
     total_kernel_ms = sum(v["ms"] for v in prof.values())
-    for name, v in ranked:
+    # the three placement stages (A5-A10) share ONE figure in SURVEY §8d (20 N bytes per tried object): one group
+    group = {"ms": sum(v["ms"] for k, v in prof.items() if k in PLACEMENT_STAGES),
+             "launches": max([v["launches"] for k, v in prof.items() if k in PLACEMENT_STAGES] or [0])}
+    entries = dict(prof)
+    entries["placement"] = group
+    kernel_table = {}
+    for name, v in sorted(entries.items(), key=lambda kv: -kv[1]["ms"]):
         per_unit, units = algorithmic_bytes(name, n_points, hw, stats, n_scans, args.steps)
         entry = {"ms": round(v["ms"], 3), "launches": v["launches"], "share": round(v["ms"] / max(total_kernel_ms, 1e-9), 4)}
+        if name == "placement":
+            entry["stages"] = [k for k in PLACEMENT_STAGES if k in prof and prof[k]["launches"]]
         if per_unit and units and v["ms"] > 0:
             gbs = per_unit * units / (v["ms"] / 1000.0) / 1e9
             entry.update(algorithmic_bytes_per_unit=per_unit, units=units, achieved_gbs=round(gbs, 1),
                          frac=round(gbs / peak, 4))
         kernel_table[name] = entry
-    for name, v in ranked:                      # dominant kernel that has a bytes model
-        e = kernel_table[name]
+    roofline = None
+    for name, e in kernel_table.items():        # dominant kernel (stage) = largest share of device time with a bytes model
         if "achieved_gbs" in e:
+            traffic = measured_traffic(name)
             roofline = {"kernel": name, "bound": "hbm", "achieved": e["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": e["frac"], "traffic": None, "peak_source": peak_src,
+                        "frac": e["frac"], "traffic": traffic["bytes_per_launch"] if traffic else None,
+                        "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
                         "bytes_per_launch": e["algorithmic_bytes_per_unit"] * e["units"] / max(e["launches"], 1),
                         "avg_launch_ms": e["ms"] / max(e["launches"], 1), "share_of_kernel_time": e["share"]}
             break

@@ -45,6 +45,7 @@ struct r3d_engine {
     cudaStream_t stream = nullptr;
     int n_scans = 0;
     int max_n0 = 0;
+    int n_sms = 148;
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
     int last_rounds = 0;
     // device buffers
@@ -54,7 +55,7 @@ struct r3d_engine {
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
     DevBuf<unsigned short> col, cand_list;
-    DevBuf<int> pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
+    DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -62,7 +63,7 @@ struct r3d_engine {
     DevBuf<ScanState> st;
     DevBuf<Box> boxes;
     DevBuf<BoxTest> box_tests;
-    DevBuf<ObjBox> obj;
+    DevBuf<ObjBox> obj, try_obj;
     DevBuf<ClassCfg> classes;
     // host copies needed for re-arming
     std::vector<Box> h_boxes;
@@ -125,6 +126,7 @@ void drain_events(r3d_engine* eng) {
     eng->pending_events.clear();
 }
 
+size_t occl_smem_bytes(const EngineDev& d) { return (size_t)d.dwords * sizeof(unsigned) + (size_t)(d.K + 2) * sizeof(unsigned short); }
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // dynamic shared memory of k_select_emit: sort keys, ranges, object tile, pixel ids, dilation + visibility bits
 size_t select_smem_bytes(int max_pts) {
@@ -185,6 +187,10 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->gcell.alloc(B * (size_t)d.G * d.G)); TRY(eng->gpts.alloc(B * d.max_points));
     TRY(eng->col_off.alloc(B * (size_t)(d.cols + 1))); TRY(eng->col_idx.alloc(B * d.max_points));
     TRY(eng->acell.alloc(B * (size_t)d.G * d.G)); TRY(eng->apts.alloc(B * d.max_points));
+    TRY(eng->try_obj.alloc(B));
+    d.max_chunks = (d.P + CHUNK - 1) / CHUNK;
+    TRY(eng->chunk_cnt.alloc(B * (size_t)d.max_chunks));
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&eng->n_sms, cudaDevAttrMultiProcessorCount, dev); }
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
     R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
@@ -219,6 +225,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
     d.gcell = eng->gcell.p; d.gpts = eng->gpts.p;
     d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.acell = eng->acell.p; d.apts = eng->apts.p;
+    d.try_obj = eng->try_obj.p; d.chunk_cnt = eng->chunk_cnt.p;
     d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
     *out = eng;
     return R3D_OK;
@@ -294,7 +301,9 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     const size_t sel_smem = select_smem_bytes(max_pts);
     if (sel_smem > 200 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: a cut object is too large for the selection kernel's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
-    R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(d.dwords * sizeof(unsigned))));
+    R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occl_smem_bytes(d)));
+    if (onmap_smem_bytes(d.K) > 100 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: too many yaw steps for the placement kernel's shared memory");
+    R3D_CUDA(cudaFuncSetAttribute(k_onmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onmap_smem_bytes(d.K)));
     eng->objects_set = true;
     return R3D_OK;
 }
@@ -424,7 +433,9 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     cudaStream_t st = eng->stream;
     const int P_live = eng->max_n0 + d.max_inserted;
     const int chunks_all = (P_live + CHUNK - 1) / CHUNK;
-    const int kwarps = (d.K + 7) / 8;
+    const size_t onmap_smem = onmap_smem_bytes(d.K);
+    const int task_ctas = eng->n_sms * TASK_CTAS_PER_SM;
+    const size_t pref_smem = (size_t)(n + 1) * sizeof(int);
     const size_t sel_smem = select_smem_bytes(d.max_obj_points);
     const int key_cap = next_pow2(d.max_obj_points);
     R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * 2 * sizeof(int), st));
@@ -466,11 +477,12 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
                                                                  d.far_arr, d.cf_rect);
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_od<<<dim3(kwarps, n), PLACE_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_HEIGHT); k_height<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_ONMAP); k_onmap<<<n, TRY_THREADS, onmap_smem, st>>>(d, n); }
+        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
+        { Launcher l(eng, KID_HEIGHT); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
         if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 1024, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_COLLIDE); k_collide<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, d.dwords * sizeof(unsigned), st>>>(d, n); }
+        { Launcher l(eng, KID_COLLIDE); k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
+        { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, occl_smem_bytes(d), st>>>(d, n); }
         { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n, key_cap); }
         // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
         if (round >= 1) {
@@ -488,9 +500,9 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     eng->last_rounds = round;
     {
         Launcher l(eng, KID_OUT);
-        k_out_count<<<n, 256, 0, st>>>(d, n);
-        k_out_offsets<<<1, 32, 0, st>>>(d, n);
-        k_out_write<<<n, 1024, 0, st>>>(d, n);
+        k_out_count<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);
+        k_out_offsets<<<1, 1024, 0, st>>>(d, n, chunks_all);
+        k_out_write<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);
         r3d_count_launch(2);
     }
     R3D_CUDA(cudaMemcpyAsync(eng->h_offsets, eng->out_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
@@ -688,11 +700,14 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
     k_probe_setup<<<n, 128, 0, st>>>(d, n, scan, object_id, (int)n_rows); r3d_count_launch();
     const int chunks_all = (n0 + (int)n_rows + CHUNK - 1) / CHUNK;
     if (d.task == 1) { k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); r3d_count_launch(); }
-    const int kwarps = (d.K + 7) / 8;
-    if (d.task == 0) { k_onmap_od<<<dim3(kwarps, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch(); }
-    k_height<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch();
+    const int task_ctas = eng->n_sms * TASK_CTAS_PER_SM;
+    const size_t pref_smem = (size_t)(n + 1) * sizeof(int);
+    k_onmap<<<n, TRY_THREADS, onmap_smem_bytes(d.K), st>>>(d, n); r3d_count_launch();
+    if (d.task == 0) { k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch(); }
+    k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch();
     if (d.task == 1) { k_onmap_ss<<<n, 1024, 0, st>>>(d, n); r3d_count_launch(); }
-    k_collide<<<dim3(PLACE_G, n), PLACE_THREADS, 0, st>>>(d, n); r3d_count_launch();
+    k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch();
+    k_feasible_list<<<n, 128, 0, st>>>(d, n); r3d_count_launch();
     std::vector<ScanState> hs(1);
     R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p + scan, sizeof(ScanState), cudaMemcpyDeviceToHost, st));
     R3D_CUDA(cudaStreamSynchronize(st));

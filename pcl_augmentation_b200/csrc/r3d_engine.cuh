@@ -111,6 +111,7 @@ struct EngineDev {       // passed by value to kernels
     unsigned* unplaceable;            // [B][ceil(n_objects/32)]
     // object DB
     const ObjBox* obj;
+    ObjBox* try_obj;                  // [B] record of the cut object each scan is trying (written by k_onmap)
     const double *obj_x, *obj_y, *obj_z;
     const float* obj_i;
     const unsigned* obj_label;
@@ -134,6 +135,8 @@ struct EngineDev {       // passed by value to kernels
     int* inserted;                    // [B][E][4]
     double* inserted_box;             // [B][E][8]
     float* check;                     // [B][max_inserted][5]
+    int* chunk_cnt;                   // [B][max_chunks] live points per CHUNK of the working cloud (output compaction)
+    int max_chunks;
     long long* out_count;             // [B] rows per scan ; out_off [B+1]
     long long* out_off;
     long long* check_off;

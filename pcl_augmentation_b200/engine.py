@@ -354,7 +354,8 @@ class Real3DEngine:
         out = np.zeros(8, dtype=np.uint64)
         _lib.check(self.lib.r3d_engine_stats(self.handle, out.ctypes.data), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
-                'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5])}
+                'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5]),
+                'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7])}
 
     def cuda_stream(self):
         import torch
