@@ -143,9 +143,9 @@ def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
     per_try = stats["tried_objects"]
     per_mask = stats["masked_scans"]
     table = {
-        "project_zbuffer": (20 * n_points + 8 * hw, per_project),      # z-buffer pass
-        "clear_images": (8 * hw, per_project),
-        "close_fill": (16 * hw, per_project),
+        "project_zbuffer_full": (20 * n_points + 8 * hw, per_project), # z-buffer pass, round 0 of every run
+        "clear_images_full": (8 * hw, per_project),
+        "close_fill_full": (16 * hw, per_project),
         "update_mask_patch": (5 * n_points, per_mask),                 # occlusion mask
         "placement": (20 * n_points, per_try),                         # placement pass over the scene, all stages
         "compact_output": (40 * n_points, n_scans * steps),
@@ -238,6 +238,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sub-batches", type=int, default=4, help="sub-batches one engine advances concurrently (own streams)")
     ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -275,7 +276,7 @@ def main():
     # PIPE_DEPTH engines (own stream, own device-resident batch, own host thread): the e2e leg streams batches through
     # all of them so H2D, compute and D2H of consecutive batches overlap; the device-resident leg uses the first one
     pipe = ScanPipeline("od", cases[0].config, cases[0].db, depth=args.depth, max_scans=n_scans, max_points=n_points,
-                        rows=ROWS, cols=COLS, yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1)
+                        rows=ROWS, cols=COLS, yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1, sub_batches=args.sub_batches)
     eng = pipe.engines[0]
     staged = eng.stage([scan_input_from_case(c) for c in cases])
     stream = eng.cuda_stream()
@@ -285,7 +286,6 @@ def main():
     eng.sync()
     for _ in range(args.warmup):
         eng.reset(); eng.run(); eng.sync()
-    eng.profile(True)
     sampler = ClockSampler(local_rank)
     sampler.start()
     barrier()
@@ -303,9 +303,19 @@ def main():
     barrier()
     dev_ms = ev0.elapsed_time(ev1)
     launches = eng.launch_count() - launches0
+    # per-kernel CUDA-event times: a second, untimed pass over the same steps with the engine's event profiling on
+    # (two event records per launch would otherwise sit inside the timed region)
+    # and ONE sub-batch, so that kernels run strictly one after the other and an event pair times one kernel alone
+    eng.set_sub_batches(1)
+    eng.profile(True)
+    for _ in range(args.steps):
+        eng.reset()
+        eng.run()
+    eng.sync()
     prof = eng.profile_read()
     stats = eng.stats()
     eng.profile(False)
+    eng.set_sub_batches(args.sub_batches)
     dev_ms = max_over_ranks(dev_ms)
     value = world * n_scans * args.steps / (dev_ms / 1000.0)
 
@@ -378,8 +388,10 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h / args.steps), "pipeline_depth": args.depth,
-                    "ms_per_step": 1000.0 * e2e_s / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks,
+                    "ms_per_step": 1000.0 * e2e_s / args.steps,
+                    "pcie_gbs_each_way": round(max(h2d, d2h / args.steps) / (e2e_s / args.steps) / 1e9, 1)},
+            "gpu_launches": int(launches), "clocks": clocks, "sub_batches": args.sub_batches,
+            "kernel_times": "CUDA events around every launch in a separate pass with one sub-batch (serial)",
             "step_roofline": step_roofline, "kernels": kernel_table,
             "rounds_per_step": results[0].extra["rounds"], "objects_inserted_per_scan": inserted_all / (world * n_scans),
             "engine_stats": stats}))

@@ -112,7 +112,8 @@ typedef struct r3d_engine_cfg {
     int32_t map_window;                       /* semseg: side of the per-scan occupied-cell window (cells) */
     int32_t grid_half;                        /* road-level search grid: cells per half side (grid covers +-grid_half*grid_cell m) */
     double grid_cell;                         /* road-level search grid: cell size in metres (0 -> 0.5) */
-    int32_t flags;                            /* bit0: re-project every slot in full (disable the in-place image patch) */
+    int32_t flags;                            /* bit0: re-project every slot in full (disable the in-place image patch);
+                                                 bits 8-11: sub-batches advanced concurrently on their own streams (0 = default 4) */
     double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */
     int32_t radii_ok[R3D_NUM_RADII];          /* 0 where the pass's "radius > 5" check already fails */
     r3d_class_cfg classes[R3D_MAX_CLASSES];
@@ -179,6 +180,9 @@ int r3d_engine_run(r3d_engine* eng);
 /* device -> host copy of the results of the last run */
 int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* result);
 /* blocking wait for the engine stream */
+/* Number of contiguous sub-batches r3d_engine_run advances concurrently, each on its own stream (1..8).  1 runs the
+ * rounds strictly one kernel after the other (what the per-kernel CUDA-event profile needs). */
+int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub);
 int r3d_engine_sync(r3d_engine* eng);
 /* total output rows of the last run (valid after r3d_engine_run + r3d_engine_sync) */
 int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check);

@@ -4,6 +4,7 @@
 #include "r3d_host.h"
 
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -11,15 +12,19 @@
 
 using namespace r3d;
 
+#define R3D_MAX_SUB 8
+
 namespace {
 
 enum KernelId {
     KID_INGEST, KID_CTRL, KID_UPDATE, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT, KID_COLLIDE,
-    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_COUNT
+    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_PROJECT0, KID_CLOSEFILL0, KID_CLEAR0, KID_MINMAX0, KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
     "ingest_spherical", "ctrl", "update_mask_patch", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
-    "onmap", "road_level", "collide", "index_build", "occlusion_count", "select_emit", "compact_output", "minmax_elevation"};
+    "onmap", "road_level", "collide", "index_build", "occlusion_count", "select_emit", "compact_output", "minmax_elevation",
+    // round 0 of a run re-projects every scan in full; later rounds only the scans whose elevation range moved
+    "project_zbuffer_full", "close_fill_full", "clear_images_full", "minmax_elevation_full"};
 
 template <class T>
 struct DevBuf {
@@ -46,6 +51,10 @@ struct r3d_engine {
     int n_scans = 0;
     int max_n0 = 0;
     int n_sms = 148;
+    int n_sub = 4;                               // sub-batches advanced concurrently, each on its own stream
+    cudaStream_t sub_stream[R3D_MAX_SUB] = {nullptr};
+    cudaEvent_t sub_done[R3D_MAX_SUB] = {nullptr};
+    cudaEvent_t ev_armed = nullptr;
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
     int last_rounds = 0;
     // device buffers
@@ -90,14 +99,15 @@ __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
-struct Launcher {          // wraps every launch: launch counter + optional CUDA-event timing on the engine stream
+struct Launcher {          // wraps every launch: launch counter + optional CUDA-event timing on the launching stream
     r3d_engine* eng;
     int kid;
+    cudaStream_t st;
     cudaEvent_t a = nullptr, b = nullptr;
-    Launcher(r3d_engine* e, int k) : eng(e), kid(k) {
+    Launcher(r3d_engine* e, int k, cudaStream_t stream = nullptr) : eng(e), kid(k), st(stream ? stream : e->stream) {
         if (eng->profile) {
             a = get_event(); b = get_event();
-            cudaEventRecord(a, eng->stream);
+            cudaEventRecord(a, st);
         }
     }
     cudaEvent_t get_event() {
@@ -108,7 +118,7 @@ struct Launcher {          // wraps every launch: launch counter + optional CUDA
         r3d_count_launch();
         eng->prof_launches[kid] += 1;
         if (eng->profile) {
-            cudaEventRecord(b, eng->stream);
+            cudaEventRecord(b, st);
             eng->pending_events.push_back({kid, {a, b}});
         }
     }
@@ -152,11 +162,21 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     r3d_engine* eng = new r3d_engine();
     eng->cfg = *cfg;
     R3D_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    eng->n_sub = (cfg->flags >> 8) & 15;
+    if (const char* env = getenv("R3D_SUBBATCHES")) eng->n_sub = atoi(env);
+    if (eng->n_sub <= 0) eng->n_sub = 4;
+    eng->n_sub = std::min(eng->n_sub, R3D_MAX_SUB);
+    for (int i = 0; i < R3D_MAX_SUB; ++i) {
+        R3D_CUDA(cudaStreamCreateWithFlags(&eng->sub_stream[i], cudaStreamNonBlocking));
+        R3D_CUDA(cudaEventCreateWithFlags(&eng->sub_done[i], cudaEventDisableTiming));
+    }
+    R3D_CUDA(cudaEventCreateWithFlags(&eng->ev_armed, cudaEventDisableTiming));
     EngineDev& d = eng->dev;
     memset(&d, 0, sizeof(d));
     d.task = cfg->task; d.rows = cfg->rows; d.cols = cfg->cols; d.hw = cfg->rows * cfg->cols; d.K = cfg->yaw_steps;
     d.max_tries = cfg->max_tries; d.n_classes = cfg->n_classes; d.B = cfg->max_scans; d.max_points = cfg->max_points;
-    d.max_inserted = cfg->max_inserted; d.P = cfg->max_points + cfg->max_inserted; d.max_boxes = cfg->max_boxes;
+    d.max_inserted = cfg->max_inserted + (16 - (cfg->max_points + cfg->max_inserted) % 16) % 16;   // rows of P: 16-aligned
+    d.P = cfg->max_points + d.max_inserted; d.max_boxes = cfg->max_boxes;
     d.max_events = cfg->max_events; d.road_label = cfg->road_label; d.n_road_indexes = cfg->n_road_indexes;
     d.map_window = cfg->task == 1 ? cfg->map_window : 32; d.dwords = (d.hw + 31) / 32;
     for (int i = 0; i < R3D_MAX_SURFACE; ++i) d.road_indexes[i] = cfg->road_indexes[i];
@@ -172,7 +192,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->alive.alloc(B * P)); TRY(eng->zraw.alloc(B * HW)); TRY(eng->obj_raw.alloc(B * HW)); TRY(eng->smooth.alloc(B * HW));
     TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
     TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
-    TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(64 * 2));
+    TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(R3D_MAX_SUB * 64 * 2));
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -193,8 +213,8 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&eng->n_sms, cudaDevAttrMultiProcessorCount, dev); }
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
-    R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, 64 * sizeof(unsigned long long), cudaHostAllocMapped));
-    memset(eng->h_words, 0, 64 * sizeof(unsigned long long));
+    R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, R3D_MAX_SUB * 64 * sizeof(unsigned long long), cudaHostAllocMapped));
+    memset(eng->h_words, 0, R3D_MAX_SUB * 64 * sizeof(unsigned long long));
     R3D_CUDA(cudaHostGetDevicePointer((void**)&eng->d_words, eng->h_words, 0));
     R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, 2 * (B + 1) * sizeof(long long)));
     std::vector<ClassCfg> cls(R3D_MAX_CLASSES);
@@ -238,6 +258,11 @@ extern "C" int r3d_engine_destroy(r3d_engine* eng) {
     for (cudaEvent_t ev : eng->event_pool) cudaEventDestroy(ev);
     if (eng->h_words) cudaFreeHost(eng->h_words);
     if (eng->h_offsets) cudaFreeHost(eng->h_offsets);
+    for (int i = 0; i < R3D_MAX_SUB; ++i) {
+        if (eng->sub_stream[i]) { cudaStreamSynchronize(eng->sub_stream[i]); cudaStreamDestroy(eng->sub_stream[i]); }
+        if (eng->sub_done[i]) cudaEventDestroy(eng->sub_done[i]);
+    }
+    if (eng->ev_armed) cudaEventDestroy(eng->ev_armed);
     cudaStreamDestroy(eng->stream);
     delete eng;
     return R3D_OK;
@@ -426,79 +451,127 @@ extern "C" int r3d_engine_reset_batch(r3d_engine* eng) {
     return arm_batch(eng, false);
 }
 
+// view of the device data model that starts at scan b0: every per-scan array is [scan][...], so offsetting the base
+// pointers lets the kernels run unchanged on a contiguous sub-batch
+static EngineDev sub_view(const EngineDev& d, int b0) {
+    if (b0 == 0) return d;
+    EngineDev v = d;
+    const size_t b = (size_t)b0;
+    const size_t gg = (size_t)d.G * d.G, k1 = (size_t)d.K + 1, ww = (size_t)d.map_window * d.map_window / 32;
+#define R3D_OFF(field, stride) if (d.field) v.field = d.field + b * (size_t)(stride)
+    R3D_OFF(gcell, gg); R3D_OFF(gpts, d.max_points); R3D_OFF(acell, gg); R3D_OFF(apts, d.max_points);
+    R3D_OFF(xyzi, d.max_points); R3D_OFF(tail_x, d.max_inserted); R3D_OFF(tail_y, d.max_inserted);
+    R3D_OFF(tail_z, d.max_inserted); R3D_OFF(tail_i, d.max_inserted); R3D_OFF(label, d.P); R3D_OFF(r, d.P); R3D_OFF(el, d.P);
+    R3D_OFF(col, d.P); R3D_OFF(pix, d.P); R3D_OFF(alive, d.P); R3D_OFF(zraw, d.hw); R3D_OFF(obj_raw, d.hw);
+    R3D_OFF(smooth, d.hw); R3D_OFF(dmask, d.dwords); R3D_OFF(vmask, d.dwords); R3D_OFF(st, 1); R3D_OFF(gate_update, 1);
+    R3D_OFF(gate_try, 1); R3D_OFF(gate_apply, 1); R3D_OFF(gate_full, 1); R3D_OFF(gate_patch, 1); R3D_OFF(cf_rect, 4);
+    R3D_OFF(col_off, d.cols + 1); R3D_OFF(col_idx, d.max_points); R3D_OFF(far_arr, 1); R3D_OFF(boxes, d.max_boxes);
+    R3D_OFF(box_tests, d.max_boxes); R3D_OFF(od_map_off, 2); R3D_OFF(od_map_dims, 8); R3D_OFF(poses, 16); R3D_OFF(occ_win, ww);
+    R3D_OFF(counts, d.n_classes); R3D_OFF(perms, (size_t)d.n_perm_events * d.n_classes * d.max_tries);
+    R3D_OFF(unplaceable, (d.n_objects + 31) / 32); R3D_OFF(try_obj, 1); R3D_OFF(cand_flags, k1); R3D_OFF(cand_level, k1);
+    R3D_OFF(cand_v, k1); R3D_OFF(cand_list, k1); R3D_OFF(n_list, 1); R3D_OFF(tickets, 4); R3D_OFF(feas, d.K);
+    R3D_OFF(occ_pix, (size_t)OCC_G * d.max_obj_points); R3D_OFF(sel_pix, d.max_obj_points); R3D_OFF(inserted, (size_t)d.max_events * 4);
+    R3D_OFF(inserted_box, (size_t)d.max_events * 8); R3D_OFF(check, (size_t)d.max_inserted * 5); R3D_OFF(chunk_cnt, d.max_chunks);
+    R3D_OFF(out_count, 1);
+#undef R3D_OFF
+    return v;
+}
+
 extern "C" int r3d_engine_run(r3d_engine* eng) {
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: no batch loaded");
-    EngineDev d = eng->dev;
+    const EngineDev& d0 = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
-    const int P_live = eng->max_n0 + d.max_inserted;
+    const int P_live = eng->max_n0 + d0.max_inserted;
     const int chunks_all = (P_live + CHUNK - 1) / CHUNK;
-    const size_t onmap_smem = onmap_smem_bytes(d.K);
-    const int task_ctas = eng->n_sms * TASK_CTAS_PER_SM;
-    const size_t pref_smem = (size_t)(n + 1) * sizeof(int);
-    const size_t sel_smem = select_smem_bytes(d.max_obj_points);
-    const int key_cap = next_pow2(d.max_obj_points);
-    R3D_CUDA(cudaMemsetAsync(eng->active_count.p, 0, 64 * 2 * sizeof(int), st));
-    const int max_rounds = d.max_events * (3 * d.max_tries + 2) + 8;
+    const size_t sel_smem = select_smem_bytes(d0.max_obj_points);
+    const int key_cap = next_pow2(d0.max_obj_points);
+    const size_t onmap_smem = onmap_smem_bytes(d0.K);
+    const int max_rounds = d0.max_events * (3 * d0.max_tries + 2) + 8;
+    // The batch is advanced as n_sub contiguous sub-batches, each on its own stream: every kernel of a round is a
+    // short chain of dependent loads that leaves most of the SMs' issue slots idle, so the rounds of different
+    // sub-batches overlap on the device.
+    const int nsub = std::max(1, std::min(eng->n_sub, n));
+    struct Sub { int b0, n, round; bool done; unsigned seq_prev; EngineDev d; cudaStream_t st; };
+    Sub sub[R3D_MAX_SUB];
+    R3D_CUDA(cudaEventRecord(eng->ev_armed, st));
+    for (int i = 0; i < nsub; ++i) {
+        Sub& s = sub[i];
+        s.b0 = (int)((long long)n * i / nsub); s.n = (int)((long long)n * (i + 1) / nsub) - s.b0;
+        s.round = 0; s.done = false; s.seq_prev = 0; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
+        R3D_CUDA(cudaStreamWaitEvent(s.st, eng->ev_armed, 0));
+        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + (size_t)i * 128, 0, 128 * sizeof(int), s.st));
+    }
+    const int task_ctas = std::max(eng->n_sms, eng->n_sms * TASK_CTAS_PER_SM / nsub);
     // wait until the k_ctrl of `round` has published its word; returns the number of unfinished scans (< 0: error)
-    auto wait_round = [&](int round, unsigned seq) -> long long {
-        volatile unsigned long long* w = eng->h_words + (round & 63);
+    auto wait_round = [&](int i, int round, unsigned seq) -> long long {
+        volatile unsigned long long* w = eng->h_words + (size_t)i * 64 + (round & 63);
         for (unsigned spins = 0;; ++spins) {
             const unsigned long long v = *w;
             if ((unsigned)(v >> 32) == seq) return (long long)(v & 0xffffffffull);
             if ((spins & 0xfff) == 0xfff) {
-                const cudaError_t q = cudaStreamQuery(st);
+                const cudaError_t q = cudaStreamQuery(sub[i].st);
                 if (q != cudaSuccess && q != cudaErrorNotReady) return -1;
                 if (q == cudaSuccess && (unsigned)(*w >> 32) != seq) return -1;      // stream drained without the word
             }
         }
     };
-    int round = 0;
-    bool done = false;
-    unsigned seq_prev = 0;
-    for (; round < max_rounds && !done; ++round) {
-        const int slot = round & 63;
-        d.active_count = eng->active_count.p + 2 * slot;
-        d.host_word = eng->d_words + slot;
-        if (++eng->seq == 0) ++eng->seq;
-        d.ctrl_seq = eng->seq;
-        const unsigned seq_now = eng->seq;
-        { Launcher l(eng, KID_CTRL); k_ctrl<<<n, 128, 0, st>>>(d, n); }
-        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + 2 * ((slot + 32) & 63), 0, 2 * sizeof(int), st));
-        { Launcher l(eng, KID_UPDATE); k_update<<<dim3(UPDATE_G, n), UPDATE_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_MINMAX); k_minmax<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_CLEAR); k_clear_images<<<dim3(32, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_PROJECT); k_project<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        {
-            Launcher l(eng, KID_CLOSEFILL);
-            RawImage in{d.zraw};
-            dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, n);
-            k_close_fill<RawImage><<<grid, CF_THREADS, 0, st>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
-                                                                 d.far_arr, d.cf_rect);
+    int n_done = 0, rounds_max = 0;
+    while (n_done < nsub) {
+        for (int i = 0; i < nsub; ++i) {
+            Sub& s = sub[i];
+            if (s.done) continue;
+            if (s.round >= max_rounds) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
+            EngineDev& d = s.d;
+            const int ns = s.n, slot = s.round & 63;
+            cudaStream_t ss = s.st;
+            int* ac = eng->active_count.p + (size_t)i * 128;
+            d.active_count = ac + 2 * slot;
+            d.host_word = eng->d_words + (size_t)i * 64 + slot;
+            if (++eng->seq == 0) ++eng->seq;
+            d.ctrl_seq = eng->seq;
+            const unsigned seq_now = eng->seq;
+            const size_t pref_smem = (size_t)(ns + 1) * sizeof(int);
+            { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 128, 0, ss>>>(d, ns); }
+            R3D_CUDA(cudaMemsetAsync(ac + 2 * ((slot + 32) & 63), 0, 2 * sizeof(int), ss));
+            { Launcher l(eng, KID_UPDATE, ss); k_update<<<dim3(UPDATE_G, ns), UPDATE_THREADS, 0, ss>>>(d, ns); }
+            const bool r0 = s.round == 0;
+            { Launcher l(eng, r0 ? KID_MINMAX0 : KID_MINMAX, ss); k_minmax<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+            { Launcher l(eng, r0 ? KID_CLEAR0 : KID_CLEAR, ss); k_clear_images<<<dim3(32, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+            { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+            {
+                Launcher l(eng, r0 ? KID_CLOSEFILL0 : KID_CLOSEFILL, ss);
+                RawImage in{d.zraw};
+                dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, ns);
+                k_close_fill<RawImage><<<grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
+                                                                     d.far_arr, d.cf_rect);
+            }
+            if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+            { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }
+            if (d.task == 0) { Launcher l(eng, KID_ONMAP, ss); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+            { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+            if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
+            { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+            { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
+            { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap); }
+            // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
+            if (s.round >= 1) {
+                const long long left = wait_round(i, s.round - 1, s.seq_prev);
+                if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
+                if (left == 0) { s.done = true; ++n_done; }
+            }
+            s.seq_prev = seq_now;
+            s.round += 1;
+            rounds_max = std::max(rounds_max, s.round);
         }
-        if (d.task == 1) { Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_ONMAP); k_onmap<<<n, TRY_THREADS, onmap_smem, st>>>(d, n); }
-        if (d.task == 0) { Launcher l(eng, KID_ONMAP); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
-        { Launcher l(eng, KID_HEIGHT); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
-        if (d.task == 1) { Launcher l(eng, KID_ONMAP); k_onmap_ss<<<n, 1024, 0, st>>>(d, n); }
-        { Launcher l(eng, KID_COLLIDE); k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); }
-        { Launcher l(eng, KID_OCCL); k_occl_count<<<dim3(OCC_G, n), 128, occl_smem_bytes(d), st>>>(d, n); }
-        { Launcher l(eng, KID_SELECT); k_select_emit<<<n, 512, sel_smem, st>>>(d, n, key_cap); }
-        // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
-        if (round >= 1) {
-            const long long left = wait_round(round - 1, seq_prev);
-            if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
-            if (left == 0) done = true;
-        }
-        seq_prev = seq_now;
     }
-    if (!done) {
-        const long long left = wait_round(round - 1, seq_prev);
-        if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
-        if (left != 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
+    eng->last_rounds = rounds_max;
+    for (int i = 0; i < nsub; ++i) {
+        R3D_CUDA(cudaEventRecord(eng->sub_done[i], sub[i].st));
+        R3D_CUDA(cudaStreamWaitEvent(st, eng->sub_done[i], 0));
     }
-    eng->last_rounds = round;
     {
+        const EngineDev& d = d0;
         Launcher l(eng, KID_OUT);
         k_out_count<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);
         k_out_offsets<<<1, 1024, 0, st>>>(d, n, chunks_all);
@@ -506,9 +579,15 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         r3d_count_launch(2);
     }
     R3D_CUDA(cudaMemcpyAsync(eng->h_offsets, eng->out_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
-    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets + (d.B + 1), eng->check_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets + (d0.B + 1), eng->check_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
     eng->ran = true;
     return r3d_check_launch("r3d_engine_run");
+}
+
+extern "C" int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub) {
+    if (!eng || n_sub < 1 || n_sub > R3D_MAX_SUB) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_sub_batches: 1..8");
+    eng->n_sub = n_sub;
+    return R3D_OK;
 }
 
 extern "C" int r3d_engine_sync(r3d_engine* eng) {

@@ -363,15 +363,35 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_s
     const int p0 = blockIdx.x * CHUNK;
     if (p0 >= n) return;
     const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
-    const size_t base = (size_t)b * e.P;
+    const size_t base = (size_t)b * e.P;           // P is a multiple of 16: the 4-point vectors below are aligned
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
-        if (!e.alive[base + p]) continue;
-        const int row = bin_row(g, e.el[base + p]);
-        if (row < 0 || row >= g.rows) { set_error(s, R3D_ERR_ASSERT); continue; }      // od/ins:111
-        const int pix = row * g.cols + (int)e.col[base + p];
-        e.pix[base + p] = pix;
-        atomicMin(&z[pix], dbl_bits(e.r[base + p]));
+    auto one = [&](bool alive, double el, unsigned col, double r) -> int {
+        if (!alive) return -1;
+        const int row = bin_row(g, el);
+        if (row < 0 || row >= g.rows) { set_error(s, R3D_ERR_ASSERT); return -1; }          // od/ins:111
+        const int pix = row * g.cols + (int)col;
+        atomicMin(&z[pix], dbl_bits(r));
+        return pix;
+    };
+#pragma unroll 2
+    for (int it = 0; it < CHUNK / (STREAM_THREADS * 4); ++it) {
+        const int p = p0 + it * STREAM_THREADS * 4 + threadIdx.x * 4;
+        if (p >= n) break;
+        if (p + 3 < n) {                           // four points per thread: 4 + 32 + 8 + 32 bytes in, 16 out
+            const uchar4 a = *reinterpret_cast<const uchar4*>(e.alive + base + p);
+            if (!(a.x | a.y | a.z | a.w)) continue;
+            const double2 e01 = *reinterpret_cast<const double2*>(e.el + base + p);
+            const double2 e23 = *reinterpret_cast<const double2*>(e.el + base + p + 2);
+            const ushort4 c = *reinterpret_cast<const ushort4*>(e.col + base + p);
+            const double2 r01 = *reinterpret_cast<const double2*>(e.r + base + p);
+            const double2 r23 = *reinterpret_cast<const double2*>(e.r + base + p + 2);
+            int4 px;
+            px.x = one(a.x, e01.x, c.x, r01.x); px.y = one(a.y, e01.y, c.y, r01.y);
+            px.z = one(a.z, e23.x, c.z, r23.x); px.w = one(a.w, e23.y, c.w, r23.y);
+            *reinterpret_cast<int4*>(e.pix + base + p) = px;
+        } else {
+            for (int q = p; q < n; ++q) e.pix[base + q] = one(e.alive[base + q], e.el[base + q], e.col[base + q], e.r[base + q]);
+        }
     }
 }
 

@@ -61,7 +61,8 @@ class Real3DEngine:
 
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
-                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200, force_full_projection=False):
+                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200, force_full_projection=False,
+                 sub_batches=0):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -87,7 +88,8 @@ class Real3DEngine:
             cfg.road_indexes[i] = int(v)
         cfg.map_window = int(map_window)
         cfg.grid_half, cfg.grid_cell = int(grid_half), float(grid_cell)
-        cfg.flags = 1 if force_full_projection else 0
+        # bit 0: full re-projection every slot; bits 8-11: sub-batches advanced concurrently (0 = library default)
+        cfg.flags = (1 if force_full_projection else 0) | ((int(sub_batches) & 15) << 8)
         r2, ok = bx.search_radii()
         for i in range(50):
             cfg.radii_sq[i] = float(r2[i])
@@ -247,6 +249,10 @@ class Real3DEngine:
 
     def run(self):
         _lib.check(self.lib.r3d_engine_run(self.handle), "run")
+
+    def set_sub_batches(self, n):
+        """How many contiguous sub-batches ``run`` advances concurrently on their own streams (1 = strictly serial)."""
+        _lib.check(self.lib.r3d_engine_set_sub_batches(self.handle, int(n)), "set_sub_batches")
 
     def sync(self):
         _lib.check(self.lib.r3d_engine_sync(self.handle), "sync")

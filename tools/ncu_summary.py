@@ -1,0 +1,64 @@
+"""Summarise `ncu --set full` captures into small tracked files under profiles/:
+
+  python tools/ncu_summary.py <round tag> <rep> [<rep> ...]
+
+writes profiles/<tag>_ncu_<rep name>.csv (one row per captured launch, the metrics the roofline discussion uses) and
+merges dram traffic per launch into profiles/ncu_traffic.json (read by bench.py for `roofline.traffic`)."""
+import csv, io, json, os, subprocess, sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+           "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+           "launch__block_size", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+           "smsp__thread_inst_executed_per_inst_executed.ratio"]
+# ncu kernel name -> bench.py kernel-table name
+BENCH_NAME = {"k_project": "project_zbuffer_full", "k_close_fill": "close_fill_full", "k_clear_images": "clear_images_full",
+              "k_minmax": "minmax_elevation_full", "k_ingest": "ingest_spherical", "k_update": "update_mask_patch",
+              "k_out_write": "compact_output", "k_out_count": "compact_output", "k_onmap": "placement",
+              "k_onmap_full": "placement", "k_road_level": "placement", "k_collide": "placement",
+              "k_occl_count": "occlusion_count", "k_select_emit": "select_emit"}
+SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+
+
+def main():
+    tag, reps = sys.argv[1], sys.argv[2:]
+    traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
+    for rep in reps:
+        out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        rows = list(csv.reader(io.StringIO(out)))
+        h, units, data = rows[0], rows[1], rows[2:]
+        metrics = [m for m in METRICS if m in h]
+        idx = [h.index(m) for m in metrics]
+        kn = h.index("Kernel Name")
+        name = os.path.splitext(os.path.basename(rep))[0]
+        dst = os.path.join(ROOT, "profiles", f"{tag}_ncu_{name.replace(tag + '_', '')}.csv")
+        agg = {}
+        with open(dst, "w", newline="") as f:
+            w = csv.writer(f)
+            w.writerow(["kernel"] + [f"{m} [{units[i]}]" for m, i in zip(metrics, idx)])
+            for r in data:
+                k = r[kn].split("(")[0].replace("void ", "").split("<")[0]
+                w.writerow([k] + [r[i] for i in idx])
+                rd = float(r[idx[1]].replace(",", "")) * SCALE.get(units[idx[1]], 1.0)
+                wr = float(r[idx[2]].replace(",", "")) * SCALE.get(units[idx[2]], 1.0)
+                b = BENCH_NAME.get(k)
+                if b:
+                    agg.setdefault(b, []).append((k, rd + wr))
+        for b, items in agg.items():
+            per_kernel = {}
+            for k, v in items:
+                per_kernel.setdefault(k, []).append(v)
+            total = sum(sum(v) / len(v) for v in per_kernel.values())      # mean per launch, summed over the stage's kernels
+            traffic[b] = {"bytes_per_launch": round(total), "kernels": sorted(per_kernel),
+                          "source": f"profiles/{os.path.basename(dst)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
+                                    f"all scans of the batch active in the captured launch)"}
+        print("wrote", dst)
+    with open(traffic_path, "w") as f:
+        json.dump(traffic, f, indent=1, sort_keys=True)
+    print("wrote", traffic_path)
+
+
+if __name__ == "__main__":
+    main()
