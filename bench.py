@@ -199,7 +199,7 @@ def _ref_worker(seed):
     return time.perf_counter() - t0
 
 
-def run_reference(args):
+def run_reference(args, json_out):
     """--impl reference: the CPU implementation of the path (the oracle port: the Python reference itself cannot
     travel to the GPU box) on all host cores, one scan per worker process per step."""
     rank = int(os.environ.get("RANK", "0"))
@@ -220,17 +220,21 @@ def run_reference(args):
         dt = time.perf_counter() - t0
     value = done / dt
     sample = f"{cores} whole scans per step (one per worker process), {args.steps} steps"
-    print(json.dumps({
+    print(file=json_out, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})])
 
 
 def main():
+    # Libraries (NCCL's version banner, for one) write to fd 1: keep the real stdout for the ONE JSON line and send
+    # everything else written to fd 1 during the run to stderr
+    json_out = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -242,7 +246,7 @@ def main():
     ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
     args = ap.parse_args()
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, json_out)
         return
 
     import torch
@@ -253,6 +257,9 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     if world > 1:
+        # NCCL_DEBUG=VERSION / INFO print to stdout; rank 0's stdout must carry the JSON line only
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -381,7 +388,7 @@ def main():
                "host_cpus": os.cpu_count()}
     inserted_all = sum_over_ranks(inserted_total)
     if rank == 0:
-        print(json.dumps({
+        print(file=json_out, flush=True, *[json.dumps({
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
@@ -394,7 +401,7 @@ def main():
             "kernel_times": "CUDA events around every launch in a separate pass with one sub-batch (serial)",
             "step_roofline": step_roofline, "kernels": kernel_table,
             "rounds_per_step": results[0].extra["rounds"], "objects_inserted_per_scan": inserted_all / (world * n_scans),
-            "engine_stats": stats}))
+            "engine_stats": stats})])
     pipe.close()
     if world > 1:
         dist.destroy_process_group()

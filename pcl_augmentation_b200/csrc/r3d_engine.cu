@@ -4,7 +4,9 @@
 #include "r3d_host.h"
 
 #include <cmath>
+#include <chrono>
 #include <cstdlib>
+#include <thread>
 #include <cstring>
 #include <map>
 #include <string>
@@ -51,6 +53,7 @@ struct r3d_engine {
     int n_scans = 0;
     int max_n0 = 0;
     int n_sms = 148;
+    int device = 0;                              // every API call binds the calling thread to the engine's device first
     int n_sub = 4;                               // sub-batches advanced concurrently, each on its own stream
     cudaStream_t sub_stream[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t sub_done[R3D_MAX_SUB] = {nullptr};
@@ -59,7 +62,8 @@ struct r3d_engine {
     int last_rounds = 0;
     // device buffers
     DevBuf<float4> xyzi, out_xyzi, gpts, apts;
-    DevBuf<double> tail_x, tail_y, tail_z, r, el, smooth, poses, obj_x, obj_y, obj_z, cos_k, sin_k, radii_sq, cand_level,
+    DevBuf<unsigned long long> sel_keys;
+    DevBuf<double> sel_r, tail_x, tail_y, tail_z, r, el, smooth, poses, obj_x, obj_y, obj_z, cos_k, sin_k, radii_sq, cand_level,
         inserted_box;
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
@@ -137,6 +141,7 @@ void drain_events(r3d_engine* eng) {
 }
 
 size_t occl_smem_bytes(const EngineDev& d) { return (size_t)d.dwords * sizeof(unsigned) + (size_t)(d.K + 2) * sizeof(unsigned short); }
+constexpr int SEL_SMEM_PTS = 4096;       // object points k_select_emit keeps in shared memory; larger objects use global scratch
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 // dynamic shared memory of k_select_emit: sort keys, ranges, object tile, pixel ids, dilation + visibility bits
 size_t select_smem_bytes(int max_pts) {
@@ -161,6 +166,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
         return r3d_fail(R3D_ERR_CUDA, "r3d_engine_create: no CUDA device (this library has no CPU fallback)");
     r3d_engine* eng = new r3d_engine();
     eng->cfg = *cfg;
+    R3D_CUDA(cudaGetDevice(&eng->device));
     R3D_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
     eng->n_sub = (cfg->flags >> 8) & 15;
     if (const char* env = getenv("R3D_SUBBATCHES")) eng->n_sub = atoi(env);
@@ -252,6 +258,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
 }
 
 extern "C" int r3d_engine_destroy(r3d_engine* eng) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng) return R3D_OK;
     cudaStreamSynchronize(eng->stream);
     drain_events(eng);
@@ -269,6 +276,7 @@ extern "C" int r3d_engine_destroy(r3d_engine* eng) {
 }
 
 extern "C" int r3d_engine_set_yaw_tables(r3d_engine* eng, const double* cos_k, const double* sin_k) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !cos_k || !sin_k) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_yaw_tables: null argument");
     const size_t n = (size_t)eng->dev.K + 1;
     R3D_CUDA(cudaMemcpy(eng->cos_k.p, cos_k, n * sizeof(double), cudaMemcpyHostToDevice));
@@ -278,6 +286,7 @@ extern "C" int r3d_engine_set_yaw_tables(r3d_engine* eng, const double* cos_k, c
 }
 
 extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !db || db->n_objects <= 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_objects: bad argument");
     EngineDev& d = eng->dev;
     const int n = db->n_objects;
@@ -323,8 +332,12 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     d.obj_x = eng->obj_x.p; d.obj_y = eng->obj_y.p; d.obj_z = eng->obj_z.p; d.obj_i = eng->obj_i.p; d.obj_label = eng->obj_label.p;
     d.obj = eng->obj.p; d.class_list_off = eng->class_list_off.p; d.class_list = eng->class_list.p;
     d.unplaceable = eng->unplaceable.p; d.occ_pix = eng->occ_pix.p; d.sel_pix = eng->sel_pix.p;
-    const size_t sel_smem = select_smem_bytes(max_pts);
-    if (sel_smem > 200 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: a cut object is too large for the selection kernel's shared memory");
+    const size_t sel_smem = select_smem_bytes(std::min(max_pts, SEL_SMEM_PTS));
+    d.sel_key_cap = next_pow2(max_pts);
+    if (max_pts > SEL_SMEM_PTS) {
+        TRY(eng->sel_keys.alloc((size_t)d.B * d.sel_key_cap)); TRY(eng->sel_r.alloc((size_t)d.B * max_pts));
+    }
+    d.sel_keys = eng->sel_keys.p; d.sel_r = eng->sel_r.p;
     R3D_CUDA(cudaFuncSetAttribute(k_select_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sel_smem));
     R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occl_smem_bytes(d)));
     if (onmap_smem_bytes(d.K) > 100 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: too many yaw steps for the placement kernel's shared memory");
@@ -335,6 +348,7 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
 
 extern "C" int r3d_engine_set_ss_map(r3d_engine* eng, const uint8_t* map, int32_t size_x, int32_t size_y, int64_t move_x,
                                      int64_t move_y) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !map || size_x <= 0 || size_y <= 0) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_ss_map: bad argument");
     TRY(eng->ss_map.alloc((size_t)size_x * size_y));
     R3D_CUDA(cudaMemcpy(eng->ss_map.p, map, (size_t)size_x * size_y, cudaMemcpyHostToDevice));
@@ -375,6 +389,7 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
 }
 
 extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !bt) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: null argument");
     if (!eng->objects_set || !eng->yaw_set) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: set objects and yaw tables first");
     EngineDev& d = eng->dev;
@@ -447,6 +462,7 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
 }
 
 extern "C" int r3d_engine_reset_batch(r3d_engine* eng) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_reset_batch: no batch loaded");
     return arm_batch(eng, false);
 }
@@ -470,7 +486,8 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     R3D_OFF(counts, d.n_classes); R3D_OFF(perms, (size_t)d.n_perm_events * d.n_classes * d.max_tries);
     R3D_OFF(unplaceable, (d.n_objects + 31) / 32); R3D_OFF(try_obj, 1); R3D_OFF(cand_flags, k1); R3D_OFF(cand_level, k1);
     R3D_OFF(cand_v, k1); R3D_OFF(cand_list, k1); R3D_OFF(n_list, 1); R3D_OFF(tickets, 4); R3D_OFF(feas, d.K);
-    R3D_OFF(occ_pix, (size_t)OCC_G * d.max_obj_points); R3D_OFF(sel_pix, d.max_obj_points); R3D_OFF(inserted, (size_t)d.max_events * 4);
+    R3D_OFF(occ_pix, (size_t)OCC_G * d.max_obj_points); R3D_OFF(sel_pix, d.max_obj_points);
+    R3D_OFF(sel_keys, d.sel_key_cap); R3D_OFF(sel_r, d.max_obj_points); R3D_OFF(inserted, (size_t)d.max_events * 4);
     R3D_OFF(inserted_box, (size_t)d.max_events * 8); R3D_OFF(check, (size_t)d.max_inserted * 5); R3D_OFF(chunk_cnt, d.max_chunks);
     R3D_OFF(out_count, 1);
 #undef R3D_OFF
@@ -478,14 +495,16 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
 }
 
 extern "C" int r3d_engine_run(r3d_engine* eng) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: no batch loaded");
     const EngineDev& d0 = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
     const int P_live = eng->max_n0 + d0.max_inserted;
     const int chunks_all = (P_live + CHUNK - 1) / CHUNK;
-    const size_t sel_smem = select_smem_bytes(d0.max_obj_points);
-    const int key_cap = next_pow2(d0.max_obj_points);
+    const int sel_pts = std::min(d0.max_obj_points, SEL_SMEM_PTS);
+    const size_t sel_smem = select_smem_bytes(sel_pts);
+    const int key_cap = next_pow2(sel_pts);
     const size_t onmap_smem = onmap_smem_bytes(d0.K);
     const int max_rounds = d0.max_events * (3 * d0.max_tries + 2) + 8;
     // The batch is advanced as n_sub contiguous sub-batches, each on its own stream: every kernel of a round is a
@@ -509,6 +528,9 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         for (unsigned spins = 0;; ++spins) {
             const unsigned long long v = *w;
             if ((unsigned)(v >> 32) == seq) return (long long)(v & 0xffffffffull);
+            // the word is one round behind the launches: poll briefly, then sleep in short steps instead of burning a
+            // host core per engine thread (8 ranks x 3 pipelined engines share the box's cores)
+            if (spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(20));
             if ((spins & 0xfff) == 0xfff) {
                 const cudaError_t q = cudaStreamQuery(sub[i].st);
                 if (q != cudaSuccess && q != cudaErrorNotReady) return -1;
@@ -553,7 +575,7 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
             if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
             { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
             { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
-            { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap); }
+            { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap, sel_pts); }
             // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
             if (s.round >= 1) {
                 const long long left = wait_round(i, s.round - 1, s.seq_prev);
@@ -585,12 +607,14 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
 }
 
 extern "C" int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || n_sub < 1 || n_sub > R3D_MAX_SUB) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_sub_batches: 1..8");
     eng->n_sub = n_sub;
     return R3D_OK;
 }
 
 extern "C" int r3d_engine_sync(r3d_engine* eng) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_sync: null engine");
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
     drain_events(eng);
@@ -598,6 +622,7 @@ extern "C" int r3d_engine_sync(r3d_engine* eng) {
 }
 
 extern "C" int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_output_rows: run first");
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
     if (total_points) *total_points = eng->h_offsets[eng->n_scans];
@@ -606,6 +631,7 @@ extern "C" int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, in
 }
 
 extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !res || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_fetch: run first");
     EngineDev& d = eng->dev;
     const int n = eng->n_scans;
@@ -633,6 +659,7 @@ extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
 }
 
 extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_profile_enable: null engine");
     cudaStreamSynchronize(eng->stream);
     drain_events(eng);
@@ -643,16 +670,19 @@ extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
 }
 
 extern "C" int r3d_engine_stats(r3d_engine* eng, uint64_t* out8) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !out8) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats: null argument");
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
     R3D_CUDA(cudaMemcpy(out8, eng->stats.p, 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return R3D_OK;
 }
 
-extern "C" void* r3d_engine_stream(r3d_engine* eng) { return eng ? (void*)eng->stream : nullptr; }
+extern "C" void* r3d_engine_stream(r3d_engine* eng) {
+    if (eng) cudaSetDevice(eng->device); return eng ? (void*)eng->stream : nullptr; }
 
 extern "C" int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int names_cap, double* ms_out,
                                        int64_t* launches_out, int max_kernels, int* n_kernels_out) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_profile_read: null engine");
     cudaStreamSynchronize(eng->stream);
     drain_events(eng);
@@ -669,6 +699,7 @@ extern "C" int r3d_engine_profile_read(r3d_engine* eng, char* names_out, int nam
 }
 
 extern "C" int r3d_engine_debug_image(r3d_engine* eng, int scan, double* smooth_out) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || scan < 0 || scan >= eng->n_scans || !smooth_out) return r3d_fail(R3D_ERR_ARG, "r3d_engine_debug_image: bad argument");
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
     R3D_CUDA(cudaMemcpy(smooth_out, eng->smooth.p + (size_t)scan * eng->dev.hw, (size_t)eng->dev.hw * sizeof(double), cudaMemcpyDeviceToHost));
@@ -676,6 +707,7 @@ extern "C" int r3d_engine_debug_image(r3d_engine* eng, int scan, double* smooth_
 }
 
 extern "C" int r3d_engine_debug_candidates(r3d_engine* eng, int scan, uint8_t* flags_out, double* level_out, int32_t* visible_out) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || scan < 0 || scan >= eng->n_scans) return r3d_fail(R3D_ERR_ARG, "r3d_engine_debug_candidates: bad argument");
     const size_t K1 = eng->dev.K + 1;
     R3D_CUDA(cudaStreamSynchronize(eng->stream));
@@ -745,6 +777,7 @@ __global__ void k_probe_points(EngineDev e, int scan, int obj, int n_feasible, d
 extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const double* scene_rows9, int64_t n_rows,
                                        uint8_t* flags_out, double* box_out, double* xyz_out, int xyz_capacity,
                                        int32_t* n_feasible_out) {
+    if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->batch_loaded || scan < 0 || scan >= eng->n_scans || object_id < 0 || object_id >= eng->dev.n_objects ||
         n_rows < 0 || (n_rows > 0 && !scene_rows9) || !flags_out || !box_out || !n_feasible_out)
         return r3d_fail(R3D_ERR_ARG, "r3d_engine_probe_places: bad argument");

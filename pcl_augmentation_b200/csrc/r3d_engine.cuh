@@ -130,7 +130,10 @@ struct EngineDev {       // passed by value to kernels
     unsigned* tickets;                // [B][4]  "last CTA done" counters of the staged kernels (zeroed by k_ctrl)
     int* feas;                        // [B][K]
     int* occ_pix;                     // [B][OCC_G][max_obj_points] scratch
-    int* sel_pix;                     // [B][max_obj_points]
+    int* sel_pix;                     // [B][max_obj_points]  scratch of k_select_emit for objects too large for shared memory
+    unsigned long long* sel_keys;     // [B][sel_key_cap]
+    double* sel_r;                    // [B][max_obj_points]
+    int sel_key_cap;
     // outputs
     int* inserted;                    // [B][E][4]
     double* inserted_box;             // [B][E][8]

@@ -1260,19 +1260,26 @@ __device__ __forceinline__ bool tile_pixel_value(const unsigned long long* tile,
 // candidate's z-buffer (in a shared-memory tile around the object when it fits, else in a global scratch image),
 // closes / fills it, compares with the scene image (strict <) into the vis_px bit mask, and on acceptance appends the
 // visible object points in (pix_id, index) order to the scene tail, the `check` record and the scene boxes.
-__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, int key_cap) {
+__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, int key_cap, int smem_pts) {
     const int b = blockIdx.x;
     if (b >= n_scans || !e.gate_try[b]) return;
     ScanState& s = e.st[b];
     const int nf = s.n_feasible;
     if (nf == 0) return;
     extern __shared__ unsigned long long s_dyn[];
+    // sort keys / ranges / pixel ids of the object's points: shared memory for objects up to smem_pts points, the
+    // per-scan global scratch for larger ones (trucks with > 10k points)
     unsigned long long* s_keys = s_dyn;                                   // [key_cap]
-    double* s_r = reinterpret_cast<double*>(s_dyn + key_cap);            // [max_obj_points]
-    unsigned long long* s_tile = s_dyn + key_cap + e.max_obj_points;     // [SEL_TILE_PX]
-    int* s_pix = reinterpret_cast<int*>(s_tile + SEL_TILE_PX);           // [max_obj_points]
-    unsigned* s_dil = reinterpret_cast<unsigned*>(s_pix + e.max_obj_points);   // [SEL_TILE_PX / 32]
+    double* s_r = reinterpret_cast<double*>(s_dyn + key_cap);            // [smem_pts]
+    unsigned long long* s_tile = s_dyn + key_cap + smem_pts;             // [SEL_TILE_PX]
+    int* s_pix = reinterpret_cast<int*>(s_tile + SEL_TILE_PX);           // [smem_pts]
+    unsigned* s_dil = reinterpret_cast<unsigned*>(s_pix + smem_pts);     // [SEL_TILE_PX / 32]
     unsigned* s_vis = s_dil + SEL_TILE_PX / 32;                          // [SEL_TILE_PX / 32]
+    if (e.try_obj[b].count > smem_pts) {
+        s_keys = e.sel_keys + (size_t)b * e.sel_key_cap;
+        s_r = e.sel_r + (size_t)b * e.max_obj_points;
+        s_pix = e.sel_pix + (size_t)b * e.max_obj_points;
+    }
     __shared__ int s_nvis;
     __shared__ int s_rect[4];
     __shared__ unsigned long long s_el[2];

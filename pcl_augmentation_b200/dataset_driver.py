@@ -1,0 +1,190 @@
+"""The script part of the reference's two ``insertion.py`` (od/ins:301-630, ss/ins:290-601) on top of the batched
+CUDA engine: walk a dataset in the reference's on-disk formats, augment ``batch_size`` frames at a time and write the
+files the reference writes (augmented cloud, ``check`` record, annotation / label files, ``added_objects/<frame>.txt``).
+
+What is kept from the reference's loop: the per-frame marker file that makes concurrent runs skip frames in progress
+(od/ins:335-347) and is removed when nothing could be inserted (od/ins:616-620); ``generate_seed`` drawing the class
+counts from ``np.random`` (od/ins:171-187) and ``random.shuffle`` ordering each class's sample list (od/ins:400) — the
+draws happen here on the host, once per frame, and are handed to the engine as tables, so a seeded ``random`` /
+``np.random`` gives a reproducible run; ``setting.txt``; the run-folder numbering.
+"""
+from __future__ import annotations
+
+import glob
+import os
+import random
+
+import numpy as np
+
+from .engine import MAX_NUM_TRIES, Real3DEngine, ScanInput
+
+
+def load_object_db(sample_path, classes, folder_of=str):
+    """Cut-object database ``{class: [(name, {'pcl', 'anno'})]}`` from ``<sample_path>/<folder>/*.npz``
+    (od/ins:393, 432; ss/ins:374, 413), in sorted file-name order (the order the shuffle tables index)."""
+    db = {}
+    for cls in classes:
+        items = []
+        for path in sorted(glob.glob(f'{sample_path}/{folder_of(cls)}/*.npz')):
+            with np.load(path, allow_pickle=True) as z:
+                items.append((os.path.basename(path).split('.')[0], {'pcl': z['pcl'], 'anno': z['anno']}))
+        if not items:
+            raise FileNotFoundError(f'no cut objects for class {cls!r} under {sample_path}/{folder_of(cls)}')
+        db[cls] = items
+    return db
+
+
+def generate_seed(config):
+    """Objects to insert per class (od/ins:171-187, ss/ins:171-187)."""
+    ins = config['insertion']
+    if ins['random']:
+        seed = np.zeros(len(ins['classes']))
+        for i in np.random.randint(len(ins['classes']), size=ins['number_of_object']):
+            seed[i] += 1
+    else:
+        seed = np.array(ins['number_of_classes'])
+    return seed
+
+
+def draw_schedule(config, list_lens, tries=MAX_NUM_TRIES):
+    """Pre-draw one frame's randomness exactly where the reference draws it: the class counts, then one
+    ``random.shuffle`` of every class's (sorted) sample list per possible window (od/ins:399-402); only the first
+    ``tries`` entries of a shuffle can be visited before the next shuffle (the rest follow in index order)."""
+    counts = generate_seed(config).astype(np.int64)
+    events = int(counts.sum()) + 1
+    perms = np.full((events, len(list_lens), tries), -1, dtype=np.int32)
+    for e in range(events):
+        for c, n in enumerate(list_lens):
+            order = list(range(n))
+            random.shuffle(order)
+            k = min(tries, n)
+            perms[e, c, :k] = order[:k]
+    return counts, perms
+
+
+def _marker(out_dir, name):
+    return f'{out_dir}/added_objects/{name}.txt'
+
+
+def _claim(out_dir, name):
+    """Frame marker (od/ins:335-347).  Returns False when another run already holds it."""
+    path = _marker(out_dir, name)
+    if os.path.exists(path):
+        return False
+    open(path, 'w').close()
+    return True
+
+
+def _finish(dataset, out_dir, folder, name, result, yaw_step_deg=1.0):
+    """Write one frame's outputs, or drop the marker when nothing was inserted (od/ins:616-620)."""
+    if not result.inserted:
+        os.remove(_marker(out_dir, name))
+        return False
+    with open(_marker(out_dir, name), 'w') as f:
+        for obj_name, rot, _ in result.inserted:
+            rot = rot * yaw_step_deg
+            f.write(f'{obj_name} with rotation: {int(rot) if float(rot).is_integer() else rot}\n')        # od/ins:537
+    dataset.save_result(result, folder, name)
+    return True
+
+
+def _max_points(files, bytes_per_point=16):
+    return max(os.path.getsize(f) // bytes_per_point for f in files)
+
+
+def augment_kitti(config, batch_size=64, yaw_steps=360, folder_number=None, engine_kwargs=None, log=print,
+                  engine_cls=Real3DEngine):
+    """object_detection/Real3DAug/insertion.py ``__main__`` (od/ins:301-630) for the whole ``train.txt`` list.
+    Returns (save folder, frames written, frames without an insertion)."""
+    from .object_detection.Real3DAug.tools.datasets import KITTI
+    dataset = KITTI(config)
+    save_folder, _ = dataset.create_directories('random' if config['insertion']['random'] else 'chosen', folder_number)
+    out_dir = f"{config['path']['output_path']}/{save_folder}"
+    classes = config['insertion']['classes']
+    db = load_object_db(config['path']['sample_path'], classes)
+    list_lens = [len(db[c]) for c in classes]
+    maps_path = config['path']['maps_path']
+    files = list(dataset.velodyne_list)
+    if not files:
+        return save_folder, 0, 0
+    engine = engine_cls('od', config, db, max_scans=min(batch_size, len(files)), max_points=_max_points(files),
+                          yaw_steps=yaw_steps, **(engine_kwargs or {}))
+    written = skipped = 0
+    try:
+        for i0 in range(0, len(files), batch_size):
+            scans, names = [], []
+            for idx in range(i0, min(i0 + batch_size, len(files))):
+                name = dataset.frame_name(files[idx])
+                if not _claim(out_dir, name):
+                    log(f'{name}: already in progress')
+                    continue
+                xyzi, labels, _ = dataset.read_frame(idx)
+                with open(f'{dataset.data_path}/label_2/{name}.txt') as f:
+                    box_lines = [line for line in f if len(line.strip()) > 0]                     # od/ins:133-157
+                maps = {}
+                for key, sub in (('Road', 'road_maps'), ('Sidewalk', 'pedestrian_area')):        # od/ins:361-362
+                    with np.load(f'{maps_path}/maps/{sub}/npz/{name}.npz', allow_pickle=True) as z:
+                        maps[key] = {'map': z['map'], 'min_x': z['min_x'], 'min_y': z['min_y']}
+                counts, perms = draw_schedule(config, list_lens)
+                scans.append(ScanInput(xyzi=xyzi, labels=labels, box_lines=box_lines, counts=counts, perms=perms, maps=maps))
+                names.append(name)
+            if not scans:
+                continue
+            for name, result in zip(names, engine.augment_batch(scans)):
+                if _finish(dataset, out_dir, save_folder, name, result, 360.0 / yaw_steps):
+                    written += 1
+                else:
+                    skipped += 1
+                log(f'{name}: inserted {[(n, r) for n, r, _ in result.inserted]}')
+    finally:
+        engine.close()
+    return save_folder, written, skipped
+
+
+def augment_semantic_kitti(config, sequence, batch_size=64, yaw_steps=360, folder_number=None, reverse=False,
+                           skip_scenes=0, engine_kwargs=None, log=print, dataset=None, engine_cls=Real3DEngine):
+    """semantic_segmentation/Real3DAug/insertion.py ``__main__`` (ss/ins:290-601) for one sequence (SemanticKITTI, or
+    a prepared ``Waymo`` adapter through ``dataset``).  Returns (save folder of the sequence, written, skipped)."""
+    from .semantic_segmentation.Real3DAug.tools.datasets import SemanticKITTI
+    if dataset is None:
+        dataset = SemanticKITTI(config, sequence, reverse=reverse, skip_scenes=skip_scenes)
+    save_folder, _ = dataset.create_directories('random' if config['insertion']['random'] else 'chosen', folder_number)
+    save_folder = f'{save_folder}/{sequence}'                                                    # ss/ins:306
+    out_dir = f"{config['path']['output_path']}/{save_folder}"
+    classes = config['insertion']['classes']
+    db = load_object_db(config['path']['bbox_path'], classes, folder_of=lambda c: config['labels'][c])
+    list_lens = [len(db[c]) for c in classes]
+    with np.load(f"{config['path']['maps_path']}/{sequence}.npz", allow_pickle=True) as z:      # ss/ins:312-313
+        map_data = {'map': z['map'], 'move': z['move']}
+    files = list(dataset.velodyne_list)
+    if not files:
+        return save_folder, 0, 0
+    per_point = 16 if files[0].endswith('.bin') else 24
+    engine = engine_cls('ss', config, db, max_scans=min(batch_size, len(files)), max_points=_max_points(files, per_point),
+                          yaw_steps=yaw_steps, map_data=map_data, **(engine_kwargs or {}))
+    written = skipped = 0
+    try:
+        for i0 in range(0, len(files), batch_size):
+            scans, names = [], []
+            for idx in range(i0, min(i0 + batch_size, len(files))):
+                name = dataset.frame_name(files[idx])
+                if not _claim(out_dir, name):
+                    log(f'{sequence}/{name}: already in progress')
+                    continue
+                xyzi, labels, pose, anno_path, _ = dataset.read_frame(idx)
+                with open(anno_path) as f:
+                    box_lines = [line for line in f if len(line.strip()) > 0]
+                counts, perms = draw_schedule(config, list_lens)
+                scans.append(ScanInput(xyzi=xyzi, labels=labels, box_lines=box_lines, counts=counts, perms=perms, pose=pose))
+                names.append(name)
+            if not scans:
+                continue
+            for name, result in zip(names, engine.augment_batch(scans)):
+                if _finish(dataset, out_dir, save_folder, name, result, 360.0 / yaw_steps):
+                    written += 1
+                else:
+                    skipped += 1
+                log(f'{sequence}/{name}: inserted {[(n, r) for n, r, _ in result.inserted]}')
+    finally:
+        engine.close()
+    return save_folder, written, skipped

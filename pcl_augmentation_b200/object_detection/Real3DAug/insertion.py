@@ -2,8 +2,13 @@
 
 The projection functions (add_space_for_spherical :55, fill_spherical :68, geometrical_front_view :85) run in CUDA;
 ``generate_seed`` (:171), ``extract_anno`` (:133) and ``create_annotation_line`` (:227) are the reference's tiny host
-helpers.  The script part of the reference (its ``while len(dataset_functions) > 0`` loop, :321-628) is replaced by
-``pcl_augmentation_b200.engine.Real3DEngine.augment_batch`` — see INTEGRATION.md.
+helpers.  The script part of the reference (its ``while len(dataset_functions) > 0`` loop, :321-628) is
+``pcl_augmentation_b200.dataset_driver.augment_kitti`` on top of ``Real3DEngine.augment_batch``:
+
+    python -m pcl_augmentation_b200.object_detection.Real3DAug.insertion [--config ../config/KITTI.yaml] [--batch 64]
+
+reads the reference's YAML (:293-294), walks ``train.txt`` and writes ``<output_path>/<random|chosen>/<NN>/``
+``{velodyne, check, label_2, added_objects}`` like the reference.
 """
 import numpy as np
 
@@ -44,3 +49,24 @@ def generate_seed(config):
             inserted_class = config['insertion']['classes'][i]
             break
     return seed, inserted_class
+
+
+def main(argv=None):
+    import argparse
+    import yaml
+    from ...dataset_driver import augment_kitti
+    ap = argparse.ArgumentParser(description="Real3D-Aug insertion (KITTI object detection) on the CUDA engine")
+    ap.add_argument("--config", default="../config/KITTI.yaml")          # od/ins:293
+    ap.add_argument("--batch", type=int, default=64, help="frames augmented per engine batch")
+    ap.add_argument("--folder", type=int, default=None, help="run folder number 0-99 (default 00, od/ds:130)")
+    ap.add_argument("--yaw-steps", type=int, default=360, help="yaw candidates per cut object (reference: 360)")
+    args = ap.parse_args(argv)
+    with open(args.config, "r") as f:
+        config = yaml.safe_load(f)
+    folder, written, skipped = augment_kitti(config, batch_size=args.batch, yaw_steps=args.yaw_steps,
+                                             folder_number=args.folder)
+    print(f"{folder}: {written} frames written, {skipped} without an insertion")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,6 +1,10 @@
 """Drop-in for the function layer of the reference's semantic-segmentation ``insertion.py`` (projection functions
 :54-129, ``addjust_map_2`` :202, ``generate_seed`` :171); CUDA inside.  The script loop (:317-599) is replaced by
-``Real3DEngine('ss', ...).augment_batch`` — see INTEGRATION.md."""
+``pcl_augmentation_b200.dataset_driver.augment_semantic_kitti`` on top of ``Real3DEngine('ss', ...).augment_batch``:
+
+    python -m pcl_augmentation_b200.semantic_segmentation.Real3DAug.insertion --sequence 0 [--config ../config/semantic-kitti.yaml]
+    python -m pcl_augmentation_b200.semantic_segmentation.Real3DAug.insertion --dataset waymo [--config ../config/waymo.yaml]
+"""
 import numpy as np
 
 from ... import _lib
@@ -47,3 +51,43 @@ def addjust_map_2(map_data, point_cloud, transformation_matrix):
         map_arr[...] = out                   # the reference edits the array it was handed in place
         out = map_arr
     return out, map_move
+
+
+def main(argv=None):
+    import argparse
+    import yaml
+    from ...dataset_driver import augment_semantic_kitti
+    ap = argparse.ArgumentParser(description="Real3D-Aug insertion (semantic segmentation) on the CUDA engine")
+    ap.add_argument("--dataset", default="semantic-kitti", choices=["semantic-kitti", "waymo"])        # ss/ins:227-243
+    ap.add_argument("--config", default=None)
+    ap.add_argument("--sequence", default=None, help="SemanticKITTI sequence (must be in split.train, ss/ins:254-258)")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--folder", type=int, default=None)
+    ap.add_argument("--reverse", action="store_true", help="process the frames in reverse order (ss/ds:117-141)")
+    ap.add_argument("--skip", type=int, default=0, help="skip the first frames of the sequence (ss/ds:117-141)")
+    ap.add_argument("--yaw-steps", type=int, default=360)
+    args = ap.parse_args(argv)
+    cfg_path = args.config or ("../config/semantic-kitti.yaml" if args.dataset == "semantic-kitti" else "../config/waymo.yaml")
+    with open(cfg_path, "r") as f:
+        config = yaml.safe_load(f)
+    if args.dataset == "semantic-kitti":
+        assert args.sequence is not None and int(args.sequence) in config["split"]["train"], "choose a training sequence"
+        runs = [(f"{int(args.sequence):02d}", None)]
+    else:
+        from .tools.datasets import Waymo
+        probe = Waymo(config)
+        runs = []
+        for seq in probe.sequence_names:
+            ds = Waymo(config, reverse=args.reverse, skip_scenes=0)
+            ds.velodyne_list = ds.velodyne_list[[f.split("/")[-3] == seq for f in ds.velodyne_list]]
+            ds.sequence = seq
+            runs.append((seq, ds))
+    for seq, ds in runs:
+        folder, written, skipped = augment_semantic_kitti(config, seq, batch_size=args.batch, yaw_steps=args.yaw_steps,
+                                                          folder_number=args.folder, reverse=args.reverse,
+                                                          skip_scenes=args.skip, dataset=ds)
+        print(f"{folder}: {written} frames written, {skipped} without an insertion")
+
+
+if __name__ == "__main__":
+    main()

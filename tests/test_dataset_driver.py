@@ -1,0 +1,111 @@
+"""CPU tier: dataset adapters (reference file formats in and out), schedule drawing and the frame-marker logic of the
+dataset driver.  The engine is replaced by an oracle-backed stand-in (tests/dataset_helpers.py) so that the HOST logic
+is checked against what the unmodified reference's insertion.py wrote (tests/golden/e2e_*.npz)."""
+import os
+import random
+
+import numpy as np
+import pytest
+
+from pcl_augmentation_b200 import dataset_driver as drv
+from pcl_augmentation_b200 import synth_io
+from pcl_augmentation_b200.object_detection.Real3DAug.tools.datasets import KITTI
+from pcl_augmentation_b200.semantic_segmentation.Real3DAug.tools.datasets import SemanticKITTI
+from tests.dataset_helpers import OracleEngine, PredrawnShuffle, check_outputs_against_golden
+from tests.helpers import case_from_golden, load_golden
+
+
+def test_kitti_adapter_reads_and_writes_reference_formats(tmp_path):
+    g = load_golden("e2e_od_a")
+    _, case = case_from_golden(g)
+    _, out, cfg = synth_io.write_od_dataset([case], str(tmp_path), fixed_counts=case.schedule.counts)
+    ds = KITTI(cfg)
+    assert len(ds) == 1
+    pcl, anno, instance, calib, img = ds[0]                                   # od/ds:56-71
+    assert pcl.dtype == np.float64 and pcl.shape == (len(case.pcl5), 5)
+    np.testing.assert_array_equal(pcl, np.hstack((case.pcl5[:, :4].astype(np.float32), case.pcl5[:, 4:5])))
+    assert anno.endswith("label_2/000000.txt") and instance.shape == (len(pcl), 1)
+    folder, number = ds.create_directories("chosen")
+    assert (folder, number) == ("chosen/00", 0)
+    for sub in ("velodyne", "check", "label_2", "added_objects"):
+        assert os.path.isdir(os.path.join(out, sub))
+    assert "2x   Cyclist" in open(os.path.join(out, "setting.txt")).read()
+    rows9 = np.full((3, 9), -1.0)
+    rows9[:, 0:3] = [[1.5, 2.25, -1.0], [0.1, 0.2, 0.3], [7, 8, 9]]
+    rows9[:, 6] = [0.5, 0.25, 0.125]
+    ds.save_data(rows9, rows9[:1], folder, "000000", 0, ["Pedestrian 0 0 0 0 0 0 0 1 1 1 1 1 1 0\n"])   # od/ds:76-95
+    assert len(ds) == 0                                                        # save_data deletes the item
+    np.testing.assert_array_equal(np.fromfile(os.path.join(out, "velodyne/000000.bin"), np.float32).reshape(-1, 4),
+                                  np.hstack((rows9[:, 0:3], rows9[:, 6:7])).astype(np.float32))
+    lines = open(os.path.join(out, "label_2/000000.txt")).read().splitlines()
+    assert lines[:len(case.box_lines)] == case.box_lines and lines[-1].startswith("Pedestrian")
+    with pytest.raises(ValueError):
+        ds.create_directories("chosen", folder_number=100)
+
+
+def test_semantic_kitti_adapter_pose_and_files(tmp_path):
+    g = load_golden("e2e_ss_a")
+    _, case = case_from_golden(g)
+    _, out, cfg = synth_io.write_ss_dataset([case], str(tmp_path), fixed_counts=case.schedule.counts)
+    ds = SemanticKITTI(cfg, "00")
+    pcl, pose, anno, instance, seq = ds[0]                                     # ss/ds:45-62
+    assert seq == "00" and pcl.shape == (len(case.pcl5), 5)
+    np.testing.assert_array_equal(pose, g["used_pose"])                        # bit-identical to the reference's matrix
+    folder, _ = ds.create_directories("chosen")
+    assert folder == "chosen/00/sequences"
+    for s in cfg["split"]["train"]:
+        assert os.path.isdir(os.path.join(cfg["path"]["output_path"], folder, f"{s:02d}", "labels"))
+    rows9 = np.full((2, 9), -1.0)
+    rows9[:, 0:3] = [[1, 2, 3], [4, 5, 6]]; rows9[:, 6] = [0.5, 0.75]; rows9[:, 7] = [30, 40]
+    ds.save_data(rows9, rows9[:1], f"{folder}/00", "000000", 0)                # ss/ds:72-91
+    np.testing.assert_array_equal(np.fromfile(os.path.join(out, "labels/000000.label"), np.uint32), [30, 40])
+    np.testing.assert_array_equal(np.fromfile(os.path.join(out, "check/000000.bin"), np.float32), [1, 2, 3, 0.5, 30])
+
+
+def test_draw_schedule_uses_the_reference_rng_sources():
+    cfg = {"insertion": {"random": True, "classes": ["a", "b", "c"], "number_of_object": 7}}
+    random.seed(3); np.random.seed(3)
+    counts, perms = drv.draw_schedule(cfg, [120, 5, 100])
+    random.seed(3); np.random.seed(3)
+    counts2, perms2 = drv.draw_schedule(cfg, [120, 5, 100])
+    np.testing.assert_array_equal(counts, counts2); np.testing.assert_array_equal(perms, perms2)
+    assert counts.sum() == 7 and perms.shape == (8, 3, 100)
+    assert sorted(perms[0, 1][perms[0, 1] >= 0]) == [0, 1, 2, 3, 4] and (perms[0, 1, 5:] == -1).all()
+    assert len(set(perms[2, 0])) == 100 and perms[2, 0].max() < 120
+    cfg["insertion"].update(random=False, number_of_classes=[1, 0, 2])
+    counts, perms = drv.draw_schedule(cfg, [120, 5, 100])
+    assert list(counts) == [1, 0, 2] and perms.shape[0] == 4
+
+
+@pytest.mark.parametrize("name", ["e2e_od_a", "e2e_ss_b"])
+def test_driver_host_logic_matches_reference_run(tmp_path, name):
+    """Whole driver (adapters, markers, schedule tables, writers) with the oracle in the engine's place: the output
+    files equal what the reference's own insertion.py wrote, byte for byte where the reference is deterministic."""
+    g = load_golden(name)
+    spec, case = case_from_golden(g)
+    task = spec["task"]
+    write = synth_io.write_od_dataset if task == "od" else synth_io.write_ss_dataset
+    _, out, cfg = write([case], str(tmp_path), fixed_counts=case.schedule.counts)
+    with PredrawnShuffle(case.schedule.perms, len(cfg["insertion"]["classes"])):
+        if task == "od":
+            folder, written, skipped = drv.augment_kitti(cfg, batch_size=4, engine_cls=OracleEngine, log=lambda *a: None)
+        else:
+            folder, written, skipped = drv.augment_semantic_kitti(cfg, "00", batch_size=4, engine_cls=OracleEngine,
+                                                                  log=lambda *a: None)
+    assert (written, skipped) == (1, 0) and os.path.join(cfg["path"]["output_path"], folder) == out
+    check_outputs_against_golden(g, case, out, task)
+    # a second run finds the marker and leaves the frame alone (od/ins:335-338)
+    before = os.path.getmtime(os.path.join(out, "velodyne/000000.bin"))
+    run = drv.augment_kitti if task == "od" else (lambda c, **k: drv.augment_semantic_kitti(c, "00", **k))
+    _, written, skipped = run(cfg, batch_size=4, engine_cls=OracleEngine, log=lambda *a: None)
+    assert (written, skipped) == (0, 0) and os.path.getmtime(os.path.join(out, "velodyne/000000.bin")) == before
+
+
+def test_driver_removes_marker_when_nothing_was_inserted(tmp_path):
+    g = load_golden("e2e_od_b")
+    _, case = case_from_golden(g)
+    _, out, cfg = synth_io.write_od_dataset([case], str(tmp_path), fixed_counts=[0, 0])       # nothing requested
+    _, written, skipped = drv.augment_kitti(cfg, engine_cls=OracleEngine, log=lambda *a: None)
+    assert (written, skipped) == (0, 1)
+    assert not os.path.exists(os.path.join(out, "added_objects/000000.txt"))                   # od/ins:616-620
+    assert not os.path.exists(os.path.join(out, "velodyne/000000.bin"))
