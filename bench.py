@@ -341,7 +341,7 @@ def main():
     clocks = sampler.stop()
     d2h = sum(out_bytes)
     e2e_value = world * n_scans * args.steps / e2e_s
-    h2d = staged["total"] * 20 + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
+    h2d = staged["xyzi"].nbytes + staged["labels"].nbytes + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
     results = eng.unpack(pipe._buffers[0])
     inserted_total = sum(len(r.inserted) for r in results)
 

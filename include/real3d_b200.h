@@ -134,7 +134,7 @@ typedef struct r3d_batch {
     int32_t n_scans;
     const int64_t* point_offsets; /* n_scans + 1 */
     const float* xyzi;            /* total x 4 float32, as read from velodyne/ *.bin (od/ds:62) */
-    const uint32_t* labels;       /* total, semantic label & 0xFFFF (od/ds:65) */
+    const uint32_t* labels;       /* total, semantic label & 0xFFFF (od/ds:65); NULL when labels16 is given */
     const int32_t* box_offsets;   /* n_scans + 1 */
     const double* boxes;          /* total boxes x R3D_BOX_DOUBLES (scene annotations, extract_anno od/ins:133-157) */
     /* OD: two uint8 maps per scan (road, pedestrian area): dims[scan][map] = {size_x, size_y, min_x, min_y} */
@@ -147,6 +147,8 @@ typedef struct r3d_batch {
     const int32_t* counts;        /* n_scans x n_classes */
     const int32_t* perms;         /* n_scans x n_events x n_classes x max_tries (object ids in class-list order) */
     int32_t n_events;
+    const uint16_t* labels16;     /* total: the same labels packed to 16 bits (they are & 0xFFFF) — 2 instead of 4 bytes
+                                     per point over PCIe; widened on the device */
 } r3d_batch;
 
 typedef struct r3d_batch_result {

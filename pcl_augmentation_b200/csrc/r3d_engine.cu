@@ -67,7 +67,8 @@ struct r3d_engine {
         inserted_box;
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
-    DevBuf<unsigned short> col, cand_list;
+    DevBuf<unsigned short> col, cand_list, label16;
+    DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
@@ -98,6 +99,15 @@ namespace {
 __global__ void k_box_tests(const Box* boxes, BoxTest* tests, int n) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) tests[i] = make_box_test(boxes[i]);
+}
+// packed 16-bit labels (contiguous, per-scan offsets) -> the engine's u32 label rows
+__global__ void k_widen_labels(const unsigned short* src, const long long* pt_off, unsigned* label, int P, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const long long o = pt_off[b] - pt_off[0];
+    const int cnt = (int)(pt_off[b + 1] - pt_off[b]);
+    const int p0 = blockIdx.x * CHUNK;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, cnt); p += blockDim.x) label[(size_t)b * P + p] = src[o + p];
 }
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
@@ -167,13 +177,17 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     r3d_engine* eng = new r3d_engine();
     eng->cfg = *cfg;
     R3D_CUDA(cudaGetDevice(&eng->device));
-    R3D_CUDA(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking));
+    // the round kernels (short, latency bound) run on high-priority streams; uploads, the one-off spherical ingest /
+    // index builds and the output compaction of OTHER engines on the same GPU (ScanPipeline) must not sit in front of them
+    int prio_least = 0, prio_greatest = 0;
+    R3D_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    R3D_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_least));
     eng->n_sub = (cfg->flags >> 8) & 15;
     if (const char* env = getenv("R3D_SUBBATCHES")) eng->n_sub = atoi(env);
     if (eng->n_sub <= 0) eng->n_sub = 4;
     eng->n_sub = std::min(eng->n_sub, R3D_MAX_SUB);
     for (int i = 0; i < R3D_MAX_SUB; ++i) {
-        R3D_CUDA(cudaStreamCreateWithFlags(&eng->sub_stream[i], cudaStreamNonBlocking));
+        R3D_CUDA(cudaStreamCreateWithPriority(&eng->sub_stream[i], cudaStreamNonBlocking, prio_greatest));
         R3D_CUDA(cudaEventCreateWithFlags(&eng->sub_done[i], cudaEventDisableTiming));
     }
     R3D_CUDA(cudaEventCreateWithFlags(&eng->ev_armed, cudaEventDisableTiming));
@@ -395,7 +409,7 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     EngineDev& d = eng->dev;
     const int n = bt->n_scans;
     if (n <= 0 || n > d.B) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: n_scans exceeds max_scans");
-    if (!bt->point_offsets || !bt->xyzi || !bt->labels || !bt->counts || !bt->perms || bt->n_events <= 0)
+    if (!bt->point_offsets || !bt->xyzi || (!bt->labels && !bt->labels16) || !bt->counts || !bt->perms || bt->n_events <= 0)
         return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: missing arrays");
     if (d.task == 1 && (!bt->poses || !d.ss_map)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: semseg needs poses and the map");
     if (d.task == 0 && (!bt->maps || !bt->map_offsets || !bt->map_dims)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: OD needs maps");
@@ -444,17 +458,32 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     // points: packed host rows -> per-scan strided device rows (one pitched copy when every scan has the same size)
     bool uniform = true;
     for (int s = 1; s < n; ++s) uniform &= n0[s] == n0[0];
+    const bool packed = bt->labels == nullptr;         // 16-bit labels: staged contiguously, widened on the device
+    if (packed) {
+        const size_t total = (size_t)(bt->point_offsets[n] - bt->point_offsets[0]);
+        if (total > eng->label16.n) TRY(eng->label16.alloc(total));
+        if ((size_t)n + 1 > eng->pt_off.n) TRY(eng->pt_off.alloc((size_t)d.B + 1));
+        R3D_CUDA(cudaMemcpyAsync(eng->label16.p, bt->labels16 + bt->point_offsets[0], total * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->pt_off.p, bt->point_offsets, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+    }
     if (uniform) {
         R3D_CUDA(cudaMemcpy2DAsync(eng->xyzi.p, (size_t)d.max_points * sizeof(float4), bt->xyzi + bt->point_offsets[0] * 4,
                                    (size_t)n0[0] * sizeof(float4), (size_t)n0[0] * sizeof(float4), n, cudaMemcpyHostToDevice, st));
-        R3D_CUDA(cudaMemcpy2DAsync(eng->label.p, (size_t)d.P * sizeof(unsigned), bt->labels + bt->point_offsets[0],
-                                   (size_t)n0[0] * sizeof(unsigned), (size_t)n0[0] * sizeof(unsigned), n, cudaMemcpyHostToDevice, st));
+        if (!packed)
+            R3D_CUDA(cudaMemcpy2DAsync(eng->label.p, (size_t)d.P * sizeof(unsigned), bt->labels + bt->point_offsets[0],
+                                       (size_t)n0[0] * sizeof(unsigned), (size_t)n0[0] * sizeof(unsigned), n, cudaMemcpyHostToDevice, st));
     } else {
         for (int s = 0; s < n; ++s) {
             const int64_t o = bt->point_offsets[s];
             R3D_CUDA(cudaMemcpyAsync(eng->xyzi.p + (size_t)s * d.max_points, bt->xyzi + o * 4, (size_t)n0[s] * sizeof(float4), cudaMemcpyHostToDevice, st));
-            R3D_CUDA(cudaMemcpyAsync(eng->label.p + (size_t)s * d.P, bt->labels + o, (size_t)n0[s] * sizeof(unsigned), cudaMemcpyHostToDevice, st));
+            if (!packed)
+                R3D_CUDA(cudaMemcpyAsync(eng->label.p + (size_t)s * d.P, bt->labels + o, (size_t)n0[s] * sizeof(unsigned), cudaMemcpyHostToDevice, st));
         }
+    }
+    if (packed) {
+        const int chunks = (eng->max_n0 + CHUNK - 1) / CHUNK;
+        k_widen_labels<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(eng->label16.p, eng->pt_off.p, eng->label.p, d.P, n);
+        r3d_count_launch();
     }
     // the std::vectors above are pageable: the copies from them completed before cudaMemcpyAsync returned
     eng->batch_loaded = true;
@@ -511,38 +540,42 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     // short chain of dependent loads that leaves most of the SMs' issue slots idle, so the rounds of different
     // sub-batches overlap on the device.
     const int nsub = std::max(1, std::min(eng->n_sub, n));
-    struct Sub { int b0, n, round; bool done; unsigned seq_prev; EngineDev d; cudaStream_t st; };
+    struct Sub { int b0, n, round; bool done; unsigned seq_of[64]; EngineDev d; cudaStream_t st; };
     Sub sub[R3D_MAX_SUB];
     R3D_CUDA(cudaEventRecord(eng->ev_armed, st));
     for (int i = 0; i < nsub; ++i) {
         Sub& s = sub[i];
         s.b0 = (int)((long long)n * i / nsub); s.n = (int)((long long)n * (i + 1) / nsub) - s.b0;
-        s.round = 0; s.done = false; s.seq_prev = 0; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
+        s.round = 0; s.done = false; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
         R3D_CUDA(cudaStreamWaitEvent(s.st, eng->ev_armed, 0));
         R3D_CUDA(cudaMemsetAsync(eng->active_count.p + (size_t)i * 128, 0, 128 * sizeof(int), s.st));
     }
     const int task_ctas = std::max(eng->n_sms, eng->n_sms * TASK_CTAS_PER_SM / nsub);
-    // wait until the k_ctrl of `round` has published its word; returns the number of unfinished scans (< 0: error)
-    auto wait_round = [&](int i, int round, unsigned seq) -> long long {
+    // The k_ctrl of every round publishes (sequence number, unfinished scans) into mapped host memory.  The host keeps
+    // up to `ahead` rounds of a sub-batch in flight: round r is launched once the word of round r - ahead is there
+    // (rounds launched after the last scan finished are gated off on the device and cost a few microseconds each),
+    // so neither the device nor the other sub-batches ever wait for a word that is stuck behind bulk PCIe traffic.
+    const int ahead = 3;
+    auto poll_round = [&](int i, int round, long long& left) -> int {       // 1: published, 0: not yet, -1: device error
         volatile unsigned long long* w = eng->h_words + (size_t)i * 64 + (round & 63);
-        for (unsigned spins = 0;; ++spins) {
-            const unsigned long long v = *w;
-            if ((unsigned)(v >> 32) == seq) return (long long)(v & 0xffffffffull);
-            // the word is one round behind the launches: poll briefly, then sleep in short steps instead of burning a
-            // host core per engine thread (8 ranks x 3 pipelined engines share the box's cores)
-            if (spins > 64) std::this_thread::sleep_for(std::chrono::microseconds(20));
-            if ((spins & 0xfff) == 0xfff) {
-                const cudaError_t q = cudaStreamQuery(sub[i].st);
-                if (q != cudaSuccess && q != cudaErrorNotReady) return -1;
-                if (q == cudaSuccess && (unsigned)(*w >> 32) != seq) return -1;      // stream drained without the word
-            }
-        }
+        const unsigned long long v = *w;
+        if ((unsigned)(v >> 32) == sub[i].seq_of[round & 63]) { left = (long long)(v & 0xffffffffull); return 1; }
+        return 0;
     };
     int n_done = 0, rounds_max = 0;
+    unsigned idle_polls = 0;
     while (n_done < nsub) {
+        bool progressed = false;
         for (int i = 0; i < nsub; ++i) {
             Sub& s = sub[i];
             if (s.done) continue;
+            if (s.round >= ahead) {                   // the word of round (s.round - ahead) gates the next launch
+                long long left = 0;
+                const int got = poll_round(i, s.round - ahead, left);
+                if (got == 0) continue;
+                if (left == 0) { s.done = true; ++n_done; progressed = true; rounds_max = std::max(rounds_max, s.round - ahead + 1); continue; }
+            }
+            progressed = true;
             if (s.round >= max_rounds) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
             EngineDev& d = s.d;
             const int ns = s.n, slot = s.round & 63;
@@ -576,15 +609,22 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
             { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
             { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
             { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap, sel_pts); }
-            // the host only looks at the word written by the PREVIOUS round's k_ctrl, so the device never idles
-            if (s.round >= 1) {
-                const long long left = wait_round(i, s.round - 1, s.seq_prev);
-                if (left < 0) return r3d_fail_cuda(cudaGetLastError(), "r3d_engine_run: device error while waiting for a round");
-                if (left == 0) { s.done = true; ++n_done; }
-            }
-            s.seq_prev = seq_now;
+            s.seq_of[slot] = seq_now;
             s.round += 1;
-            rounds_max = std::max(rounds_max, s.round);
+        }
+        if (progressed) { idle_polls = 0; continue; }
+        // nothing to launch: every unfinished sub-batch waits for a word.  Poll briefly, then sleep in short steps
+        // instead of burning a host core per engine thread (8 ranks x 3 pipelined engines share the box's cores)
+        if (++idle_polls > 64) std::this_thread::sleep_for(std::chrono::microseconds(20));
+        if ((idle_polls & 0x3ff) == 0x3ff) {
+            for (int i = 0; i < nsub; ++i) {
+                if (sub[i].done) continue;
+                const cudaError_t q = cudaStreamQuery(sub[i].st);
+                long long left = 0;
+                if ((q != cudaSuccess && q != cudaErrorNotReady) ||
+                    (q == cudaSuccess && poll_round(i, sub[i].round - ahead, left) == 0))        // drained without the word
+                    return r3d_fail_cuda(q == cudaSuccess ? cudaErrorUnknown : q, "r3d_engine_run: device error while waiting for a round");
+            }
         }
     }
     eng->last_rounds = rounds_max;

@@ -49,7 +49,7 @@ class ScanResult:
 def _pinned(shape, dtype):
     """numpy array backed by page-locked host memory (owned by a torch tensor kept alive on the array)."""
     import torch
-    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64,
+    tdt = {np.float32: torch.float32, np.float64: torch.float64, np.int32: torch.int32, np.int64: torch.int64, np.int16: torch.int16,
            np.uint8: torch.uint8}[np.dtype(dtype).type]
     pin = torch.cuda.is_available()
     t = torch.empty(tuple(int(s) for s in np.atleast_1d(shape)), dtype=tdt, pin_memory=pin)
@@ -62,7 +62,7 @@ class Real3DEngine:
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
                  map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200, force_full_projection=False,
-                 sub_batches=0):
+                 sub_batches=0, fetch_labels=None):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -130,6 +130,8 @@ class Real3DEngine:
                                                       int(mv[1])), "set_ss_map")
         self._keep = []
         self._n_scans = 0
+        # labels/<frame>.label exists only in the semseg outputs (ss/ds:82-84); OD writes velodyne + check + label_2
+        self.fetch_labels = (task == 'ss') if fetch_labels is None else bool(fetch_labels)
 
     # ------------------------------------------------------------------------------------------ database
     def _prepare_db(self, db):
@@ -182,7 +184,7 @@ class Real3DEngine:
             pt_off[i + 1] = pt_off[i] + len(s.xyzi)
         total = int(pt_off[-1])
         xyzi = _pinned((total, 4), np.float32)
-        labels = _pinned((total,), np.int32)
+        labels = _pinned((total,), np.int16)          # labels are & 0xFFFF (od/ds:65): 2 bytes per point over PCIe
         box_off = np.zeros(n + 1, dtype=np.int32)
         box_rows = []
         n_events = max(int(np.asarray(s.perms).shape[0]) for s in scans)
@@ -193,7 +195,9 @@ class Real3DEngine:
         perms[:] = -1
         for i, s in enumerate(scans):
             xyzi[pt_off[i]:pt_off[i + 1]] = s.xyzi
-            labels[pt_off[i]:pt_off[i + 1]] = np.asarray(s.labels).astype(np.uint32).view(np.int32)
+            lab = np.asarray(s.labels)
+            assert lab.size == 0 or int(lab.max()) < 65536, "semantic labels must be masked with 0xFFFF (od/ds:65)"
+            labels[pt_off[i]:pt_off[i + 1]] = lab.astype(np.uint16).view(np.int16)
             for anno in (s.box_dicts if s.box_dicts is not None else [read(line) for line in s.box_lines]):
                 box_rows.append(bx.box_record(anno))
             box_off[i + 1] = len(box_rows)
@@ -227,7 +231,8 @@ class Real3DEngine:
         b.n_scans = staged['n']
         b.point_offsets = staged['pt_off'].ctypes.data
         b.xyzi = staged['xyzi'].ctypes.data
-        b.labels = staged['labels'].ctypes.data
+        b.labels = None
+        b.labels16 = staged['labels'].ctypes.data
         b.box_offsets = staged['box_off'].ctypes.data
         b.boxes = staged['boxes'].ctypes.data if staged['boxes'].size else None
         if self.task == 'od':
@@ -241,7 +246,7 @@ class Real3DEngine:
         b.n_events = staged['n_events']
         self._keep = [staged, b]
         self._n_scans = staged['n']
-        self._in_bytes = staged['total'] * 20
+        self._in_bytes = staged['total'] * 18
         _lib.check(self.lib.r3d_engine_load_batch(self.handle, C.byref(b)), "load_batch")
 
     def reset(self):
@@ -277,7 +282,7 @@ class Real3DEngine:
         r = _lib.BatchResult()
         r.out_offsets = buffers['out_off'].ctypes.data
         r.out_xyzi = buffers['xyzi'].ctypes.data
-        r.out_labels = buffers['labels'].ctypes.data
+        r.out_labels = buffers['labels'].ctypes.data if self.fetch_labels else None
         r.capacity_points = buffers['cap_points']
         r.check_offsets = buffers['check_off'].ctypes.data
         r.check_xyzil = buffers['check'].ctypes.data
@@ -288,7 +293,7 @@ class Real3DEngine:
         r.status = buffers['status'].ctypes.data
         r.rounds = buffers['rounds'].ctypes.data
         _lib.check(self.lib.r3d_engine_fetch(self.handle, C.byref(r)), "fetch")
-        buffers['out_bytes'] = rows * 20 + chk * 20
+        buffers['out_bytes'] = rows * (20 if self.fetch_labels else 16) + chk * 20
         return buffers
 
     def unpack(self, buffers, raise_on_error=True):
@@ -313,7 +318,8 @@ class Real3DEngine:
                     lines.append(bx.create_annotation_line(self.obj_strings[obj], box, rot * (360.0 / self.yaw_steps)))
             chk = np.array(buffers['check'][ca:cb])
             out.append(ScanResult(velodyne=np.array(buffers['xyzi'][a:b]),
-                                  labels=np.array(buffers['labels'][a:b]).view(np.uint32),
+                                  labels=(np.array(buffers['labels'][a:b]).view(np.uint32) if self.fetch_labels
+                                          else np.zeros(0, dtype=np.uint32)),
                                   check=chk if ss else chk[:, :4], inserted=inserted, lines=lines, boxes=boxes,
                                   visible=visible, status=st, extra={'rounds': int(buffers['rounds'][0])}))
         return out
