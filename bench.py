@@ -242,8 +242,10 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sub-batches", type=int, default=4, help="sub-batches one engine advances concurrently (own streams)")
-    ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
+    ap.add_argument("--sub-batches", type=int, default=8,
+                    help="sub-batches the engine advances concurrently (own streams) in the device-resident leg")
+    ap.add_argument("--e2e-sub-batches", type=int, default=2, help="same, per engine of the e2e pipeline")
+    ap.add_argument("--depth", type=int, default=4, help="engines (streams) the e2e leg pipelines batches through")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, json_out)
@@ -287,6 +289,7 @@ def main():
     eng = pipe.engines[0]
     staged = eng.stage([scan_input_from_case(c) for c in cases])
     stream = eng.cuda_stream()
+    eng.set_sub_batches(args.sub_batches)
 
     # ---- device-resident throughput ("value") --------------------------------------------------------
     eng.load(staged)
@@ -329,6 +332,8 @@ def main():
     # ---- end to end through the public API with host buffers ("e2e") -----------------------------------
     # every step = one staged batch in pinned host memory: H2D of all points / labels / maps / schedules, the
     # spherical ingest, the augmentation rounds, D2H of the augmented clouds into pinned host buffers
+    for e in pipe.engines:
+        e.set_sub_batches(args.e2e_sub_batches)
     pipe.warmup(staged)
     pipe.warmup(staged)
     barrier()
@@ -395,6 +400,7 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h / args.steps), "pipeline_depth": args.depth,
+                    "sub_batches_per_engine": args.e2e_sub_batches,
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
                     "pcie_gbs_each_way": round(max(h2d, d2h / args.steps) / (e2e_s / args.steps) / 1e9, 1)},
             "gpu_launches": int(launches), "clocks": clocks, "sub_batches": args.sub_batches,

@@ -185,6 +185,10 @@ int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* result);
 /* Number of contiguous sub-batches r3d_engine_run advances concurrently, each on its own stream (1..8).  1 runs the
  * rounds strictly one kernel after the other (what the per-kernel CUDA-event profile needs). */
 int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub);
+/* r3d_engine_run in two (or more) calls: returns with *still_running = 1 as soon as at most `stop_at` scans of the batch
+ * are unfinished (their rounds stay in flight); call again (stop_at = 0) to finish.  Lets a caller that serialises the
+ * busy part of several engines' runs on one GPU overlap one engine's tail with the next engine's head. */
+int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_running);
 int r3d_engine_sync(r3d_engine* eng);
 /* total output rows of the last run (valid after r3d_engine_run + r3d_engine_sync) */
 int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check);

@@ -86,6 +86,7 @@ PROTOTYPES = {
     "r3d_engine_fetch": (C.c_int, [C.c_void_p, C.POINTER(BatchResult)]),
     "r3d_engine_sync": (C.c_int, [C.c_void_p]),
     "r3d_engine_set_sub_batches": (C.c_int, [C.c_void_p, C.c_int]),
+    "r3d_engine_run_until": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "r3d_engine_output_rows": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "r3d_engine_profile_enable": (C.c_int, [C.c_void_p, C.c_int]),
     "r3d_engine_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,

@@ -58,6 +58,11 @@ struct r3d_engine {
     cudaStream_t sub_stream[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t sub_done[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t ev_armed = nullptr;
+    // state of a run in progress (r3d_engine_run_until may return before the batch is finished)
+    struct Sub { int b0, n, round; bool done; long long left; unsigned seq_of[64]; EngineDev d; cudaStream_t st; };
+    Sub sub[R3D_MAX_SUB];
+    bool run_active = false;
+    int run_nsub = 0, run_done = 0, run_rounds = 0;
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
     int last_rounds = 0;
     // device buffers
@@ -372,6 +377,7 @@ extern "C" int r3d_engine_set_ss_map(r3d_engine* eng, const uint8_t* map, int32_
 }
 
 static int arm_batch(r3d_engine* eng, bool ingest) {
+    eng->run_active = false;                     // a new batch / re-arm abandons a run that was left unfinished
     EngineDev& d = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
@@ -523,9 +529,14 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     return v;
 }
 
-extern "C" int r3d_engine_run(r3d_engine* eng) {
+extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_running);
+
+extern "C" int r3d_engine_run(r3d_engine* eng) { return r3d_engine_run_until(eng, 0, nullptr); }
+
+extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_running) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: no batch loaded");
+    if (still_running) *still_running = 0;
     const EngineDev& d0 = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
@@ -539,17 +550,24 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
     // The batch is advanced as n_sub contiguous sub-batches, each on its own stream: every kernel of a round is a
     // short chain of dependent loads that leaves most of the SMs' issue slots idle, so the rounds of different
     // sub-batches overlap on the device.
-    const int nsub = std::max(1, std::min(eng->n_sub, n));
-    struct Sub { int b0, n, round; bool done; unsigned seq_of[64]; EngineDev d; cudaStream_t st; };
-    Sub sub[R3D_MAX_SUB];
-    R3D_CUDA(cudaEventRecord(eng->ev_armed, st));
-    for (int i = 0; i < nsub; ++i) {
-        Sub& s = sub[i];
-        s.b0 = (int)((long long)n * i / nsub); s.n = (int)((long long)n * (i + 1) / nsub) - s.b0;
-        s.round = 0; s.done = false; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
-        R3D_CUDA(cudaStreamWaitEvent(s.st, eng->ev_armed, 0));
-        R3D_CUDA(cudaMemsetAsync(eng->active_count.p + (size_t)i * 128, 0, 128 * sizeof(int), s.st));
+    typedef r3d_engine::Sub Sub;
+    Sub* sub = eng->sub;
+    if (!eng->run_active) {
+        eng->run_nsub = std::max(1, std::min(eng->n_sub, n));
+        eng->run_done = 0; eng->run_rounds = 0;
+        R3D_CUDA(cudaEventRecord(eng->ev_armed, st));
+        for (int i = 0; i < eng->run_nsub; ++i) {
+            Sub& s = sub[i];
+            s.b0 = (int)((long long)n * i / eng->run_nsub); s.n = (int)((long long)n * (i + 1) / eng->run_nsub) - s.b0;
+            s.round = 0; s.done = false; s.left = s.n; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
+            R3D_CUDA(cudaStreamWaitEvent(s.st, eng->ev_armed, 0));
+            R3D_CUDA(cudaMemsetAsync(eng->active_count.p + (size_t)i * 128, 0, 128 * sizeof(int), s.st));
+        }
+        eng->run_active = true;
     }
+    const int nsub = eng->run_nsub;
+    int& n_done = eng->run_done;
+    int& rounds_max = eng->run_rounds;
     const int task_ctas = std::max(eng->n_sms, eng->n_sms * TASK_CTAS_PER_SM / nsub);
     // The k_ctrl of every round publishes (sequence number, unfinished scans) into mapped host memory.  The host keeps
     // up to `ahead` rounds of a sub-batch in flight: round r is launched once the word of round r - ahead is there
@@ -562,7 +580,6 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
         if ((unsigned)(v >> 32) == sub[i].seq_of[round & 63]) { left = (long long)(v & 0xffffffffull); return 1; }
         return 0;
     };
-    int n_done = 0, rounds_max = 0;
     unsigned idle_polls = 0;
     while (n_done < nsub) {
         bool progressed = false;
@@ -573,10 +590,11 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
                 long long left = 0;
                 const int got = poll_round(i, s.round - ahead, left);
                 if (got == 0) continue;
+                s.left = left;
                 if (left == 0) { s.done = true; ++n_done; progressed = true; rounds_max = std::max(rounds_max, s.round - ahead + 1); continue; }
             }
             progressed = true;
-            if (s.round >= max_rounds) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached");
+            if (s.round >= max_rounds) { eng->run_active = false; return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached"); }
             EngineDev& d = s.d;
             const int ns = s.n, slot = s.round & 63;
             cudaStream_t ss = s.st;
@@ -612,6 +630,11 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
             s.seq_of[slot] = seq_now;
             s.round += 1;
         }
+        if (stop_at > 0 && n_done < nsub) {             // hand the device to the next engine once only a tail is left
+            long long left_total = 0;
+            for (int i = 0; i < nsub; ++i) left_total += sub[i].done ? 0 : sub[i].left;
+            if (left_total <= stop_at) { if (still_running) *still_running = 1; return R3D_OK; }
+        }
         if (progressed) { idle_polls = 0; continue; }
         // nothing to launch: every unfinished sub-batch waits for a word.  Poll briefly, then sleep in short steps
         // instead of burning a host core per engine thread (8 ranks x 3 pipelined engines share the box's cores)
@@ -623,11 +646,12 @@ extern "C" int r3d_engine_run(r3d_engine* eng) {
                 long long left = 0;
                 if ((q != cudaSuccess && q != cudaErrorNotReady) ||
                     (q == cudaSuccess && poll_round(i, sub[i].round - ahead, left) == 0))        // drained without the word
-                    return r3d_fail_cuda(q == cudaSuccess ? cudaErrorUnknown : q, "r3d_engine_run: device error while waiting for a round");
+                    { eng->run_active = false; return r3d_fail_cuda(q == cudaSuccess ? cudaErrorUnknown : q, "r3d_engine_run: device error while waiting for a round"); }
             }
         }
     }
     eng->last_rounds = rounds_max;
+    eng->run_active = false;
     for (int i = 0; i < nsub; ++i) {
         R3D_CUDA(cudaEventRecord(eng->sub_done[i], sub[i].st));
         R3D_CUDA(cudaStreamWaitEvent(st, eng->sub_done[i], 0));

@@ -516,7 +516,8 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int
     }
 }
 
-// exclusive prefix sum of the per-cell counts (one CTA per scan); after the scatter pass cell[c] = END of cell c
+// exclusive prefix sum of the per-cell counts (one CTA per scan, four cells per thread and step); after the scatter
+// pass cell[c] = END of cell c
 __global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans) return;
@@ -526,18 +527,26 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, i
     if (threadIdx.x == 0) s_run = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i0 = 0; i0 < n; i0 += 1024) {
-        const int i = i0 + threadIdx.x;
-        const int v = i < n ? cell[i] : 0;
-        int inc = v;
+    const bool vec = (stride & 3) == 0;                  // rows of `arr` 16-byte aligned: int4 loads / stores
+    for (int i0 = 0; i0 < n; i0 += 4096) {
+        const int i = i0 + threadIdx.x * 4;
+        int v[4] = {0, 0, 0, 0};
+        if (vec && i + 3 < n) { const int4 t = *reinterpret_cast<const int4*>(cell + i); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else for (int u = 0; u < 4; ++u) if (i + u < n) v[u] = cell[i + u];
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int inc = mine;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) s_w[w] = inc;
         __syncthreads();
-        int off = s_run;
-        for (int j = 0; j < w; ++j) off += s_w[j];
-        if (i < n) cell[i] = off + inc - v;
+        int off = s_run, tot = 0;
+        for (int j = 0; j < 32; ++j) { if (j < w) off += s_w[j]; tot += s_w[j]; }
+        int e0 = off + inc - mine;                        // exclusive prefix of this thread's first cell
+        int o4[4];
+        for (int u = 0; u < 4; ++u) { o4[u] = e0; e0 += v[u]; }
+        if (vec && i + 3 < n) *reinterpret_cast<int4*>(cell + i) = make_int4(o4[0], o4[1], o4[2], o4[3]);
+        else for (int u = 0; u < 4; ++u) if (i + u < n) cell[i + u] = o4[u];
         __syncthreads();
-        if (threadIdx.x == 0) { int t = 0; for (int j = 0; j < 32; ++j) t += s_w[j]; s_run += t; }
+        if (threadIdx.x == 0) s_run += tot;
         __syncthreads();
     }
 }

@@ -61,7 +61,7 @@ class Real3DEngine:
 
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
-                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=200, force_full_projection=False,
+                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=120, force_full_projection=False,
                  sub_batches=0, fetch_labels=None):
         _lib.require_cuda()
         self.lib = _lib.load()
@@ -254,6 +254,12 @@ class Real3DEngine:
 
     def run(self):
         _lib.check(self.lib.r3d_engine_run(self.handle), "run")
+
+    def run_until(self, stop_at):
+        """``run`` that returns True (still running) once at most ``stop_at`` scans are unfinished; call again with 0."""
+        more = C.c_int(0)
+        _lib.check(self.lib.r3d_engine_run_until(self.handle, int(stop_at), C.byref(more)), "run_until")
+        return bool(more.value)
 
     def set_sub_batches(self, n):
         """How many contiguous sub-batches ``run`` advances concurrently on their own streams (1 = strictly serial)."""

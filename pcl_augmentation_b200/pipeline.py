@@ -18,9 +18,11 @@ from .engine import Real3DEngine
 
 
 class ScanPipeline:
-    def __init__(self, task, config, db, *, depth=3, exclusive_run=True, **engine_kwargs):
+    def __init__(self, task, config, db, *, depth=4, exclusive_run=True, tail_fraction=8, **engine_kwargs):
         assert depth >= 1
+        self.tail_fraction = tail_fraction
         self._run_lock = threading.Lock() if exclusive_run else None
+        engine_kwargs.setdefault('sub_batches', 2)       # measured best when several engines share the GPU
         self.engines = [Real3DEngine(task, config, db, **engine_kwargs) for _ in range(depth)]
         self.depth = depth
         self._buffers = [None] * depth
@@ -61,8 +63,12 @@ class ScanPipeline:
                     t1 = time.perf_counter()
                     if self._run_lock is not None:
                         eng.sync()                        # the upload must not hold up the engine that computes
+                        # only the busy head of a run is exclusive: once a quarter of the scans is left the next
+                        # engine may start, its first rounds fill the SMs this engine's thinning rounds leave idle
                         with self._run_lock:
-                            eng.run()
+                            more = eng.run_until(max(1, st['n'] // self.tail_fraction))
+                        if more:
+                            eng.run_until(0)
                     else:
                         eng.run()
                     if trace is not None:
