@@ -82,6 +82,19 @@ int r3d_adjust_map(const double* rows9, int64_t n, const double* pose16_host, in
                    const int32_t* ground_labels, int n_ground, double* map_dev, int size_x, int size_y,
                    r3d_stream stream);
 
+/* ------------------------------------------------------------------------------------------------- rich maps */
+/* object_detection/rich_map/single_drivable_area_map.py:123-194, batched over frames (all pointers: device).
+ * xyzi: total x 4 float32, labels: total uint32 (semantic label & 0xFFFF), point_offsets: n_scans + 1.
+ * Step 1 writes dims[scan] = {size_x, size_y, min_x, min_y} (1 m cells over the xy extent of ALL points, int()
+ * truncation toward zero, :123-133).  The caller turns the sizes into cell offsets (map_offsets[scan], n_scans + 1) and
+ * step 2 writes the road map (road points rasterised, closing(disk(4)), :136-161) and the pedestrian-area map
+ * (8-neighbour ring of the road, dilation(disk(2)), :164-193) as uint8 {0, 1}, size_x * size_y cells each, row-major
+ * [x][y]; scratch: 2 * total_cells bytes. */
+int r3d_rich_map_od_extents(const float* xyzi, const int64_t* point_offsets, int32_t n_scans, int32_t* dims, r3d_stream stream);
+int r3d_rich_map_od_build(const float* xyzi, const uint32_t* labels, const int64_t* point_offsets, int32_t n_scans,
+                          uint32_t road_label, const int32_t* dims, const int64_t* map_offsets, int64_t total_cells,
+                          uint8_t* road_out, uint8_t* ped_out, uint8_t* scratch, r3d_stream stream);
+
 /* --------------------------------------------------------------------------------------------------- engine */
 /* Device-resident batched driver of the per-scan loop (od/ins:351-628, ss/ins:355-599): placement search
  * (find_possible_places od/fs:227-304, ss/fs:192-273), occlusion (od/ins:468-501), accept rule and insertion

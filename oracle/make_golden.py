@@ -309,7 +309,38 @@ def gen_fn_places(task):
     print(f"fn_places_{task}: {time.time() - t0:.1f}s feasible per sample {n_feasible}")
 
 
+def gen_rich_map_od():
+    """the reference's per-frame rich-map script on two synthetic frames (written with
+    pcl_augmentation_b200.synth_io in the reference's dataset layout)."""
+    from pcl_augmentation_b200 import synth_io
+    t0 = time.time()
+    cases = [build_case(dict(task="od", seed=s, counts=[1, 1], n_cars=c)) for s, c in ((31, 3), (32, 8))]
+    root = tempfile.mkdtemp(prefix="r3d_golden_")
+    try:
+        cwd, _, cfg = synth_io.write_od_dataset(cases, root)
+        shutil.rmtree(os.path.join(root, "maps"))                     # the script must create everything itself
+        os.makedirs(os.path.join(root, "maps"))
+        shim.run_rich_map_od(cwd)
+        rec = {"meta": json.dumps(dict(seeds=[31, 32], n_cars=[3, 8])), "digest0": synth.case_digest(cases[0]),
+               "digest1": synth.case_digest(cases[1])}
+        for i in range(2):
+            for key, sub in (("road", "road_maps"), ("ped", "pedestrian_area")):
+                z = np.load(os.path.join(root, f"maps/maps/{sub}/npz/{i:06d}.npz"))
+                m = z["map"]
+                assert set(np.unique(m)) <= {0, 1}
+                rec[f"{key}{i}_shape"] = np.array(m.shape)
+                rec[f"{key}{i}_dtype"] = str(m.dtype)
+                rec[f"{key}{i}_bits"] = np.packbits(m.astype(bool))
+                rec[f"{key}{i}_min"] = np.array([int(z["min_x"]), int(z["min_y"])])
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "rich_map_od.npz"), **rec)
+        print(f"rich_map_od: {time.time() - t0:.1f}s shapes", rec["road0_shape"], rec["road1_shape"], rec["road0_dtype"],
+              "road cells", int(np.unpackbits(rec["road0_bits"]).sum()), "ped cells", int(np.unpackbits(rec["ped0_bits"]).sum()))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 GENERATORS = {
+    "rich_map_od": gen_rich_map_od,
     "fn_projection": gen_fn_projection,
     "fn_cut_bbox": gen_fn_cut_bbox,
     "fn_places_od": lambda: gen_fn_places("od"),

@@ -9,7 +9,7 @@ What is patched (all results-neutral):
                                      (used at semantic_segmentation/Real3DAug/tools/find_spot.py:238, insertion.py:218)
   * ``Rotation.as_dcm/from_dcm``     removed in scipy>=1.6 -> ``as_matrix/from_matrix``
                                      (tools/cut_bbox.py:28, tools/find_spot.py:83,90,213)
-  * ``skimage`` (not installed)      stub modules: ``img_as_ubyte``, ``rectangle``, ``closing`` built on
+  * ``skimage`` (not installed)      stub modules: ``img_as_ubyte``, ``rectangle``, ``disk``, ``closing``, ``dilation`` built on
                                      ``scipy.ndimage.grey_dilation/grey_erosion`` (mode='reflect', which is what
                                      ``skimage.morphology.closing`` wraps).  scikit-image is an un-pinned third-party
                                      dependency of the reference (tools/closing.py:2-4): parity of the closing step is
@@ -72,9 +72,19 @@ def _install_compat():
             dil = ndimage.grey_dilation(image, footprint=fp)
             return ndimage.grey_erosion(dil, footprint=fp)
 
+        def disk(radius, dtype=np.uint8):
+            L = np.arange(-radius, radius + 1)
+            X, Y = np.meshgrid(L, L)
+            return np.array((X ** 2 + Y ** 2) <= radius ** 2, dtype=dtype)
+
+        def dilation(image, footprint=None, out=None):
+            return ndimage.grey_dilation(image, footprint=np.asarray(footprint, dtype=bool))
+
         util.img_as_ubyte = img_as_ubyte
         morph.rectangle = rectangle
         morph.closing = closing
+        morph.disk = disk
+        morph.dilation = dilation
         sk.util, sk.morphology, sk.io = util, morph, sio
         sys.modules.update({"skimage": sk, "skimage.util": util, "skimage.morphology": morph, "skimage.io": sio})
 
@@ -155,4 +165,26 @@ def run_main(which, cwd, inputs=(), shuffle_fn=None, quiet=True):
     finally:
         os.chdir(old_cwd)
         builtins.input, _glob.glob, _random.shuffle = old_input, old_glob, old_shuffle
+    return out.getvalue()
+
+
+def run_rich_map_od(cwd, quiet=True):
+    """Execute the reference's ``object_detection/rich_map/single_drivable_area_map.py`` as ``__main__`` (unmodified);
+    it reads ``../config/KITTI.yaml`` relative to ``cwd`` and imports ``object_detection.Real3DAug.tools.datasets``."""
+    _install_compat()
+    old_cwd = os.getcwd()
+    out = io.StringIO()
+    for k in [k for k in sys.modules if k == "object_detection" or k.startswith("object_detection.")]:
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        os.chdir(cwd)
+        with (contextlib.redirect_stdout(out) if quiet else contextlib.nullcontext()):
+            runpy.run_path(os.path.join(REFERENCE_ROOT, "object_detection/rich_map/single_drivable_area_map.py"),
+                           run_name="__main__")
+    finally:
+        os.chdir(old_cwd)
+        sys.path.remove(REFERENCE_ROOT)
+        for k in [k for k in sys.modules if k == "object_detection" or k.startswith("object_detection.")]:
+            del sys.modules[k]
     return out.getvalue()

@@ -163,3 +163,23 @@ def test_e2e_closed_form_equals_cumulative(name):
     spec, case = case_from_golden(g)
     res = run_oracle_e2e(g, case, mode="closed")
     check_e2e_against_golden(g, case, res, exact_bytes=False)
+
+
+def test_rich_map_od_matches_reference_script():
+    """rich-map oracle vs what the unmodified single_drivable_area_map.py wrote."""
+    import json
+    from oracle import rich_map_oracle as rmo
+    from tests.helpers import case_from_spec
+    g = load_golden("rich_map_od")
+    meta = json.loads(str(g["meta"]))
+    for i, (seed, n_cars) in enumerate(zip(meta["seeds"], meta["n_cars"])):
+        case = case_from_spec(dict(task="od", seed=seed, counts=[1, 1], n_cars=n_cars))
+        assert synth.case_digest(case) == str(g[f"digest{i}"])
+        pcl5 = np.hstack((case.pcl5[:, :4].astype(np.float32), case.pcl5[:, 4:5]))       # KITTI.__getitem__ (od/ds:62-66)
+        road, ped, min_x, min_y = rmo.rich_map_od(pcl5, case.config["labels"]["Road"])
+        for key, got in (("road", road), ("ped", ped)):
+            shape = tuple(g[f"{key}{i}_shape"])
+            want = np.unpackbits(g[f"{key}{i}_bits"])[:shape[0] * shape[1]].reshape(shape)
+            assert got.shape == shape and got.dtype == np.uint8 == np.dtype(str(g[f"{key}{i}_dtype"]))
+            np.testing.assert_array_equal(got, want)
+            assert [min_x, min_y] == list(g[f"{key}{i}_min"])
