@@ -95,6 +95,26 @@ int r3d_rich_map_od_build(const float* xyzi, const uint32_t* labels, const int64
                           uint32_t road_label, const int32_t* dims, const int64_t* map_offsets, int64_t total_cells,
                           uint8_t* road_out, uint8_t* ped_out, uint8_t* scratch, r3d_stream stream);
 
+/* semantic_segmentation/rich_map/drivable_area_map.py:122-206: ONE map per sequence, built from frames that may be
+ * fed in several calls (all pointers: device).  xyzi / labels / point_offsets as above; poses: n_frames x 16 float64
+ * (row-major 4 x 4 lidar -> world, what SemanticKITTI.create_transform_matrix returns); max_points: the largest frame.
+ * Step 1, r3d_rich_map_ss_extents: world-frame xy extent of all points (:130-146).  ext_state: 4 uint64 carried between
+ * calls (first_call != 0 resets it); if out5 != NULL it receives {min_x, min_y, size_x, size_y, any_point} with
+ * min = int(floor(min)), max = int(max) + 1 (:158-166).
+ * Step 2, r3d_rich_map_ss_raster: the surface points of the frames in order (:172-200) into keymap (size_x * size_y
+ * uint64, zeroed by the caller before the first call).  surface_labels[i] belongs to map class surface_classes[i]
+ * (1 road: written unless the cell holds 3; 2 parking: likewise; 3 sidewalk: sticky); order_base = number of points
+ * of the frames rasterised by earlier calls.  *error_flag becomes 1 where the reference's assert (:190) would fire,
+ * 2 where it would raise IndexError.
+ * Step 3, r3d_rich_map_ss_finalize: keymap -> map_out uint8 {0, 1, 2, 3}, row-major [x][y]. */
+int r3d_rich_map_ss_extents(const float* xyzi, const int64_t* point_offsets, const double* poses, int32_t n_frames,
+                            int32_t max_points, int32_t first_call, uint64_t* ext_state, int64_t* out5, r3d_stream stream);
+int r3d_rich_map_ss_raster(const float* xyzi, const uint32_t* labels, const int64_t* point_offsets, const double* poses,
+                           int32_t n_frames, int32_t max_points, const int32_t* surface_labels,
+                           const int32_t* surface_classes, int32_t n_surface, int64_t min_x, int64_t min_y, int32_t size_x,
+                           int32_t size_y, int64_t order_base, uint64_t* keymap, int32_t* error_flag, r3d_stream stream);
+int r3d_rich_map_ss_finalize(const uint64_t* keymap, int64_t cells, uint8_t* map_out, r3d_stream stream);
+
 /* --------------------------------------------------------------------------------------------------- engine */
 /* Device-resident batched driver of the per-scan loop (od/ins:351-628, ss/ins:355-599): placement search
  * (find_possible_places od/fs:227-304, ss/fs:192-273), occlusion (od/ins:468-501), accept rule and insertion
@@ -126,7 +146,10 @@ typedef struct r3d_engine_cfg {
     int32_t grid_half;                        /* road-level search grid: cells per half side (grid covers +-grid_half*grid_cell m) */
     double grid_cell;                         /* road-level search grid: cell size in metres (0 -> 0.5) */
     int32_t flags;                            /* bit0: re-project every slot in full (disable the in-place image patch);
-                                                 bits 8-11: sub-batches advanced concurrently on their own streams (0 = default 4) */
+                                                 bit1: launch the kernels of a round one by one instead of replaying the
+                                                 round's CUDA graph;
+                                                 bits 8-12: sub-batches advanced concurrently on their own streams
+                                                 (1..16, 0 = default 4) */
     double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */
     int32_t radii_ok[R3D_NUM_RADII];          /* 0 where the pass's "radius > 5" check already fails */
     r3d_class_cfg classes[R3D_MAX_CLASSES];

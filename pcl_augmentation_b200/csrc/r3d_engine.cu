@@ -14,7 +14,7 @@
 
 using namespace r3d;
 
-#define R3D_MAX_SUB 8
+#define R3D_MAX_SUB 16
 
 namespace {
 
@@ -59,8 +59,13 @@ struct r3d_engine {
     cudaEvent_t sub_done[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t ev_armed = nullptr;
     // state of a run in progress (r3d_engine_run_until may return before the batch is finished)
-    struct Sub { int b0, n, round; bool done; long long left; unsigned seq_of[64]; EngineDev d; cudaStream_t st; };
+    struct Sub { int b0, n, round; bool done; long long left; unsigned seq_base; EngineDev d; cudaStream_t st; };
     Sub sub[R3D_MAX_SUB];
+    // one round of a sub-batch (k_ctrl ... k_select_emit) captured as a CUDA graph: every argument is constant between
+    // rounds (the round number lives on the device), so a round costs the host ONE launch instead of twelve
+    struct RoundGraph { cudaGraphExec_t exec = nullptr; EngineDev d; int ns = 0, chunks_all = 0, task_ctas = 0, sel_pts = 0, kernels = 0; };
+    RoundGraph round_graph[R3D_MAX_SUB];
+    bool use_graphs = true, capturing = false;
     bool run_active = false;
     int run_nsub = 0, run_done = 0, run_rounds = 0;
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
@@ -76,6 +81,7 @@ struct r3d_engine {
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
+    DevBuf<unsigned> round_ctl;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
@@ -114,6 +120,7 @@ __global__ void k_widen_labels(const unsigned short* src, const long long* pt_of
     const int p0 = blockIdx.x * CHUNK;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, cnt); p += blockDim.x) label[(size_t)b * P + p] = src[o + p];
 }
+__global__ void k_set_round(unsigned* round_ctl, unsigned seq_base) { round_ctl[0] = 0u; round_ctl[1] = seq_base; }
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -134,6 +141,7 @@ struct Launcher {          // wraps every launch: launch counter + optional CUDA
         cudaEvent_t ev; cudaEventCreate(&ev); return ev;
     }
     ~Launcher() {
+        if (eng->capturing) return;          // counted per graph launch
         r3d_count_launch();
         eng->prof_launches[kid] += 1;
         if (eng->profile) {
@@ -187,7 +195,9 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     int prio_least = 0, prio_greatest = 0;
     R3D_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
     R3D_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_least));
-    eng->n_sub = (cfg->flags >> 8) & 15;
+    eng->n_sub = (cfg->flags >> 8) & 31;
+    eng->use_graphs = !(cfg->flags & 2);
+    if (const char* env = getenv("R3D_GRAPHS")) eng->use_graphs = atoi(env) != 0;
     if (const char* env = getenv("R3D_SUBBATCHES")) eng->n_sub = atoi(env);
     if (eng->n_sub <= 0) eng->n_sub = 4;
     eng->n_sub = std::min(eng->n_sub, R3D_MAX_SUB);
@@ -218,6 +228,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
     TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
     TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(R3D_MAX_SUB * 64 * 2));
+    TRY(eng->round_ctl.alloc(R3D_MAX_SUB * 32));
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -289,6 +300,7 @@ extern "C" int r3d_engine_destroy(r3d_engine* eng) {
         if (eng->sub_done[i]) cudaEventDestroy(eng->sub_done[i]);
     }
     if (eng->ev_armed) cudaEventDestroy(eng->ev_armed);
+    for (int i = 0; i < R3D_MAX_SUB; ++i) if (eng->round_graph[i].exec) cudaGraphExecDestroy(eng->round_graph[i].exec);
     cudaStreamDestroy(eng->stream);
     delete eng;
     return R3D_OK;
@@ -560,8 +572,14 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
             Sub& s = sub[i];
             s.b0 = (int)((long long)n * i / eng->run_nsub); s.n = (int)((long long)n * (i + 1) / eng->run_nsub) - s.b0;
             s.round = 0; s.done = false; s.left = s.n; s.d = sub_view(d0, s.b0); s.st = eng->sub_stream[i];
+            s.d.active_count = eng->active_count.p + (size_t)i * 128;
+            s.d.host_word = eng->d_words + (size_t)i * 64;
+            s.d.round_ctl = eng->round_ctl.p + (size_t)i * 32;
+            if (eng->seq > 0xF0000000u) eng->seq = 0;                       // sequence numbers are never 0 (= a fresh word)
+            s.seq_base = eng->seq + 1; eng->seq += (unsigned)max_rounds + 8u;
             R3D_CUDA(cudaStreamWaitEvent(s.st, eng->ev_armed, 0));
-            R3D_CUDA(cudaMemsetAsync(eng->active_count.p + (size_t)i * 128, 0, 128 * sizeof(int), s.st));
+            R3D_CUDA(cudaMemsetAsync(s.d.active_count, 0, 128 * sizeof(int), s.st));
+            k_set_round<<<1, 1, 0, s.st>>>(s.d.round_ctl, s.seq_base); r3d_count_launch();
         }
         eng->run_active = true;
     }
@@ -574,12 +592,59 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
     // (rounds launched after the last scan finished are gated off on the device and cost a few microseconds each),
     // so neither the device nor the other sub-batches ever wait for a word that is stuck behind bulk PCIe traffic.
     const int ahead = 3;
-    auto poll_round = [&](int i, int round, long long& left) -> int {       // 1: published, 0: not yet, -1: device error
+    auto poll_round = [&](int i, int round, long long& left) -> int {       // 1: published, 0: not yet
         volatile unsigned long long* w = eng->h_words + (size_t)i * 64 + (round & 63);
         const unsigned long long v = *w;
-        if ((unsigned)(v >> 32) == sub[i].seq_of[round & 63]) { left = (long long)(v & 0xffffffffull); return 1; }
+        if ((unsigned)(v >> 32) == sub[i].seq_base + (unsigned)round) { left = (long long)(v & 0xffffffffull); return 1; }
         return 0;
     };
+    // the launch sequence of one round; also what a round graph is captured from
+    auto launch_round = [&](const EngineDev& d, int ns, cudaStream_t ss, bool r0) {
+        const size_t pref_smem = (size_t)(ns + 1) * sizeof(int);
+        { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 128, 0, ss>>>(d, ns); }
+        { Launcher l(eng, KID_UPDATE, ss); k_update<<<dim3(UPDATE_G, ns), UPDATE_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_MINMAX0 : KID_MINMAX, ss); k_minmax<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_CLEAR0 : KID_CLEAR, ss); k_clear_images<<<dim3(32, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+        {
+            Launcher l(eng, r0 ? KID_CLOSEFILL0 : KID_CLOSEFILL, ss);
+            RawImage in{d.zraw};
+            dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, ns);
+            k_close_fill<RawImage><<<grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
+                                                                 d.far_arr, d.cf_rect);
+        }
+        if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }
+        if (d.task == 0) { Launcher l(eng, KID_ONMAP, ss); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+        { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+        if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
+        { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+        { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
+        { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap, sel_pts); }
+    };
+    const bool graphs = eng->use_graphs && !eng->profile;
+    if (graphs) {
+        for (int i = 0; i < nsub; ++i) {
+            r3d_engine::RoundGraph& g = eng->round_graph[i];
+            const Sub& s = sub[i];
+            if (g.exec && g.ns == s.n && g.chunks_all == chunks_all && g.task_ctas == task_ctas && g.sel_pts == sel_pts &&
+                memcmp(&g.d, &s.d, sizeof(EngineDev)) == 0) continue;
+            if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            R3D_CUDA(cudaStreamBeginCapture(s.st, cudaStreamCaptureModeThreadLocal));
+            eng->capturing = true;
+            launch_round(s.d, s.n, s.st, false);
+            eng->capturing = false;
+            R3D_CUDA(cudaStreamEndCapture(s.st, &graph));
+            size_t n_nodes = 0;
+            R3D_CUDA(cudaGraphGetNodes(graph, nullptr, &n_nodes));
+            const cudaError_t ie = cudaGraphInstantiate(&g.exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (ie != cudaSuccess) { g.exec = nullptr; return r3d_fail_cuda(ie, "r3d_engine_run: cudaGraphInstantiate"); }
+            memcpy(&g.d, &s.d, sizeof(EngineDev));
+            g.ns = s.n; g.chunks_all = chunks_all; g.task_ctas = task_ctas; g.sel_pts = sel_pts; g.kernels = (int)n_nodes;
+        }
+    }
     unsigned idle_polls = 0;
     while (n_done < nsub) {
         bool progressed = false;
@@ -595,39 +660,12 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
             }
             progressed = true;
             if (s.round >= max_rounds) { eng->run_active = false; return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: round limit reached"); }
-            EngineDev& d = s.d;
-            const int ns = s.n, slot = s.round & 63;
-            cudaStream_t ss = s.st;
-            int* ac = eng->active_count.p + (size_t)i * 128;
-            d.active_count = ac + 2 * slot;
-            d.host_word = eng->d_words + (size_t)i * 64 + slot;
-            if (++eng->seq == 0) ++eng->seq;
-            d.ctrl_seq = eng->seq;
-            const unsigned seq_now = eng->seq;
-            const size_t pref_smem = (size_t)(ns + 1) * sizeof(int);
-            { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 128, 0, ss>>>(d, ns); }
-            R3D_CUDA(cudaMemsetAsync(ac + 2 * ((slot + 32) & 63), 0, 2 * sizeof(int), ss));
-            { Launcher l(eng, KID_UPDATE, ss); k_update<<<dim3(UPDATE_G, ns), UPDATE_THREADS, 0, ss>>>(d, ns); }
-            const bool r0 = s.round == 0;
-            { Launcher l(eng, r0 ? KID_MINMAX0 : KID_MINMAX, ss); k_minmax<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-            { Launcher l(eng, r0 ? KID_CLEAR0 : KID_CLEAR, ss); k_clear_images<<<dim3(32, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-            { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-            {
-                Launcher l(eng, r0 ? KID_CLOSEFILL0 : KID_CLOSEFILL, ss);
-                RawImage in{d.zraw};
-                dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, ns);
-                k_close_fill<RawImage><<<grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
-                                                                     d.far_arr, d.cf_rect);
+            if (graphs) {
+                R3D_CUDA(cudaGraphLaunch(eng->round_graph[i].exec, s.st));
+                r3d_count_launch(eng->round_graph[i].kernels);
+            } else {
+                launch_round(s.d, s.n, s.st, s.round == 0);
             }
-            if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-            { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }
-            if (d.task == 0) { Launcher l(eng, KID_ONMAP, ss); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
-            { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
-            if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
-            { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
-            { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
-            { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap, sel_pts); }
-            s.seq_of[slot] = seq_now;
             s.round += 1;
         }
         if (stop_at > 0 && n_done < nsub) {             // hand the device to the next engine once only a tail is left
@@ -672,7 +710,7 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
 
 extern "C" int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub) {
     if (eng) cudaSetDevice(eng->device);
-    if (!eng || n_sub < 1 || n_sub > R3D_MAX_SUB) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_sub_batches: 1..8");
+    if (!eng || n_sub < 1 || n_sub > R3D_MAX_SUB) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_sub_batches: 1..16");
     eng->n_sub = n_sub;
     return R3D_OK;
 }

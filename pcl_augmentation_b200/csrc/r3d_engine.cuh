@@ -88,9 +88,11 @@ struct EngineDev {       // passed by value to kernels
     int* cf_rect;                     // [B][4] rows r0..r1, cols c0..c1 (inclusive) close/fill must recompute
     int force_full;                   // debug / test: always take the full re-projection path
     int *col_off, *col_idx;           // [B][cols+1], [B][max_points]: original points bucketed by azimuth bin
-    int* active_count;                // [2] device counters of the current round: unfinished scans, finished k_ctrl CTAs
-    unsigned long long* host_word;    // mapped pinned host word the last k_ctrl CTA publishes (seq << 32 | unfinished scans)
-    unsigned ctrl_seq;
+    // round control of ONE sub-batch.  The round number lives on the device (round_ctl[0], advanced by the last k_ctrl
+    // CTA) so that the launch sequence of a round has constant arguments and can be replayed as a CUDA graph.
+    int* active_count;                // [64][2] per round slot: unfinished scans, finished k_ctrl CTAs
+    unsigned long long* host_word;    // [64] mapped pinned host words; slot = round & 63 gets (seq << 32 | unfinished scans)
+    unsigned* round_ctl;              // [2]: round number, sequence number of round 0 (seq of round r = base + r)
     unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
     // scene boxes

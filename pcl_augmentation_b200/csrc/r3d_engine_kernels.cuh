@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
     if (b >= n_scans) return;
     ScanState& s = e.st[b];
     if (threadIdx.x == 0) {
+        const unsigned round = *(volatile unsigned*)&e.round_ctl[0];
+        const int slot = (int)(round & 63u);
         int apply = 0, project = 0, tryact = 0;
         if (s.phase != PH_DONE && s.phase != PH_ERROR) {
             const int uw = (e.n_objects + 31) / 32;
@@ -178,14 +180,18 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
         s.n_feasible = 0; s.found_rank = INT_MAX; s.accepted = 0; s.chosen_rot = 0;
         e.gate_update[b] = project; e.gate_try[b] = tryact; e.gate_apply[b] = apply;
         for (int i = 0; i < 4; ++i) e.tickets[(size_t)b * 4 + i] = 0u;
-        if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(&e.active_count[0], 1);
+        int* ac = e.active_count + 2 * slot;
+        if (s.phase != PH_DONE && s.phase != PH_ERROR) atomicAdd(&ac[0], 1);
         // the last CTA publishes the number of unfinished scans straight into mapped host memory: the host polls this
         // word instead of waiting for a D2H copy (which would queue behind another engine's bulk transfers)
         __threadfence();
-        if (atomicAdd(&e.active_count[1], 1) == n_scans - 1) {
-            const unsigned left = (unsigned)atomicAdd(&e.active_count[0], 0);
-            *(volatile unsigned long long*)e.host_word = ((unsigned long long)e.ctrl_seq << 32) | left;
+        if (atomicAdd(&ac[1], 1) == n_scans - 1) {
+            const unsigned left = (unsigned)atomicAdd(&ac[0], 0);
+            *(volatile unsigned long long*)(e.host_word + slot) = ((unsigned long long)(e.round_ctl[1] + round) << 32) | left;
             __threadfence_system();
+            int* nx = e.active_count + 2 * ((slot + 32) & 63);      // re-arm the counters half a ring ahead
+            nx[0] = 0; nx[1] = 0;
+            e.round_ctl[0] = round + 1u;                            // every other CTA has read it (it took its ticket)
         }
         if (tryact) atomicAdd(&e.stats[1], 1ull);
         if (apply) atomicAdd(&e.stats[2], 1ull);

@@ -3,6 +3,7 @@
 // Per frame: 1 m grid over the scan's xy extent; road points rasterised; closing(disk(4)) -> road map; the
 // 8-neighbour ring around the road, dilation(disk(2)) -> pedestrian-area map.  One CTA per frame walks the passes
 // with the (tiny, ~160 x 160) maps ping-ponging through global scratch that stays in L1 / L2.
+#include <algorithm>
 #include "r3d_common.cuh"
 #include "r3d_host.h"
 #include "../../include/real3d_b200.h"
@@ -111,7 +112,170 @@ __global__ void __launch_bounds__(RM_THREADS) k_rm_build(const float4* __restric
     disk_pass<2, true>(A, ped, sx, sy);                                 // od/rm:182-188 dilation(disk(2))
 }
 
+
+// ------------------------------------------------------------------------------------------- semantic segmentation
+// semantic_segmentation/rich_map/drivable_area_map.py:122-206 (abbreviated ss/rm): ONE map per sequence.  Every frame is
+// moved to the world frame (points = T . [x y z 1], ss/rm:134-137), the 1 m grid spans the xy extent of all frames
+// (floor of the minimum, int() + 1 of the maximum, ss/rm:158-166) and the surface points are rasterised IN ORDER
+// (frames, then points): road labels write 1, parking labels 2 unless the cell already holds 3; sidewalk labels
+// write 3 for good (ss/rm:190-200).  So a cell ends as 3 if any sidewalk point fell in it, else as the class of the
+// LAST road / parking point that fell in it: an order-independent atomicMax over keys
+// (global point order + 1) << 2 | class, with all-ones for the sticky 3.
+constexpr int RMS_THREADS = 256;
+constexpr int RMS_CHUNK = 4096;          // points per CTA
+constexpr int RMS_MAX_LABELS = 32;
+
+// monotone u64 image of a double (total order of the finite values)
+__device__ __forceinline__ unsigned long long ord_bits(double v) {
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+
+struct Pose34 { double t[12]; };
+__device__ __forceinline__ Pose34 load_pose(const double* __restrict__ poses, int f) {
+    Pose34 p;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) p.t[i] = poses[(size_t)f * 16 + i];
+    return p;
+}
+// row r of T . [x y z 1] as numpy's `t_matrix @ points.T` (ss/rm:136) evaluates it: the BLAS dgemm micro-kernel keeps
+// one accumulator per output element and walks k = 0..3 with fused multiply-adds (acc = fma(t_k, p_k, acc) from 0).
+// Verified against numpy 2.3 / OpenBLAS 0.3.30 in the build container: 6000 of 6000 sampled coordinates bit-equal to
+// this chain (5675 of 6000 to the unfused sum).
+__device__ __forceinline__ double pose_row(const Pose34& p, int r, double x, double y, double z) {
+    return __fma_rn(p.t[4 * r + 3], 1.0, __fma_rn(p.t[4 * r + 2], z, __fma_rn(p.t[4 * r + 1], y, __dmul_rn(p.t[4 * r], x))));
+}
+
+// ss/rm:130-146: world-frame xy extent of ALL points of the frames; ext[4] = ord_bits of {min x, max x, min y, max y}
+__global__ void __launch_bounds__(RMS_THREADS) k_rms_extents(const float4* __restrict__ xyzi, const long long* __restrict__ pt_off,
+                                                             const double* __restrict__ poses, int n_frames,
+                                                             unsigned long long* __restrict__ ext) {
+    const int f = blockIdx.y;
+    if (f >= n_frames) return;
+    const long long o = pt_off[f];
+    const int n = (int)(pt_off[f + 1] - o);
+    const int p0 = blockIdx.x * RMS_CHUNK;
+    if (p0 >= n) return;
+    const Pose34 T = load_pose(poses, f);
+    double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
+    for (int i = p0 + threadIdx.x; i < min(p0 + RMS_CHUNK, n); i += RMS_THREADS) {
+        const float4 v = __ldg(&xyzi[o + i]);
+        const double wx = pose_row(T, 0, v.x, v.y, v.z), wy = pose_row(T, 1, v.x, v.y, v.z);
+        mnx = fmin(mnx, wx); mxx = fmax(mxx, wx); mny = fmin(mny, wy); mxy = fmax(mxy, wy);
+    }
+    for (int s = 16; s > 0; s >>= 1) {
+        mnx = fmin(mnx, __shfl_xor_sync(0xffffffffu, mnx, s)); mxx = fmax(mxx, __shfl_xor_sync(0xffffffffu, mxx, s));
+        mny = fmin(mny, __shfl_xor_sync(0xffffffffu, mny, s)); mxy = fmax(mxy, __shfl_xor_sync(0xffffffffu, mxy, s));
+    }
+    if ((threadIdx.x & 31) == 0 && mnx <= mxx) {
+        atomicMin(&ext[0], ord_bits(mnx)); atomicMax(&ext[1], ord_bits(mxx));
+        atomicMin(&ext[2], ord_bits(mny)); atomicMax(&ext[3], ord_bits(mxy));
+    }
+}
+
+__global__ void k_rms_extents_init(unsigned long long* ext) {
+    ext[0] = ~0ull; ext[1] = 0ull; ext[2] = ~0ull; ext[3] = 0ull;
+}
+// ss/rm:158-166: min = int(floor(min)), max = int(max) + 1; out = {min_x, min_y, size_x, size_y, any point}
+__global__ void k_rms_extents_finish(const unsigned long long* ext, long long* out) {
+    auto dec = [](unsigned long long o) { return __longlong_as_double((long long)((o >> 63) ? (o & 0x7fffffffffffffffull) : ~o)); };
+    if (ext[0] == ~0ull) { out[0] = out[1] = out[2] = out[3] = out[4] = 0; return; }
+    const long long min_x = (long long)floor(dec(ext[0])), min_y = (long long)floor(dec(ext[2]));
+    const long long max_x = (long long)dec(ext[1]) + 1, max_y = (long long)dec(ext[3]) + 1;
+    out[0] = min_x; out[1] = min_y; out[2] = max_x - min_x; out[3] = max_y - min_y; out[4] = 1;
+}
+
+// ss/rm:172-200 for the frames of one call; `order_base` = number of points of the frames rasterised before
+__global__ void __launch_bounds__(RMS_THREADS) k_rms_raster(const float4* __restrict__ xyzi, const unsigned* __restrict__ labels,
+                                                            const long long* __restrict__ pt_off, const double* __restrict__ poses,
+                                                            int n_frames, const int* __restrict__ surf_label,
+                                                            const int* __restrict__ surf_class, int n_surf, long long min_x,
+                                                            long long min_y, int sx, int sy, long long order_base,
+                                                            unsigned long long* __restrict__ keymap, int* __restrict__ err) {
+    const int f = blockIdx.y;
+    if (f >= n_frames) return;
+    __shared__ unsigned s_lab[RMS_MAX_LABELS];
+    __shared__ int s_cls[RMS_MAX_LABELS];
+    if (threadIdx.x < RMS_MAX_LABELS) {
+        s_lab[threadIdx.x] = threadIdx.x < n_surf ? (unsigned)surf_label[threadIdx.x] : 0xFFFFFFFFu;
+        s_cls[threadIdx.x] = threadIdx.x < n_surf ? surf_class[threadIdx.x] : 0;
+    }
+    __syncthreads();
+    const long long o = pt_off[f];
+    const int n = (int)(pt_off[f + 1] - o);
+    const int p0 = blockIdx.x * RMS_CHUNK;
+    if (p0 >= n) return;
+    const Pose34 T = load_pose(poses, f);
+    const double dminx = (double)min_x, dminy = (double)min_y;
+    for (int i = p0 + threadIdx.x; i < min(p0 + RMS_CHUNK, n); i += RMS_THREADS) {
+        const unsigned lab = __ldg(&labels[o + i]);
+        int cls = 0;
+        for (int j = 0; j < n_surf; ++j) if (lab == s_lab[j]) { cls = s_cls[j]; break; }       // ss/rm:185
+        if (!cls) continue;
+        const float4 v = __ldg(&xyzi[o + i]);
+        const double px = __dsub_rn(pose_row(T, 0, v.x, v.y, v.z), dminx), py = __dsub_rn(pose_row(T, 1, v.x, v.y, v.z), dminy);
+        if (px < 0.0 || py < 0.0) { atomicExch(err, 1); continue; }                            // ss/rm:190 assert
+        const long long ix = (long long)px, iy = (long long)py;                                 // int(): truncation
+        if (ix >= sx || iy >= sy) { atomicExch(err, 2); continue; }                            // IndexError in the reference
+        const unsigned long long key = cls == 3 ? ~0ull : ((unsigned long long)(order_base + (o - pt_off[0]) + i + 1) << 2) | (unsigned)cls;
+        atomicMax(&keymap[ix * sy + iy], key);
+    }
+}
+
+__global__ void k_rms_finalize(const unsigned long long* __restrict__ keymap, unsigned char* __restrict__ map, long long cells) {
+    for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < cells; c += (long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = keymap[c];
+        map[c] = k == 0ull ? 0 : (k == ~0ull ? 3 : (unsigned char)(k & 3ull));
+    }
+}
+
 }  // namespace
+
+extern "C" int r3d_rich_map_ss_extents(const float* xyzi, const int64_t* point_offsets, const double* poses, int32_t n_frames,
+                                       int32_t max_points, int32_t first_call, uint64_t* ext_state, int64_t* out5,
+                                       r3d_stream stream_) {
+    if (!xyzi || !point_offsets || !poses || !ext_state || n_frames <= 0 || max_points < 0)
+        return r3d_fail(R3D_ERR_ARG, "r3d_rich_map_ss_extents: bad argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    if (first_call) { k_rms_extents_init<<<1, 1, 0, st>>>((unsigned long long*)ext_state); r3d_count_launch(); }
+    const int chunks = (max_points + RMS_CHUNK - 1) / RMS_CHUNK;
+    if (chunks > 0) {
+        k_rms_extents<<<dim3(chunks, n_frames), RMS_THREADS, 0, st>>>((const float4*)xyzi, (const long long*)point_offsets, poses,
+                                                                        n_frames, (unsigned long long*)ext_state);
+        r3d_count_launch();
+    }
+    if (out5) { k_rms_extents_finish<<<1, 1, 0, st>>>((const unsigned long long*)ext_state, (long long*)out5); r3d_count_launch(); }
+    return r3d_check_launch("r3d_rich_map_ss_extents");
+}
+
+extern "C" int r3d_rich_map_ss_raster(const float* xyzi, const uint32_t* labels, const int64_t* point_offsets, const double* poses,
+                                      int32_t n_frames, int32_t max_points, const int32_t* surface_labels,
+                                      const int32_t* surface_classes, int32_t n_surface, int64_t min_x, int64_t min_y,
+                                      int32_t size_x, int32_t size_y, int64_t order_base, uint64_t* keymap, int32_t* error_flag,
+                                      r3d_stream stream_) {
+    if (!xyzi || !labels || !point_offsets || !poses || !surface_labels || !surface_classes || !keymap || !error_flag ||
+        n_frames <= 0 || n_surface < 0 || n_surface > RMS_MAX_LABELS || size_x <= 0 || size_y <= 0 || max_points < 0)
+        return r3d_fail(R3D_ERR_ARG, "r3d_rich_map_ss_raster: bad argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int chunks = (max_points + RMS_CHUNK - 1) / RMS_CHUNK;
+    if (chunks > 0) {
+        k_rms_raster<<<dim3(chunks, n_frames), RMS_THREADS, 0, st>>>((const float4*)xyzi, labels, (const long long*)point_offsets,
+                                                                       poses, n_frames, surface_labels, surface_classes, n_surface,
+                                                                       (long long)min_x, (long long)min_y, size_x, size_y,
+                                                                       (long long)order_base, (unsigned long long*)keymap, error_flag);
+        r3d_count_launch();
+    }
+    return r3d_check_launch("r3d_rich_map_ss_raster");
+}
+
+extern "C" int r3d_rich_map_ss_finalize(const uint64_t* keymap, int64_t cells, uint8_t* map_out, r3d_stream stream_) {
+    if (!keymap || !map_out || cells <= 0) return r3d_fail(R3D_ERR_ARG, "r3d_rich_map_ss_finalize: bad argument");
+    cudaStream_t st = (cudaStream_t)stream_;
+    const int blocks = (int)std::min<long long>((cells + 255) / 256, 148 * 8);
+    k_rms_finalize<<<blocks, 256, 0, st>>>((const unsigned long long*)keymap, map_out, (long long)cells);
+    r3d_count_launch();
+    return r3d_check_launch("r3d_rich_map_ss_finalize");
+}
 
 extern "C" int r3d_rich_map_od_extents(const float* xyzi, const int64_t* point_offsets, int32_t n_scans, int32_t* dims,
                                        r3d_stream stream_) {
