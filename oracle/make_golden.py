@@ -339,8 +339,41 @@ def gen_rich_map_od():
         shutil.rmtree(root, ignore_errors=True)
 
 
+def gen_rich_map_ss():
+    """the reference's sequence-wide rich-map script on a four-frame synthetic sequence."""
+    import yaml
+    from pcl_augmentation_b200 import synth_io
+    from pcl_augmentation_b200.semantic_segmentation.Real3DAug.tools.datasets import SemanticKITTI
+    from tests.helpers import RICH_MAP_SS_SEEDS, rich_map_ss_cases
+    t0 = time.time()
+    cases = rich_map_ss_cases()
+    root = tempfile.mkdtemp(prefix="r3d_golden_")
+    try:
+        cwd, _, cfg = synth_io.write_ss_dataset(cases, root)
+        cfg["path"]["maps_path"] = os.path.join(root, "maps", "small", "npz")      # the script pops three components
+        with open(os.path.join(root, "config/semantic-kitti.yaml"), "w") as f:
+            yaml.safe_dump(cfg, f)
+        shim.run_rich_map_ss(cwd, ["1", "00", "no"])
+        z = np.load(os.path.join(root, "maps/small/npz/00.npz"))
+        m, move = z["map"], z["move"]
+        assert set(np.unique(m)) <= {0.0, 1.0, 2.0, 3.0}
+        poses = np.loadtxt(os.path.join(root, "data/sequences/00/poses.txt"))
+        ds = SemanticKITTI.__new__(SemanticKITTI)
+        rec = {"meta": json.dumps(dict(seeds=list(RICH_MAP_SS_SEEDS))), "map_dtype": str(m.dtype), "map": m.astype(np.uint8),
+               "move": move, "poses": np.stack([ds.create_transform_matrix(poses, i) for i in range(len(cases))]),
+               "placement_labels": json.dumps({int(k): [int(x) for x in v] for k, v in cfg["insertion"]["placement_labels"].items()})}
+        for i, c in enumerate(cases):
+            rec[f"digest{i}"] = synth.case_digest(c)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "rich_map_ss.npz"), **rec)
+        print(f"rich_map_ss: {time.time() - t0:.1f}s map", m.shape, m.dtype, "move", move.ravel(),
+              "cells per class", [int((m == v).sum()) for v in (1, 2, 3)])
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 GENERATORS = {
     "rich_map_od": gen_rich_map_od,
+    "rich_map_ss": gen_rich_map_ss,
     "fn_projection": gen_fn_projection,
     "fn_cut_bbox": gen_fn_cut_bbox,
     "fn_places_od": lambda: gen_fn_places("od"),

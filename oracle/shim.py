@@ -188,3 +188,31 @@ def run_rich_map_od(cwd, quiet=True):
         for k in [k for k in sys.modules if k == "object_detection" or k.startswith("object_detection.")]:
             del sys.modules[k]
     return out.getvalue()
+
+
+def run_rich_map_ss(cwd, inputs, quiet=True):
+    """Execute the reference's ``semantic_segmentation/rich_map/drivable_area_map.py`` as ``__main__`` (unmodified);
+    it reads ``../config/semantic-kitti.yaml`` relative to ``cwd``, imports ``semantic_segmentation.Real3DAug.tools.datasets``
+    and asks for the dataset, the sequence and the frame order on ``input()`` (answers: ``inputs``)."""
+    _install_compat()
+    old_cwd, old_input, old_glob = os.getcwd(), builtins.input, _glob.glob
+    it = iter(inputs)
+    builtins.input = lambda *a: next(it)
+    _glob.glob = lambda *a, **k: sorted(old_glob(*a, **k))
+    out = io.StringIO()
+    mods = lambda: [k for k in sys.modules if k == "semantic_segmentation" or k.startswith("semantic_segmentation.")]
+    for k in mods():
+        del sys.modules[k]
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        os.chdir(cwd)
+        with (contextlib.redirect_stdout(out) if quiet else contextlib.nullcontext()):
+            runpy.run_path(os.path.join(REFERENCE_ROOT, "semantic_segmentation/rich_map/drivable_area_map.py"),
+                           run_name="__main__")
+    finally:
+        os.chdir(old_cwd)
+        builtins.input, _glob.glob = old_input, old_glob
+        sys.path.remove(REFERENCE_ROOT)
+        for k in mods():
+            del sys.modules[k]
+    return out.getvalue()

@@ -87,6 +87,12 @@ PROTOTYPES = {
     "r3d_rich_map_od_extents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]),
     "r3d_rich_map_od_build": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_uint32, C.c_void_p, C.c_void_p,
                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r3d_rich_map_ss_extents": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                          C.c_void_p, C.c_void_p]),
+    "r3d_rich_map_ss_raster": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
+                                         C.c_void_p, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int64,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r3d_rich_map_ss_finalize": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "r3d_engine_sync": (C.c_int, [C.c_void_p]),
     "r3d_engine_set_sub_batches": (C.c_int, [C.c_void_p, C.c_int]),
     "r3d_engine_run_until": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

@@ -131,11 +131,11 @@ __device__ __forceinline__ unsigned long long ord_bits(double v) {
     return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
 }
 
-struct Pose34 { double t[12]; };
+struct Pose34 { double t[16]; };
 __device__ __forceinline__ Pose34 load_pose(const double* __restrict__ poses, int f) {
     Pose34 p;
 #pragma unroll
-    for (int i = 0; i < 12; ++i) p.t[i] = poses[(size_t)f * 16 + i];
+    for (int i = 0; i < 16; ++i) p.t[i] = poses[(size_t)f * 16 + i];
     return p;
 }
 // row r of T . [x y z 1] as numpy's `t_matrix @ points.T` (ss/rm:136) evaluates it: the BLAS dgemm micro-kernel keeps
@@ -160,7 +160,8 @@ __global__ void __launch_bounds__(RMS_THREADS) k_rms_extents(const float4* __res
     double mnx = INFINITY, mny = INFINITY, mxx = -INFINITY, mxy = -INFINITY;
     for (int i = p0 + threadIdx.x; i < min(p0 + RMS_CHUNK, n); i += RMS_THREADS) {
         const float4 v = __ldg(&xyzi[o + i]);
-        const double wx = pose_row(T, 0, v.x, v.y, v.z), wy = pose_row(T, 1, v.x, v.y, v.z);
+        const double w = pose_row(T, 3, v.x, v.y, v.z);                                       // ss/rm:137
+        const double wx = __ddiv_rn(pose_row(T, 0, v.x, v.y, v.z), w), wy = __ddiv_rn(pose_row(T, 1, v.x, v.y, v.z), w);
         mnx = fmin(mnx, wx); mxx = fmax(mxx, wx); mny = fmin(mny, wy); mxy = fmax(mxy, wy);
     }
     for (int s = 16; s > 0; s >>= 1) {
@@ -213,7 +214,9 @@ __global__ void __launch_bounds__(RMS_THREADS) k_rms_raster(const float4* __rest
         for (int j = 0; j < n_surf; ++j) if (lab == s_lab[j]) { cls = s_cls[j]; break; }       // ss/rm:185
         if (!cls) continue;
         const float4 v = __ldg(&xyzi[o + i]);
-        const double px = __dsub_rn(pose_row(T, 0, v.x, v.y, v.z), dminx), py = __dsub_rn(pose_row(T, 1, v.x, v.y, v.z), dminy);
+        const double w = pose_row(T, 3, v.x, v.y, v.z);                                       // ss/rm:178
+        const double px = __dsub_rn(__ddiv_rn(pose_row(T, 0, v.x, v.y, v.z), w), dminx);
+        const double py = __dsub_rn(__ddiv_rn(pose_row(T, 1, v.x, v.y, v.z), w), dminy);
         if (px < 0.0 || py < 0.0) { atomicExch(err, 1); continue; }                            // ss/rm:190 assert
         const long long ix = (long long)px, iy = (long long)py;                                 // int(): truncation
         if (ix >= sx || iy >= sy) { atomicExch(err, 2); continue; }                            // IndexError in the reference

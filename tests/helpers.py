@@ -36,3 +36,20 @@ def parse_inserted(text):
             name, rot = line.split(" with rotation: ")
             out.append((name, int(rot)))
     return out
+
+
+RICH_MAP_SS_SEEDS = (41, 42, 43, 44)
+
+
+def rich_map_ss_cases():
+    """Four frames of one synthetic sequence: the poses are chained so that the frames overlap (cells written by
+    several frames and by several surface classes: the last-writer and the sticky-sidewalk rules both matter)."""
+    cases = [case_from_spec(dict(task="ss", seed=s, counts=[1] * 8, n_cars=c)) for s, c in zip(RICH_MAP_SS_SEEDS, (0, 3, 5, 2))]
+    base = cases[0].pose
+    for i, case in enumerate(cases[1:], 1):
+        a = 0.35 * i
+        step = np.eye(4)
+        step[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        step[:3, 3] = [7.3 * i, -2.1 * i, 0.05 * i]
+        case.pose = base @ step
+    return cases

@@ -65,3 +65,70 @@ def test_engine_runs_on_generated_maps():
                            maps={"Road": road, "Sidewalk": ped}, mode="closed")
     assert [(n, int(r)) for n, r, _ in res.inserted] == [(n, int(r)) for n, r, _ in ref["inserted"]]
     assert len(res.velodyne) == len(ref["scene"])
+
+
+# ------------------------------------------------------------------------------------------------ semseg (ss/rm)
+def _chained_frames(seeds, shape, stride=6.5):
+    from pcl_augmentation_b200.semantic_segmentation.Real3DAug.tools.datasets import SemanticKITTI
+    base = synth.make_pose(seeds[0])
+    frames = []
+    for i, seed in enumerate(seeds):
+        pcl, labels = synth.make_scan(seed, shape, synth.make_scene_cars(seed, 4))
+        a = 0.2 * i
+        step = np.eye(4)
+        step[:3, :3] = [[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]]
+        step[:3, 3] = [stride * i, 1.7 * i, 0.02 * i]
+        frames.append((pcl, labels & 0xFFFF, base @ step))
+    return frames
+
+
+def _oracle_frames(frames):
+    return [(np.hstack((p.astype(np.float64), np.asarray(l, dtype=np.float64).reshape(-1, 1))), T) for p, l, T in frames]
+
+
+def test_sequence_map_matches_reference_script_file(tmp_path):
+    import yaml
+    from pcl_augmentation_b200.semantic_segmentation.rich_map import drivable_area_map as srm
+    from tests.helpers import rich_map_ss_cases
+    g = load_golden("rich_map_ss")
+    cases = rich_map_ss_cases()
+    _, _, cfg = synth_io.write_ss_dataset(cases, str(tmp_path))
+    cfg["path"]["maps_path"] = str(tmp_path / "maps" / "small" / "npz")
+    out = srm.generate_map(cfg, "00", chunk_frames=3, log=lambda *a: None)
+    z = np.load(tmp_path / "maps" / "small" / "npz" / "00.npz")
+    assert z["map"].dtype == np.dtype(str(g["map_dtype"])) and z["map"].shape == g["map"].shape
+    np.testing.assert_array_equal(z["map"], g["map"].astype(np.float64))
+    np.testing.assert_array_equal(z["move"], g["move"])
+    np.testing.assert_array_equal(out["map"], z["map"])
+    # frames re-read for the raster pass (nothing kept on the device) give the same map
+    out2 = srm.generate_map(cfg, "00", chunk_frames=1, device_budget_bytes=0, log=lambda *a: None)
+    np.testing.assert_array_equal(out2["map"], z["map"])
+
+
+def test_sequence_map_full_size_vs_oracle():
+    from pcl_augmentation_b200.semantic_segmentation.rich_map import drivable_area_map as srm
+    labels = synth.load_config("ss")["insertion"]["placement_labels"]
+    frames = _chained_frames([61, 62, 63, 64, 65, 66], synth.KITTI_SHAPE)
+    frames += _chained_frames([67], synth.OS128_SHAPE) + _chained_frames([68], synth.SMALL_SHAPE)      # ragged
+    frames.append((np.array([[1.0, 2.0, -1.7, 0.3]], dtype=np.float32), np.array([1], dtype=np.uint32), frames[0][2]))  # no surface point
+    want = rmo.rich_map_ss(_oracle_frames(frames), labels)
+    for chunk in (256, 4, 1):
+        got = srm.sequence_map(frames, labels, chunk_frames=chunk)
+        assert got["map"].dtype == np.float64
+        np.testing.assert_array_equal(got["map"], want["map"])
+        np.testing.assert_array_equal(got["move"], want["move"])
+    assert {1.0, 2.0, 3.0} <= set(np.unique(want["map"]))
+
+
+def test_sequence_map_projective_pose_and_label_precedence():
+    """ss/rm:137 divides by the homogeneous coordinate; ss/rm:192-200 tests class 1 first, then 3, else 2."""
+    from pcl_augmentation_b200.semantic_segmentation.rich_map import drivable_area_map as srm
+    frames = _chained_frames([71, 72], synth.SMALL_SHAPE)
+    T = frames[1][2].copy()
+    T[3] = [0.0, 0.0, 1e-3, 2.0]
+    frames[1] = (frames[1][0], frames[1][1], T)
+    labels = {1: [40, 44], 2: [48, 70], 3: [44, 48]}               # 44 -> 1 (class 1 wins), 48 -> 3, 70 -> 2
+    want = rmo.rich_map_ss(_oracle_frames(frames), labels)
+    got = srm.sequence_map(frames, labels)
+    np.testing.assert_array_equal(got["map"], want["map"])
+    np.testing.assert_array_equal(got["move"], want["move"])

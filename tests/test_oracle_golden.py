@@ -183,3 +183,34 @@ def test_rich_map_od_matches_reference_script():
             assert got.shape == shape and got.dtype == np.uint8 == np.dtype(str(g[f"{key}{i}_dtype"]))
             np.testing.assert_array_equal(got, want)
             assert [min_x, min_y] == list(g[f"{key}{i}_min"])
+
+
+def test_rich_map_ss_matches_reference_script():
+    """sequence-map oracle vs what the unmodified drivable_area_map.py wrote."""
+    import json
+    from oracle import rich_map_oracle as rmo
+    from tests.helpers import rich_map_ss_cases
+    g = load_golden("rich_map_ss")
+    cases = rich_map_ss_cases()
+    frames = []
+    for i, case in enumerate(cases):
+        assert synth.case_digest(case) == str(g[f"digest{i}"])
+        pcl5 = np.hstack((case.pcl5[:, :4].astype(np.float32), case.pcl5[:, 4:5]))       # SemanticKITTI.__getitem__ (ss/ds:45-62)
+        frames.append((pcl5, g["poses"][i]))
+    labels = {int(k): v for k, v in json.loads(str(g["placement_labels"])).items()}
+    got = rmo.rich_map_ss(frames, labels)
+    assert got["map"].dtype == np.dtype(str(g["map_dtype"])) and got["map"].shape == g["map"].shape
+    np.testing.assert_array_equal(got["map"], g["map"].astype(np.float64))
+    np.testing.assert_array_equal(got["move"], g["move"])
+    # the fixture exercises both ordering rules: cells hit by road AND parking points, and sticky sidewalk cells
+    table = rmo.surface_classes(labels)
+    world = [(T @ np.c_[p[:, :3], np.ones(len(p))].T).T for p, T in frames]
+    cells = {}
+    for (p, _), w in zip(frames, world):
+        for lab, x, y in zip(p[:, 4], w[:, 0], w[:, 1]):
+            c = table.get(int(lab))
+            if c:
+                cells.setdefault((int(x - got["move"][0, 0]), int(y - got["move"][1, 0])), set()).add(c)
+    assert sum(1 for v in cells.values() if {1, 2} <= v) > 10
+    assert sum(1 for v in cells.values() if 3 in v and len(v) > 1) > 10
+
