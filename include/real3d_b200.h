@@ -115,6 +115,31 @@ int r3d_rich_map_ss_raster(const float* xyzi, const uint32_t* labels, const int6
                            int32_t size_y, int64_t order_base, uint64_t* keymap, int32_t* error_flag, r3d_stream stream);
 int r3d_rich_map_ss_finalize(const uint64_t* keymap, int64_t cells, uint8_t* map_out, r3d_stream stream);
 
+/* ------------------------------------------------------------------------------------- cut-object database */
+/* The point-in-box passes of object_detection/cut_object/object_cut_out.py:90-168 and
+ * semantic_segmentation/cut_object/cut_out.py:103-157, batched over frames and boxes (all pointers: device).
+ * xyzi / labels / point_offsets as above; boxes: n_boxes x R3D_BOX_DOUBLES, the boxes of frame f are
+ * [box_offsets[f], box_offsets[f+1]) (at most 64 per frame: max_boxes_per_frame is the caller's promise).
+ * Per box: keep_label >= 0 emits only the points carrying that label (cut_out.py:143), -1 any label, -2 none (the box is
+ * only counted); use_drop != 0 additionally drops the labels of drop_labels (object_cut_out.py:150-152).
+ * cameras: NULL or n_frames x 27 float64 = {M1 = V2C.T @ R0.T (4 x 3 row-major), P2 (3 x 4), image height, width, enabled}
+ * for the field-of-view test of object_cut_out.py:144 (cutout.py:73-122).
+ * r3d_cut_objects_count writes count_inside[box] (points strictly inside, cut_bbox.py:7-68), count_fov[box] (those the
+ * camera sees), chunk_counts (scratch: n_boxes x ceil(max_points / 4096), kept for the write pass) and out_offsets
+ * (n_boxes + 1: where the emitted points of each box start in the packed output).
+ * r3d_cut_objects_write writes the emitted points of every box in their original order: out_xyzi (x, y, z, intensity
+ * as read), out_labels, and optionally out_index (index of the point inside its frame). */
+int r3d_cut_objects_count(const float* xyzi, const uint32_t* labels, const int64_t* point_offsets, int32_t n_frames,
+                          int32_t max_points, const double* boxes, const int32_t* box_offsets, const int32_t* keep_label,
+                          const int32_t* use_drop, int32_t n_boxes, int32_t max_boxes_per_frame, const double* cameras,
+                          const int32_t* drop_labels, int32_t n_drop, int32_t* count_inside, int32_t* count_fov,
+                          int32_t* chunk_counts, int64_t* out_offsets, r3d_stream stream);
+int r3d_cut_objects_write(const float* xyzi, const uint32_t* labels, const int64_t* point_offsets, int32_t n_frames,
+                          int32_t max_points, const double* boxes, const int32_t* box_offsets, const int32_t* keep_label,
+                          const int32_t* use_drop, int32_t n_boxes, const int32_t* drop_labels, int32_t n_drop,
+                          const int32_t* chunk_counts, const int64_t* out_offsets, float* out_xyzi, uint32_t* out_labels,
+                          int32_t* out_index, r3d_stream stream);
+
 /* --------------------------------------------------------------------------------------------------- engine */
 /* Device-resident batched driver of the per-scan loop (od/ins:351-628, ss/ins:355-599): placement search
  * (find_possible_places od/fs:227-304, ss/fs:192-273), occlusion (od/ins:468-501), accept rule and insertion

@@ -371,7 +371,85 @@ def gen_rich_map_ss():
         shutil.rmtree(root, ignore_errors=True)
 
 
+def _pack_samples(rec, prefix, samples):
+    """{name: (anno, pcl)} -> flat arrays (names joined, annotation strings, point counts, concatenated float64 rows)."""
+    names = sorted(samples)
+    rec[prefix + "_names"] = json.dumps(names)
+    rec[prefix + "_annos"] = json.dumps([samples[n][0] for n in names])
+    rec[prefix + "_counts"] = np.array([len(samples[n][1]) for n in names], dtype=np.int64)
+    rec[prefix + "_pcl"] = (np.concatenate([samples[n][1] for n in names]) if names else np.zeros((0, 5)))
+    assert rec[prefix + "_pcl"].dtype == np.float64
+
+
+def gen_cut_objects_od():
+    """the reference's object_cut_out.py on three synthetic frames holding 36 annotated objects."""
+    import yaml
+    from pcl_augmentation_b200 import synth_io
+    from tests.helpers import cut_object_cases, write_kitti_camera_files, read_sample_dir
+    t0 = time.time()
+    cases = cut_object_cases("od")
+    root = tempfile.mkdtemp(prefix="r3d_golden_")
+    try:
+        cwd, _, cfg = synth_io.write_od_dataset(cases, root)
+        write_kitti_camera_files(root, len(cases))
+        cfg["path"]["sample_path"] = os.path.join(root, "cut")
+        os.makedirs(cfg["path"]["sample_path"])
+        with open(os.path.join(root, "config/KITTI.yaml"), "w") as f:
+            yaml.safe_dump(cfg, f)
+        shim.run_cut_objects_od(cwd)
+        rec = {"meta": json.dumps(dict(task="od"))}
+        total = 0
+        for i, c in enumerate(cases):
+            rec[f"digest{i}"] = synth.array_digest(c.pcl5)
+        for cls in cfg["insertion"]["classes"]:
+            samples = read_sample_dir(os.path.join(root, "cut", cls))
+            _pack_samples(rec, cls, samples)
+            total += len(samples)
+        n_lines = sum(len(c.box_lines) for c in cases)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "cut_objects_od.npz"), **rec)
+        print(f"cut_objects_od: {time.time() - t0:.1f}s {total} samples saved of {n_lines} annotation lines")
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+def gen_cut_objects_ss():
+    """cut_out.py, then filter_objects.py, on a three-frame synthetic sequence."""
+    import yaml
+    from pcl_augmentation_b200 import synth_io
+    from tests.helpers import cut_object_cases, read_sample_dir
+    t0 = time.time()
+    cases = cut_object_cases("ss")
+    root = tempfile.mkdtemp(prefix="r3d_golden_")
+    try:
+        cwd, _, cfg = synth_io.write_ss_dataset(cases, root)
+        cfg["path"]["bbox_path"] = os.path.join(root, "cut")
+        with open(os.path.join(root, "config/semantic-kitti.yaml"), "w") as f:
+            yaml.safe_dump(cfg, f)
+        shim.run_cut_objects_ss(cwd, ["1", 0, "no"])       # the sequence prompt must yield an int, see shim
+        rec = {"meta": json.dumps(dict(task="ss"))}
+        for i, c in enumerate(cases):
+            rec[f"digest{i}"] = synth.array_digest(c.pcl5)
+        total = 0
+        folders = [cfg["labels"][c] for c in cfg["insertion"]["classes"]]
+        for folder in folders:
+            samples = read_sample_dir(os.path.join(root, "cut", folder))
+            _pack_samples(rec, folder, samples)
+            total += len(samples)
+        shim.run_filter_objects_ss(cwd, ["1", 0, "no"])
+        kept = 0
+        for folder in folders:
+            names = sorted(read_sample_dir(os.path.join(root, "cut", folder)))
+            rec[folder + "_kept"] = json.dumps(names)
+            kept += len(names)
+        np.savez_compressed(os.path.join(GOLDEN_DIR, "cut_objects_ss.npz"), **rec)
+        print(f"cut_objects_ss: {time.time() - t0:.1f}s {total} samples saved, {kept} left after filter_objects")
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 GENERATORS = {
+    "cut_objects_od": gen_cut_objects_od,
+    "cut_objects_ss": gen_cut_objects_ss,
     "rich_map_od": gen_rich_map_od,
     "rich_map_ss": gen_rich_map_ss,
     "fn_projection": gen_fn_projection,

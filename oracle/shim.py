@@ -80,6 +80,11 @@ def _install_compat():
         def dilation(image, footprint=None, out=None):
             return ndimage.grey_dilation(image, footprint=np.asarray(footprint, dtype=bool))
 
+        def imread(fname, *a, **k):
+            from PIL import Image
+            return np.asarray(Image.open(fname))
+
+        sio.imread = imread
         util.img_as_ubyte = img_as_ubyte
         morph.rectangle = rectangle
         morph.closing = closing
@@ -216,3 +221,63 @@ def run_rich_map_ss(cwd, inputs, quiet=True):
         for k in mods():
             del sys.modules[k]
     return out.getvalue()
+
+
+def _run_script(rel_path, extra_paths, cwd, inputs, prepare=None, quiet=True):
+    """Execute a reference script as ``__main__`` (unmodified) from ``cwd`` with scripted ``input()`` answers,
+    ``REFERENCE_ROOT`` + ``extra_paths`` (relative to it) on ``sys.path``."""
+    _install_compat()
+    old_cwd, old_input, old_glob = os.getcwd(), builtins.input, _glob.glob
+    it = iter(inputs)
+    builtins.input = lambda *a: next(it)
+    _glob.glob = lambda *a, **k: sorted(old_glob(*a, **k))
+    out = io.StringIO()
+    roots = ("semantic_segmentation", "object_detection", "tools", "cut_bbox", "cutout")
+    mods = lambda: [k for k in sys.modules if k.split(".")[0] in roots]
+    for k in mods():
+        del sys.modules[k]
+    paths = [REFERENCE_ROOT] + [os.path.join(REFERENCE_ROOT, p) for p in extra_paths]
+    for p in reversed(paths):
+        sys.path.insert(0, p)
+    try:
+        os.chdir(cwd)
+        if prepare is not None:
+            prepare()
+        with (contextlib.redirect_stdout(out) if quiet else contextlib.nullcontext()):
+            runpy.run_path(os.path.join(REFERENCE_ROOT, rel_path), run_name="__main__")
+    finally:
+        os.chdir(old_cwd)
+        builtins.input, _glob.glob = old_input, old_glob
+        for p in paths:
+            sys.path.remove(p)
+        for k in mods():
+            del sys.modules[k]
+    return out.getvalue()
+
+
+def run_cut_objects_od(cwd, quiet=True):
+    """``object_detection/cut_object/object_cut_out.py`` (unmodified): reads ``../config/KITTI.yaml``, imports its
+    sibling modules ``cut_bbox`` / ``cutout`` and ``object_detection.Real3DAug.tools.datasets``."""
+    return _run_script("object_detection/cut_object/object_cut_out.py", ["object_detection/cut_object"], cwd, [], quiet=quiet)
+
+
+def _accept_subdirectories_keyword():
+    """Reference defect, results-neutral patch: ``cut_out.py:98`` calls ``delete_item(0, subdirectoties=False)``, a
+    keyword only ``Waymo.delete_item`` accepts (ss/ds:266) — with ``SemanticKITTI`` the script raises TypeError."""
+    ds = importlib.import_module("semantic_segmentation.Real3DAug.tools.datasets")
+    plain = ds.SemanticKITTI.delete_item
+    ds.SemanticKITTI.delete_item = lambda self, idx, subdirectoties=True: plain(self, idx)
+
+
+def run_cut_objects_ss(cwd, inputs, quiet=True):
+    """``semantic_segmentation/cut_object/cut_out.py`` (unmodified but for the keyword patch above).  Second reference
+    defect: ``cut_out.py:55`` / ``filter_objects.py:56`` format the ``input()`` string with ``:02d`` (ValueError for any
+    str), so the scripted answer to the sequence prompt has to be an ``int`` (``inputs = ["1", 0, "no"]``)."""
+    return _run_script("semantic_segmentation/cut_object/cut_out.py", ["semantic_segmentation/cut_object"], cwd, inputs,
+                       prepare=_accept_subdirectories_keyword, quiet=quiet)
+
+
+def run_filter_objects_ss(cwd, inputs, quiet=True):
+    """``semantic_segmentation/cut_object/filter_objects.py`` (unmodified)."""
+    return _run_script("semantic_segmentation/cut_object/filter_objects.py", ["semantic_segmentation/cut_object"], cwd,
+                       inputs, prepare=_accept_subdirectories_keyword, quiet=quiet)
