@@ -60,8 +60,17 @@ __device__ __forceinline__ bool in_fov(const Camera& c, double x, double y, doub
     return u >= 0.0 && u < c.img_w && v >= 0.0 && v < c.img_h && depth >= 0.0;         // cutout.py:106-112
 }
 
+// coarse xy grid over +-81.92 m (5.12 m cells, the border cells also stand for everything beyond): cell -> bits of the
+// boxes whose bounding sphere touches the cell, so a point looks at the zero to two boxes near it instead of all of them
+constexpr int CD_GRID = 32;
+constexpr float CD_GRID_HALF = 81.92f, CD_GRID_INV = 1.0f / 5.12f;
+__device__ __forceinline__ int grid_cell(float v) {
+    return (int)fminf(fmaxf((v + CD_GRID_HALF) * CD_GRID_INV, 0.0f), (float)(CD_GRID - 1));     // monotone; NaN -> 0
+}
+
 struct FrameCtx {
     CutBox box[CD_MAX_BOXES];
+    unsigned long long grid[CD_GRID * CD_GRID];
     Camera cam;
     unsigned drop[CD_MAX_DROP];
     int n_boxes, n_drop;
@@ -71,13 +80,22 @@ __device__ void load_frame(FrameCtx& s, const double* __restrict__ boxes, const 
                            const int* __restrict__ keep_label, const int* __restrict__ use_drop,
                            const double* __restrict__ cameras, const int* __restrict__ drop_labels, int n_drop, int f) {
     const int b0 = box_off[f], nb = min(box_off[f + 1] - b0, CD_MAX_BOXES);
+    for (int i = threadIdx.x; i < CD_GRID * CD_GRID; i += blockDim.x) s.grid[i] = 0ull;
+    __syncthreads();
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
         const double* r = boxes + (size_t)(b0 + j) * R3D_BOX_DOUBLES;
         Box b;
         b.cx = r[0]; b.cy = r[1]; b.cz = r[2];
         for (int i = 0; i < 9; ++i) b.m[i] = r[3 + i];
         b.length = r[12]; b.width = r[13]; b.height = r[14]; b.reach = r[15];
-        s.box[j] = make_cut_box(b, keep_label[b0 + j], use_drop[b0 + j]);
+        const CutBox cb = make_cut_box(b, keep_label[b0 + j], use_drop[b0 + j]);
+        s.box[j] = cb;
+        const float rr = sqrtf(cb.r2) * 1.0001f + 1e-3f;
+        const bool finite = rr < 1e30f && fabsf(cb.cx) < 1e30f && fabsf(cb.cy) < 1e30f;
+        const int x0 = finite ? grid_cell(cb.cx - rr) : 0, x1 = finite ? grid_cell(cb.cx + rr) : CD_GRID - 1;
+        const int y0 = finite ? grid_cell(cb.cy - rr) : 0, y1 = finite ? grid_cell(cb.cy + rr) : CD_GRID - 1;
+        for (int y = y0; y <= y1; ++y)
+            for (int x = x0; x <= x1; ++x) atomicOr(&s.grid[y * CD_GRID + x], 1ull << j);
     }
     if (threadIdx.x < CD_MAX_DROP) s.drop[threadIdx.x] = threadIdx.x < n_drop ? (unsigned)drop_labels[threadIdx.x] : 0xFFFFFFFFu;
     if (threadIdx.x == 0) {
@@ -95,7 +113,9 @@ __device__ void load_frame(FrameCtx& s, const double* __restrict__ boxes, const 
 // bits of the boxes of the frame that strictly contain the point (cut_bounding_box, cb:30-66)
 __device__ __forceinline__ unsigned long long inside_bits(const FrameCtx& s, const float4& v) {
     unsigned long long m = 0ull;
-    for (int j = 0; j < s.n_boxes; ++j) {
+    unsigned long long near = s.grid[grid_cell(v.y) * CD_GRID + grid_cell(v.x)];
+    while (near) {
+        const int j = __ffsll((long long)near) - 1; near &= near - 1;
         const CutBox& b = s.box[j];
         const float dx = v.x - b.cx, dy = v.y - b.cy, dz = v.z - b.cz;
         if (dx * dx + dy * dy + dz * dz > b.r2) continue;

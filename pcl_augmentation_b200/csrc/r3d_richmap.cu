@@ -208,20 +208,41 @@ __global__ void __launch_bounds__(RMS_THREADS) k_rms_raster(const float4* __rest
     if (p0 >= n) return;
     const Pose34 T = load_pose(poses, f);
     const double dminx = (double)min_x, dminy = (double)min_y;
-    for (int i = p0 + threadIdx.x; i < min(p0 + RMS_CHUNK, n); i += RMS_THREADS) {
-        const unsigned lab = __ldg(&labels[o + i]);
+    const int p1 = min(p0 + RMS_CHUNK, n);
+    const int lane = threadIdx.x & 31;
+    for (int i0 = p0; i0 < p1; i0 += RMS_THREADS) {              // warp-uniform trip count (the warp votes below)
+        const int i = i0 + threadIdx.x;
         int cls = 0;
-        for (int j = 0; j < n_surf; ++j) if (lab == s_lab[j]) { cls = s_cls[j]; break; }       // ss/rm:185
-        if (!cls) continue;
-        const float4 v = __ldg(&xyzi[o + i]);
-        const double w = pose_row(T, 3, v.x, v.y, v.z);                                       // ss/rm:178
-        const double px = __dsub_rn(__ddiv_rn(pose_row(T, 0, v.x, v.y, v.z), w), dminx);
-        const double py = __dsub_rn(__ddiv_rn(pose_row(T, 1, v.x, v.y, v.z), w), dminy);
-        if (px < 0.0 || py < 0.0) { atomicExch(err, 1); continue; }                            // ss/rm:190 assert
-        const long long ix = (long long)px, iy = (long long)py;                                 // int(): truncation
-        if (ix >= sx || iy >= sy) { atomicExch(err, 2); continue; }                            // IndexError in the reference
-        const unsigned long long key = cls == 3 ? ~0ull : ((unsigned long long)(order_base + (o - pt_off[0]) + i + 1) << 2) | (unsigned)cls;
-        atomicMax(&keymap[ix * sy + iy], key);
+        long long cell = -1;
+        if (i < p1) {
+            const unsigned lab = __ldg(&labels[o + i]);
+            for (int j = 0; j < n_surf; ++j) if (lab == s_lab[j]) { cls = s_cls[j]; break; }   // ss/rm:185
+        }
+        if (cls) {
+            const float4 v = __ldg(&xyzi[o + i]);
+            const double w = pose_row(T, 3, v.x, v.y, v.z);                                       // ss/rm:178
+            const double px = __dsub_rn(__ddiv_rn(pose_row(T, 0, v.x, v.y, v.z), w), dminx);
+            const double py = __dsub_rn(__ddiv_rn(pose_row(T, 1, v.x, v.y, v.z), w), dminy);
+            if (px < 0.0 || py < 0.0) atomicExch(err, 1);                                      // ss/rm:190 assert
+            else {
+                const long long ix = (long long)px, iy = (long long)py;                         // int(): truncation
+                if (ix >= sx || iy >= sy) atomicExch(err, 2);                                  // IndexError in the reference
+                else cell = ix * sy + iy;
+            }
+        }
+        // Neighbouring points of a LiDAR ring fall into the same 1 m cell, and along a drive hundreds of frames hit
+        // it: one atomic per (warp, cell) instead of one per point.  Within a warp the lane order is the point order,
+        // so the group's largest key is its highest lane's — unless a sticky class-3 point is in the group.
+        const unsigned active = __ballot_sync(0xffffffffu, cell >= 0);
+        if (cell >= 0) {
+            const unsigned group = __match_any_sync(active, (unsigned long long)cell);
+            const unsigned sticky = __ballot_sync(group, cls == 3);
+            if (lane == 31 - __clz(group)) {
+                const unsigned long long key = sticky ? ~0ull
+                    : ((unsigned long long)(order_base + (o - pt_off[0]) + i + 1) << 2) | (unsigned)cls;
+                atomicMax(&keymap[cell], key);
+            }
+        }
     }
 }
 

@@ -111,6 +111,18 @@ def test_tilted_boxes_counts_and_indices_vs_cut_bounding_box():
                       'rotation': {'x': q[0], 'y': q[1], 'z': q[2], 'w': q[3]},
                       'length': rng.uniform(1, 6), 'width': rng.uniform(1, 6), 'height': rng.uniform(0.5, 3), 'class': 0})
     boxes.append(dict(boxes[0]))                                   # a duplicate: a point may belong to several boxes
+    # beyond the kernel's pruning grid (+-81.92 m): clusters at 100 - 140 m with their boxes, and a box far from everything
+    far = []
+    for cx, cy in ((101.0, -93.0), (-120.0, 5.0), (3.0, 139.0)):
+        far.append(np.c_[rng.uniform(-1.5, 1.5, (300, 2)) + [cx, cy], rng.uniform(-1.5, 0.5, 300), rng.uniform(0, 1, 300)])
+        boxes.append({'center': {'x': cx, 'y': cy, 'z': -1.0}, 'rotation': {'x': 0.0, 'y': 0.0, 'z': 0.38268343, 'w': 0.92387953},
+                      'length': 2.0, 'width': 2.2, 'height': 1.2, 'class': 0})
+    boxes.append({'center': {'x': 500.0, 'y': 500.0, 'z': 0.0}, 'rotation': {'x': 0.0, 'y': 0.0, 'z': 0.0, 'w': 1.0},
+                  'length': 2.0, 'width': 2.0, 'height': 2.0, 'class': 0})
+    far = np.vstack(far).astype(np.float32)
+    pcl = np.vstack((pcl, far))
+    labels = np.concatenate((labels, np.full(len(far), 7, dtype=labels.dtype)))
+    pts5 = np.hstack((pcl.astype(np.float64), labels.reshape(-1, 1).astype(np.float64)))
     (calib_path := "/tmp/r3d_calib_test.txt") and open(calib_path, "w").write("\n".join(KITTI_CALIB_LINES) + "\n")
     calib = coo.read_calib(calib_path)
     cam = co.camera_record(calib, KITTI_IMAGE_SHAPE)
@@ -126,3 +138,4 @@ def test_tilted_boxes_counts_and_indices_vs_cut_bounding_box():
         assert cut.count_fov == int(coo.fov_flag(pts5[idx, :3], calib, KITTI_IMAGE_SHAPE).sum())
         hits += len(idx)
     assert hits > 2000
+    assert all(c.count_inside > 20 for c in cuts[-4:-1]) and cuts[-1].count_inside == 0

@@ -39,7 +39,7 @@ def main():
             w = csv.writer(f)
             w.writerow(["kernel"] + [f"{m} [{units[i]}]" for m, i in zip(metrics, idx)])
             for r in data:
-                k = r[kn].split("(")[0].replace("void ", "").split("<")[0]
+                k = r[kn].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").split("(")[0].replace("void ", "").split("<")[0]
                 w.writerow([k] + [r[i] for i in idx])
                 rd = float(r[idx[1]].replace(",", "")) * SCALE.get(units[idx[1]], 1.0)
                 wr = float(r[idx[2]].replace(",", "")) * SCALE.get(units[idx[2]], 1.0)
