@@ -16,22 +16,14 @@ constexpr int CF_HR = 4, CF_HC = 2;                    // halo: two 5x3 passes
 constexpr int CF_SH = CF_TH + 2 * CF_HR;               // staged rows
 constexpr int CF_SW = CF_TW + 2 * CF_HC;               // staged cols
 
+// one CF_TH x CF_TW output tile at (r0, c0) of image z; every thread of the CTA calls it (it synchronises)
 template <class In>
-__global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, int64_t img_stride,
-                                                            double* __restrict__ out_train, double* __restrict__ out_label,
-                                                            uint8_t* __restrict__ closed_out, int* __restrict__ far_flag,
-                                                            const int* __restrict__ rect) {
-    const int z = blockIdx.z;
-    if (rect) {          // per-image rectangle (rows r0..r1, cols c0..c1) that needs recomputing; tiles outside skip
-        const int* q = rect + (size_t)z * 4;
-        const int tr0 = blockIdx.y * CF_TH, tc0 = blockIdx.x * CF_TW;
-        if (q[1] < q[0] || tr0 > q[1] || tr0 + CF_TH - 1 < q[0] || tc0 > q[3] || tc0 + CF_TW - 1 < q[2]) return;
-    }
+__device__ __forceinline__ void close_fill_tile(const In& in, int H, int W, int64_t base, int r0, int c0, int z,
+                                                double* __restrict__ out_train, double* __restrict__ out_label,
+                                                uint8_t* __restrict__ closed_out, int* __restrict__ far_flag) {
     __shared__ double s_val[CF_SH][CF_SW];
     __shared__ uint8_t s_occ[CF_SH][CF_SW];            // bit0: occupancy (clip(label,0,1) > 0), bit1: label == 1
     __shared__ uint8_t s_dil[CF_TH + 4][CF_TW + 2];
-    const int r0 = blockIdx.y * CF_TH, c0 = blockIdx.x * CF_TW;
-    const int64_t base = (int64_t)z * img_stride;
     for (int i = threadIdx.x; i < CF_SH * CF_SW; i += CF_THREADS) {
         const int lr = i / CF_SW, lc = i % CF_SW;
         const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
@@ -88,4 +80,31 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, 
         far |= t > r3d::kEmptyRange;
     }
     if (far_flag && far) atomicOr(&far_flag[z], 1);
+}
+
+// one image per blockIdx.z, tiles on the (x, y) grid
+template <class In>
+__global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, int64_t img_stride,
+                                                            double* __restrict__ out_train, double* __restrict__ out_label,
+                                                            uint8_t* __restrict__ closed_out, int* __restrict__ far_flag) {
+    const int z = blockIdx.z;
+    close_fill_tile(in, H, W, (int64_t)z * img_stride, (int)blockIdx.y * CF_TH, (int)blockIdx.x * CF_TW, z, out_train, out_label,
+                    closed_out, far_flag);
+}
+
+// the engine's variant: a persistent grid walks the (image, tile) tasks k_update listed for this round — after the
+// first round only the few tiles around an inserted object change, so a grid over every tile of every image would be
+// tens of thousands of CTAs that exit at once.  task = image * tiles_per_image + tile.
+template <class In>
+__global__ void __launch_bounds__(CF_THREADS) k_close_fill_tasks(In in, int H, int W, int64_t img_stride,
+                                                                  double* __restrict__ out_train, int* __restrict__ far_flag,
+                                                                  const int* __restrict__ tasks, const int* __restrict__ n_tasks) {
+    const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles = tiles_x * ((H + CF_TH - 1) / CF_TH);
+    const int n = *n_tasks;
+    for (int t = blockIdx.x; t < n; t += gridDim.x) {
+        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        close_fill_tile(in, H, W, (int64_t)z * img_stride, (tile / tiles_x) * CF_TH, (tile % tiles_x) * CF_TW, z, out_train,
+                        (double*)nullptr, (uint8_t*)nullptr, far_flag);
+        __syncthreads();                                 // the tile buffers are reused by the next task
+    }
 }

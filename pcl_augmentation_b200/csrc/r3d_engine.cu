@@ -80,7 +80,7 @@ struct r3d_engine {
     DevBuf<unsigned short> col, cand_list, label16;
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
-        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr;
+        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks;
     DevBuf<unsigned> round_ctl;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -229,6 +229,10 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
     TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(R3D_MAX_SUB * 64 * 2));
     TRY(eng->round_ctl.alloc(R3D_MAX_SUB * 32));
+    d.cf_tiles_x = (d.cols + CF_TW - 1) / CF_TW;
+    d.cf_tiles = d.cf_tiles_x * ((d.rows + CF_TH - 1) / CF_TH);
+    TRY(eng->work_cnt.alloc(B * 4)); TRY(eng->full_list.alloc(B)); TRY(eng->cf_tasks.alloc(B * (size_t)d.cf_tiles));
+    R3D_CUDA(cudaMemset(eng->work_cnt.p, 0, B * 4 * sizeof(int)));
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -272,6 +276,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.zraw = eng->zraw.p; d.obj_raw = eng->obj_raw.p; d.smooth = eng->smooth.p; d.dmask = eng->dmask.p; d.vmask = eng->vmask.p;
     d.st = eng->st.p; d.gate_update = eng->gate_update.p; d.gate_try = eng->gate_try.p; d.gate_apply = eng->gate_apply.p;
     d.gate_full = eng->gate_full.p; d.gate_patch = eng->gate_patch.p; d.cf_rect = eng->cf_rect.p;
+    d.work_cnt = eng->work_cnt.p; d.full_list = eng->full_list.p; d.cf_tasks = eng->cf_tasks.p;
     d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
     d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
     d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
@@ -528,6 +533,7 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     R3D_OFF(col, d.P); R3D_OFF(pix, d.P); R3D_OFF(alive, d.P); R3D_OFF(zraw, d.hw); R3D_OFF(obj_raw, d.hw);
     R3D_OFF(smooth, d.hw); R3D_OFF(dmask, d.dwords); R3D_OFF(vmask, d.dwords); R3D_OFF(st, 1); R3D_OFF(gate_update, 1);
     R3D_OFF(gate_try, 1); R3D_OFF(gate_apply, 1); R3D_OFF(gate_full, 1); R3D_OFF(gate_patch, 1); R3D_OFF(cf_rect, 4);
+    R3D_OFF(work_cnt, 4); R3D_OFF(full_list, 1); R3D_OFF(cf_tasks, d.cf_tiles);
     R3D_OFF(col_off, d.cols + 1); R3D_OFF(col_idx, d.max_points); R3D_OFF(far_arr, 1); R3D_OFF(boxes, d.max_boxes);
     R3D_OFF(box_tests, d.max_boxes); R3D_OFF(od_map_off, 2); R3D_OFF(od_map_dims, 8); R3D_OFF(poses, 16); R3D_OFF(occ_win, ww);
     R3D_OFF(counts, d.n_classes); R3D_OFF(perms, (size_t)d.n_perm_events * d.n_classes * d.max_tries);
@@ -601,17 +607,20 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
     // the launch sequence of one round; also what a round graph is captured from
     auto launch_round = [&](const EngineDev& d, int ns, cudaStream_t ss, bool r0) {
         const size_t pref_smem = (size_t)(ns + 1) * sizeof(int);
-        { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 128, 0, ss>>>(d, ns); }
+        // the three full re-projection kernels and close/fill walk the work lists k_update wrote (all scans in round
+        // 0, a handful later): grids sized for "some scans", not for every (chunk, scan) / (tile, scan) pair
+        const int full_y = std::min(ns, 32);
+        const int cf_grid = std::min(ns * d.cf_tiles, eng->n_sms * 8);
+        { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 32, 0, ss>>>(d, ns); }
         { Launcher l(eng, KID_UPDATE, ss); k_update<<<dim3(UPDATE_G, ns), UPDATE_THREADS, 0, ss>>>(d, ns); }
-        { Launcher l(eng, r0 ? KID_MINMAX0 : KID_MINMAX, ss); k_minmax<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-        { Launcher l(eng, r0 ? KID_CLEAR0 : KID_CLEAR, ss); k_clear_images<<<dim3(32, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
-        { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_MINMAX0 : KID_MINMAX, ss); k_minmax<<<dim3(chunks_all, full_y), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_CLEAR0 : KID_CLEAR, ss); k_clear_images<<<dim3(32, full_y), STREAM_THREADS, 0, ss>>>(d, ns); }
+        { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, full_y), STREAM_THREADS, 0, ss>>>(d, ns); }
         {
             Launcher l(eng, r0 ? KID_CLOSEFILL0 : KID_CLOSEFILL, ss);
             RawImage in{d.zraw};
-            dim3 grid((d.cols + CF_TW - 1) / CF_TW, (d.rows + CF_TH - 1) / CF_TH, ns);
-            k_close_fill<RawImage><<<grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, nullptr, nullptr,
-                                                                 d.far_arr, d.cf_rect);
+            k_close_fill_tasks<RawImage><<<cf_grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr,
+                                                                         d.cf_tasks, d.work_cnt + 1);
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
         { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }

@@ -86,6 +86,13 @@ struct EngineDev {       // passed by value to kernels
     ScanState* st;
     int *gate_update, *gate_try, *gate_apply, *gate_full, *gate_patch;
     int* cf_rect;                     // [B][4] rows r0..r1, cols c0..c1 (inclusive) close/fill must recompute
+    // work lists of the current round (per sub-batch; k_ctrl re-arms the counters, k_update fills them): the scans that
+    // re-project in full, and the (scan, tile) tasks of close/fill — so those kernels run a small persistent grid
+    // instead of one CTA per (chunk, scan) / (tile, scan) of which all but a few exit at once
+    int* work_cnt;                    // [4]: scans in full_list, tasks in cf_tasks
+    int* full_list;                   // [B]
+    int* cf_tasks;                    // [B][cf_tiles]: scan * cf_tiles + tile
+    int cf_tiles, cf_tiles_x;         // close/fill tiles per image, per image row of tiles
     int force_full;                   // debug / test: always take the full re-projection path
     int *col_off, *col_idx;           // [B][cols+1], [B][max_points]: original points bucketed by azimuth bin
     // round control of ONE sub-batch.  The round number lives on the device (round_ctl[0], advanced by the last k_ctrl
@@ -150,7 +157,10 @@ struct EngineDev {       // passed by value to kernels
     float* out_check;
 };
 
-constexpr int OCC_G = 16;        // CTAs per scan in the occlusion-count kernel
+#ifndef R3D_OCC_G
+#define R3D_OCC_G 8
+#endif
+constexpr int OCC_G = R3D_OCC_G;        // CTAs per scan in the occlusion-count kernel (8: +3.6 % over 16 with 8 engines in flight)
 constexpr double kFix = 1099511627776.0;   // 2^40 fixed point for the order-independent road-level sum
 
 __device__ __forceinline__ void load_xyz(const EngineDev& e, int b, int p, int n0, double& x, double& y, double& z) {

@@ -93,7 +93,7 @@ __device__ int list_entry(const EngineDev& e, int b, int ev, int ci, int sidx, i
     return -1;
 }
 
-__global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(32) k_ctrl(EngineDev e, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans) return;
     ScanState& s = e.st[b];
@@ -191,6 +191,7 @@ __global__ void __launch_bounds__(128) k_ctrl(EngineDev e, int n_scans) {
             __threadfence_system();
             int* nx = e.active_count + 2 * ((slot + 32) & 63);      // re-arm the counters half a ring ahead
             nx[0] = 0; nx[1] = 0;
+            e.work_cnt[0] = 0; e.work_cnt[1] = 0;                   // this round's work lists (filled by k_update)
             e.round_ctl[0] = round + 1u;                            // every other CTA has read it (it took its ticket)
         }
         if (tryact) atomicAdd(&e.stats[1], 1ull);
@@ -216,7 +217,10 @@ __device__ __forceinline__ bool pix_removed(const EngineDev& e, int b, const Sca
 //  3. patch: the z-buffer changes only at the pixels of vis_px — all their scene points were removed (od/ins:491)
 //     and the visible object points were appended there (od/ins:545).
 constexpr int UPDATE_THREADS = 256;
-constexpr int UPDATE_G = 8;          // CTAs per scan; the last one to finish takes the decision and patches
+#ifndef R3D_UPDATE_G
+#define R3D_UPDATE_G 8
+#endif
+constexpr int UPDATE_G = R3D_UPDATE_G;   // CTAs per scan; the last one to finish takes the decision and patches
 __device__ __forceinline__ bool last_block_done(unsigned* ticket, unsigned n_blocks) {
     __shared__ bool s_last;
     __threadfence();
@@ -293,6 +297,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_sc
         s.extreme_removed = 0;
         e.gate_full[b] = full; e.gate_patch[b] = patch;
         s_patch = patch;
+        if (full) e.full_list[atomicAdd(&e.work_cnt[0], 1)] = b;
+        if (rect[1] >= rect[0] && rect[3] >= rect[2]) {             // close/fill tiles that overlap the rectangle
+            const int ty0 = rect[0] / CF_TH, ty1 = rect[1] / CF_TH, tx0 = rect[2] / CF_TW, tx1 = rect[3] / CF_TW;
+            const int nt = (ty1 - ty0 + 1) * (tx1 - tx0 + 1);
+            int* task = e.cf_tasks + atomicAdd(&e.work_cnt[1], nt);
+            for (int ty = ty0; ty <= ty1; ++ty)
+                for (int tx = tx0; tx <= tx1; ++tx) *task++ = b * e.cf_tiles + ty * e.cf_tiles_x + tx;
+        }
     }
     __syncthreads();
     if (do_update && e.task == 1) {
@@ -318,12 +330,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_sc
 
 // A2 (od/ins:79-80) on the cached elevations: min / max over the live points (full path only)
 __global__ void __launch_bounds__(STREAM_THREADS) k_minmax(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_full[b]) return;
+    __shared__ unsigned long long s_min[STREAM_THREADS / 32], s_max[STREAM_THREADS / 32];
+    const int n_full = e.work_cnt[0];
+    for (int li = blockIdx.y; li < n_full; li += gridDim.y) {       // the scans k_update listed for a full re-projection
+    const int b = e.full_list[li];
     ScanState& s = e.st[b];
     const int n = s.n0 + s.n_tail;
     const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n) return;
+    if (p0 >= n) continue;
     const size_t base = (size_t)b * e.P;
     unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
@@ -336,38 +350,42 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_minmax(EngineDev e, int n_sc
         lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
     }
-    __shared__ unsigned long long s_min[STREAM_THREADS / 32], s_max[STREAM_THREADS / 32];
     if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lmin; s_max[threadIdx.x >> 5] = lmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < STREAM_THREADS / 32; ++w) { lmin = min(lmin, s_min[w]); lmax = max(lmax, s_max[w]); }
         if (lmax >= lmin) { atomicMin(&s.min_el_bits, lmin); atomicMax(&s.max_el_bits, lmax); }
     }
+    __syncthreads();
+    }
 }
 
 // clear the z-buffer of the scans that re-project in full and fix their image geometry
 __global__ void __launch_bounds__(STREAM_THREADS) k_clear_images(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_full[b]) return;
-    ScanState& s = e.st[b];
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        e.far_arr[b] = 0;
-        if (s.min_el_bits == R3D_EMPTY_U64) { set_error(s, R3D_ERR_ASSERT); }
-        s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+    const int n_full = e.work_cnt[0];
+    for (int li = blockIdx.y; li < n_full; li += gridDim.y) {
+        const int b = e.full_list[li];
+        ScanState& s = e.st[b];
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            e.far_arr[b] = 0;
+            if (s.min_el_bits == R3D_EMPTY_U64) { set_error(s, R3D_ERR_ASSERT); }
+            s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+        }
+        unsigned long long* z = e.zraw + (size_t)b * e.hw;
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.hw; i += gridDim.x * blockDim.x) z[i] = R3D_EMPTY_U64;
     }
-    unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < e.hw; i += gridDim.x * blockDim.x) z[i] = R3D_EMPTY_U64;
 }
 
 // A3 (od/ins:85-130): bin every live point with the reference's truncation rule, write pix_id, 64-bit atomicMin of
 // the range bits into the z-buffer.  Algorithmic traffic 20 B/point (+ 8 B/pixel for the z-buffer).
 __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_full[b]) return;
+    const int n_full = e.work_cnt[0];
+    for (int li = blockIdx.y; li < n_full; li += gridDim.y) {
+    const int b = e.full_list[li];
     ScanState& s = e.st[b];
     const int n = s.n0 + s.n_tail;
     const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n) return;
+    if (p0 >= n) continue;
     const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
     const size_t base = (size_t)b * e.P;           // P is a multiple of 16: the 4-point vectors below are aligned
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
@@ -398,6 +416,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_project(EngineDev e, int n_s
         } else {
             for (int q = p; q < n; ++q) e.pix[base + q] = one(e.alive[base + q], e.el[base + q], e.col[base + q], e.r[base + q]);
         }
+    }
     }
 }
 
@@ -575,7 +594,10 @@ constexpr int OBJ_SMEM_PTS = 1024;       // object points staged in shared memor
 constexpr int ONMAP_PRE_PTS = 8;         // points of the on-map prefilter
 constexpr int GRP = 8;                   // lanes per (scan, rotation) task in the balanced stages
 constexpr int TASK_THREADS = 256;
-constexpr int TASK_CTAS_PER_SM = 4;
+#ifndef R3D_TASK_CTAS_PER_SM
+#define R3D_TASK_CTAS_PER_SM 4
+#endif
+constexpr int TASK_CTAS_PER_SM = R3D_TASK_CTAS_PER_SM;
 
 __host__ __device__ __forceinline__ size_t onmap_smem_bytes(int K) {
     return (size_t)(3 * OBJ_SMEM_PTS) * 8 + (size_t)((K + 4) & ~3) * 2 + (size_t)((K + 8) & ~7);
@@ -1238,7 +1260,10 @@ __device__ void bitonic_sort_u64(unsigned long long* keys, int n_pow2) {
 // candidate's z-buffer in a scratch image, closes / fills it around the object, compares with the scene image
 // (strict <) into the vis_px bit mask, and on acceptance appends the visible object points in (pix_id, index) order
 // to the scene tail, the `check` record and the scene boxes.
-constexpr int SEL_TILE_PX = 8192;      // pixels of the shared-memory object tile (64 KB of fp64 ranges)
+#ifndef R3D_SEL_TILE_PX
+#define R3D_SEL_TILE_PX 8192
+#endif
+constexpr int SEL_TILE_PX = R3D_SEL_TILE_PX;      // pixels of the shared-memory object tile (8 B of fp64 range each)
 
 // local variant of obj_pixel_value on the shared-memory tile (rows r_lo.., cols c_lo.., nr x nc).  Pixels outside the
 // tile but inside the image hold no object point and are farther than the 5x3 window from every object pixel, so

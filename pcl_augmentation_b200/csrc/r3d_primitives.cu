@@ -124,8 +124,7 @@ extern "C" int r3d_close_fill(const double* train_in, const double* label_in, in
         return r3d_fail(R3D_ERR_ARG, "r3d_close_fill: bad argument");
     F64Image in{train_in, label_in};
     dim3 grid((num_col + CF_TW - 1) / CF_TW, (num_row + CF_TH - 1) / CF_TH, 1);
-    k_close_fill<F64Image><<<grid, CF_THREADS, 0, stream>>>(in, num_row, num_col, 0, train_out, label_out, closed_out,
-                                                            nullptr, nullptr);
+    k_close_fill<F64Image><<<grid, CF_THREADS, 0, stream>>>(in, num_row, num_col, 0, train_out, label_out, closed_out, nullptr);
     r3d_count_launch();
     return r3d_check_launch("r3d_close_fill");
 }
