@@ -82,7 +82,7 @@ struct r3d_engine {
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks;
     DevBuf<unsigned> round_ctl;
-    DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags;
+    DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags, gnear, gscratch;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
     DevBuf<ScanState> st;
@@ -245,6 +245,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->check_off.alloc(B + 1)); TRY(eng->out_xyzi.alloc(B * P)); TRY(eng->out_label.alloc(B * P));
     TRY(eng->out_check.alloc(B * d.max_inserted * 5)); TRY(eng->n0_arr.alloc(B)); TRY(eng->nbox0_arr.alloc(B));
     TRY(eng->gcell.alloc(B * (size_t)d.G * d.G)); TRY(eng->gpts.alloc(B * d.max_points));
+    TRY(eng->gnear.alloc(B * (size_t)d.G * d.G)); TRY(eng->gscratch.alloc(B * (size_t)d.G * d.G));
     TRY(eng->col_off.alloc(B * (size_t)(d.cols + 1))); TRY(eng->col_idx.alloc(B * d.max_points));
     TRY(eng->acell.alloc(B * (size_t)d.G * d.G)); TRY(eng->apts.alloc(B * d.max_points));
     TRY(eng->try_obj.alloc(B));
@@ -284,7 +285,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.cand_v = eng->cand_v.p; d.feas = eng->feas.p; d.inserted = eng->inserted.p; d.inserted_box = eng->inserted_box.p;
     d.check = eng->check.p; d.out_count = eng->out_count.p; d.out_off = eng->out_off.p; d.check_off = eng->check_off.p;
     d.out_xyzi = eng->out_xyzi.p; d.out_label = eng->out_label.p; d.out_check = eng->out_check.p;
-    d.gcell = eng->gcell.p; d.gpts = eng->gpts.p;
+    d.gcell = eng->gcell.p; d.gpts = eng->gpts.p; d.gnear = eng->gnear.p; d.gscratch = eng->gscratch.p;
     d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.acell = eng->acell.p; d.apts = eng->apts.p;
     d.try_obj = eng->try_obj.p; d.chunk_cnt = eng->chunk_cnt.p;
     d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
@@ -346,6 +347,14 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
         t.cls = db->class_index[o];
         t.first = (int)db->point_offsets[o]; t.count = (int)(db->point_offsets[o + 1] - db->point_offsets[o]);
         t.pad = 0;
+        t.eu0 = t.ev0 = t.ez0 = 1e300; t.eu1 = t.ev1 = t.ez1 = -1e300;
+        for (int i = t.first; i < t.first + t.count; ++i) {
+            const double dx = x[i] - t.cx, dy = y[i] - t.cy;
+            const double u = dx * t.a + dy * t.b, v = -dx * t.b + dy * t.a, w = z[i] - t.cz;
+            t.eu0 = std::min(t.eu0, u); t.eu1 = std::max(t.eu1, u); t.ev0 = std::min(t.ev0, v); t.ev1 = std::max(t.ev1, v);
+            t.ez0 = std::min(t.ez0, w); t.ez1 = std::max(t.ez1, w);
+        }
+        t.eu0 -= 1e-6; t.ev0 -= 1e-6; t.ez0 -= 1e-6; t.eu1 += 1e-6; t.ev1 += 1e-6; t.ez1 += 1e-6;
         if (t.cls < 0 || t.cls >= d.n_classes) return r3d_fail(R3D_ERR_ARG, "r3d_engine_set_objects: class index out of range");
         max_pts = std::max(max_pts, t.count);
     }
@@ -413,7 +422,9 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
         k_bucket_scan<<<n, 1024, 0, st>>>(eng->acell.p, (size_t)d.G * d.G, d.G * d.G, n);
         k_grid_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
         k_index_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        r3d_count_launch(6);
+        k_grid_near<1><<<dim3((d.G * d.G + 255) / 256, n), 256, 0, st>>>(d, n);
+        k_grid_near<2><<<dim3((d.G * d.G + 255) / 256, n), 256, 0, st>>>(d, n);
+        r3d_count_launch(8);
     } else {
         k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
         // scene boxes: drop the boxes appended by the previous run
@@ -527,7 +538,7 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     const size_t b = (size_t)b0;
     const size_t gg = (size_t)d.G * d.G, k1 = (size_t)d.K + 1, ww = (size_t)d.map_window * d.map_window / 32;
 #define R3D_OFF(field, stride) if (d.field) v.field = d.field + b * (size_t)(stride)
-    R3D_OFF(gcell, gg); R3D_OFF(gpts, d.max_points); R3D_OFF(acell, gg); R3D_OFF(apts, d.max_points);
+    R3D_OFF(gcell, gg); R3D_OFF(gpts, d.max_points); R3D_OFF(gnear, gg); R3D_OFF(gscratch, gg); R3D_OFF(acell, gg); R3D_OFF(apts, d.max_points);
     R3D_OFF(xyzi, d.max_points); R3D_OFF(tail_x, d.max_inserted); R3D_OFF(tail_y, d.max_inserted);
     R3D_OFF(tail_z, d.max_inserted); R3D_OFF(tail_i, d.max_inserted); R3D_OFF(label, d.P); R3D_OFF(r, d.P); R3D_OFF(el, d.P);
     R3D_OFF(col, d.P); R3D_OFF(pix, d.P); R3D_OFF(alive, d.P); R3D_OFF(zraw, d.hw); R3D_OFF(obj_raw, d.hw);

@@ -36,6 +36,11 @@ struct ObjBox {          // one cut object: box from read_label_line (od/fs:175-
     double length, width, height;
     double rho, psi0;    // range / azimuth of the box centre about the sensor (pruning only)
     double reach;        // horizontal bounding radius (pruning only)
+    // extent of the object's POINTS in the box frame (they may stick out of the annotated box: the cut-out box of
+    // object_cut_out.py:133 is 5 cm wider per side than the box read_label_line parses): along the box x / y axis
+    // relative to the box centre and in z relative to the box bottom, padded by 1e-6 m.  Invariant under the candidate
+    // rotations (points and box turn together); used only to prune the object-points-vs-scene-box test.
+    double eu0, eu1, ev0, ev1, ez0, ez1;
     int cls, first, count, pad;
 };
 
@@ -69,6 +74,8 @@ struct EngineDev {       // passed by value to kernels
     double grid_cell;
     int* gcell;                       // [B][G*G]   CSR end offsets (cell c holds gpts[gcell[c-1] .. gcell[c]) )
     float4* gpts;                     // [B][max_points]  surface points sorted by cell: x, y, z, label bits
+    unsigned char* gnear;             // [B][G*G]   Chebyshev distance (cells, capped) to the nearest non-empty cell of gcell
+    unsigned char* gscratch;          // [B][G*G]   row pass of the distance transform
     int* acell;                       // [B][G*G]   same grid over ALL original points (collision test)
     float4* apts;                     // [B][max_points]  x, y, z, point index bits
     // per-scan resident data

@@ -522,6 +522,37 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int 
     }
 }
 
+// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell to the nearest cell that holds a surface point:
+// the road-level search of a candidate whose surroundings are empty starts at that ring instead of growing through
+// the empty ones.  Separable: row pass (min |dx| along the row), then column pass (min over dy of max(|dy|, row value)).
+constexpr int NEAR_CAP = 12;
+template <int PASS>
+__global__ void __launch_bounds__(256) k_grid_near(EngineDev e, int n_scans) {
+    const int b = blockIdx.y, G = e.G;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (b >= n_scans || c >= G * G) return;
+    const int y = c / G, x = c % G;
+    const size_t gb = (size_t)b * G * G;
+    int best = NEAR_CAP;
+    if (PASS == 1) {
+        const int* cell = e.gcell + gb;
+        for (int dx = -(NEAR_CAP - 1); dx <= NEAR_CAP - 1; ++dx) {
+            const int x1 = x + dx;
+            if (x1 < 0 || x1 >= G) continue;
+            const int q = y * G + x1;
+            if (cell[q] > (q > 0 ? cell[q - 1] : 0)) best = min(best, abs(dx));
+        }
+        e.gscratch[gb + c] = (unsigned char)best;
+    } else {
+        for (int dy = -(NEAR_CAP - 1); dy <= NEAR_CAP - 1; ++dy) {
+            const int y1 = y + dy;
+            if (y1 < 0 || y1 >= G) continue;
+            best = min(best, max(abs(dy), (int)e.gscratch[gb + (size_t)y1 * G + x]));
+        }
+        e.gnear[gb + c] = (unsigned char)best;
+    }
+}
+
 // One more once-per-scan CSR index over the ORIGINAL points (their azimuth bin never changes): by image column,
 // for k_apply_window.
 template <int PASS>     // 1: count, 2: scatter point indices
@@ -693,7 +724,15 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     double best = 1e300;
     CellRect hole{0, -1, 0, -1};
     const double step = e.grid_cell;
-    for (double R = 0.5 * step;; R = fmin(R < step ? step : R + step, 5.0)) {
+    double R = 0.5 * step;
+    // every cell closer than `ring` cells (Chebyshev) to the centre's cell is empty: start at the radius whose square
+    // of cells still lies inside that empty block and treat the block as already visited
+    const int ring = e.gnear[(size_t)b * G * G + (size_t)grid_coord(e, (float)cy) * G + grid_coord(e, (float)cx)];
+    if (ring >= 2) {
+        R = fmin((ring - 1) * step, 5.0);
+        hole = cells_within(e, cx, cy, R - 0.01);
+    }
+    for (;; R = fmin(R < step ? step : R + step, 5.0)) {
         const CellRect rc = cells_within(e, cx, cy, R);
         group_visit(cell, pts, G, rc, hole, gl, gm, [&](const float4& v) {
             if (!in_surface(surf, __float_as_uint(v.w))) return;
@@ -802,6 +841,30 @@ __device__ __noinline__ bool object_in_scene_box(const BoxTest* box_test, const 
     return false;
 }
 
+// Can the rectangle that holds every point of candidate k (ObjBox extents in the frame of the rotated box) and a
+// yaw-only scene box overlap?  Separating-axis test on the four edge directions plus the z intervals, with 1e-9 m of
+// slack; "false" proves that no object point is inside the scene box, "true" only means: test the points.
+__device__ __forceinline__ bool extent_may_touch_box(const ObjBox& ob, const YawBox& yb, double level, const Box& bx) {
+    if (bx.m[2] != 0.0 || bx.m[5] != 0.0 || bx.m[6] != 0.0 || bx.m[7] != 0.0 || !(bx.m[8] > 0.999999)) return true;   // tilted box: no pruning
+    if (level + ob.ez1 <= bx.cz - 1e-9) return false;                        // every object point at or below the box bottom
+    if (level + ob.ez0 >= bx.cz + bx.height + 1e-9) return false;            // ... at or above its top
+    const double ux = yb.m00, uy = yb.m10, vx = -yb.m10, vy = yb.m00;              // axes of the candidate's box
+    const double s0x = bx.m[0], s0y = bx.m[3], s1x = bx.m[1], s1y = bx.m[4];        // axes of the scene box
+    const double mu = 0.5 * (ob.eu0 + ob.eu1), mv = 0.5 * (ob.ev0 + ob.ev1);
+    const double hu = 0.5 * (ob.eu1 - ob.eu0), hv = 0.5 * (ob.ev1 - ob.ev0);
+    const double dx = yb.cx + ux * mu + vx * mv - bx.cx, dy = yb.cy + uy * mu + vy * mv - bx.cy;
+    const double hl = 0.5 * bx.length, hw = 0.5 * bx.width;
+    const double ax[4] = {ux, vx, s0x, s1x}, ay[4] = {uy, vy, s0y, s1y};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const double nn = sqrt(ax[i] * ax[i] + ay[i] * ay[i]);
+        const double ro = hu * fabs(ux * ax[i] + uy * ay[i]) + hv * fabs(vx * ax[i] + vy * ay[i]);
+        const double rb = hl * fabs(s0x * ax[i] + s0y * ay[i]) + hw * fabs(s1x * ax[i] + s1y * ay[i]);
+        if (fabs(dx * ax[i] + dy * ay[i]) > ro + rb + 1e-9 * nn) return false;
+    }
+    return true;
+}
+
 // A8 + A9 (od/fs:109-135, ss/fs:79-104) for one candidate with road level `level`, one 8-lane group:
 //  (i)  obstacle scene points strictly inside the candidate box: the ORIGINAL points come from the all-points grid
 //       (only the cells within the box reach of the candidate centre), the INSERTED points from the tails of the
@@ -867,7 +930,7 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
         if (bi < s.n_boxes) {
             const Box& bx = e.boxes[(size_t)b * e.max_boxes + bi];
             const double ddx = yb.cx - bx.cx, ddy = yb.cy - bx.cy, rr = ob.reach + bx.reach + 0.05;
-            near = ddx * ddx + ddy * ddy <= rr * rr;
+            near = ddx * ddx + ddy * ddy <= rr * rr && extent_may_touch_box(ob, yb, level, bx);
         }
         unsigned m = (__ballot_sync(gm, near) & gm) >> gshift;
         while (m) {
