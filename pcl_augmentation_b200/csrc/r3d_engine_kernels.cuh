@@ -624,7 +624,10 @@ constexpr int TRY_THREADS = 512;
 constexpr int OBJ_SMEM_PTS = 1024;       // object points staged in shared memory (x, y, z fp64 = 24 KB); larger: global
 constexpr int ONMAP_PRE_PTS = 8;         // points of the on-map prefilter
 constexpr int GRP = 8;                   // lanes per (scan, rotation) task in the balanced stages
-constexpr int TASK_THREADS = 256;
+#ifndef R3D_TASK_THREADS
+#define R3D_TASK_THREADS 256
+#endif
+constexpr int TASK_THREADS = R3D_TASK_THREADS;
 #ifndef R3D_TASK_CTAS_PER_SM
 #define R3D_TASK_CTAS_PER_SM 4
 #endif
