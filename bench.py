@@ -261,6 +261,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    from pcl_augmentation_b200 import sharding as _sh
+    numa_cpus = _sh.bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("R3D_NUMA_BIND", "1") != "0") else None
     if world > 1:
         # NCCL_DEBUG=VERSION / INFO print to stdout; rank 0's stdout must carry the JSON line only
         if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
@@ -448,7 +450,7 @@ def main():
                     "ms_per_step": 1000.0 * e2e_s / args.steps,
                     "pcie_gbs_each_way": round(max(h2d, d2h / args.steps) / (e2e_s / args.steps) / 1e9, 1)},
             "gpu_launches": int(launches), "clocks": clocks, "sub_batches": args.sub_batches,
-            "resident_engines": res_depth, "single_batch_ms": single_batch_ms,
+            "resident_engines": res_depth, "single_batch_ms": single_batch_ms, "numa_bound_cpus": numa_cpus,
             "single_batch_scans_per_s": world * n_scans / (single_batch_ms / 1000.0),
             "kernel_times": "CUDA events around every launch in a separate pass with one sub-batch (serial)",
             "step_roofline": step_roofline, "kernels": kernel_table,

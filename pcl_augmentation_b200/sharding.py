@@ -37,3 +37,26 @@ def whole_job_rate(units_this_rank, seconds_this_rank, device="cpu"):
     total = all_reduce_scalar(units_this_rank, "sum", device)
     slowest = all_reduce_scalar(seconds_this_rank, "max", device)
     return total / slowest
+
+
+def bind_to_gpu_numa_node(device_index):
+    """Pin the calling thread (and the threads / pinned allocations it creates afterwards) to the CPUs next to GPU
+    ``device_index``: with one process per GPU the pinned staging buffers then sit in the memory of the socket the GPU
+    hangs off, and the H2D / D2H DMA of 8 ranks does not funnel through one memory controller.  Returns the number of
+    CPUs the thread may run on afterwards, or None if NVML cannot tell (the affinity is left alone)."""
+    import os
+    try:
+        import pynvml
+        import torch
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(device_index).uuid)
+        handle = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        before = os.sched_getaffinity(0)
+        pynvml.nvmlDeviceSetCpuAffinity(handle)
+        after = os.sched_getaffinity(0)
+        if not after or not (after & before):          # NVML named CPUs outside our cpuset: keep what we had
+            os.sched_setaffinity(0, before)
+            return None
+        return len(after)
+    except Exception:
+        return None
