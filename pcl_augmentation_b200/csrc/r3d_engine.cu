@@ -58,6 +58,7 @@ struct r3d_engine {
     cudaStream_t sub_stream[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t sub_done[R3D_MAX_SUB] = {nullptr};
     cudaEvent_t ev_armed = nullptr;
+    cudaEvent_t ev_wait = nullptr;               // blocking-sync event for host waits on the engine stream
     // state of a run in progress (r3d_engine_run_until may return before the batch is finished)
     struct Sub { int b0, n, round; bool done; long long left; unsigned seq_base; EngineDev d; cudaStream_t st; };
     Sub sub[R3D_MAX_SUB];
@@ -175,6 +176,19 @@ size_t select_smem_bytes(int max_pts) {
 }  // namespace
 
 #define TRY(x) do { int _rc = (x); if (_rc != R3D_OK) return _rc; } while (0)
+
+// Wait for the engine stream WITHOUT spinning: the waits below cover millisecond-long transfers and whole runs, and a
+// rank keeps several engine threads; cudaStreamSynchronize would burn a host core per waiting thread (8 ranks x 4
+// pipelined engines on a 32-vCPU box starve the threads that launch the rounds).  A blocking-sync event sleeps instead.
+static cudaError_t engine_wait(r3d_engine* eng) {
+    if (!eng->ev_wait) {
+        cudaError_t e = cudaEventCreateWithFlags(&eng->ev_wait, cudaEventBlockingSync | cudaEventDisableTiming);
+        if (e != cudaSuccess) return e;
+    }
+    cudaError_t e = cudaEventRecord(eng->ev_wait, eng->stream);
+    if (e != cudaSuccess) return e;
+    return cudaEventSynchronize(eng->ev_wait);
+}
 
 extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     if (!cfg || !out) return r3d_fail(R3D_ERR_ARG, "r3d_engine_create: null argument");
@@ -306,6 +320,7 @@ extern "C" int r3d_engine_destroy(r3d_engine* eng) {
         if (eng->sub_done[i]) cudaEventDestroy(eng->sub_done[i]);
     }
     if (eng->ev_armed) cudaEventDestroy(eng->ev_armed);
+    if (eng->ev_wait) cudaEventDestroy(eng->ev_wait);
     for (int i = 0; i < R3D_MAX_SUB; ++i) if (eng->round_graph[i].exec) cudaGraphExecDestroy(eng->round_graph[i].exec);
     cudaStreamDestroy(eng->stream);
     delete eng;
@@ -738,7 +753,7 @@ extern "C" int r3d_engine_set_sub_batches(r3d_engine* eng, int n_sub) {
 extern "C" int r3d_engine_sync(r3d_engine* eng) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng) return r3d_fail(R3D_ERR_ARG, "r3d_engine_sync: null engine");
-    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    R3D_CUDA(engine_wait(eng));
     drain_events(eng);
     return R3D_OK;
 }
@@ -746,7 +761,7 @@ extern "C" int r3d_engine_sync(r3d_engine* eng) {
 extern "C" int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_output_rows: run first");
-    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    R3D_CUDA(engine_wait(eng));
     if (total_points) *total_points = eng->h_offsets[eng->n_scans];
     if (total_check) *total_check = eng->h_offsets[eng->dev.B + 1 + eng->n_scans];
     return R3D_OK;
@@ -758,7 +773,7 @@ extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
     EngineDev& d = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
-    R3D_CUDA(cudaStreamSynchronize(st));
+    R3D_CUDA(engine_wait(eng));
     const long long total = eng->h_offsets[n], total_check = eng->h_offsets[d.B + 1 + n];
     if (total > res->capacity_points || total_check > res->capacity_check)
         return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_fetch: result buffers too small");
@@ -771,7 +786,7 @@ extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
     if (res->inserted_box) R3D_CUDA(cudaMemcpyAsync(res->inserted_box, eng->inserted_box.p, (size_t)n * d.max_events * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));
     std::vector<ScanState> hs(n);
     R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p, n * sizeof(ScanState), cudaMemcpyDeviceToHost, st));
-    R3D_CUDA(cudaStreamSynchronize(st));
+    R3D_CUDA(engine_wait(eng));
     for (int s = 0; s < n; ++s) {
         if (res->n_inserted) res->n_inserted[s] = hs[s].n_inserted;
         if (res->status) res->status[s] = hs[s].status;
