@@ -16,36 +16,67 @@ constexpr int CF_HR = 4, CF_HC = 2;                    // halo: two 5x3 passes
 constexpr int CF_SH = CF_TH + 2 * CF_HR;               // staged rows
 constexpr int CF_SW = CF_TW + 2 * CF_HC;               // staged cols
 
-// one CF_TH x CF_TW output tile at (r0, c0) of image z; every thread of the CTA calls it (it synchronises)
+// one CF_TH x CF_TW output tile at (r0, c0) of image z; every thread of the CTA calls it (it synchronises).
+// The binary morphology runs on BIT ROWS: a staged row of 68 pixels is three 32-bit words built with one warp ballot
+// per 32 pixels while the values are staged; the 5 x 3 dilation / erosion are a handful of shifts and ORs / ANDs per
+// row word (out-of-image positions: occupancy 0, dilation 1 = neutral for the erosion), so the per-pixel work that
+// remains is the ordered fp64 neighbour mean of the pixels the closing switched on.
+constexpr int CF_WORDS = 4;                            // 68 staged columns -> 3 words (+ 1 zero word for the funnel shifts)
 template <class In>
 __device__ __forceinline__ void close_fill_tile(const In& in, int H, int W, int64_t base, int r0, int c0, int z,
                                                 double* __restrict__ out_train, double* __restrict__ out_label,
                                                 uint8_t* __restrict__ closed_out, int* __restrict__ far_flag) {
     __shared__ double s_val[CF_SH][CF_SW];
-    __shared__ uint8_t s_occ[CF_SH][CF_SW];            // bit0: occupancy (clip(label,0,1) > 0), bit1: label == 1
-    __shared__ uint8_t s_dil[CF_TH + 4][CF_TW + 2];
-    for (int i = threadIdx.x; i < CF_SH * CF_SW; i += CF_THREADS) {
-        const int lr = i / CF_SW, lc = i % CF_SW;
-        const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
-        uint8_t o = 0;
-        double v = 0.0;
-        if (r >= 0 && r < H && c >= 0 && c < W) in.load(base + (int64_t)r * W + c, v, o);
-        s_val[lr][lc] = v;
-        s_occ[lr][lc] = o;
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < (CF_TH + 4) * (CF_TW + 2); i += CF_THREADS) {
-        const int lr = i / (CF_TW + 2), lc = i % (CF_TW + 2);
-        const int r = r0 - 2 + lr, c = c0 - 1 + lc;
-        uint8_t d = 1;                                   // outside the image: neutral for the erosion
-        if (r >= 0 && r < H && c >= 0 && c < W) {
-            d = 0;
+    __shared__ unsigned s_occ[CF_SH][CF_WORDS];        // clip(label, 0, 1) > 0
+    __shared__ unsigned s_one[CF_SH][CF_WORDS];        // label == 1
+    __shared__ unsigned s_in[CF_SH][CF_WORDS];         // inside the image
+    __shared__ unsigned s_dil[CF_SH][CF_WORDS];
+    __shared__ unsigned s_ero[CF_SH][CF_WORDS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // (row, word) units, one warp each: all loads of a warp are issued before the first ballot waits for one
+    constexpr int UNITS = CF_SH * 3, PER_WARP = UNITS / (CF_THREADS / 32);
+    static_assert(UNITS % (CF_THREADS / 32) == 0, "close/fill staging: units must divide evenly over the warps");
+    constexpr int BATCH = 5;                           // loads in flight per lane
+    static_assert(PER_WARP % BATCH == 0, "close/fill staging: batches must divide the units of a warp");
+    for (int k0 = 0; k0 < PER_WARP; k0 += BATCH) {
+        double v[BATCH];
+        uint8_t o[BATCH];
 #pragma unroll
-            for (int dr = 0; dr < 5; ++dr)
-#pragma unroll
-                for (int dc = 0; dc < 3; ++dc) d |= s_occ[lr + dr][lc + dc + 0] & 1;
+        for (int k = 0; k < BATCH; ++k) {
+            const int u = warp + (k0 + k) * (CF_THREADS / 32), lr = u / 3, lc = (u % 3) * 32 + lane;
+            const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
+            v[k] = 0.0; o[k] = 0;
+            if (lc < CF_SW && r >= 0 && r < H && c >= 0 && c < W) { in.load(base + (int64_t)r * W + c, v[k], o[k]); o[k] |= 4; }
         }
-        s_dil[lr][lc] = d;
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int u = warp + (k0 + k) * (CF_THREADS / 32), lr = u / 3, w = u % 3, lc = w * 32 + lane;
+            if (lc < CF_SW) s_val[lr][lc] = v[k];
+            const unsigned b_occ = __ballot_sync(0xffffffffu, o[k] & 1), b_one = __ballot_sync(0xffffffffu, o[k] & 2);
+            const unsigned b_in = __ballot_sync(0xffffffffu, o[k] & 4);
+            if (lane == 0) { s_occ[lr][w] = b_occ; s_one[lr][w] = b_one; s_in[lr][w] = b_in; }
+        }
+    }
+    if (threadIdx.x < CF_SH) { s_occ[threadIdx.x][3] = 0u; s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; }
+    __syncthreads();
+    // horizontal 3-window of a bit row: bit c <- f(c - 1, c, c + 1), shifts carried across the words
+    auto left = [](const unsigned* a, int w) { return (a[w] << 1) | (w > 0 ? a[w - 1] >> 31 : 0u); };
+    auto right = [](const unsigned* a, int w) { return (a[w] >> 1) | (a[w + 1] << 31); };
+    if (threadIdx.x < (CF_SH - 4) * 3) {               // dilation, staged rows 2 .. CF_SH - 3
+        const int lr = 2 + threadIdx.x / 3, w = threadIdx.x % 3;
+        unsigned d = 0u;
+#pragma unroll
+        for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_occ[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
+        s_dil[lr][w] = d | ~s_in[lr][w];               // outside the image: neutral for the erosion
+    }
+    if (threadIdx.x < CF_SH) s_dil[threadIdx.x][3] = ~0u;
+    __syncthreads();
+    if (threadIdx.x < CF_TH * 3) {                     // erosion, staged rows 4 .. CF_SH - 5 (the output rows)
+        const int lr = CF_HR + threadIdx.x / 3, w = threadIdx.x % 3;
+        unsigned e = ~0u;
+#pragma unroll
+        for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_dil[lr + dr]; e &= a[w] & left(a, w) & right(a, w); }
+        s_ero[lr][w] = e;
     }
     __syncthreads();
     bool far = false;
@@ -53,23 +84,22 @@ __device__ __forceinline__ void close_fill_tile(const In& in, int H, int W, int6
         const int lr = i / CF_TW, lc = i % CF_TW;
         const int r = r0 + lr, c = c0 + lc;
         if (r >= H || c >= W) continue;
-        uint8_t e = 1;
-#pragma unroll
-        for (int dr = 0; dr < 5; ++dr)
-#pragma unroll
-            for (int dc = 0; dc < 3; ++dc) e &= s_dil[lr + dr][lc + dc];
         const int sr = lr + CF_HR, sc = lc + CF_HC;
+        const bool e = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
+        const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
         double t = s_val[sr][sc];
-        const bool one = (s_occ[sr][sc] & 2) != 0;
         bool filled = false;
         if (e && !one) {                                  // cl:41-43: closed == 255 and label != 1
             int neighbors = 0;
             double sum = 0.0;
+            const int q = sc - 1, qw = q >> 5, qb = q & 31;
 #pragma unroll
-            for (int dr = -2; dr <= 2; ++dr)
-#pragma unroll
-                for (int dc = -1; dc <= 1; ++dc)           // out-of-image neighbours were staged as "not 1"
-                    if (s_occ[sr + dr][sc + dc] & 2) { neighbors += 1; sum = r3d::add(sum, s_val[sr + dr][sc + dc]); }
+            for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51: (drow, dcol) order; out-of-image neighbours are "not 1"
+                const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
+                if (m & 1u) { neighbors += 1; sum = r3d::add(sum, s_val[sr + dr][sc - 1]); }
+                if (m & 2u) { neighbors += 1; sum = r3d::add(sum, s_val[sr + dr][sc]); }
+                if (m & 4u) { neighbors += 1; sum = r3d::add(sum, s_val[sr + dr][sc + 1]); }
+            }
             if (neighbors > 0) t = __ddiv_rn(sum, (double)neighbors);        // cl:57
             filled = true;                                                   // cl:55,58: label = 1
         }
@@ -96,7 +126,7 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill(In in, int H, int W, 
 // first round only the few tiles around an inserted object change, so a grid over every tile of every image would be
 // tens of thousands of CTAs that exit at once.  task = image * tiles_per_image + tile.
 template <class In>
-__global__ void __launch_bounds__(CF_THREADS) k_close_fill_tasks(In in, int H, int W, int64_t img_stride,
+__global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_tasks(In in, int H, int W, int64_t img_stride,
                                                                   double* __restrict__ out_train, int* __restrict__ far_flag,
                                                                   const int* __restrict__ tasks, const int* __restrict__ n_tasks) {
     const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles = tiles_x * ((H + CF_TH - 1) / CF_TH);
@@ -108,3 +138,101 @@ __global__ void __launch_bounds__(CF_THREADS) k_close_fill_tasks(In in, int H, i
         __syncthreads();                                 // the tile buffers are reused by the next task
     }
 }
+
+// The engine's z-buffer variant, software pipelined: while a CTA closes / fills one tile out of shared memory, the raw
+// 64-bit range words of its NEXT task are already on their way (cp.async, 16 bytes per request, double buffered), so
+// the HBM latency of a tile is hidden behind the work on the previous one instead of being paid once per tile.
+// Needs an even image width (16-byte aligned row segments); the launch falls back to k_close_fill_tasks otherwise.
+static __device__ __forceinline__ void cf_async_copy16(void* smem, const void* gmem) {
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
+}
+static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_raw_pipelined(const unsigned long long* __restrict__ raw, int H, int W,
+                                                                           int64_t img_stride, double* __restrict__ out_train,
+                                                                           int* __restrict__ far_flag, const int* __restrict__ tasks,
+                                                                           const int* __restrict__ n_tasks) {
+    __shared__ __align__(16) unsigned long long s_raw[2][CF_SH][CF_SW];
+    __shared__ unsigned s_one[CF_SH][CF_WORDS], s_in[CF_SH][CF_WORDS], s_dil[CF_SH][CF_WORDS], s_ero[CF_SH][CF_WORDS];
+    const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles = tiles_x * ((H + CF_TH - 1) / CF_TH);
+    const int n = *n_tasks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int CHUNKS = CF_SW / 2;                  // 16-byte requests per staged row
+    auto issue = [&](int t, int buf) {
+        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        const int r0 = (tile / tiles_x) * CF_TH, c0 = (tile % tiles_x) * CF_TW;
+        const unsigned long long* img = raw + (int64_t)z * img_stride;
+        for (int i = threadIdx.x; i < CF_SH * CHUNKS; i += CF_THREADS) {
+            const int lr = i / CHUNKS, ch = i % CHUNKS;
+            const int r = r0 - CF_HR + lr, c = c0 - CF_HC + 2 * ch;
+            if (r >= 0 && r < H && c >= 0 && c + 1 < W) cf_async_copy16(&s_raw[buf][lr][2 * ch], img + (int64_t)r * W + c);
+        }
+    };
+    auto left = [](const unsigned* a, int w) { return (a[w] << 1) | (w > 0 ? a[w - 1] >> 31 : 0u); };
+    auto right = [](const unsigned* a, int w) { return (a[w] >> 1) | (a[w + 1] << 31); };
+    int t = blockIdx.x;
+    if (t < n) issue(t, 0);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    if (threadIdx.x < CF_SH) { s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; s_dil[threadIdx.x][3] = ~0u; }
+    for (int buf = 0; t < n; t += gridDim.x, buf ^= 1) {
+        if (t + (int)gridDim.x < n) issue(t + gridDim.x, buf ^ 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");          // everything but the newest group has landed
+        __syncthreads();
+        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        const int r0 = (tile / tiles_x) * CF_TH, c0 = (tile % tiles_x) * CF_TW;
+        const int64_t base = (int64_t)z * img_stride;
+        for (int u = warp; u < CF_SH * 3; u += CF_THREADS / 32) {     // bit rows of the staged tile
+            const int lr = u / 3, w = u % 3, lc = w * 32 + lane;
+            const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
+            const bool inside = lc < CF_SW && r >= 0 && r < H && c >= 0 && c < W;
+            const bool hit = inside && s_raw[buf][lr][min(lc, CF_SW - 1)] != R3D_EMPTY_U64;
+            const unsigned b_one = __ballot_sync(0xffffffffu, hit), b_in = __ballot_sync(0xffffffffu, inside);
+            if (lane == 0) { s_one[lr][w] = b_one; s_in[lr][w] = b_in; }
+        }
+        __syncthreads();
+        if (threadIdx.x < (CF_SH - 4) * 3) {
+            const int lr = 2 + threadIdx.x / 3, w = threadIdx.x % 3;
+            unsigned d = 0u;
+#pragma unroll
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_one[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
+            s_dil[lr][w] = d | ~s_in[lr][w];
+        }
+        __syncthreads();
+        if (threadIdx.x < CF_TH * 3) {
+            const int lr = CF_HR + threadIdx.x / 3, w = threadIdx.x % 3;
+            unsigned e = ~0u;
+#pragma unroll
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_dil[lr + dr]; e &= a[w] & left(a, w) & right(a, w); }
+            s_ero[lr][w] = e;
+        }
+        __syncthreads();
+        bool far = false;
+        for (int i = threadIdx.x; i < CF_TH * CF_TW; i += CF_THREADS) {
+            const int lr = i / CF_TW, lc = i % CF_TW;
+            const int r = r0 + lr, c = c0 + lc;
+            if (r >= H || c >= W) continue;
+            const int sr = lr + CF_HR, sc = lc + CF_HC;
+            const bool e = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
+            const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
+            double tv = one ? r3d::bits_dbl(s_raw[buf][sr][sc]) : r3d::kEmptyRange;      // od/ins:100: empty = 500
+            if (e && !one) {                                  // cl:41-43
+                int neighbors = 0;
+                double sum = 0.0;
+                const int q = sc - 1, qw = q >> 5, qb = q & 31;
+#pragma unroll
+                for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51, (drow, dcol) order
+                    const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
+                    if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc - 1])); }
+                    if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc])); }
+                    if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + 1])); }
+                }
+                if (neighbors > 0) tv = __ddiv_rn(sum, (double)neighbors);       // cl:57
+            }
+            out_train[base + (int64_t)r * W + c] = tv;
+            far |= tv > r3d::kEmptyRange;
+        }
+        if (far) atomicOr(&far_flag[z], 1);
+        __syncthreads();                                  // s_raw[buf] is the target of the loads issued two tasks ahead
+    }
+}
+

@@ -644,9 +644,14 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
         { Launcher l(eng, r0 ? KID_PROJECT0 : KID_PROJECT, ss); k_project<<<dim3(chunks_all, full_y), STREAM_THREADS, 0, ss>>>(d, ns); }
         {
             Launcher l(eng, r0 ? KID_CLOSEFILL0 : KID_CLOSEFILL, ss);
-            RawImage in{d.zraw};
-            k_close_fill_tasks<RawImage><<<cf_grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr,
-                                                                         d.cf_tasks, d.work_cnt + 1);
+            if ((d.cols & 1) == 0 && ((uintptr_t)d.zraw & 15) == 0) {
+                k_close_fill_raw_pipelined<<<std::min(cf_grid, eng->n_sms * 4), CF_THREADS, 0, ss>>>(d.zraw, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr,
+                                                                           d.cf_tasks, d.work_cnt + 1);
+            } else {
+                RawImage in{d.zraw};
+                k_close_fill_tasks<RawImage><<<cf_grid, CF_THREADS, 0, ss>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr,
+                                                                             d.cf_tasks, d.work_cnt + 1);
+            }
         }
         if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
         { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }
