@@ -253,6 +253,13 @@ int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_running);
 int r3d_engine_sync(r3d_engine* eng);
 /* total output rows of the last run (valid after r3d_engine_run + r3d_engine_sync) */
 int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, int64_t* total_check);
+/* The packed outputs of the last run where they are, in device memory, for a consumer on the same GPU (a training
+ * step that takes the augmented clouds without a round trip over PCIe): out_xyzi (total_points x 4 float32, the
+ * velodyne rows of tools/datasets.py:86-93), out_labels (total_points uint32), check (total_check x 5 float32); the
+ * per-scan row offsets go to the caller's HOST arrays (n_scans + 1 each, may be NULL).  Waits for the run; the
+ * pointers stay valid until the engine is re-armed, loaded or run again. */
+int r3d_engine_output_device(r3d_engine* eng, const float** out_xyzi, const uint32_t** out_labels, const float** check,
+                             int64_t* out_offsets_host, int64_t* check_offsets_host);
 
 /* per-kernel device time of the runs since the last reset, measured with CUDA events on the engine stream.
  * names_out: caller buffer receiving '\n'-separated kernel names; ms_out / launches_out: up to max_kernels entries. */

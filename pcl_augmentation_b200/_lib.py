@@ -99,6 +99,8 @@ PROTOTYPES = {
     "r3d_cut_objects_write": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "r3d_engine_output_device": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                           C.c_void_p, C.c_void_p]),
     "r3d_engine_sync": (C.c_int, [C.c_void_p]),
     "r3d_engine_set_sub_batches": (C.c_int, [C.c_void_p, C.c_int]),
     "r3d_engine_run_until": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

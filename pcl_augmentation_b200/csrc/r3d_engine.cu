@@ -772,6 +772,20 @@ extern "C" int r3d_engine_output_rows(r3d_engine* eng, int64_t* total_points, in
     return R3D_OK;
 }
 
+extern "C" int r3d_engine_output_device(r3d_engine* eng, const float** out_xyzi, const uint32_t** out_labels, const float** check,
+                                        int64_t* out_offsets_host, int64_t* check_offsets_host) {
+    if (eng) cudaSetDevice(eng->device);
+    if (!eng || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_output_device: run first");
+    R3D_CUDA(engine_wait(eng));
+    const int n = eng->n_scans;
+    if (out_xyzi) *out_xyzi = reinterpret_cast<const float*>(eng->out_xyzi.p);
+    if (out_labels) *out_labels = eng->out_label.p;
+    if (check) *check = eng->out_check.p;
+    if (out_offsets_host) memcpy(out_offsets_host, eng->h_offsets, (n + 1) * sizeof(long long));
+    if (check_offsets_host) memcpy(check_offsets_host, eng->h_offsets + eng->dev.B + 1, (n + 1) * sizeof(long long));
+    return R3D_OK;
+}
+
 extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng || !res || !eng->ran) return r3d_fail(R3D_ERR_ARG, "r3d_engine_fetch: run first");

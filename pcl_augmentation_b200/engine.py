@@ -302,6 +302,29 @@ class Real3DEngine:
         buffers['out_bytes'] = rows * (20 if self.fetch_labels else 16) + chk * 20
         return buffers
 
+    def outputs_on_device(self):
+        """The packed outputs of the last run as CUDA tensors that alias the engine's device buffers (no copy, nothing
+        crosses PCIe): ``{'xyzi': float32 [total, 4], 'labels': int32 [total], 'check': float32 [total_check, 5],
+        'offsets': int64 [n + 1] (host), 'check_offsets': int64 [n + 1] (host)}``; scan s owns rows
+        ``offsets[s]:offsets[s + 1]``.  Valid until the engine is re-armed, loaded or run again."""
+        import torch
+        n = self._n_scans
+        px, pl, pc = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        off, coff = np.zeros(n + 1, dtype=np.int64), np.zeros(n + 1, dtype=np.int64)
+        _lib.check(self.lib.r3d_engine_output_device(self.handle, C.byref(px), C.byref(pl), C.byref(pc), off.ctypes.data,
+                                                     coff.ctypes.data), "output_device")
+
+        class _View:
+            def __init__(self, ptr, shape, typestr):
+                self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (int(ptr), False), "version": 3,
+                                                 "strides": None}
+        dev = torch.device("cuda", torch.cuda.current_device())
+        total, total_c = int(off[n]), int(coff[n])
+        view = lambda ptr, shape, ts, dt: (torch.as_tensor(_View(ptr.value, shape, ts), device=dev) if shape[0] > 0
+                                           else torch.empty(shape, dtype=dt, device=dev))
+        return {"xyzi": view(px, (total, 4), "<f4", torch.float32), "labels": view(pl, (total,), "<i4", torch.int32),
+                "check": view(pc, (total_c, 5), "<f4", torch.float32), "offsets": off, "check_offsets": coff}
+
     def unpack(self, buffers, raise_on_error=True):
         """Per-scan output records in the reference's formats."""
         out = []
