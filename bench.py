@@ -230,6 +230,39 @@ def run_reference(args, json_out):
         "gpu_launches": 0})])
 
 
+def run_side(args, json_out):
+    """GPU numbers of an offline tool (tools/bench_*.py) + its CPU baseline (bench.py is the only
+    place besides tests/ that executes oracle/)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    if args.side == "rich_map_od":
+        import bench_rich_map as tool
+        from oracle import rich_map_oracle as rmo                  # CPU baseline leg only
+        res, clouds = tool.gpu_bench(256, 10)
+        t0, k = time.perf_counter(), 0
+        while time.perf_counter() - t0 < 5.0:
+            rmo.rich_map_od(clouds[k % len(clouds)], 40)
+            k += 1
+        unit, cpu, sample = "frames/s", k / (time.perf_counter() - t0), f"{k} frames"
+    elif args.side == "rich_map_ss":
+        import bench_rich_map_ss as tool
+        from oracle import rich_map_oracle as rmo                  # CPU baseline leg only
+        res, (frames, labels_cfg) = tool.gpu_bench(256, 10)
+        t0 = time.perf_counter()
+        rmo.rich_map_ss([(np.hstack((p.astype(np.float64), l.reshape(-1, 1).astype(np.float64))), T) for p, l, T in frames],
+                        labels_cfg)
+        unit, cpu, sample = "frames/s", len(frames) / (time.perf_counter() - t0), f"a {len(frames)}-frame sequence"
+    else:
+        import bench_cut_objects as tool
+        from oracle import cut_objects_oracle as coo               # CPU baseline leg only
+        res, (frames, cfg) = tool.gpu_bench(64, 10)
+        t0 = time.perf_counter()
+        for f in frames:
+            coo.cut_objects_ss(np.hstack((f[0].astype(np.float64), f[1].reshape(-1, 1).astype(np.float64))), f[2], cfg, f[3], f[4])
+        unit, cpu, sample = "frames/s", len(frames) / (time.perf_counter() - t0), f"{len(frames)} frames"
+    res["cpu_baseline"] = {"value": round(cpu, 2), "unit": unit, "cores": 1, "kind": "port", "sample": sample}
+    print(json.dumps(res), file=json_out, flush=True)
+
+
 def main():
     # Libraries (NCCL's version banner, for one) write to fd 1: keep the real stdout for the ONE JSON line and send
     # everything else written to fd 1 during the run to stderr
@@ -249,7 +282,13 @@ def main():
                          "the thinning last rounds of one step overlap the busy first rounds of the next")
     ap.add_argument("--e2e-sub-batches", type=int, default=2, help="same, per engine of the e2e pipeline")
     ap.add_argument("--depth", type=int, default=4, help="engines (streams) the e2e leg pipelines batches through")
+    ap.add_argument("--side", default=None, choices=["rich_map_od", "rich_map_ss", "cut_objects"],
+                    help="instead of the headline bench: one of the offline tools either side of the path (SURVEY 8f rows "
+                         "3-4), GPU numbers from tools/bench_*.py plus the CPU baseline (numpy oracle port, one host core)")
     args = ap.parse_args()
+    if args.side:
+        run_side(args, json_out)
+        return
     if args.impl == "reference":
         run_reference(args, json_out)
         return

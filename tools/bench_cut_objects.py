@@ -1,6 +1,7 @@
 """Cut-object database building: frames/s of the CUDA path (semseg cut_out: every annotated box of a
-frame in one pass) vs the numpy oracle port on one host core.  Prints one JSON line.
-usage: python tools/bench_cut_objects.py [frames] [steps]"""
+frame in one pass).  Prints one JSON line.
+usage: python tools/bench_cut_objects.py [frames] [steps]
+`python bench.py --side cut_objects` runs the same and adds the CPU baseline (the numpy oracle port on one host core)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,13 +9,11 @@ import numpy as np
 import torch
 from pcl_augmentation_b200 import _lib, boxes as bx, cut_objects as co, synth
 from pcl_augmentation_b200.semantic_segmentation.cut_object import cut_out
-from oracle import cut_objects_oracle as coo       # CPU baseline leg only
 from tests.helpers import cut_object_cases
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+def gpu_bench(n=64, steps=10):
+    """Returns (result dict, CPU-baseline inputs: (frames, config))."""
     cases = cut_object_cases("ss", shape=synth.KITTI_SHAPE)
     cfg = cases[0].config
     frames = []
@@ -59,17 +58,19 @@ def main():
         both()
     ev1.record(); torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1) / steps
-    sample = frames[:min(n, 6)]
-    t1 = time.perf_counter()
-    for f in sample:
-        coo.cut_objects_ss(np.hstack((f[0].astype(np.float64), f[1].reshape(-1, 1).astype(np.float64))), f[2], cfg, f[3], f[4])
-    cpu = len(sample) / (time.perf_counter() - t1)
     bytes_alg = n_points * (16 + 16)                        # each pass reads xyzi; labels only for the rare hits
-    print(json.dumps({"metric": "frames/s through cut_out (120k-pt frame, every annotated box in one pass)", "frames": n,
+    res = ({"metric": "frames/s through cut_out (120k-pt frame, every annotated box in one pass)", "frames": n,
                       "boxes": n_boxes, "samples_saved": sum(len(o) for o in out),
                       "e2e_frames_per_s": round(n * steps / dt, 1), "device_frames_per_s": round(n / (dev_ms / 1e3), 1),
                       "device_ms_per_batch": round(dev_ms, 3), "algorithmic_gbs": round(bytes_alg / (dev_ms / 1e3) / 1e9, 1),
-                      "cpu_oracle_frames_per_s_1core": round(cpu, 2)}))
+                      })
+    return res, (frames[:min(n, 6)], cfg)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 64
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    print(json.dumps(gpu_bench(n, steps)[0]))
 
 
 if __name__ == "__main__":

@@ -1,5 +1,6 @@
-"""Rich-map generation: frames/s of the CUDA operator vs the numpy oracle port on one host core.
-Prints one JSON line.  usage: python tools/bench_rich_map.py [frames per batch] [steps]"""
+"""Rich-map generation (object detection): frames/s of the CUDA operator, host-to-host and device-only.
+Prints one JSON line.  usage: python tools/bench_rich_map.py [frames per batch] [steps]
+`python bench.py --side rich_map_od` runs the same and adds the CPU baseline (the numpy oracle port on one host core)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -7,11 +8,9 @@ import numpy as np
 import torch
 from pcl_augmentation_b200 import _lib, synth
 from pcl_augmentation_b200.object_detection.rich_map import single_drivable_area_map as rm
-from oracle import rich_map_oracle as rmo           # CPU baseline leg only
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+def gpu_bench(n=256, steps=10):
+    """Returns (result dict, CPU-baseline inputs: list of N x 5 float64 clouds)."""
     base = [synth.make_scan(7000 + i, synth.KITTI_SHAPE, synth.make_scene_cars(7000 + i, 6)) for i in range(16)]
     xyzi = [base[i % 16][0] for i in range(n)]
     labels = [base[i % 16][1] & 0xFFFF for i in range(n)]
@@ -40,15 +39,18 @@ def main():
                                   road.data_ptr(), ped.data_ptr(), scr.data_ptr(), st)
     ev1.record(); torch.cuda.synchronize()
     dev_ms = ev0.elapsed_time(ev1) / steps
-    t1 = time.perf_counter(); k = 0
-    while time.perf_counter() - t1 < 5.0:
-        rmo.rich_map_od(np.hstack((xyzi[k % n], labels[k % n].reshape(-1, 1))).astype(np.float64), 40); k += 1
-    cpu = k / (time.perf_counter() - t1)
     bytes_alg = n * len(xyzi[0]) * 20 * 2                      # both kernels read the 20 B point record once
-    print(json.dumps({"metric": "rich maps/s (120k-pt KITTI frame: road + pedestrian-area map)", "frames_per_batch": n,
+    res = ({"metric": "rich maps/s (120k-pt KITTI frame: road + pedestrian-area map)", "frames_per_batch": n,
                       "e2e_frames_per_s": round(n * steps / dt, 1), "device_frames_per_s": round(n / (dev_ms / 1e3), 1),
                       "device_ms_per_batch": round(dev_ms, 3), "algorithmic_gbs": round(bytes_alg / (dev_ms / 1e3) / 1e9, 1),
-                      "cpu_oracle_frames_per_s_1core": round(cpu, 2), "map_cells_per_frame": int(total / n)}))
+                      "map_cells_per_frame": int(total / n)})
+    return res, [np.hstack((xyzi[k], labels[k].reshape(-1, 1))).astype(np.float64) for k in range(min(n, 16))]
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    print(json.dumps(gpu_bench(n, steps)[0]))
 
 if __name__ == "__main__":
     main()

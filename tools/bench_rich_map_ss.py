@@ -1,6 +1,7 @@
 """Sequence-wide semseg rich map (semantic_segmentation/rich_map/drivable_area_map.py):
-frames/s of the CUDA operator (device-resident and host-to-host) vs the numpy oracle port on one host core.
-Prints one JSON line.  usage: python tools/bench_rich_map_ss.py [frames] [steps]"""
+frames/s of the CUDA operator (device-resident and host-to-host).
+Prints one JSON line.  usage: python tools/bench_rich_map_ss.py [frames] [steps]
+`python bench.py --side rich_map_ss` runs the same and adds the CPU baseline (the numpy oracle port on one host core)."""
 import json, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -8,12 +9,10 @@ import numpy as np
 import torch
 from pcl_augmentation_b200 import synth
 from pcl_augmentation_b200.semantic_segmentation.rich_map import drivable_area_map as srm
-from oracle import rich_map_oracle as rmo           # CPU baseline leg only
 
 
-def main():
-    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
-    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+def gpu_bench(n=256, steps=10):
+    """Returns (result dict, CPU-baseline inputs: (frames, placement labels))."""
     labels_cfg = synth.load_config("ss")["insertion"]["placement_labels"]
     base = [synth.make_scan(7100 + i, synth.SEMKITTI_SHAPE, synth.make_scene_cars(7100 + i, 6)) for i in range(16)]
     pose0 = synth.make_pose(7100)
@@ -50,16 +49,19 @@ def main():
     dev_ms = ev0.elapsed_time(ev1) / steps
     res = b.finish()
     assert np.array_equal(res["map"], out["map"])
-    sample = frames[:min(n, 24)]
-    t1 = time.perf_counter()
-    rmo.rich_map_ss([(np.hstack((p.astype(np.float64), l.reshape(-1, 1).astype(np.float64))), T) for p, l, T in sample], labels_cfg)
-    cpu = len(sample) / (time.perf_counter() - t1)
     bytes_alg = n_points * (16 + 20)                      # extent pass reads xyzi, raster pass reads xyzi + label
-    print(json.dumps({"metric": "frames/s into the sequence map (125k-pt SemanticKITTI frame, two passes)", "frames": n,
+    res = ({"metric": "frames/s into the sequence map (125k-pt SemanticKITTI frame, two passes)", "frames": n,
                       "e2e_frames_per_s": round(n * steps / dt, 1), "device_frames_per_s": round(n / (dev_ms / 1e3), 1),
                       "device_ms_per_sequence": round(dev_ms, 3), "algorithmic_gbs": round(bytes_alg / (dev_ms / 1e3) / 1e9, 1),
-                      "cpu_oracle_frames_per_s_1core": round(cpu, 2), "map_shape": list(out["map"].shape),
-                      "cells_per_class": [int((out["map"] == v).sum()) for v in (1, 2, 3)]}))
+                      "map_shape": list(out["map"].shape),
+                      "cells_per_class": [int((out["map"] == v).sum()) for v in (1, 2, 3)]})
+    return res, (frames[:min(n, 24)], labels_cfg)
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    steps = int(sys.argv[2]) if len(sys.argv) > 2 else 10
+    print(json.dumps(gpu_bench(n, steps)[0]))
 
 
 if __name__ == "__main__":

@@ -4,8 +4,8 @@
 TAG=${1:-r1b}
 mkdir -p gpurun_out
 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-python tools/bench_cut_objects.py 64 10 > gpurun_out/${TAG}_cut_objects_bench.json 2> gpurun_out/${TAG}_cut_objects_bench.err; tail -1 gpurun_out/${TAG}_cut_objects_bench.json
-python tools/bench_rich_map_ss.py 256 10 > gpurun_out/${TAG}_rich_map_ss_bench.json 2> gpurun_out/${TAG}_rich_map_ss_bench.err; tail -1 gpurun_out/${TAG}_rich_map_ss_bench.json
+python bench.py --side cut_objects > gpurun_out/${TAG}_cut_objects_bench.json 2> gpurun_out/${TAG}_cut_objects_bench.err; tail -1 gpurun_out/${TAG}_cut_objects_bench.json
+python bench.py --side rich_map_ss > gpurun_out/${TAG}_rich_map_ss_bench.json 2> gpurun_out/${TAG}_rich_map_ss_bench.err; tail -1 gpurun_out/${TAG}_rich_map_ss_bench.json
 timeout 400 python bench.py > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err
 for d in 12 16; do timeout 300 python bench.py --no-cpu-baseline --resident-depth $d > gpurun_out/${TAG}_bench_d$d.json 2>/dev/null; done
 for f in gpurun_out/${TAG}_bench*.json; do python - $f <<'PY'
