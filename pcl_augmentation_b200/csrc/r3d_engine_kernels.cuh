@@ -315,9 +315,14 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_sc
     if (!s_patch) return;
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
     const unsigned* dm = e.dmask + (size_t)b * e.dwords;
-    if (s.d_r1 >= s.d_r0) {
-        const int w0 = (s.d_r0 * e.cols) >> 5, w1 = ((s.d_r1 + 1) * e.cols - 1) >> 5;
-        for (int w = w0 + threadIdx.x; w <= w1; w += UPDATE_THREADS) {
+    if (s.d_r1 >= s.d_r0 && s.d_c1 >= s.d_c0) {
+        // vis_px lies inside the rectangle select_emit recorded: visit only the mask words that hold its columns, row
+        // by row (a word may be visited for two rows when the width is no multiple of 32; clearing twice is harmless)
+        const int nw = (s.d_c1 >> 5) - (s.d_c0 >> 5) + 2, nrow = s.d_r1 - s.d_r0 + 1;
+        for (int i = threadIdx.x; i < nrow * nw; i += UPDATE_THREADS) {
+            const int r = s.d_r0 + i / nw;
+            const int w = ((r * e.cols + s.d_c0) >> 5) + i % nw;
+            if (w > ((r * e.cols + s.d_c1) >> 5)) continue;
             unsigned m = dm[w];
             while (m) { const int bit = __ffs(m) - 1; m &= m - 1; z[(w << 5) + bit] = R3D_EMPTY_U64; }
         }
