@@ -635,7 +635,10 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
         const size_t pref_smem = (size_t)(ns + 1) * sizeof(int);
         // the three full re-projection kernels and close/fill walk the work lists k_update wrote (all scans in round
         // 0, a handful later): grids sized for "some scans", not for every (chunk, scan) / (tile, scan) pair
-        const int full_y = std::min(ns, 32);
+#ifndef R3D_FULL_Y
+#define R3D_FULL_Y 32
+#endif
+        const int full_y = std::min(ns, R3D_FULL_Y);
         const int cf_grid = std::min(ns * d.cf_tiles, eng->n_sms * 8);
         { Launcher l(eng, KID_CTRL, ss); k_ctrl<<<ns, 32, 0, ss>>>(d, ns); }
         { Launcher l(eng, KID_UPDATE, ss); k_update<<<dim3(UPDATE_G, ns), UPDATE_THREADS, 0, ss>>>(d, ns); }
