@@ -213,3 +213,39 @@ def test_outputs_on_device_alias_the_fetched_results():
         np.testing.assert_array_equal(dev["check"][ca:cb].cpu().numpy(), r.check)
     eng.close()
 
+
+
+def test_error_conventions_index_capacity_and_arguments():
+    """SURVEY §8b error conventions: IndexError where the reference raises it (a class list shorter than a
+    MAX_NUM_TRIES window, od/ins:410), Real3DError for capacity / argument problems, per-scan status otherwise."""
+    from pcl_augmentation_b200._lib import Real3DError
+    # (1) 6 samples per class, nothing placeable (all objects far outside the map): the first window runs past the list
+    case = synth.make_case("od", 861, shape=GOLDEN_SHAPE, counts=[1, 0], n_per_class=6, obj_range=(4.0, 16.0))
+    for items in case.db.values():
+        for _, s in items:
+            s["pcl"][:, 0] += 500.0                                  # off the 64 m map: never on the road
+    eng = make_engine(case)
+    staged = eng.stage([scan_input_from_case(case)])
+    eng.load(staged)
+    eng.run()
+    buf = eng.fetch_raw()
+    with pytest.raises(IndexError):
+        eng.unpack(buf)
+    res = eng.unpack(buf, raise_on_error=False)                       # the scan keeps its points, status says why
+    assert res[0].status == -4 and res[0].inserted == [] and len(res[0].velodyne) == len(case.pcl5)
+    with pytest.raises(IndexError):                                   # the oracle raises where the reference does
+        oracle_run(case)
+    eng.close()
+    # (2) more scans / points than the engine was built for
+    case2 = synth.make_case("od", 862, shape=GOLDEN_SHAPE, counts=[1, 1], obj_range=(4.0, 16.0))
+    eng = make_engine(case2, n_scans=1)
+    with pytest.raises((Real3DError, AssertionError)):
+        eng.stage([scan_input_from_case(case2)] * 2)
+    small = Real3DEngine("od", case2.config, case2.db, max_scans=1, max_points=len(case2.pcl5) - 5)
+    with pytest.raises(Real3DError):
+        small.load(small.stage([scan_input_from_case(case2)]))
+    small.close()
+    # (3) run before load
+    with pytest.raises(Real3DError):
+        eng.run()
+    eng.close()
