@@ -249,3 +249,25 @@ def test_error_conventions_index_capacity_and_arguments():
     with pytest.raises(Real3DError):
         eng.run()
     eng.close()
+
+
+@pytest.mark.parametrize("task,counts", [("od", [2, 2]), ("ss", [1, 1, 1, 1, 0, 0])])
+def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts):
+    """16 seeded scans per pipeline with 8 - 15 scene boxes each (the collision pruning — bounding circles, the
+    separating-axis test on the object's point extents — and the ring-skipping road-level search see many near
+    misses), one batch, every scan against the oracle: placement choices and keep-masks exact, xyz within 1e-6 m."""
+    cases = [synth.make_case(task, 930 + i, shape=GOLDEN_SHAPE, counts=counts, obj_range=(4.0, 16.0), n_cars=8 + i % 8)
+             for i in range(16)]
+    if task == "ss":                                   # one engine = one sequence map: give every scan the first pose / map
+        for c in cases[1:]:
+            c.pose, c.map_data = cases[0].pose, cases[0].map_data
+    eng = Real3DEngine(task, cases[0].config, cases[0].db, max_scans=len(cases), max_points=max(len(c.pcl5) for c in cases),
+                       map_data=cases[0].map_data, sub_batches=3)
+    res = eng.augment_batch([scan_input_from_case(c) for c in cases])
+    eng.close()
+    placed = 0
+    for case, got in zip(cases, res):
+        ref, want = oracle_run(case)
+        assert_matches_oracle(case, got, ref, want)
+        placed += len(got.inserted)
+    assert placed >= 24
