@@ -481,7 +481,9 @@ def main():
         print(file=json_out, flush=True, *[json.dumps({
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(world),
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(world), steps_in_flight=f"{res_depth} (one 256-scan step per resident engine; "
+                           f"`single_batch_ms` is a step alone)"),
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h / args.steps), "pipeline_depth": args.depth,
