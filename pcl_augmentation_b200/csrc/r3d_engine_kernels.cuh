@@ -1458,20 +1458,17 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, i
                 }
         }
         __syncthreads();
-        for (int t = threadIdx.x; t < ob.count * 15; t += blockDim.x) {
-            const int i = t / 15, o = t % 15;
-            const int pix = s_pix[i];
-            if (pix < 0) continue;
-            const int r = pix / W + (o / 3 - 2), cc = pix % W + (o % 3 - 1);
-            if (r < 0 || r >= H || cc < 0 || cc >= W) continue;
-            const int lq = (r - wr0) * nc + (cc - wc0);
-            if (s_vis[lq >> 5] & (1u << (lq & 31))) continue;
+        // Only a pixel inside the dilated occupancy can survive the closing, and the dilation bits cover exactly the
+        // 5x3 neighbourhoods of the object's pixels: one visit per such pixel of the tile (instead of one per
+        // (object point, neighbour) pair, which evaluated most pixels many times).
+        for (int lq = threadIdx.x; lq < npx; lq += blockDim.x) {
+            if (!(s_dil[lq >> 5] & (1u << (lq & 31)))) continue;
+            const int r = wr0 + lq / nc, cc = wc0 + lq % nc;
             double val;
             if (tile_pixel_value(s_tile, s_dil, H, W, wr0, wc0, nr, nc, r, cc, val) && val < smooth[r * W + cc]) {   // od/ins:486
-                if (!(atomicOr(&s_vis[lq >> 5], 1u << (lq & 31)) & (1u << (lq & 31)))) {
-                    const int q = r * W + cc;
-                    atomicOr(&dm[q >> 5], 1u << (q & 31));
-                }
+                atomicOr(&s_vis[lq >> 5], 1u << (lq & 31));
+                const int q = r * W + cc;
+                atomicOr(&dm[q >> 5], 1u << (q & 31));
             }
         }
         __syncthreads();
