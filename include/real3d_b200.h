@@ -173,6 +173,8 @@ typedef struct r3d_engine_cfg {
     int32_t flags;                            /* bit0: re-project every slot in full (disable the in-place image patch);
                                                  bit1: launch the kernels of a round one by one instead of replaying the
                                                  round's CUDA graph;
+                                                 bit2: evaluate every yaw candidate of a try at once (no ordered
+                                                 early-out window; what r3d_engine_debug_candidates should see);
                                                  bits 8-12: sub-batches advanced concurrently on their own streams
                                                  (1..16, 0 = default 4) */
     double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */

@@ -81,7 +81,7 @@ struct r3d_engine {
     DevBuf<unsigned short> col, cand_list, label16;
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
-        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks;
+        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks, need2;
     DevBuf<unsigned> round_ctl;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags, gnear, gscratch;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -247,6 +247,11 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.cf_tiles = d.cf_tiles_x * ((d.rows + CF_TH - 1) / CF_TH);
     TRY(eng->work_cnt.alloc(B * 4)); TRY(eng->full_list.alloc(B)); TRY(eng->cf_tasks.alloc(B * (size_t)d.cf_tiles));
     R3D_CUDA(cudaMemset(eng->work_cnt.p, 0, B * 4 * sizeof(int)));
+    TRY(eng->need2.alloc(B));
+    R3D_CUDA(cudaMemset(eng->need2.p, 0, B * sizeof(int)));
+    d.cand_window = (cfg->flags & 4) ? 0 : 48;
+    if (const char* env = getenv("R3D_WINDOW")) d.cand_window = std::max(0, atoi(env));
+    if (d.task != 0) d.cand_window = 0;          // semseg walks the yaws with a carried z shift (ss/fs:146-147): no window
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
@@ -291,7 +296,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.zraw = eng->zraw.p; d.obj_raw = eng->obj_raw.p; d.smooth = eng->smooth.p; d.dmask = eng->dmask.p; d.vmask = eng->vmask.p;
     d.st = eng->st.p; d.gate_update = eng->gate_update.p; d.gate_try = eng->gate_try.p; d.gate_apply = eng->gate_apply.p;
     d.gate_full = eng->gate_full.p; d.gate_patch = eng->gate_patch.p; d.cf_rect = eng->cf_rect.p;
-    d.work_cnt = eng->work_cnt.p; d.full_list = eng->full_list.p; d.cf_tasks = eng->cf_tasks.p;
+    d.work_cnt = eng->work_cnt.p; d.full_list = eng->full_list.p; d.cf_tasks = eng->cf_tasks.p; d.need2 = eng->need2.p;
     d.active_count = eng->active_count.p; d.far_arr = eng->far_arr.p; d.boxes = eng->boxes.p; d.box_tests = eng->box_tests.p;
     d.poses = eng->poses.p; d.occ_win = eng->occ_win.p; d.counts = eng->counts.p; d.cos_k = eng->cos_k.p; d.sin_k = eng->sin_k.p;
     d.radii_sq = eng->radii_sq.p; d.radii_ok = eng->radii_ok.p; d.classes = eng->classes.p; d.cand_flags = eng->cand_flags.p;
@@ -559,7 +564,7 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     R3D_OFF(col, d.P); R3D_OFF(pix, d.P); R3D_OFF(alive, d.P); R3D_OFF(zraw, d.hw); R3D_OFF(obj_raw, d.hw);
     R3D_OFF(smooth, d.hw); R3D_OFF(dmask, d.dwords); R3D_OFF(vmask, d.dwords); R3D_OFF(st, 1); R3D_OFF(gate_update, 1);
     R3D_OFF(gate_try, 1); R3D_OFF(gate_apply, 1); R3D_OFF(gate_full, 1); R3D_OFF(gate_patch, 1); R3D_OFF(cf_rect, 4);
-    R3D_OFF(work_cnt, 4); R3D_OFF(full_list, 1); R3D_OFF(cf_tasks, d.cf_tiles);
+    R3D_OFF(work_cnt, 4); R3D_OFF(full_list, 1); R3D_OFF(cf_tasks, d.cf_tiles); R3D_OFF(need2, 1);
     R3D_OFF(col_off, d.cols + 1); R3D_OFF(col_idx, d.max_points); R3D_OFF(far_arr, 1); R3D_OFF(boxes, d.max_boxes);
     R3D_OFF(box_tests, d.max_boxes); R3D_OFF(od_map_off, 2); R3D_OFF(od_map_dims, 8); R3D_OFF(poses, 16); R3D_OFF(occ_win, ww);
     R3D_OFF(counts, d.n_classes); R3D_OFF(perms, (size_t)d.n_perm_events * d.n_classes * d.max_tries);
@@ -659,10 +664,17 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
         if (d.task == 1) { Launcher l(eng, KID_ADJUST, ss); k_adjust_map<<<dim3(chunks_all, ns), STREAM_THREADS, 0, ss>>>(d, ns); }
         { Launcher l(eng, KID_ONMAP, ss); k_onmap<<<ns, TRY_THREADS, onmap_smem, ss>>>(d, ns); }
         if (d.task == 0) { Launcher l(eng, KID_ONMAP, ss); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
-        { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
+        const int ph = d.cand_window > 0 ? 1 : 0;           // OD: first window of candidates, then the rest where needed
+        { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, ph); }
         if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
-        { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns); }
-        { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns); }
+        { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, ph); }
+        { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns, ph); }
+        if (ph) {
+            { Launcher l(eng, KID_CTRL, ss); k_phase_gate<<<(ns + 127) / 128, 128, 0, ss>>>(d, ns); }
+            { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, 2); }
+            { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, 2); }
+            { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns, 2); }
+        }
         { Launcher l(eng, KID_SELECT, ss); k_select_emit<<<ns, 512, sel_smem, ss>>>(d, ns, key_cap, sel_pts); }
     };
     const bool graphs = eng->use_graphs && !eng->profile;
@@ -975,9 +987,9 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
     const size_t pref_smem = (size_t)(n + 1) * sizeof(int);
     k_onmap<<<n, TRY_THREADS, onmap_smem_bytes(d.K), st>>>(d, n); r3d_count_launch();
     if (d.task == 0) { k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch(); }
-    k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch();
+    k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n, 0); r3d_count_launch();
     if (d.task == 1) { k_onmap_ss<<<n, 1024, 0, st>>>(d, n); r3d_count_launch(); }
-    k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n); r3d_count_launch();
+    k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n, 0); r3d_count_launch();
     k_feasible_list<<<n, 128, 0, st>>>(d, n); r3d_count_launch();
     std::vector<ScanState> hs(1);
     R3D_CUDA(cudaMemcpyAsync(hs.data(), eng->st.p + scan, sizeof(ScanState), cudaMemcpyDeviceToHost, st));

@@ -96,6 +96,11 @@ struct EngineDev {       // passed by value to kernels
     // work lists of the current round (per sub-batch; k_ctrl re-arms the counters, k_update fills them): the scans that
     // re-project in full, and the (scan, tile) tasks of close/fill — so those kernels run a small persistent grid
     // instead of one CTA per (chunk, scan) / (tile, scan) of which all but a few exit at once
+    // ordered early-out of the placement search (OD): the reference takes the FIRST feasible yaw that keeps min_points,
+    // so road level / collision / occlusion first look at the first `cand_window` on-map candidates (in yaw order) and
+    // only the scans that found nothing there (need2) look at the rest, in the same round
+    int cand_window;                  // 0 = evaluate every candidate at once
+    int* need2;                       // [B]
     int* work_cnt;                    // [4]: scans in full_list, tasks in cf_tasks
     int* full_list;                   // [B]
     int* cf_tasks;                    // [B][cf_tiles]: scan * cf_tiles + tile

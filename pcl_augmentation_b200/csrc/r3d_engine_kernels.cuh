@@ -1019,14 +1019,22 @@ __global__ void __launch_bounds__(TRY_THREADS) k_onmap(EngineDev e, int n_scans)
 }
 
 // prefix sum of the per-scan list lengths into shared memory (every CTA of a balanced stage); returns the total
-__device__ int task_prefix(const EngineDev& e, int n_scans, int* s_pref) {
+// phase 0: every listed rotation; 1: the first cand_window of each scan; 2: the rest, for the scans flagged in need2
+__device__ __forceinline__ int task_count(const EngineDev& e, int b, int phase) {
+    if (!e.gate_try[b]) return 0;
+    const int n = e.n_list[b];
+    if (phase == 0) return n;
+    if (phase == 1) return min(n, e.cand_window);
+    return e.need2[b] ? max(n - e.cand_window, 0) : 0;
+}
+__device__ int task_prefix(const EngineDev& e, int n_scans, int* s_pref, int phase = 0) {
     __shared__ int s_w[TASK_THREADS / 32];
     __shared__ int s_carry;
     if (threadIdx.x == 0) { s_carry = 0; s_pref[0] = 0; }
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     for (int b0 = 0; b0 < n_scans; b0 += TASK_THREADS) {
         const int b = b0 + threadIdx.x;
-        const int v = (b < n_scans && e.gate_try[b]) ? e.n_list[b] : 0;
+        const int v = b < n_scans ? task_count(e, b, phase) : 0;
         int inc = v;
         for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
         if (lane == 31) s_w[w] = inc;
@@ -1095,16 +1103,18 @@ __global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_onmap_full(c
 }
 
 // stage 2: A7 for the listed rotations (OD: the on-map ones, od/fs:281; semseg: all, the map test comes after)
-__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_road_level(const __grid_constant__ EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_road_level(const __grid_constant__ EngineDev e, int n_scans,
+                                                                                int phase) {
     extern __shared__ int s_pref[];
-    const int total = task_prefix(e, n_scans, s_pref);
+    const int total = task_prefix(e, n_scans, s_pref, phase);
+    const int first = phase == 2 ? e.cand_window : 0;
     const int gl = threadIdx.x & (GRP - 1);
     const unsigned gm = group_mask();
     const int n_groups = gridDim.x * (TASK_THREADS / GRP);
     for (int t = blockIdx.x * (TASK_THREADS / GRP) + threadIdx.x / GRP; t < total; t += n_groups) {
         const int b = task_scan(s_pref, n_scans, t), i = t - s_pref[b];
         const size_t cb = (size_t)b * (e.K + 1);
-        const int k = e.task == 0 ? (int)e.cand_list[cb + i] : i + 1;
+        const int k = e.task == 0 ? (int)e.cand_list[cb + first + i] : i + 1;
         if (e.task == 0 && !(e.cand_flags[cb + k] & CF_ONMAP)) continue;         // failed the full on-map test
         const ObjBox& ob = e.try_obj[b];
         const SurfaceSet surf = load_surface(e.classes[ob.cls]);
@@ -1165,16 +1175,18 @@ __global__ void __launch_bounds__(1024) k_onmap_ss(EngineDev e, int n_scans) {
 }
 
 // stage 3: A8 + A9 for the listed rotations that have a road level (OD: the list still holds every on-map rotation)
-__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_collide(const __grid_constant__ EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_collide(const __grid_constant__ EngineDev e, int n_scans,
+                                                                             int phase) {
     extern __shared__ int s_pref[];
-    const int total = task_prefix(e, n_scans, s_pref);
+    const int total = task_prefix(e, n_scans, s_pref, phase);
+    const int first = phase == 2 ? e.cand_window : 0;
     const int gl = threadIdx.x & (GRP - 1);
     const unsigned gm = group_mask();
     const int n_groups = gridDim.x * (TASK_THREADS / GRP);
     for (int t = blockIdx.x * (TASK_THREADS / GRP) + threadIdx.x / GRP; t < total; t += n_groups) {
         const int b = task_scan(s_pref, n_scans, t), i = t - s_pref[b];
         const size_t cb = (size_t)b * (e.K + 1);
-        const int k = e.cand_list[cb + i];
+        const int k = e.cand_list[cb + first + i];
         if (!(e.cand_flags[cb + k] & CF_HOK)) continue;
         const ObjBox& ob = e.try_obj[b];
         if (group_collides(e, b, e.st[b], ob, e.classes[ob.cls], e.cos_k[k], e.sin_k[k], e.cand_level[cb + k], gl, gm) && gl == 0)
@@ -1227,9 +1239,14 @@ __device__ __forceinline__ ObjProj project_obj_point(const EngineDev& e, const O
 // has r < scene, so no z-buffer is needed for the count: pass 1 marks visible pixels in a shared-memory bit image,
 // pass 2 counts the points on marked pixels.  Candidates are visited in rotation order with an ordered early-out
 // (the reference stops at the first candidate that keeps >= min_points, od/ins:530-561).
-__global__ void __launch_bounds__(128) k_occl_count(EngineDev e, int n_scans) {
+__global__ void k_phase_gate(EngineDev e, int n_scans) {           // which scans found nothing in the first window
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n_scans) e.need2[b] = e.gate_try[b] && e.st[b].found_rank == INT_MAX && e.n_list[b] > e.cand_window;
+}
+
+__global__ void __launch_bounds__(128) k_occl_count(EngineDev e, int n_scans, int phase) {
     const int b = blockIdx.y;
-    if (b >= n_scans || !e.gate_try[b]) return;
+    if (b >= n_scans || !(phase == 2 ? e.need2[b] : e.gate_try[b])) return;
     ScanState& s = e.st[b];
     extern __shared__ unsigned s_bits[];
     __shared__ int s_cnt, s_stop;

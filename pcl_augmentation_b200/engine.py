@@ -62,7 +62,7 @@ class Real3DEngine:
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
                  map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=120, force_full_projection=False,
-                 sub_batches=0, fetch_labels=None, round_graphs=True):
+                 sub_batches=0, fetch_labels=None, round_graphs=True, candidate_window=True):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -89,7 +89,8 @@ class Real3DEngine:
         cfg.map_window = int(map_window)
         cfg.grid_half, cfg.grid_cell = int(grid_half), float(grid_cell)
         # bit 0: full re-projection every slot; bit 1: no round graphs; bits 8-12: concurrent sub-batches (0 = library default)
-        cfg.flags = (1 if force_full_projection else 0) | (0 if round_graphs else 2) | ((int(sub_batches) & 31) << 8)
+        cfg.flags = ((1 if force_full_projection else 0) | (0 if round_graphs else 2) | (0 if candidate_window else 4)
+                     | ((int(sub_batches) & 31) << 8))
         r2, ok = bx.search_radii()
         for i in range(50):
             cfg.radii_sq[i] = float(r2[i])

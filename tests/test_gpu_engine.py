@@ -131,7 +131,7 @@ def test_candidate_flags_match_oracle_first_try():
     trace = []
     ref, want = oracle_run(case, trace=trace)
     tries = [t for t in trace if t[0] == "try"]
-    eng = make_engine(case)
+    eng = make_engine(case, candidate_window=False)             # every candidate of the try evaluated, for inspection
     got = eng.augment_batch([scan_input_from_case(case)])[0]
     flags, level, vis = eng.debug_candidates(0)
     eng.close()
