@@ -1056,9 +1056,11 @@ __device__ __forceinline__ int task_scan(const int* s_pref, int n_scans, int t) 
 
 // stage 1b (OD): A5 + A6a (od/fs:263-279) on ALL object points for the rotations that survived the prefilter; the
 // 8 lanes of a group stride over the points, two per lane in flight, early-out on the first off-road point
-__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_onmap_full(const __grid_constant__ EngineDev e, int n_scans) {
+__global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_onmap_full(const __grid_constant__ EngineDev e, int n_scans,
+                                                                                int phase) {
     extern __shared__ int s_pref[];
-    const int total = task_prefix(e, n_scans, s_pref);
+    const int total = task_prefix(e, n_scans, s_pref, phase);
+    const int first = phase == 2 ? e.cand_window : 0;
     const int gl = threadIdx.x & (GRP - 1);
     const unsigned gm = group_mask();
     const int n_groups = gridDim.x * (TASK_THREADS / GRP);
@@ -1066,7 +1068,7 @@ __global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_onmap_full(c
     for (int t = blockIdx.x * (TASK_THREADS / GRP) + threadIdx.x / GRP; t < total; t += n_groups) {
         const int b = task_scan(s_pref, n_scans, t), i = t - s_pref[b];
         const size_t cb = (size_t)b * (e.K + 1);
-        const int k = e.cand_list[cb + i];
+        const int k = e.cand_list[cb + first + i];
         const ObjBox& ob = e.try_obj[b];
         const int first = ob.first, count = ob.count, msel = e.classes[ob.cls].map_sel;
         const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
