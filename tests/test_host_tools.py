@@ -1,0 +1,81 @@
+"""CPU tier: host-side logic of the offline-tool drop-ins — label parsing, label -> map class
+precedence, camera record, filter_objects bookkeeping — against the oracle restatement and the reference goldens.
+No CUDA call is made here."""
+import json
+
+import numpy as np
+
+from oracle import cut_objects_oracle as coo
+from oracle import rich_map_oracle as rmo
+from pcl_augmentation_b200 import cut_objects as co
+from pcl_augmentation_b200.object_detection.cut_object import object_cut_out as oco
+from pcl_augmentation_b200.semantic_segmentation.cut_object import cut_out, filter_objects
+from pcl_augmentation_b200.semantic_segmentation.rich_map import drivable_area_map as srm
+from tests.helpers import KITTI_CALIB_LINES, KITTI_IMAGE_SHAPE, cut_object_cases, load_golden
+from tests.test_oracle_cut_objects import golden_samples
+
+
+def test_od_label_boxes_match_the_oracle_parse():
+    cases = cut_object_cases("od")
+    n = 0
+    for line in cases[0].box_lines:
+        cls, occluded, base, expand, cx, cy = oco.label_boxes(line + "\n")
+        w_cls, w_occ, w_base, w_expand, w_cx, w_cy = coo.od_boxes(line + "\n")
+        assert (cls, occluded, cx, cy) == (w_cls, w_occ, w_cx, w_cy)
+        for got, want in ((base, w_base), (expand, w_expand)):
+            assert got["center"] == want["center"] and got["rotation"] == want["rotation"]
+            assert (got["length"], got["width"], got["height"]) == (want["length"], want["width"], want["height"])
+        n += 1
+    assert n >= 10
+
+
+def test_ss_line_box_matches_the_oracle_parse():
+    case = cut_object_cases("ss")[0]
+    for line in case.box_lines:
+        box, x, y = cut_out.line_box(line + "\n")
+        items = line.split(" ")
+        assert (x, y) == (float(items[1]), float(items[2]))
+        assert (box["length"], box["width"], box["height"]) == (float(items[6]), float(items[5]), float(items[4]))   # ss/co:124-139
+
+
+def test_surface_table_precedence_matches_the_oracle():
+    labels = {1: [40, 44, 60], 2: [48, 70, 44], 3: [44, 48, 72]}        # 44: class 1 wins; 48: class 3 wins over 2
+    labs, cls = srm.surface_table(labels)
+    assert dict(zip(labs.tolist(), cls.tolist())) == rmo.surface_classes(labels) == {40: 1, 44: 1, 60: 1, 48: 3, 70: 2, 72: 3}
+
+
+def test_camera_record_holds_the_float32_products_of_the_reference(tmp_path):
+    (tmp_path / "calib.txt").write_text("\n".join(KITTI_CALIB_LINES) + "\n")
+    calib = co.read_kitti_calib(str(tmp_path / "calib.txt"))
+    want = coo.read_calib(str(tmp_path / "calib.txt"))
+    for k in ("P2", "R0", "Tr_velo2cam"):
+        assert calib[k].dtype == np.float32
+        np.testing.assert_array_equal(calib[k], want[k])
+    rec = co.camera_record(calib, KITTI_IMAGE_SHAPE)
+    m1 = np.dot(want["Tr_velo2cam"].T, want["R0"].T)                    # cutout.py:80, a float32 product
+    assert m1.dtype == np.float32
+    np.testing.assert_array_equal(rec[:12], m1.astype(np.float64).ravel())
+    np.testing.assert_array_equal(rec[12:24], want["P2"].astype(np.float64).ravel())
+    assert list(rec[24:]) == [375.0, 1242.0, 1.0]
+    # the field-of-view flags the oracle derives from these matrices: points ahead are seen, points behind are not
+    pts = np.array([[10.0, 0.0, -1.0], [-10.0, 0.0, -1.0], [10.0, 30.0, -1.0]])
+    assert coo.fov_flag(pts, want, KITTI_IMAGE_SHAPE).tolist() == [True, False, False]
+
+
+def test_filter_objects_bookkeeping_matches_reference_run():
+    g = load_golden("cut_objects_ss")
+    cfg = cut_object_cases("ss")[0].config
+    removed = 0
+    for cls in cfg["insertion"]["classes"]:
+        folder = cfg["labels"][cls]
+        samples = golden_samples(g, folder)
+        kept = set(samples)
+        for d in range(100):
+            bucket = [(n, a, len(p)) for n, (a, p) in samples.items() if n.endswith(f"_{d:03d}_m")]
+            if bucket:
+                drop = filter_objects.to_delete(bucket)
+                assert drop == coo.filter_objects(bucket)
+                kept -= set(drop)
+        assert sorted(kept) == json.loads(str(g[folder + "_kept"]))
+        removed += len(samples) - len(kept)
+    assert removed >= 10
