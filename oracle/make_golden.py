@@ -40,6 +40,9 @@ E2E_CASES = {
     "e2e_od_b": dict(task="od", seed=12, counts=[1, 3], n_cars=9),
     "e2e_ss_a": dict(task="ss", seed=21, counts=[1, 0, 0, 2, 1, 0], n_cars=4),
     "e2e_ss_b": dict(task="ss", seed=22, counts=[0, 1, 1, 1, 0, 1], n_cars=7),
+    # crowded scenes (many near misses in the collision tests) and more objects per scan
+    "e2e_od_c": dict(task="od", seed=13, counts=[3, 3], n_cars=14),
+    "e2e_ss_c": dict(task="ss", seed=23, counts=[1, 1, 1, 1, 1, 1], n_cars=13),
 }
 CASE_DEFAULTS = dict(shape=GOLDEN_SHAPE, n_per_class=100, obj_range=(4.0, 16.0))
 

@@ -12,7 +12,7 @@ from tests.helpers import GOLDEN_SHAPE, case_from_golden, load_golden, parse_ins
 
 pytestmark = pytest.mark.gpu
 
-E2E = ["e2e_od_a", "e2e_od_b", "e2e_ss_a", "e2e_ss_b"]
+E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c"]
 
 
 def make_engine(case, n_scans=1, max_points=None, **kw):

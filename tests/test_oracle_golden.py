@@ -110,7 +110,7 @@ def test_find_possible_places_matches_reference(task, mode, fast):
     assert total > 100
 
 
-E2E = ["e2e_od_a", "e2e_od_b", "e2e_ss_a", "e2e_ss_b"]
+E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c"]
 
 
 def run_oracle_e2e(g, case, mode="cumulative", fast=True):
