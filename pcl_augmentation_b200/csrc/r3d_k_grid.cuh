@@ -1,0 +1,143 @@
+// Kernels of the batched Real3D-Aug engine, part: once-per-scan spatial indices (CSR grids, column index, distance transform).
+// Included by r3d_engine_kernels.cuh (inside namespace r3d, after the shared constants); not a standalone header.
+// ------------------------------------------------------------------------------------------- placement
+__device__ __forceinline__ bool surface_label(const ClassCfg& cc, unsigned lab) {
+    bool ok = false;
+    for (int i = 0; i < cc.n_surface; ++i) ok |= lab == (unsigned)cc.surface[i];
+    return ok;
+}
+
+__device__ __forceinline__ int radius_index(const double* r2, double d2) {
+    if (!(d2 <= r2[R3D_NUM_RADII - 1])) return R3D_NUM_RADII;
+    int lo = 0, hi = R3D_NUM_RADII - 1;                   // smallest j with d2 <= r2[j]
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (d2 <= r2[mid]) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// ------------------------------------------------------------------------------- road-level search grid
+// The ORIGINAL scan never changes (correct_height reads original_pcl, od/fs:282), so its surface points (any label a
+// class may stand on, z > -3) are bucketed ONCE per scan into a uniform grid (CSR by cell, rows contiguous in x).
+// Points outside the grid extent are clamped into border cells: distances are always computed from the coordinates,
+// and clamping never increases a cell-index difference, so the square searches below stay exact.
+__device__ __forceinline__ bool any_surface_label(const EngineDev& e, unsigned lab) {
+    for (int c = 0; c < e.n_classes; ++c) {
+        const ClassCfg& cc = e.classes[c];
+        for (int i = 0; i < cc.n_surface; ++i) if (lab == (unsigned)cc.surface[i]) return true;
+    }
+    return false;
+}
+__device__ __forceinline__ int grid_coord(const EngineDev& e, float v) {
+    const int i = (int)floorf(v * e.grid_inv_cell) + (e.G >> 1);
+    return max(0, min(i, e.G - 1));
+}
+
+template <int PASS>     // 1: count per cell, 2: scatter (after the prefix scan)
+__global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const int n0 = e.st[b].n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n0) return;
+    const size_t base = (size_t)b * e.P;
+    int* cell = e.gcell + (size_t)b * e.G * e.G;
+    int* acell = e.acell + (size_t)b * e.G * e.G;
+    float4* out = e.gpts + (size_t)b * e.max_points;
+    float4* aout = e.apts + (size_t)b * e.max_points;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
+        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        const unsigned lab = e.label[base + p];
+        const int c = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
+        if (!(e.task == 0 && lab == (unsigned)e.road_label)) {      // OD: Road points are never obstacles (od/ins:353-355)
+            if (PASS == 1) atomicAdd(&acell[c], 1);
+            else aout[atomicAdd(&acell[c], 1)] = make_float4(v.x, v.y, v.z, __int_as_float(p));
+        }
+        if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
+        if (PASS == 1) atomicAdd(&cell[c], 1);
+        else out[atomicAdd(&cell[c], 1)] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
+    }
+}
+
+// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell to the nearest cell that holds a surface point:
+// the road-level search of a candidate whose surroundings are empty starts at that ring instead of growing through
+// the empty ones.  Separable: row pass (min |dx| along the row), then column pass (min over dy of max(|dy|, row value)).
+constexpr int NEAR_CAP = 12;
+template <int PASS>
+__global__ void __launch_bounds__(256) k_grid_near(EngineDev e, int n_scans) {
+    const int b = blockIdx.y, G = e.G;
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (b >= n_scans || c >= G * G) return;
+    const int y = c / G, x = c % G;
+    const size_t gb = (size_t)b * G * G;
+    int best = NEAR_CAP;
+    if (PASS == 1) {
+        const int* cell = e.gcell + gb;
+        for (int dx = -(NEAR_CAP - 1); dx <= NEAR_CAP - 1; ++dx) {
+            const int x1 = x + dx;
+            if (x1 < 0 || x1 >= G) continue;
+            const int q = y * G + x1;
+            if (cell[q] > (q > 0 ? cell[q - 1] : 0)) best = min(best, abs(dx));
+        }
+        e.gscratch[gb + c] = (unsigned char)best;
+    } else {
+        for (int dy = -(NEAR_CAP - 1); dy <= NEAR_CAP - 1; ++dy) {
+            const int y1 = y + dy;
+            if (y1 < 0 || y1 >= G) continue;
+            best = min(best, max(abs(dy), (int)e.gscratch[gb + (size_t)y1 * G + x]));
+        }
+        e.gnear[gb + c] = (unsigned char)best;
+    }
+}
+
+// One more once-per-scan CSR index over the ORIGINAL points (their azimuth bin never changes): by image column,
+// for k_apply_window.
+template <int PASS>     // 1: count, 2: scatter point indices
+__global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const int n0 = e.st[b].n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (p0 >= n0) return;
+    const size_t base = (size_t)b * e.P;
+    int* coff = e.col_off + (size_t)b * (e.cols + 1);
+    int* cidx = e.col_idx + (size_t)b * e.max_points;
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
+        const int c = e.col[base + p];
+        if (PASS == 1) atomicAdd(&coff[c], 1);
+        else cidx[atomicAdd(&coff[c], 1)] = p;
+    }
+}
+
+// exclusive prefix sum of the per-cell counts (one CTA per scan, four cells per thread and step); after the scatter
+// pass cell[c] = END of cell c
+__global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    int* cell = arr + (size_t)b * stride;
+    __shared__ int s_w[32];
+    __shared__ int s_run;
+    if (threadIdx.x == 0) s_run = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const bool vec = (stride & 3) == 0;                  // rows of `arr` 16-byte aligned: int4 loads / stores
+    for (int i0 = 0; i0 < n; i0 += 4096) {
+        const int i = i0 + threadIdx.x * 4;
+        int v[4] = {0, 0, 0, 0};
+        if (vec && i + 3 < n) { const int4 t = *reinterpret_cast<const int4*>(cell + i); v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w; }
+        else for (int u = 0; u < 4; ++u) if (i + u < n) v[u] = cell[i + u];
+        const int mine = v[0] + v[1] + v[2] + v[3];
+        int inc = mine;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_w[w] = inc;
+        __syncthreads();
+        int off = s_run, tot = 0;
+        for (int j = 0; j < 32; ++j) { if (j < w) off += s_w[j]; tot += s_w[j]; }
+        int e0 = off + inc - mine;                        // exclusive prefix of this thread's first cell
+        int o4[4];
+        for (int u = 0; u < 4; ++u) { o4[u] = e0; e0 += v[u]; }
+        if (vec && i + 3 < n) *reinterpret_cast<int4*>(cell + i) = make_int4(o4[0], o4[1], o4[2], o4[3]);
+        else for (int u = 0; u < 4; ++u) if (i + u < n) cell[i + u] = o4[u];
+        __syncthreads();
+        if (threadIdx.x == 0) s_run += tot;
+        __syncthreads();
+    }
+}
