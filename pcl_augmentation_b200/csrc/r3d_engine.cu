@@ -666,7 +666,10 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
         const int ph = d.cand_window > 0 ? 1 : 0;           // OD: first window of candidates, then the rest where needed
         if (d.task == 0) { Launcher l(eng, KID_ONMAP, ss); k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, ph); }
         { Launcher l(eng, KID_HEIGHT, ss); k_road_level<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, ph); }
-        if (d.task == 1) { Launcher l(eng, KID_ONMAP, ss); k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); }
+        if (d.task == 1) {
+            Launcher l(eng, KID_ONMAP, ss);
+            if (d.K <= SS_MAX_K) k_onmap_ss<<<ns, 1024, 0, ss>>>(d, ns); else k_onmap_ss_seq<<<ns, 1024, 0, ss>>>(d, ns);
+        }
         { Launcher l(eng, KID_COLLIDE, ss); k_collide<<<task_ctas, TASK_THREADS, pref_smem, ss>>>(d, ns, ph); }
         { Launcher l(eng, KID_OCCL, ss); k_occl_count<<<dim3(OCC_G, ns), 128, occl_smem_bytes(d), ss>>>(d, ns, ph); }
         if (ph) {
@@ -989,7 +992,7 @@ extern "C" int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id,
     k_onmap<<<n, TRY_THREADS, onmap_smem_bytes(d.K), st>>>(d, n); r3d_count_launch();
     if (d.task == 0) { k_onmap_full<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n, 0); r3d_count_launch(); }
     k_road_level<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n, 0); r3d_count_launch();
-    if (d.task == 1) { k_onmap_ss<<<n, 1024, 0, st>>>(d, n); r3d_count_launch(); }
+    if (d.task == 1) { if (d.K <= SS_MAX_K) k_onmap_ss<<<n, 1024, 0, st>>>(d, n); else k_onmap_ss_seq<<<n, 1024, 0, st>>>(d, n); r3d_count_launch(); }
     k_collide<<<task_ctas, TASK_THREADS, pref_smem, st>>>(d, n, 0); r3d_count_launch();
     k_feasible_list<<<n, 128, 0, st>>>(d, n); r3d_count_launch();
     std::vector<ScanState> hs(1);

@@ -515,9 +515,105 @@ __global__ void __launch_bounds__(TASK_THREADS, TASK_CTAS_PER_SM) k_road_level(c
     }
 }
 
-// stage 2b (semseg): A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place): the yaws
-// are visited in order by one CTA; world = T . [x y z 1] - move, astype(int); every in-map cell value must be allowed.
+// stage 2b (semseg): A6b (ss/fs:231-248) with the reference's carried z shift (ss/fs:146-147 is in place):
+// world = T . [x y z 1] - move, astype(int); every in-map cell value must be allowed.  The reference visits the yaws in
+// order because the z shift of the last yaw that passed AND found a road level feeds the test of the next one:
+//   pass_k = f(k, dz_k),   dz_{k+1} = pass_k && level_k ? level_k - cz : dz_k,   dz_1 = 0.
+// k_onmap_ss solves that recurrence by fixed-point iteration: every yaw is tested in parallel (one warp per yaw) under
+// an ASSUMED dz, one thread then walks the pass flags in order and derives the dz every yaw should have seen, and the
+// yaws whose assumption was wrong are tested again.  After i sweeps the first i yaws are final (induction), so the
+// loop ends with the sequential solution; in practice the shift moves a point by millimetres (it enters the world xy
+// only through the tilt of the pose) and two or three sweeps suffice.  k_onmap_ss_seq is the literal ordered walk,
+// kept for more than SS_MAX_K yaws.
+constexpr int SS_MAX_K = 1024;
+
+struct SsMapTest {          // everything the map test of one object point needs
+    double t00, t01, t02, t03, t10, t11, t12, t13;
+    unsigned okmask;
+    const unsigned* occ;
+};
+__device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanState& s, const SsMapTest& m, double x0, double y0,
+                                                 double z0, double c, double sn, double dz) {
+    const double x = sub(mul(c, x0), mul(sn, y0)), y = add(mul(sn, x0), mul(c, y0));
+    const double z = add(z0, dz);
+    const double wx = add(add(add(mul(m.t00, x), mul(m.t01, y)), mul(m.t02, z)), m.t03);
+    const double wy = add(add(add(mul(m.t10, x), mul(m.t11, y)), mul(m.t12, z)), m.t13);
+    const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
+    const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
+    if (ix < e.ss_sx && ix > -1 && iy < e.ss_sy && iy > -1) {
+        unsigned v = e.ss_map[(size_t)ix * e.ss_sy + iy];
+        const int lx = ix - s.win_x0, ly = iy - s.win_y0;
+        if (lx >= 0 && ly >= 0 && lx < e.map_window && ly < e.map_window) {
+            const int bit = lx * e.map_window + ly;
+            if (m.occ[bit >> 5] & (1u << (bit & 31))) v = 4;
+        }
+        if (!((m.okmask >> v) & 1u)) return true;
+    }
+    return false;
+}
+
+__global__ void __launch_bounds__(1024) k_onmap_ss_seq(EngineDev e, int n_scans);
+
 __global__ void __launch_bounds__(1024) k_onmap_ss(EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    const int K = e.K;
+    const ScanState& s = e.st[b];
+    const ObjBox ob = e.try_obj[b];
+    const double* T = e.poses + (size_t)b * 16;
+    SsMapTest m;
+    m.t00 = T[0]; m.t01 = T[1]; m.t02 = T[2]; m.t03 = T[3]; m.t10 = T[4]; m.t11 = T[5]; m.t12 = T[6]; m.t13 = T[7];
+    m.okmask = e.classes[ob.cls].map_ok_mask;
+    m.occ = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    const size_t cb = (size_t)b * (K + 1);
+    __shared__ double s_dz[SS_MAX_K + 1];              // the dz yaw k was (or must be) tested under
+    __shared__ unsigned char s_pass[SS_MAX_K + 1], s_todo[SS_MAX_K + 1], s_hok[SS_MAX_K + 1];
+    __shared__ int s_changed;
+    for (int k = threadIdx.x; k <= K; k += blockDim.x) {
+        s_dz[k] = 0.0; s_pass[k] = 0; s_todo[k] = 1;
+        s_hok[k] = (e.cand_flags[cb + k] & CF_HOK) ? 1 : 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    const double *ox = e.obj_x + ob.first, *oy = e.obj_y + ob.first, *oz = e.obj_z + ob.first;
+    for (int sweep = 0; sweep <= K; ++sweep) {
+        for (int k = 1 + warp; k <= K; k += n_warps) {           // one warp per yaw that needs (re)testing
+            if (!s_todo[k]) continue;
+            const double c = e.cos_k[k], sn = e.sin_k[k], dz = s_dz[k];
+            bool bad = false;
+            for (int i0 = 0; i0 < ob.count && !bad; i0 += 32) {
+                const int i = i0 + lane;
+                const bool off = i < ob.count && ss_point_off_map(e, s, m, ox[i], oy[i], oz[i], c, sn, dz);
+                bad = __ballot_sync(0xffffffffu, off) != 0u;
+            }
+            if (lane == 0) s_pass[k] = bad ? 0 : 1;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {                                   // the ordered walk over the flags (ss/fs:144-148)
+            double run = 0.0;
+            int changed = 0;
+            for (int k = 1; k <= K; ++k) {
+                const bool redo = run != s_dz[k];                 // yaw k was tested under another shift: test it again
+                s_todo[k] = redo;
+                if (redo) { s_dz[k] = run; changed = 1; }
+                // carry on with the flag at hand: if the retest flips it, the next walk re-derives everything behind k
+                if (s_pass[k] && s_hok[k]) run = sub(e.cand_level[cb + k], ob.cz);
+            }
+            s_changed = changed;
+        }
+        __syncthreads();
+        if (!s_changed) break;
+    }
+    for (int k = 1 + threadIdx.x; k <= K; k += blockDim.x)
+        if (s_pass[k]) e.cand_flags[cb + k] = (unsigned char)(e.cand_flags[cb + k] | CF_ONMAP);
+    __threadfence_block();
+    __syncthreads();
+    __shared__ int s_warp[32];
+    const int n = block_compact(e.cand_flags + cb, K, CF_ONMAP | CF_HOK, CF_ONMAP | CF_HOK, e.cand_list + cb, s_warp);
+    if (threadIdx.x == 0) e.n_list[b] = n;
+}
+
+__global__ void __launch_bounds__(1024) k_onmap_ss_seq(EngineDev e, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans || !e.gate_try[b]) return;
     const ScanState& s = e.st[b];
