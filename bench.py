@@ -303,9 +303,7 @@ def main():
     from pcl_augmentation_b200 import sharding as _sh
     numa_cpus = _sh.bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("R3D_NUMA_BIND", "1") != "0") else None
     if world > 1:
-        # NCCL_DEBUG=VERSION / INFO print to stdout; rank 0's stdout must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL_DEBUG output goes to fd 1, which main() redirected to stderr: the JSON line keeps the real stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -356,7 +354,7 @@ def main():
         def worker(w):
             try:
                 for _ in range(w, n_steps, res_depth):
-                    res_engines[w].reset()
+                    res_engines[w].reset(from_raw_points=True)      # the whole device path: ingest + indices included
                     res_engines[w].run()
             except BaseException as exc:
                 errors.append(exc)
@@ -375,7 +373,7 @@ def main():
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
     for _ in range(3):
-        eng.reset(); eng.run()
+        eng.reset(from_raw_points=True); eng.run()
     ev1.record(stream)
     eng.sync()
     single_batch_ms = ev0.elapsed_time(ev1) / 3
@@ -404,7 +402,7 @@ def main():
     eng.set_sub_batches(1)
     eng.profile(True)
     for _ in range(args.steps):
-        eng.reset()
+        eng.reset(from_raw_points=True)
         eng.run()
     eng.sync()
     prof = eng.profile_read()

@@ -175,8 +175,12 @@ typedef struct r3d_engine_cfg {
                                                  round's CUDA graph;
                                                  bit2: evaluate every yaw candidate of a try at once (no ordered
                                                  early-out window; what r3d_engine_debug_candidates should see);
-                                                 bits 8-12: sub-batches advanced concurrently on their own streams
-                                                 (1..16, 0 = default 4) */
+                                                 bit3: advance the batch with the STAGED round kernels (every stage of a
+                                                 try is one batch-wide launch; needed by r3d_engine_debug_candidates)
+                                                 instead of the default per-scan persistent walker (one CTA takes a scan
+                                                 through all its slots and tries, ordered early exit per try);
+                                                 bits 8-12 (staged rounds only): sub-batches advanced concurrently on
+                                                 their own streams (1..16, 0 = default 4) */
     double radii_sq[R3D_NUM_RADII];           /* radius**2 of the growing search (od/fs:149-160), host-computed */
     int32_t radii_ok[R3D_NUM_RADII];          /* 0 where the pass's "radius > 5" check already fails */
     r3d_class_cfg classes[R3D_MAX_CLASSES];
@@ -240,6 +244,9 @@ int r3d_engine_set_ss_map(r3d_engine* eng, const uint8_t* map, int32_t size_x, i
 int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* batch);
 /* re-arm the already resident batch (alive flags, tails, scheduling state) without touching host memory */
 int r3d_engine_reset_batch(r3d_engine* eng);
+/* re-arm the resident batch; from_raw_points != 0 repeats the WHOLE device path from the resident float4 points
+ * (spherical ingest A1/A2, spatial indices) — what a timed device-resident step must include */
+int r3d_engine_rearm_batch(r3d_engine* eng, int from_raw_points);
 /* run every scan of the batch to completion on the device and compact the outputs (device-resident) */
 int r3d_engine_run(r3d_engine* eng);
 /* device -> host copy of the results of the last run */
@@ -284,6 +291,9 @@ int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const doub
  * objects tried, vis_px masks applied, scans patched in place, selections in the shared-memory tile, selections in
  * the global scratch image, 0, 0} — the "units one launch processes" of the roofline arithmetic */
 int r3d_engine_stats(r3d_engine* eng, uint64_t* out8);
+/* the first n (<= 16) counters: the 8 above, then {max steps of one scan in the last run, candidate windows evaluated,
+ * exact occlusion counts (candidates the two-sided bound could not decide), full re-projections inside the walker} */
+int r3d_engine_stats_ex(r3d_engine* eng, uint64_t* out, int n);
 /* the engine's cudaStream_t (so callers can bracket work with their own CUDA events) */
 void* r3d_engine_stream(r3d_engine* eng);
 

@@ -43,6 +43,14 @@ E2E_CASES = {
     # crowded scenes (many near misses in the collision tests) and more objects per scan
     "e2e_od_c": dict(task="od", seed=13, counts=[3, 3], n_cars=14),
     "e2e_ss_c": dict(task="ss", seed=23, counts=[1, 1, 1, 1, 1, 1], n_cars=13),
+    # BASELINE-size scans (configs C1 / C2: 120 000 and 124 992 points, 112 x 1440 image), minutes per scan in the reference
+    "e2e_od_full": dict(task="od", seed=14, counts=[2, 2], n_cars=6, shape=[64, 1875, 2.0, -24.8], obj_range=[5.0, 35.0]),
+    "e2e_ss_full": dict(task="ss", seed=24, counts=[1, 1, 0, 1, 1, 0], n_cars=6, shape=[64, 1953, 2.0, -24.8],
+                        obj_range=[5.0, 35.0]),
+    # one class of very close, very large cut objects (> 4096 points, pixel rectangle > 8192 px): the global-scratch
+    # branches of the candidate selection (r3d_k_occlusion.cuh)
+    "e2e_ss_big": dict(task="ss", seed=25, counts=[1], n_cars=2, shape=[48, 1200, 2.0, -24.8], obj_range=[3.2, 4.2],
+                       classes=[18], n_per_class=100),
 }
 CASE_DEFAULTS = dict(shape=GOLDEN_SHAPE, n_per_class=100, obj_range=(4.0, 16.0))
 
@@ -50,6 +58,10 @@ CASE_DEFAULTS = dict(shape=GOLDEN_SHAPE, n_per_class=100, obj_range=(4.0, 16.0))
 def build_case(spec):
     kw = dict(CASE_DEFAULTS)
     kw.update({k: v for k, v in spec.items() if k not in ("task", "seed")})
+    if isinstance(kw.get("shape"), (list, tuple)):
+        kw["shape"] = synth.ScanShape(*kw["shape"])
+    if "obj_range" in kw:
+        kw["obj_range"] = tuple(kw["obj_range"])
     return synth.make_case(spec["task"], spec["seed"], **kw)
 
 

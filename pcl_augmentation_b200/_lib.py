@@ -109,6 +109,8 @@ PROTOTYPES = {
     "r3d_engine_profile_read": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
                                           C.POINTER(C.c_int)]),
     "r3d_engine_stats": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "r3d_engine_stats_ex": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "r3d_engine_rearm_batch": (C.c_int, [C.c_void_p, C.c_int]),
     "r3d_engine_stream": (C.c_void_p, [C.c_void_p]),
     "r3d_engine_debug_image": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "r3d_engine_debug_candidates": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),

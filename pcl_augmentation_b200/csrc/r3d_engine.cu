@@ -20,13 +20,16 @@ namespace {
 
 enum KernelId {
     KID_INGEST, KID_CTRL, KID_UPDATE, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT, KID_COLLIDE,
-    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_PROJECT0, KID_CLOSEFILL0, KID_CLEAR0, KID_MINMAX0, KID_COUNT
+    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_PROJECT0, KID_CLOSEFILL0, KID_CLEAR0, KID_MINMAX0, KID_WALK, KID_PREP,
+    KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
     "ingest_spherical", "ctrl", "update_mask_patch", "clear_images", "project_zbuffer", "close_fill", "adjust_map",
     "onmap", "road_level", "collide", "index_build", "occlusion_count", "select_emit", "compact_output", "minmax_elevation",
     // round 0 of a run re-projects every scan in full; later rounds only the scans whose elevation range moved
-    "project_zbuffer_full", "close_fill_full", "clear_images_full", "minmax_elevation_full"};
+    "project_zbuffer_full", "close_fill_full", "clear_images_full", "minmax_elevation_full",
+    // the per-scan persistent walker (one CTA per scan runs all the slots / tries of its scan) and its set-up
+    "scan_walk", "walk_prepare"};
 
 template <class T>
 struct DevBuf {
@@ -67,6 +70,8 @@ struct r3d_engine {
     struct RoundGraph { cudaGraphExec_t exec = nullptr; EngineDev d; int ns = 0, chunks_all = 0, task_ctas = 0, sel_pts = 0, kernels = 0; };
     RoundGraph round_graph[R3D_MAX_SUB];
     bool use_graphs = true, capturing = false;
+    bool walked = false;                         // the last run used the walker (its step count is in h_offsets)
+    bool staged = false;                         // true: the staged round kernels (debug / probe path); false: the per-scan walker
     bool run_active = false;
     int run_nsub = 0, run_done = 0, run_rounds = 0;
     bool objects_set = false, yaw_set = false, batch_loaded = false, ran = false;
@@ -81,7 +86,7 @@ struct r3d_engine {
     DevBuf<unsigned short> col, cand_list, label16;
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
-        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks, need2;
+        class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks, need2, occ_far;
     DevBuf<unsigned> round_ctl;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags, gnear, gscratch;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -211,6 +216,8 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     R3D_CUDA(cudaStreamCreateWithPriority(&eng->stream, cudaStreamNonBlocking, prio_least));
     eng->n_sub = (cfg->flags >> 8) & 31;
     eng->use_graphs = !(cfg->flags & 2);
+    eng->staged = (cfg->flags & 8) != 0;
+    if (const char* env = getenv("R3D_STAGED")) eng->staged = atoi(env) != 0;
     if (const char* env = getenv("R3D_GRAPHS")) eng->use_graphs = atoi(env) != 0;
     if (const char* env = getenv("R3D_SUBBATCHES")) eng->n_sub = atoi(env);
     if (eng->n_sub <= 0) eng->n_sub = 4;
@@ -271,12 +278,14 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.max_chunks = (d.P + CHUNK - 1) / CHUNK;
     TRY(eng->chunk_cnt.alloc(B * (size_t)d.max_chunks));
     { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&eng->n_sms, cudaDevAttrMultiProcessorCount, dev); }
-    TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(8));
-    R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
+    TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(R3D_N_STATS));
+    R3D_CUDA(cudaMemset(eng->stats.p, 0, R3D_N_STATS * sizeof(unsigned long long)));
+    TRY(eng->occ_far.alloc(B * (OCC_FAR_CAP + 1)));
+    R3D_CUDA(cudaMemset(eng->occ_far.p, 0xFF, B * (OCC_FAR_CAP + 1) * sizeof(int)));
     R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, R3D_MAX_SUB * 64 * sizeof(unsigned long long), cudaHostAllocMapped));
     memset(eng->h_words, 0, R3D_MAX_SUB * 64 * sizeof(unsigned long long));
     R3D_CUDA(cudaHostGetDevicePointer((void**)&eng->d_words, eng->h_words, 0));
-    R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, 2 * (B + 1) * sizeof(long long)));
+    R3D_CUDA(cudaMallocHost((void**)&eng->h_offsets, (2 * (B + 1) + 1) * sizeof(long long)));
     std::vector<ClassCfg> cls(R3D_MAX_CLASSES);
     for (int c = 0; c < R3D_MAX_CLASSES; ++c) {
         const r3d_class_cfg& s = cfg->classes[c];
@@ -307,7 +316,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.gcell = eng->gcell.p; d.gpts = eng->gpts.p; d.gnear = eng->gnear.p; d.gscratch = eng->gscratch.p;
     d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.acell = eng->acell.p; d.apts = eng->apts.p;
     d.try_obj = eng->try_obj.p; d.chunk_cnt = eng->chunk_cnt.p;
-    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p;
+    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p; d.occ_far = eng->occ_far.p;
     *out = eng;
     return R3D_OK;
 }
@@ -399,7 +408,7 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     d.unplaceable = eng->unplaceable.p; d.occ_pix = eng->occ_pix.p; d.sel_pix = eng->sel_pix.p;
     const size_t sel_smem = select_smem_bytes(std::min(max_pts, SEL_SMEM_PTS));
     d.sel_key_cap = next_pow2(max_pts);
-    if (max_pts > SEL_SMEM_PTS) {
+    if (max_pts > std::min(SEL_SMEM_PTS, WALK_SEL_PTS)) {        // objects the selection cannot keep in shared memory
         TRY(eng->sel_keys.alloc((size_t)d.B * d.sel_key_cap)); TRY(eng->sel_r.alloc((size_t)d.B * max_pts));
     }
     d.sel_keys = eng->sel_keys.p; d.sel_r = eng->sel_r.p;
@@ -407,6 +416,9 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occl_smem_bytes(d)));
     if (onmap_smem_bytes(d.K) > 100 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: too many yaw steps for the placement kernel's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_onmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onmap_smem_bytes(d.K)));
+    if (walk_smem_layout(d.K, d.dwords).total > 200 * 1024)
+        return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: range image / yaw steps too large for the walker's shared memory");
+    R3D_CUDA(cudaFuncSetAttribute(k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_layout(d.K, d.dwords).total));
     eng->objects_set = true;
     return R3D_OK;
 }
@@ -550,6 +562,17 @@ extern "C" int r3d_engine_reset_batch(r3d_engine* eng) {
     return arm_batch(eng, false);
 }
 
+extern "C" int r3d_engine_rearm_batch(r3d_engine* eng, int from_raw_points) {
+    if (eng) cudaSetDevice(eng->device);
+    if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_rearm_batch: no batch loaded");
+    if (!from_raw_points) return arm_batch(eng, false);
+    // the whole device path from the resident float4 points again: scene boxes, spherical ingest, spatial indices
+    R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, eng->stream));
+    k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, eng->stream>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
+    r3d_count_launch();
+    return arm_batch(eng, true);
+}
+
 // view of the device data model that starts at scan b0: every per-scan array is [scan][...], so offsetting the base
 // pointers lets the kernels run unchanged on a contiguous sub-batch
 static EngineDev sub_view(const EngineDev& d, int b0) {
@@ -573,7 +596,7 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     R3D_OFF(occ_pix, (size_t)OCC_G * d.max_obj_points); R3D_OFF(sel_pix, d.max_obj_points);
     R3D_OFF(sel_keys, d.sel_key_cap); R3D_OFF(sel_r, d.max_obj_points); R3D_OFF(inserted, (size_t)d.max_events * 4);
     R3D_OFF(inserted_box, (size_t)d.max_events * 8); R3D_OFF(check, (size_t)d.max_inserted * 5); R3D_OFF(chunk_cnt, d.max_chunks);
-    R3D_OFF(out_count, 1);
+    R3D_OFF(out_count, 1); R3D_OFF(occ_far, OCC_FAR_CAP + 1);
 #undef R3D_OFF
     return v;
 }
@@ -582,10 +605,60 @@ extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_run
 
 extern "C" int r3d_engine_run(r3d_engine* eng) { return r3d_engine_run_until(eng, 0, nullptr); }
 
+// The default execution model: batch-wide streaming kernels for the first range image of every scan, then ONE launch
+// of the per-scan walker (r3d_k_walk.cuh) that takes every scan through all its slots and tries, then the output
+// compaction.  Everything is queued on the engine stream; the host neither polls nor synchronises.
+static int run_walker(r3d_engine* eng) {
+    const EngineDev& d = eng->dev;
+    const int n = eng->n_scans;
+    cudaStream_t st = eng->stream;
+    const int chunks0 = (eng->max_n0 + CHUNK - 1) / CHUNK;
+    const int chunks_all = (eng->max_n0 + d.max_inserted + CHUNK - 1) / CHUNK;
+#ifndef R3D_FULL_Y
+#define R3D_FULL_Y 32
+#endif
+    const int full_y = std::min(n, R3D_FULL_Y);
+    { Launcher l(eng, KID_PREP); k_walk_prepare<<<std::min((n * d.cf_tiles + 255) / 256, eng->n_sms * 4), 256, 0, st>>>(d, n); }
+    { Launcher l(eng, KID_MINMAX0); k_minmax<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+    { Launcher l(eng, KID_CLEAR0); k_clear_images<<<dim3(32, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+    { Launcher l(eng, KID_PROJECT0); k_project<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+    {
+        Launcher l(eng, KID_CLOSEFILL0);
+        const int cf_grid = std::min(n * d.cf_tiles, eng->n_sms * 4);
+        if ((d.cols & 1) == 0 && ((uintptr_t)d.zraw & 15) == 0) {
+            k_close_fill_raw_pipelined<<<cf_grid, CF_THREADS, 0, st>>>(d.zraw, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr, d.cf_tasks,
+                                                                        d.work_cnt + 1);
+        } else {
+            RawImage in{d.zraw};
+            k_close_fill_tasks<RawImage><<<cf_grid, CF_THREADS, 0, st>>>(in, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr, d.cf_tasks,
+                                                                         d.work_cnt + 1);
+        }
+    }
+    if (d.task == 1) {
+        R3D_CUDA(cudaMemsetAsync(eng->occ_win.p, 0, (size_t)n * ((size_t)d.map_window * d.map_window / 32) * sizeof(unsigned), st));
+        Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n);
+    }
+    { Launcher l(eng, KID_WALK); k_scan_walk<<<n, WALK_THREADS, walk_smem_layout(d.K, d.dwords).total, st>>>(d, n); }
+    {
+        Launcher l(eng, KID_OUT);
+        k_out_count<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);
+        k_out_offsets<<<1, 1024, 0, st>>>(d, n, chunks_all);
+        k_out_write<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);
+        r3d_count_launch(2);
+    }
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets, eng->out_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets + (d.B + 1), eng->check_off.p, (n + 1) * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->h_offsets + 2 * (d.B + 1), eng->stats.p + 8, sizeof(long long), cudaMemcpyDeviceToHost, st));
+    eng->ran = true; eng->walked = true;
+    return r3d_check_launch("r3d_engine_run");
+}
+
 extern "C" int r3d_engine_run_until(r3d_engine* eng, int stop_at, int* still_running) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_run: no batch loaded");
     if (still_running) *still_running = 0;
+    if (!eng->staged) return run_walker(eng);
+    eng->walked = false;
     const EngineDev& d0 = eng->dev;
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
@@ -829,7 +902,7 @@ extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
         if (res->n_inserted) res->n_inserted[s] = hs[s].n_inserted;
         if (res->status) res->status[s] = hs[s].status;
     }
-    if (res->rounds) *res->rounds = eng->last_rounds;
+    if (res->rounds) *res->rounds = eng->walked ? (int)eng->h_offsets[2 * (d.B + 1)] : eng->last_rounds;
     return R3D_OK;
 }
 
@@ -840,7 +913,15 @@ extern "C" int r3d_engine_profile_enable(r3d_engine* eng, int on) {
     drain_events(eng);
     eng->profile = on != 0;
     for (int i = 0; i < KID_COUNT; ++i) { eng->prof_ms[i] = 0; eng->prof_launches[i] = 0; }
-    R3D_CUDA(cudaMemset(eng->stats.p, 0, 8 * sizeof(unsigned long long)));
+    R3D_CUDA(cudaMemset(eng->stats.p, 0, R3D_N_STATS * sizeof(unsigned long long)));
+    return R3D_OK;
+}
+
+extern "C" int r3d_engine_stats_ex(r3d_engine* eng, uint64_t* out, int n) {
+    if (eng) cudaSetDevice(eng->device);
+    if (!eng || !out || n < 0 || n > R3D_N_STATS) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats_ex: bad argument");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    R3D_CUDA(cudaMemcpy(out, eng->stats.p, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return R3D_OK;
 }
 
@@ -923,6 +1004,7 @@ __global__ void k_probe_setup(EngineDev e, int n_scans, int scan, int obj, int n
     if (!me) return;
     const int ww = e.map_window * e.map_window / 32;
     if (e.task == 1) for (int i = threadIdx.x; i < ww; i += blockDim.x) e.occ_win[(size_t)b * ww + i] = 0u;
+    if (e.task == 1) occ_far_clear(e, b, threadIdx.x);
 }
 
 __global__ void k_probe_points(EngineDev e, int scan, int obj, int n_feasible, double* xyz_out, double* box_out) {

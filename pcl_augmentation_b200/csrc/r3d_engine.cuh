@@ -112,7 +112,10 @@ struct EngineDev {       // passed by value to kernels
     int* active_count;                // [64][2] per round slot: unfinished scans, finished k_ctrl CTAs
     unsigned long long* host_word;    // [64] mapped pinned host words; slot = round & 63 gets (seq << 32 | unfinished scans)
     unsigned* round_ctl;              // [2]: round number, sequence number of round 0 (seq of round r = base + r)
-    unsigned long long* stats;        // [4] gated scan-launch counters: project, try, apply, points of applied/projected scans
+    unsigned long long* stats;        // [R3D_N_STATS] counters: 0 full projections, 1 tries, 2 masks applied, 3 in-place patches,
+                                      // 4 / 5 selections in the shared tile / global scratch, 6 prefilter survivors, 7 on-map
+                                      // rotations, 8 max steps of a scan (walker), 9 candidate windows, 10 exact occlusion
+                                      // counts, 11 in-walker full re-projections
     int* far_arr;                     // [B] any smoothed scene pixel beyond 500 m (od/ins:486 quirk)
     // scene boxes
     Box* boxes;            // [B][max_boxes]
@@ -126,6 +129,7 @@ struct EngineDev {       // passed by value to kernels
     long long ss_move_x, ss_move_y;
     const double* poses;              // [B][16]
     unsigned* occ_win;                // [B][map_window*map_window/32]
+    int* occ_far;                     // [B][64]: count + cells marked occupied outside the window (numpy-wrapped indices)
     // schedule
     const int* counts;                // [B][C]
     const int* perms;                 // [B][E][C][tries]
@@ -169,11 +173,18 @@ struct EngineDev {       // passed by value to kernels
     float* out_check;
 };
 
+#define R3D_N_STATS 16
 #ifndef R3D_OCC_G
 #define R3D_OCC_G 8
 #endif
 constexpr int OCC_G = R3D_OCC_G;        // CTAs per scan in the occlusion-count kernel (8: +3.6 % over 16 with 8 engines in flight)
+constexpr int OCC_FAR_CAP = 63;          // semseg: occupied map cells outside the per-scan bit window (see adjust_map_point)
 constexpr double kFix = 1099511627776.0;   // 2^40 fixed point for the order-independent road-level sum
+
+// thread `tid` (0 .. OCC_FAR_CAP) clears its entry of scan b's far-cell set
+__device__ __forceinline__ void occ_far_clear(const EngineDev& e, int b, int tid) {
+    if (tid <= OCC_FAR_CAP) e.occ_far[(size_t)b * (OCC_FAR_CAP + 1) + tid] = tid == 0 ? 0 : -1;
+}
 
 __device__ __forceinline__ void load_xyz(const EngineDev& e, int b, int p, int n0, double& x, double& y, double& z) {
     if (p < n0) {

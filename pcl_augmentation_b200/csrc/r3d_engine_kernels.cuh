@@ -22,5 +22,6 @@ __device__ __forceinline__ void set_error(ScanState& s, int code) {
 #include "r3d_k_placement.cuh"
 #include "r3d_k_occlusion.cuh"
 #include "r3d_k_output.cuh"
+#include "r3d_k_walk.cuh"
 
 }  // namespace r3d

@@ -176,22 +176,33 @@ __device__ __forceinline__ bool tile_pixel_value(const unsigned long long* tile,
 // candidate's z-buffer (in a shared-memory tile around the object when it fits, else in a global scratch image),
 // closes / fills it, compares with the scene image (strict <) into the vis_px bit mask, and on acceptance appends the
 // visible object points in (pix_id, index) order to the scene tail, the `check` record and the scene boxes.
-__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, int key_cap, int smem_pts) {
-    const int b = blockIdx.x;
-    if (b >= n_scans || !e.gate_try[b]) return;
-    ScanState& s = e.st[b];
-    const int nf = s.n_feasible;
-    if (nf == 0) return;
-    extern __shared__ unsigned long long s_dyn[];
-    // sort keys / ranges / pixel ids of the object's points: shared memory for objects up to smem_pts points, the
-    // per-scan global scratch for larger ones (trucks with > 10k points)
-    unsigned long long* s_keys = s_dyn;                                   // [key_cap]
-    double* s_r = reinterpret_cast<double*>(s_dyn + key_cap);            // [smem_pts]
-    unsigned long long* s_tile = s_dyn + key_cap + smem_pts;             // [SEL_TILE_PX]
-    int* s_pix = reinterpret_cast<int*>(s_tile + SEL_TILE_PX);           // [smem_pts]
-    unsigned* s_dil = reinterpret_cast<unsigned*>(s_pix + smem_pts);     // [SEL_TILE_PX / 32]
-    unsigned* s_vis = s_dil + SEL_TILE_PX / 32;                          // [SEL_TILE_PX / 32]
-    if (e.try_obj[b].count > smem_pts) {
+// shared-memory scratch of the candidate selection: sort keys, ranges, object tile, pixel ids, dilation + visibility bits
+struct SelScratch {
+    unsigned long long* keys;      // [next_pow2(pts)]
+    double* r;                     // [pts]
+    unsigned long long* tile;      // [tile_px]
+    int* pix;                      // [pts]
+    unsigned *dil, *vis;           // [tile_px / 32] each
+    int pts, tile_px;              // capacities (objects with more points / wider pixel rectangles use global scratch)
+};
+__device__ __forceinline__ SelScratch sel_scratch(unsigned long long* dyn, int key_cap, int pts, int tile_px) {
+    SelScratch q;
+    q.keys = dyn; q.r = reinterpret_cast<double*>(dyn + key_cap); q.tile = dyn + key_cap + pts;
+    q.pix = reinterpret_cast<int*>(q.tile + tile_px); q.dil = reinterpret_cast<unsigned*>(q.pix + pts);
+    q.vis = q.dil + tile_px / 32; q.pts = pts; q.tile_px = tile_px;
+    return q;
+}
+
+// every thread of the CTA (any size) calls it; k = rotation of the chosen candidate, `accepted` = it keeps min_points
+__device__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k, bool accepted, SelScratch q) {
+    unsigned long long* s_keys = q.keys;
+    double* s_r = q.r;
+    unsigned long long* s_tile = q.tile;
+    int* s_pix = q.pix;
+    unsigned* s_dil = q.dil;
+    unsigned* s_vis = q.vis;
+    const int SEL_TILE_PX = q.tile_px;
+    if (e.try_obj[b].count > q.pts) {
         s_keys = e.sel_keys + (size_t)b * e.sel_key_cap;
         s_r = e.sel_r + (size_t)b * e.max_obj_points;
         s_pix = e.sel_pix + (size_t)b * e.max_obj_points;
@@ -203,9 +214,6 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, i
         s_rect[0] = INT_MAX; s_rect[1] = -1; s_rect[2] = INT_MAX; s_rect[3] = -1; s_el[0] = R3D_EMPTY_U64; s_el[1] = 0ull;
         s_nvis = 0;
     }
-    const bool accepted = s.found_rank < nf;
-    const int rank = accepted ? s.found_rank : nf - 1;
-    const int k = e.feas[(size_t)b * e.K + rank];
     const ObjBox ob = e.obj[s.cur_obj];
     const ImageGeom g = s.geom;
     const int H = g.rows, W = g.cols;
@@ -383,4 +391,16 @@ __global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, i
         s.d_r0 = wr0; s.d_r1 = wr1; s.d_c0 = wc0; s.d_c1 = wc1;
         if (!accepted) { s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull; }
     }
+}
+
+__global__ void __launch_bounds__(512) k_select_emit(EngineDev e, int n_scans, int key_cap, int smem_pts) {
+    const int b = blockIdx.x;
+    if (b >= n_scans || !e.gate_try[b]) return;
+    ScanState& s = e.st[b];
+    const int nf = s.n_feasible;
+    if (nf == 0) return;
+    extern __shared__ unsigned long long s_dyn[];
+    const bool accepted = s.found_rank < nf;
+    const int rank = accepted ? s.found_rank : nf - 1;
+    select_emit_body(e, b, s, e.feas[(size_t)b * e.K + rank], accepted, sel_scratch(s_dyn, key_cap, smem_pts, SEL_TILE_PX));
 }

@@ -531,6 +531,7 @@ struct SsMapTest {          // everything the map test of one object point needs
     double t00, t01, t02, t03, t10, t11, t12, t13;
     unsigned okmask;
     const unsigned* occ;
+    const int* far;         // occupied cells outside the bit window (numpy-wrapped indices of addjust_map_2), [0] = count
 };
 __device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanState& s, const SsMapTest& m, double x0, double y0,
                                                  double z0, double c, double sn, double dz) {
@@ -546,6 +547,9 @@ __device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanS
         if (lx >= 0 && ly >= 0 && lx < e.map_window && ly < e.map_window) {
             const int bit = lx * e.map_window + ly;
             if (m.occ[bit >> 5] & (1u << (bit & 31))) v = 4;
+        } else if (m.far[0] > 0) {
+            const int cell = ix * e.ss_sy + iy;
+            for (int i = 0; i < OCC_FAR_CAP; ++i) if (m.far[1 + i] == cell) v = 4;
         }
         if (!((m.okmask >> v) & 1u)) return true;
     }
@@ -565,6 +569,7 @@ __global__ void __launch_bounds__(1024) k_onmap_ss(EngineDev e, int n_scans) {
     m.t00 = T[0]; m.t01 = T[1]; m.t02 = T[2]; m.t03 = T[3]; m.t10 = T[4]; m.t11 = T[5]; m.t12 = T[6]; m.t13 = T[7];
     m.okmask = e.classes[ob.cls].map_ok_mask;
     m.occ = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    m.far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);
     const size_t cb = (size_t)b * (K + 1);
     __shared__ double s_dz[SS_MAX_K + 1];              // the dz yaw k was (or must be) tested under
     __shared__ unsigned char s_pass[SS_MAX_K + 1], s_todo[SS_MAX_K + 1], s_hok[SS_MAX_K + 1];
@@ -618,33 +623,19 @@ __global__ void __launch_bounds__(1024) k_onmap_ss_seq(EngineDev e, int n_scans)
     if (b >= n_scans || !e.gate_try[b]) return;
     const ScanState& s = e.st[b];
     const ObjBox ob = e.try_obj[b];
-    const unsigned okmask = e.classes[ob.cls].map_ok_mask;
     const double* T = e.poses + (size_t)b * 16;
-    const double t00 = T[0], t01 = T[1], t02 = T[2], t03 = T[3], t10 = T[4], t11 = T[5], t12 = T[6], t13 = T[7];
-    const unsigned* o = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    SsMapTest m;
+    m.t00 = T[0]; m.t01 = T[1]; m.t02 = T[2]; m.t03 = T[3]; m.t10 = T[4]; m.t11 = T[5]; m.t12 = T[6]; m.t13 = T[7];
+    m.okmask = e.classes[ob.cls].map_ok_mask;
+    m.occ = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    m.far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);
     const size_t cb = (size_t)b * (e.K + 1);
     double dz = 0.0;
     for (int k = 1; k <= e.K; ++k) {
         const double c = e.cos_k[k], sn = e.sin_k[k];
         int bad = 0;
-        for (int i = threadIdx.x; i < ob.count; i += blockDim.x) {
-            const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
-            const double x = sub(mul(c, x0), mul(sn, y0)), y = add(mul(sn, x0), mul(c, y0));
-            const double z = add(e.obj_z[ob.first + i], dz);
-            const double wx = add(add(add(mul(t00, x), mul(t01, y)), mul(t02, z)), t03);
-            const double wy = add(add(add(mul(t10, x), mul(t11, y)), mul(t12, z)), t13);
-            const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
-            const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
-            if (ix < e.ss_sx && ix > -1 && iy < e.ss_sy && iy > -1) {
-                unsigned v = e.ss_map[(size_t)ix * e.ss_sy + iy];
-                const int lx = ix - s.win_x0, ly = iy - s.win_y0;
-                if (lx >= 0 && ly >= 0 && lx < e.map_window && ly < e.map_window) {
-                    const int bit = lx * e.map_window + ly;
-                    if (o[bit >> 5] & (1u << (bit & 31))) v = 4;
-                }
-                if (!((okmask >> v) & 1u)) bad = 1;
-            }
-        }
+        for (int i = threadIdx.x; i < ob.count; i += blockDim.x)
+            if (ss_point_off_map(e, s, m, e.obj_x[ob.first + i], e.obj_y[ob.first + i], e.obj_z[ob.first + i], c, sn, dz)) bad = 1;
         bad = __syncthreads_or(bad);
         if (!bad) {
             const unsigned f = e.cand_flags[cb + k];

@@ -32,6 +32,38 @@ __device__ __forceinline__ bool last_block_done(unsigned* ticket, unsigned n_blo
     return s_last;
 }
 
+// scene = scene[pix_id not in vis_px] (od/ins:488-501) for the calling thread's share (tid of nthr) of the points in
+// the column range of the recorded rectangle + the inserted tail; true if a removed point held the min / max elevation
+__device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, const ScanState& s, int tid, int nthr) {
+    const size_t base = (size_t)b * e.P;
+    bool extreme = false;
+    const int* off = e.col_off + (size_t)b * (e.cols + 1);
+    const int* idx = e.col_idx + (size_t)b * e.max_points;
+    int c0 = s.d_c0, c1 = s.d_c1;
+    if (e.far_arr[b]) { c0 = 0; c1 = e.cols - 1; }          // od/ins:486 quirk: covered pixels can be anywhere
+    const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
+    if (c1 >= c0) {
+        const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
+        for (int i = beg + tid; i < end; i += nthr) {
+            const int p = idx[i];
+            if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
+                e.alive[base + p] = 0;
+                const unsigned long long bits = dbl_bits(e.el[base + p]);
+                extreme |= bits == lo || bits == hi;
+            }
+        }
+    }
+    for (int t = tid; t < s.tail_before; t += nthr) {
+        const int p = s.n0 + t;
+        if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
+            e.alive[base + p] = 0;
+            const unsigned long long bits = dbl_bits(e.el[base + p]);
+            extreme |= bits == lo || bits == hi;
+        }
+    }
+    return extreme;
+}
+
 __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans) return;
@@ -46,33 +78,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_sc
     ScanState& s = e.st[b];
     const size_t base = (size_t)b * e.P;
     const int tid = blockIdx.x * UPDATE_THREADS + threadIdx.x, nthr = UPDATE_G * UPDATE_THREADS;
-    bool extreme = false;
-    if (do_apply) {
-        const int* off = e.col_off + (size_t)b * (e.cols + 1);
-        const int* idx = e.col_idx + (size_t)b * e.max_points;
-        int c0 = s.d_c0, c1 = s.d_c1;
-        if (e.far_arr[b]) { c0 = 0; c1 = e.cols - 1; }          // od/ins:486 quirk: covered pixels can be anywhere
-        const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
-        if (c1 >= c0) {
-            const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
-            for (int i = beg + tid; i < end; i += nthr) {
-                const int p = idx[i];
-                if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
-                    e.alive[base + p] = 0;
-                    const unsigned long long bits = dbl_bits(e.el[base + p]);
-                    extreme |= bits == lo || bits == hi;
-                }
-            }
-        }
-        for (int t = tid; t < s.tail_before; t += nthr) {
-            const int p = s.n0 + t;
-            if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
-                e.alive[base + p] = 0;
-                const unsigned long long bits = dbl_bits(e.el[base + p]);
-                extreme |= bits == lo || bits == hi;
-            }
-        }
-    }
+    const bool extreme = do_apply && apply_vis_mask(e, b, s, tid, nthr);
     if (__syncthreads_or(extreme) && threadIdx.x == 0) atomicOr(&s.extreme_removed, 1);
     if (!last_block_done(&e.tickets[(size_t)b * 4 + 0], UPDATE_G)) return;
     __shared__ int s_patch;
@@ -112,6 +118,7 @@ __global__ void __launch_bounds__(UPDATE_THREADS) k_update(EngineDev e, int n_sc
         const int ww = e.map_window * e.map_window / 32;
         unsigned* o = e.occ_win + (size_t)b * ww;
         for (int i = threadIdx.x; i < ww; i += UPDATE_THREADS) o[i] = 0u;
+        occ_far_clear(e, b, threadIdx.x);
     }
     if (!s_patch) return;
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
@@ -239,6 +246,43 @@ struct RawImage {        // the engine's z-buffer as close/fill input
 
 // semseg addjust_map_2 (ss/ins:202-224): map cells (value != 0) that hold a live scene point with z < 1.5 and a
 // non-ground label count as value 4 for this slot.  Kept as a per-scan bit window instead of rewriting the map.
+// The reference indexes map[ix][iy] with the truncated world coordinates as they are: a negative index wraps around
+// like any numpy index (cell size + ix), an index past the end raises IndexError (-> R3D_ERR_INDEX).  Wrapped cells
+// lie far from the scan, outside the bit window: they go to a short per-scan list (occ_far).
+__device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, ScanState& s, const double* T, int p) {
+    const size_t base = (size_t)b * e.P;
+    if (!e.alive[base + p]) return;
+    const unsigned lab = e.label[base + p];
+    bool ground = false;
+    for (int i = 0; i < e.n_road_indexes; ++i) ground |= lab == (unsigned)e.road_indexes[i];
+    if (ground) return;
+    double x, y, z;
+    load_xyz(e, b, p, s.n0, x, y, z);
+    if (!(z < 1.5)) return;
+    const double wx = add(add(add(mul(T[0], x), mul(T[1], y)), mul(T[2], z)), T[3]);
+    const double wy = add(add(add(mul(T[4], x), mul(T[5], y)), mul(T[6], z)), T[7]);
+    int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
+    int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
+    if (ix >= e.ss_sx || iy >= e.ss_sy || ix < -e.ss_sx || iy < -e.ss_sy) { set_error(s, R3D_ERR_INDEX); return; }   // IndexError
+    if (ix < 0) ix += e.ss_sx;                                   // numpy negative index
+    if (iy < 0) iy += e.ss_sy;
+    if (e.ss_map[(size_t)ix * e.ss_sy + iy] == 0) return;
+    const int lx = ix - s.win_x0, ly = iy - s.win_y0;
+    if (lx < 0 || ly < 0 || lx >= e.map_window || ly >= e.map_window) {
+        int* far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);        // small set: [0] = non-empty flag, then cells or -1
+        const int cell = ix * e.ss_sy + iy;
+        far[0] = 1;
+        for (int i = 0; i < OCC_FAR_CAP; ++i) {
+            const int old = atomicCAS(&far[1 + (cell + i) % OCC_FAR_CAP], -1, cell);
+            if (old == -1 || old == cell) return;
+        }
+        set_error(s, R3D_ERR_CAPACITY);
+        return;
+    }
+    const int bit = lx * e.map_window + ly;
+    atomicOr(&e.occ_win[(size_t)b * (e.map_window * e.map_window / 32) + (bit >> 5)], 1u << (bit & 31));
+}
+
 __global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_update[b]) return;
@@ -247,26 +291,5 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int 
     const int p0 = blockIdx.x * CHUNK;
     if (p0 >= n) return;
     const double* T = e.poses + (size_t)b * 16;
-    const size_t base = (size_t)b * e.P;
-    unsigned* o = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) {
-        if (!e.alive[base + p]) continue;
-        const unsigned lab = e.label[base + p];
-        bool ground = false;
-        for (int i = 0; i < e.n_road_indexes; ++i) ground |= lab == (unsigned)e.road_indexes[i];
-        if (ground) continue;
-        double x, y, z;
-        load_xyz(e, b, p, s.n0, x, y, z);
-        if (!(z < 1.5)) continue;
-        const double wx = add(add(add(mul(T[0], x), mul(T[1], y)), mul(T[2], z)), T[3]);
-        const double wy = add(add(add(mul(T[4], x), mul(T[5], y)), mul(T[6], z)), T[7]);
-        const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
-        const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
-        if (ix < 0 || iy < 0 || ix >= e.ss_sx || iy >= e.ss_sy) continue;   // reference: IndexError / wrap-around
-        if (e.ss_map[(size_t)ix * e.ss_sy + iy] == 0) continue;
-        const int lx = ix - s.win_x0, ly = iy - s.win_y0;
-        if (lx < 0 || ly < 0 || lx >= e.map_window || ly >= e.map_window) { set_error(s, R3D_ERR_CAPACITY); continue; }
-        const int bit = lx * e.map_window + ly;
-        atomicOr(&o[bit >> 5], 1u << (bit & 31));
-    }
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) adjust_map_point(e, b, s, T, p);
 }

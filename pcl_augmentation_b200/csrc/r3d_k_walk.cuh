@@ -1,0 +1,568 @@
+// Kernels of the batched Real3D-Aug engine, part: the per-scan persistent walker.
+// Included by r3d_engine_kernels.cuh (inside namespace r3d, after the staged round kernels); not a standalone header.
+// ------------------------------------------------------------------------------------------------ walker
+// ONE CTA per scan runs the reference's whole per-scan `while` loop (od/ins:375-614, ss/ins:371-586) without returning
+// to the host: scheduling step (A13) -> apply the last vis_px mask / refresh the range image around the inserted object
+// (A11, A12, A3, A4) -> placement search of the next cut object (A5-A10) -> occlusion count (A11) -> selection and
+// insertion (A12) -> next step.  Scans are independent, so the CTAs never talk to each other: no
+// co-residency requirement, no round barrier over the batch (the staged round kernels make every scan wait for the
+// slowest one of every stage), no launch boundary between dependent stages, and the candidates of a try are visited
+// in ORDERED WINDOWS with a real early exit at the first candidate that keeps min_points (od/ins:530-561).
+// The once-per-scan streaming work (spherical ingest, indices, first full projection + close/fill, output
+// compaction) stays in batch-wide HBM-bound kernels before / after this one.
+#ifndef R3D_WALK_THREADS
+#define R3D_WALK_THREADS 512
+#endif
+#ifndef R3D_WALK_CTAS_PER_SM
+#define R3D_WALK_CTAS_PER_SM 2
+#endif
+constexpr int WALK_THREADS = R3D_WALK_THREADS;
+constexpr int WALK_CTAS_PER_SM = R3D_WALK_CTAS_PER_SM;
+constexpr int WALK_W = WALK_THREADS / GRP;            // candidates per window = 8-lane groups of the CTA
+constexpr int WALK_SEL_PTS = 1024;                    // object points / tile pixels the selection keeps in shared memory
+constexpr int WALK_SEL_TILE = 4096;
+constexpr int WALK_SEL_KEYS = 1024;                   // next_pow2(WALK_SEL_PTS)
+constexpr int WALK_OCC_LANES = 64;                    // threads that count one feasible candidate's visible points
+constexpr int WALK_OCC_PAR = WALK_THREADS / WALK_OCC_LANES;
+constexpr int WALK_NWARPS = WALK_THREADS / 32;
+
+// dynamic shared memory: [object x | y | z (fp64)] [ordered candidate list] [prefilter flags] [scratch]; the scratch
+// holds the visible-pixel bit image of the exact occlusion count or the close/fill tile; the selection (after the
+// last window of a try) reuses everything from offset 0
+struct WalkSmem { size_t list_off, flags_off, scratch_off, total; };
+__host__ __device__ __forceinline__ size_t walk_sel_bytes() {
+    return (size_t)WALK_SEL_KEYS * 8 + (size_t)WALK_SEL_PTS * 8 + (size_t)WALK_SEL_TILE * 8 + (size_t)WALK_SEL_PTS * 4 +
+           2 * (size_t)(WALK_SEL_TILE / 32) * 4 + 16;
+}
+__host__ __device__ __forceinline__ WalkSmem walk_smem_layout(int K, int dwords) {
+    WalkSmem L;
+    size_t o = (size_t)3 * OBJ_SMEM_PTS * 8;
+    L.list_off = o; o += ((size_t)(K + 1) * 2 + 15) & ~(size_t)15;
+    L.flags_off = o; o += ((size_t)(K + 1) + 15) & ~(size_t)15;
+    L.scratch_off = o;
+    const size_t occ = (size_t)dwords * 4;
+    const size_t cf = (size_t)CF_SH * CF_SW * 8 + 4 * (size_t)CF_SH * CF_WORDS * 4;
+    o += occ > cf ? occ : cf;
+    const size_t sel = walk_sel_bytes();
+    L.total = o > sel ? o : sel;
+    return L;
+}
+
+struct WalkCtl {                 // control block of the CTA (static shared memory)
+    int apply, project, tryact;
+    int n_list, nfw, n_feas, found;
+    int found_k, last_k;
+    double found_level, last_level;
+    double dz_run, dz_next;      // semseg: the z shift carried from yaw to yaw (ss/fs:146-147)
+    int changed;
+    int cnt_lo[WALK_OCC_PAR], cnt_hi[WALK_OCC_PAR];
+    int exact_cnt;
+    int wk[WALK_W];              // rotation of the window's candidates
+    unsigned char wflag[WALK_W];
+    double wlevel[WALK_W];
+    int wfeas[WALK_W];           // window-local indices of the feasible candidates, in rotation order
+    double wdz[WALK_W];          // semseg fixed point: the shift candidate i was (or must be) tested under
+    unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
+    ObjBox ob;
+    int s_warp[WALK_NWARPS];
+    int upd_full, upd_patch, rect[4];
+    unsigned long long el_min, el_max;
+};
+
+// ---- A4 on a pixel rectangle, any CTA size (the batch-wide kernel is r3d_closefill.cuh): tiles of CF_TH x CF_TW
+// outputs staged with their halo in shared memory, bit-row morphology, ordered fp64 neighbour mean
+__device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsigned char* scratch) {
+    unsigned long long (*s_raw)[CF_SW] = reinterpret_cast<unsigned long long (*)[CF_SW]>(scratch);
+    unsigned (*s_one)[CF_WORDS] = reinterpret_cast<unsigned (*)[CF_WORDS]>(scratch + (size_t)CF_SH * CF_SW * 8);
+    unsigned (*s_in)[CF_WORDS] = s_one + CF_SH;
+    unsigned (*s_dil)[CF_WORDS] = s_in + CF_SH;
+    unsigned (*s_ero)[CF_WORDS] = s_dil + CF_SH;
+    const int H = e.rows, W = e.cols, tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = nt >> 5;
+    const unsigned long long* raw = e.zraw + (size_t)b * e.hw;
+    double* out = e.smooth + (size_t)b * e.hw;
+    auto left = [](const unsigned* a, int w) { return (a[w] << 1) | (w > 0 ? a[w - 1] >> 31 : 0u); };
+    auto right = [](const unsigned* a, int w) { return (a[w] >> 1) | (a[w + 1] << 31); };
+    bool far = false;
+    for (int r0 = rect[0]; r0 <= rect[1]; r0 += CF_TH)
+        for (int c0 = rect[2]; c0 <= rect[3]; c0 += CF_TW) {
+            for (int i = tid; i < CF_SH * CF_SW; i += nt) {
+                const int lr = i / CF_SW, lc = i % CF_SW;
+                const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
+                s_raw[lr][lc] = (r >= 0 && r < H && c >= 0 && c < W) ? raw[(size_t)r * W + c] : R3D_EMPTY_U64;
+            }
+            if (tid < CF_SH) { s_one[tid][3] = 0u; s_in[tid][3] = 0u; s_dil[tid][3] = ~0u; }
+            __syncthreads();
+            for (int u = warp; u < CF_SH * 3; u += nwarps) {          // bit rows of the staged tile
+                const int lr = u / 3, w = u % 3, lc = w * 32 + lane;
+                const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
+                const bool inside = lc < CF_SW && r >= 0 && r < H && c >= 0 && c < W;
+                const bool hit = inside && s_raw[lr][min(lc, CF_SW - 1)] != R3D_EMPTY_U64;
+                const unsigned b_one = __ballot_sync(0xffffffffu, hit), b_in = __ballot_sync(0xffffffffu, inside);
+                if (lane == 0) { s_one[lr][w] = b_one; s_in[lr][w] = b_in; }
+            }
+            __syncthreads();
+            for (int t = tid; t < (CF_SH - 4) * 3; t += nt) {
+                const int lr = 2 + t / 3, w = t % 3;
+                unsigned d = 0u;
+#pragma unroll
+                for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_one[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
+                s_dil[lr][w] = d | ~s_in[lr][w];
+            }
+            __syncthreads();
+            for (int t = tid; t < CF_TH * 3; t += nt) {
+                const int lr = CF_HR + t / 3, w = t % 3;
+                unsigned er = ~0u;
+#pragma unroll
+                for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_dil[lr + dr]; er &= a[w] & left(a, w) & right(a, w); }
+                s_ero[lr][w] = er;
+            }
+            __syncthreads();
+            for (int i = tid; i < CF_TH * CF_TW; i += nt) {
+                const int lr = i / CF_TW, lc = i % CF_TW;
+                const int r = r0 + lr, c = c0 + lc;
+                if (r >= H || c >= W) continue;
+                const int sr = lr + CF_HR, sc = lc + CF_HC;
+                const bool er = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
+                const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
+                double tv = one ? bits_dbl(s_raw[sr][sc]) : kEmptyRange;          // od/ins:100: empty = 500
+                if (er && !one) {                                                // cl:41-43
+                    int neighbors = 0;
+                    double sum = 0.0;
+                    const int q = sc - 1, qw = q >> 5, qb = q & 31;
+#pragma unroll
+                    for (int dr = -2; dr <= 2; ++dr) {                           // cl:46-51, (drow, dcol) order
+                        const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
+                        if (m & 1u) { neighbors += 1; sum = add(sum, bits_dbl(s_raw[sr + dr][sc - 1])); }
+                        if (m & 2u) { neighbors += 1; sum = add(sum, bits_dbl(s_raw[sr + dr][sc])); }
+                        if (m & 4u) { neighbors += 1; sum = add(sum, bits_dbl(s_raw[sr + dr][sc + 1])); }
+                    }
+                    if (neighbors > 0) tv = __ddiv_rn(sum, (double)neighbors);   // cl:57
+                }
+                out[(size_t)r * W + c] = tv;
+                far |= tv > kEmptyRange;
+            }
+            __syncthreads();                                  // the tile buffers are reused by the next tile
+        }
+    if (far) atomicOr(&e.far_arr[b], 1);
+}
+
+// ---- A2 + A3 for the whole scan inside the CTA: the rare slot whose elevation range moved (the first projection of
+// every scan is done batch-wide by k_minmax / k_clear_images / k_project before the walker starts)
+__device__ void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)b * e.P;
+    const int n = s.n0 + s.n_tail;
+    if (tid == 0) { c.el_min = R3D_EMPTY_U64; c.el_max = 0ull; }
+    __syncthreads();
+    unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
+    for (int p = tid; p < n; p += nt)
+        if (e.alive[base + p]) { const unsigned long long bits = dbl_bits(e.el[base + p]); lmin = min(lmin, bits); lmax = max(lmax, bits); }
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((tid & 31) == 0 && lmax >= lmin) { atomicMin(&c.el_min, lmin); atomicMax(&c.el_max, lmax); }
+    __syncthreads();
+    const unsigned long long mn = c.el_min, mx = c.el_max;
+    if (tid == 0) {
+        s.min_el_bits = mn; s.max_el_bits = mx;
+        e.far_arr[b] = 0;
+        if (mn == R3D_EMPTY_U64) set_error(s, R3D_ERR_ASSERT);
+        s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(mx), bits_dbl(mn));
+        atomicAdd(&e.stats[11], 1ull);
+    }
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    for (int i = tid; i < e.hw; i += nt) z[i] = R3D_EMPTY_U64;
+    __syncthreads();
+    const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(mx), bits_dbl(mn));
+    for (int p = tid; p < n; p += nt) {
+        int pix = -1;
+        if (e.alive[base + p]) {
+            const int row = bin_row(g, e.el[base + p]);
+            if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);                          // od/ins:111
+            else { pix = row * g.cols + (int)e.col[base + p]; atomicMin(&z[pix], dbl_bits(e.r[base + p])); }
+        }
+        e.pix[base + p] = pix;
+    }
+}
+
+// ---- semseg addjust_map_2 (ss/ins:202-224) for the scan's live points (same rule as k_adjust_map)
+__device__ void walk_adjust_map(const EngineDev& e, int b, ScanState& s) {
+    const int n = s.n0 + s.n_tail;
+    const double* T = e.poses + (size_t)b * 16;
+    for (int p = threadIdx.x; p < n; p += blockDim.x) adjust_map_point(e, b, s, T, p);
+}
+
+// ---- slot update: what k_update + the refresh kernels of a staged round do for one scan
+__device__ void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
+                            unsigned char* scratch) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const size_t base = (size_t)b * e.P;
+    const bool ext = do_apply && apply_vis_mask(e, b, s, tid, nt);
+    const int extreme = __syncthreads_or(ext);
+    if (tid == 0) {
+        int full = 0, patch = 0;
+        int* rect = c.rect;
+        rect[0] = 0; rect[1] = -1; rect[2] = 0; rect[3] = -1;
+        if (do_update) {
+            const bool extended = s.new_min_bits < s.min_el_bits || s.new_max_bits > s.max_el_bits;
+            full = s.first || extreme || extended || e.far_arr[b] || e.force_full;
+            patch = !full;
+            if (full) {
+                rect[0] = 0; rect[1] = e.rows - 1; rect[2] = 0; rect[3] = e.cols - 1;
+            } else {
+                rect[0] = max(s.d_r0 - 4, 0); rect[1] = min(s.d_r1 + 4, e.rows - 1);
+                rect[2] = max(s.d_c0 - 2, 0); rect[3] = min(s.d_c1 + 2, e.cols - 1);
+            }
+            s.first = 0;
+            s.new_min_bits = R3D_EMPTY_U64; s.new_max_bits = 0ull;
+            atomicAdd(&e.stats[full ? 0 : 3], 1ull);
+        }
+        s.extreme_removed = 0;
+        c.upd_full = full; c.upd_patch = patch;
+    }
+    __syncthreads();
+    if (do_update && e.task == 1) {
+        const int ww = e.map_window * e.map_window / 32;
+        unsigned* o = e.occ_win + (size_t)b * ww;
+        for (int i = tid; i < ww; i += nt) o[i] = 0u;
+        occ_far_clear(e, b, tid);
+        __syncthreads();
+    }
+    if (c.upd_patch) {
+        unsigned long long* z = e.zraw + (size_t)b * e.hw;
+        const unsigned* dm = e.dmask + (size_t)b * e.dwords;
+        if (s.d_r1 >= s.d_r0 && s.d_c1 >= s.d_c0) {
+            const int nw = (s.d_c1 >> 5) - (s.d_c0 >> 5) + 2, nrow = s.d_r1 - s.d_r0 + 1;
+            for (int i = tid; i < nrow * nw; i += nt) {
+                const int r = s.d_r0 + i / nw;
+                const int w = ((r * e.cols + s.d_c0) >> 5) + i % nw;
+                if (w > ((r * e.cols + s.d_c1) >> 5)) continue;
+                unsigned m = dm[w];
+                while (m) { const int bit = __ffs(m) - 1; m &= m - 1; z[(w << 5) + bit] = R3D_EMPTY_U64; }
+            }
+        }
+        __syncthreads();
+        if (s.apply_flag)                                        // points appended by the accept being applied
+            for (int p = s.n0 + s.tail_before + tid; p < s.n0 + s.n_tail; p += nt)
+                if (e.alive[base + p]) atomicMin(&z[e.pix[base + p]], dbl_bits(e.r[base + p]));
+    } else if (c.upd_full) {
+        walk_full_reproject(e, b, s, c);
+    }
+    __syncthreads();
+    if (c.rect[1] >= c.rect[0] && c.rect[3] >= c.rect[2]) walk_close_fill(e, b, c.rect, scratch);
+    if (do_update && e.task == 1) { __syncthreads(); walk_adjust_map(e, b, s); }
+    __syncthreads();
+}
+
+// ---- A5 + A6a + A7 + A8/A9 for ONE yaw candidate of an OD try, one 8-lane group (the chain the staged kernels
+// k_onmap_full -> k_road_level -> k_collide run as three launches)
+__device__ __noinline__ unsigned walk_candidate_od(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const double* ox,
+                                                   const double* oy, int k, int gl, unsigned gm, double& level) {
+    const ClassCfg& cc = e.classes[ob.cls];
+    const int count = ob.count, msel = cc.map_sel;
+    const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
+    const int sx = dims[0], sy = dims[1];
+    const double mx = (double)dims[2], my = (double)dims[3];
+    const unsigned char* map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
+    const double c = e.cos_k[k], sn = e.sin_k[k];
+    bool any_in = false, bad = false;
+    for (int i0 = 0; i0 < count; i0 += 4 * GRP) {                      // od/fs:267-279 on every object point
+        double x[4], y[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = min(i0 + u * GRP + gl, count - 1);           // the clamped repeats change nothing
+            x[u] = ox[i]; y[u] = oy[i];
+        }
+        unsigned char v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            v[u] = 1;
+            const double gx = sub(sub(mul(c, x[u]), mul(sn, y[u])), mx), gy = sub(add(mul(sn, x[u]), mul(c, y[u])), my);
+            if (!(gx < 0.0 || gx >= (double)sx || gy < 0.0 || gy >= (double)sy)) {
+                any_in = true; v[u] = __ldg(&map[(size_t)((int)gx) * sy + (int)gy]);
+            }
+        }
+        bad = v[0] != 1 || v[1] != 1 || v[2] != 1 || v[3] != 1;
+        if (__ballot_sync(gm, bad) & gm) { bad = true; break; }       // od/fs:277-279
+    }
+    const bool on = (__ballot_sync(gm, any_in) & gm) != 0u && !bad;
+    if (!on) return 0u;
+    const SurfaceSet surf = load_surface(cc);
+    if (!group_road_level(e, b, surf, sub(mul(c, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(c, ob.cy)), gl, gm, level))
+        return CF_ONMAP;                                               // od/fs:281-285
+    if (group_collides(e, b, s, ob, cc, c, sn, level, gl, gm)) return CF_ONMAP | CF_HOK | CF_COLLIDE;
+    return CF_ONMAP | CF_HOK;
+}
+
+// ---- semseg window: A6b with the carried z shift as a fixed-point iteration over the window's yaws (see k_onmap_ss),
+// the road level searched only for the yaws that pass the map test, then A8/A9
+__device__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
+                               const double* oz, int base, int nw) {
+    const int tid = threadIdx.x, g = tid / GRP, gl = tid % GRP;
+    const unsigned gm = group_mask();
+    const ObjBox& ob = c.ob;
+    const ClassCfg& cc = e.classes[ob.cls];
+    if (tid < nw) {
+        c.wk[tid] = base + tid + 1; c.wdz[tid] = c.dz_run; c.wpass[tid] = 0; c.wtodo[tid] = 1; c.whas[tid] = 0; c.whok[tid] = 0;
+        c.wlevel[tid] = 0.0; c.wflag[tid] = 0;
+    }
+    __syncthreads();
+    const double* T = e.poses + (size_t)b * 16;
+    SsMapTest m;
+    m.t00 = T[0]; m.t01 = T[1]; m.t02 = T[2]; m.t03 = T[3]; m.t10 = T[4]; m.t11 = T[5]; m.t12 = T[6]; m.t13 = T[7];
+    m.okmask = cc.map_ok_mask;
+    m.occ = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
+    m.far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);
+    const int k = base + g + 1;
+    const double cs = g < nw ? e.cos_k[k] : 1.0, sn = g < nw ? e.sin_k[k] : 0.0;
+    for (int sweep = 0; sweep <= nw; ++sweep) {
+        if (g < nw && c.wtodo[g]) {                               // ss/fs:231-248 under the assumed shift
+            const double dz = c.wdz[g];
+            bool bad = false;
+            for (int i0 = 0; i0 < ob.count && !bad; i0 += GRP) {
+                const int i = i0 + gl;
+                const bool off = i < ob.count && ss_point_off_map(e, s, m, ox[i], oy[i], oz[i], cs, sn, dz);
+                bad = (__ballot_sync(gm, off) & gm) != 0u;
+            }
+            if (gl == 0) c.wpass[g] = bad ? 0 : 1;
+        }
+        __syncthreads();
+        if (g < nw && c.wpass[g] && !c.whas[g]) {                 // ss/fs:250: correct_height of a yaw on the map
+            const SurfaceSet surf = load_surface(cc);
+            double level = 0.0;
+            const bool ok = group_road_level(e, b, surf, sub(mul(cs, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(cs, ob.cy)), gl,
+                                             gm, level);
+            if (gl == 0) { c.whas[g] = 1; c.whok[g] = ok ? 1 : 0; c.wlevel[g] = level; }
+        }
+        __syncthreads();
+        if (tid == 0) {                                           // the ordered walk over the flags (ss/fs:144-148)
+            double run = c.dz_run;
+            int changed = 0;
+            for (int i = 0; i < nw; ++i) {
+                const bool redo = run != c.wdz[i];
+                c.wtodo[i] = redo;
+                if (redo) { c.wdz[i] = run; changed = 1; }
+                if (c.wpass[i] && c.whok[i]) run = sub(c.wlevel[i], ob.cz);
+            }
+            c.changed = changed; c.dz_next = run;
+        }
+        __syncthreads();
+        if (!c.changed) break;
+    }
+    if (g < nw) {
+        unsigned f = 0u;
+        if (c.wpass[g]) {
+            f = CF_ONMAP;
+            if (c.whok[g]) {
+                f |= CF_HOK;
+                if (group_collides(e, b, s, ob, cc, cs, sn, c.wlevel[g], gl, gm)) f |= CF_COLLIDE;
+            }
+        }
+        if (gl == 0) c.wflag[g] = (unsigned char)f;
+    }
+    if (tid == 0) c.dz_run = c.dz_next;
+}
+
+// ---- exact A11 count of one candidate with the whole CTA (visible-pixel bit image in shared memory), for the
+// candidates the two-sided bound of walk_try cannot decide
+__device__ int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int k, double level, unsigned* bits) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const ObjBox& ob = c.ob;
+    const ImageGeom g = s.geom;
+    const double* smooth = e.smooth + (size_t)b * e.hw;
+    int* pixbuf = e.occ_pix + (size_t)b * OCC_G * e.max_obj_points;
+    for (int i = tid; i < e.dwords; i += nt) bits[i] = 0u;
+    if (tid == 0) { c.exact_cnt = 0; atomicAdd(&e.stats[10], 1ull); }
+    __syncthreads();
+    const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(level, ob.cz);
+    for (int i = tid; i < ob.count; i += nt) {
+        const ObjProj o = project_obj_point(e, ob, g, i, cs, sn, dz, s);
+        pixbuf[i] = o.pix;
+        if (o.pix >= 0 && o.r < smooth[o.pix]) atomicOr(&bits[o.pix >> 5], 1u << (o.pix & 31));
+    }
+    __syncthreads();
+    int cnt = 0;
+    for (int i = tid; i < ob.count; i += nt) {
+        const int pix = pixbuf[i];
+        if (pix >= 0 && (bits[pix >> 5] & (1u << (pix & 31)))) ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((tid & 31) == 0 && cnt) atomicAdd(&c.exact_cnt, cnt);
+    __syncthreads();
+    const int v = c.exact_cnt;
+    __syncthreads();
+    return v;
+}
+
+// ---- one tried cut object (od/ins:430-561)
+__device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, unsigned char* dyn, const WalkSmem& L) {
+    const int K = e.K, tid = threadIdx.x, nt = blockDim.x;
+    double* s_ox = reinterpret_cast<double*>(dyn);
+    double* s_oy = s_ox + OBJ_SMEM_PTS;
+    double* s_oz = s_oy + OBJ_SMEM_PTS;
+    unsigned short* s_list = reinterpret_cast<unsigned short*>(dyn + L.list_off);
+    unsigned char* s_flags = dyn + L.flags_off;
+    unsigned char* scratch = dyn + L.scratch_off;
+    if (tid == 0) {
+        c.ob = e.obj[s.cur_obj];
+        e.try_obj[b] = c.ob;
+        c.n_feas = 0; c.found = -1; c.last_k = 0; c.last_level = 0.0; c.dz_run = 0.0;
+        atomicAdd(&e.stats[1], 1ull);
+    }
+    __syncthreads();
+    const ObjBox& ob = c.ob;
+    const ClassCfg& cc = e.classes[ob.cls];
+    const double *ox = e.obj_x + ob.first, *oy = e.obj_y + ob.first, *oz = e.obj_z + ob.first;
+    if (ob.count <= OBJ_SMEM_PTS) {
+        for (int i = tid; i < ob.count; i += nt) { s_ox[i] = ox[i]; s_oy[i] = oy[i]; s_oz[i] = oz[i]; }
+        ox = s_ox; oy = s_oy; oz = s_oz;
+    }
+    int n_list = K;
+    if (e.task == 0) {                   // A5 + A6a prefilter: the first few points decide most rotations (off the road)
+        for (int k = tid; k <= K; k += nt) s_flags[k] = 0;
+        OdMap m;
+        {
+            const int msel = cc.map_sel;
+            const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
+            m.sx = dims[0]; m.sy = dims[1]; m.mx = (double)dims[2]; m.my = (double)dims[3];
+            m.map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
+        }
+        __syncthreads();
+        const int npre = min(ob.count, ONMAP_PRE_PTS);
+        for (int k = 1 + tid; k <= K; k += nt) {
+            bool any_in = false, bad = false;
+            thread_onmap_od(m, ox, oy, 0, npre, e.cos_k[k], e.sin_k[k], any_in, bad);
+            if (!bad) s_flags[k] = CF_PRE;
+        }
+        __syncthreads();
+        n_list = block_compact(s_flags, K, CF_PRE, CF_PRE, s_list, c.s_warp);
+        if (tid == 0) atomicAdd(&e.stats[6], (unsigned long long)n_list);
+    } else {
+        __syncthreads();
+    }
+    const int g = tid / GRP, gl = tid % GRP;
+    const unsigned gm = group_mask();
+    const int min_pts = max(cc.min_points, 1);                     // od/ins:530: V == 0 or V < min_points -> rejected
+    const ImageGeom geom = s.geom;
+    const double* smooth = e.smooth + (size_t)b * e.hw;
+    for (int base = 0; base < n_list; base += WALK_W) {
+        const int nw = min(WALK_W, n_list - base);
+        // stage A: placement tests of the window's candidates, one 8-lane group each
+        if (e.task == 0) {
+            if (g < nw) {
+                const int k = s_list[base + g];
+                double level = 0.0;
+                const unsigned f = walk_candidate_od(e, b, s, ob, ox, oy, k, gl, gm, level);
+                if (gl == 0) { c.wk[g] = k; c.wflag[g] = (unsigned char)f; c.wlevel[g] = level; }
+            }
+        } else {
+            walk_window_ss(e, b, s, c, ox, oy, oz, base, nw);
+        }
+        __syncthreads();
+        // stage B: the window's feasible candidates in rotation order (od/fs:288-296)
+        if (tid == 0) {
+            int nfw = 0;
+            for (int i = 0; i < nw; ++i)
+                if ((c.wflag[i] & (CF_ONMAP | CF_HOK | CF_COLLIDE)) == (CF_ONMAP | CF_HOK)) c.wfeas[nfw++] = i;
+            c.nfw = nfw;
+            if (nfw) { c.last_k = c.wk[c.wfeas[nfw - 1]]; c.last_level = c.wlevel[c.wfeas[nfw - 1]]; }
+            c.n_feas += nfw;
+            atomicAdd(&e.stats[9], 1ull);
+        }
+        __syncthreads();
+        // stage C: A11 in rotation order with an early exit.  lo = points that are individually closer than the
+        // scene, hi = points that fall into the image: lo <= V <= hi, and lo == 0 <=> V == 0, so most candidates are
+        // decided without building the visible-pixel image
+        const int nfw = c.nfw;
+        const int sg = tid / WALK_OCC_LANES, sl = tid % WALK_OCC_LANES;
+        for (int j0 = 0; j0 < nfw && c.found < 0; j0 += WALK_OCC_PAR) {
+            if (tid < WALK_OCC_PAR) { c.cnt_lo[tid] = 0; c.cnt_hi[tid] = 0; }
+            __syncthreads();
+            const int j = j0 + sg;
+            if (j < nfw) {
+                const int i = c.wfeas[j], k = c.wk[i];
+                const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(c.wlevel[i], ob.cz);
+                int lo = 0, hi = 0;
+                for (int p = sl; p < ob.count; p += WALK_OCC_LANES) {
+                    const ObjProj o = project_obj_point(e, ob, geom, p, cs, sn, dz, s);
+                    if (o.pix >= 0) { ++hi; if (o.r < smooth[o.pix]) ++lo; }
+                }
+                for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+                if ((tid & 31) == 0) { if (lo) atomicAdd(&c.cnt_lo[sg], lo); if (hi) atomicAdd(&c.cnt_hi[sg], hi); }
+            }
+            __syncthreads();
+            int found = -1;
+            for (int q = 0; q < WALK_OCC_PAR && j0 + q < nfw; ++q) {          // uniform over the CTA
+                const int lo = c.cnt_lo[q], hi = c.cnt_hi[q];
+                bool ok = lo >= min_pts;
+                if (!ok && lo > 0 && hi >= min_pts) {
+                    const int i = c.wfeas[j0 + q];
+                    ok = walk_exact_visible(e, b, s, c, c.wk[i], c.wlevel[i], reinterpret_cast<unsigned*>(scratch)) >= min_pts;
+                }
+                if (ok) { found = j0 + q; break; }
+            }
+            if (found >= 0 && tid == 0) {
+                const int i = c.wfeas[found];
+                c.found = found; c.found_k = c.wk[i]; c.found_level = c.wlevel[i];
+            }
+            __syncthreads();
+        }
+        if (c.found >= 0) break;
+    }
+    // A11 + A12 for the chosen candidate: the first one that keeps min_points, else the last feasible one (its
+    // vis_px still deletes scene points in the reference, od/ins:472-501)
+    const int n_feas = c.n_feas;
+    if (tid == 0) s.n_feasible = n_feas;
+    if (n_feas > 0) {
+        const bool accepted = c.found >= 0;
+        const int k = accepted ? c.found_k : c.last_k;
+        if (tid == 0) e.cand_level[(size_t)b * (K + 1) + k] = accepted ? c.found_level : c.last_level;
+        __syncthreads();
+        select_emit_body(e, b, s, k, accepted,
+                         sel_scratch(reinterpret_cast<unsigned long long*>(dyn), WALK_SEL_KEYS, WALK_SEL_PTS, WALK_SEL_TILE));
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(const __grid_constant__ EngineDev e, int n_scans) {
+    const int b = blockIdx.x;
+    if (b >= n_scans) return;
+    extern __shared__ __align__(16) unsigned char w_dyn[];
+    __shared__ WalkCtl c;
+    ScanState& s = e.st[b];
+    const WalkSmem L = walk_smem_layout(e.K, e.dwords);
+    int steps = 0;
+    for (;;) {
+        if (threadIdx.x == 0) {
+            int apply = 0, project = 0, tryact = 0;
+            ctrl_advance(e, b, s, apply, project, tryact);
+            c.apply = apply; c.project = project; c.tryact = tryact;
+            if (apply) atomicAdd(&e.stats[2], 1ull);
+        }
+        __syncthreads();
+        const int apply = c.apply, project = c.project, tryact = c.tryact;
+        if (apply || project) walk_update(e, b, s, c, apply, project, w_dyn + L.scratch_off);
+        if (!tryact) break;                              // PH_DONE or PH_ERROR
+        walk_try(e, b, s, c, w_dyn, L);
+        ++steps;
+    }
+    if (threadIdx.x == 0) atomicMax(&e.stats[8], (unsigned long long)steps);
+}
+
+// what the first round of the staged engine sets up, for the walker: every scan is listed for the batch-wide full
+// projection and every tile for close/fill; the state machine starts with its first range image already built
+__global__ void k_walk_prepare(EngineDev e, int n_scans) {
+    const int tiles = e.cf_tiles;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_scans * tiles; i += gridDim.x * blockDim.x) e.cf_tasks[i] = i;
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_scans; b += gridDim.x * blockDim.x) {
+        e.full_list[b] = b;
+        e.gate_update[b] = 1;                            // k_adjust_map (semseg) runs for every scan
+        if (e.task == 1) for (int i = 0; i <= OCC_FAR_CAP; ++i) occ_far_clear(e, b, i);
+        ScanState& s = e.st[b];
+        s.first = 0; s.scene_changed = 0;
+        s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
+        atomicAdd(&e.stats[0], 1ull);
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) { e.work_cnt[0] = n_scans; e.work_cnt[1] = n_scans * tiles; e.stats[8] = 0ull; }
+}

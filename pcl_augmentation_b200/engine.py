@@ -62,7 +62,7 @@ class Real3DEngine:
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
                  map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=120, force_full_projection=False,
-                 sub_batches=0, fetch_labels=None, round_graphs=True, candidate_window=True):
+                 sub_batches=0, fetch_labels=None, round_graphs=True, candidate_window=True, staged_rounds=False):
         _lib.require_cuda()
         self.lib = _lib.load()
         self.task = task
@@ -88,9 +88,12 @@ class Real3DEngine:
             cfg.road_indexes[i] = int(v)
         cfg.map_window = int(map_window)
         cfg.grid_half, cfg.grid_cell = int(grid_half), float(grid_cell)
-        # bit 0: full re-projection every slot; bit 1: no round graphs; bits 8-12: concurrent sub-batches (0 = library default)
+        # bit 0: full re-projection every slot; bit 1: no round graphs; bit 2: no ordered early-out window; bit 3: the
+        # staged round kernels instead of the per-scan persistent walker (needed by debug_candidates, which wants every
+        # candidate of a try evaluated); bits 8-12: concurrent sub-batches of the staged rounds (0 = library default)
+        self.staged_rounds = bool(staged_rounds) or not candidate_window
         cfg.flags = ((1 if force_full_projection else 0) | (0 if round_graphs else 2) | (0 if candidate_window else 4)
-                     | ((int(sub_batches) & 31) << 8))
+                     | (8 if self.staged_rounds else 0) | ((int(sub_batches) & 31) << 8))
         r2, ok = bx.search_radii()
         for i in range(50):
             cfg.radii_sq[i] = float(r2[i])
@@ -250,8 +253,10 @@ class Real3DEngine:
         self._in_bytes = staged['total'] * 18
         _lib.check(self.lib.r3d_engine_load_batch(self.handle, C.byref(b)), "load_batch")
 
-    def reset(self):
-        _lib.check(self.lib.r3d_engine_reset_batch(self.handle), "reset_batch")
+    def reset(self, from_raw_points=False):
+        """Re-arm the resident batch.  ``from_raw_points`` repeats the whole device path from the resident float4
+        points (spherical ingest, spatial indices) instead of only resetting the flags and the scheduling state."""
+        _lib.check(self.lib.r3d_engine_rearm_batch(self.handle, 1 if from_raw_points else 0), "rearm_batch")
 
     def run(self):
         _lib.check(self.lib.r3d_engine_run(self.handle), "run")
@@ -393,11 +398,13 @@ class Real3DEngine:
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
     def stats(self):
-        out = np.zeros(8, dtype=np.uint64)
-        _lib.check(self.lib.r3d_engine_stats(self.handle, out.ctypes.data), "stats")
+        out = np.zeros(16, dtype=np.uint64)
+        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 16), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
                 'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5]),
-                'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7])}
+                'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7]), 'max_steps_per_scan': int(out[8]),
+                'candidate_windows': int(out[9]), 'exact_occlusion_counts': int(out[10]),
+                'walker_full_reprojections': int(out[11])}
 
     def cuda_stream(self):
         import torch

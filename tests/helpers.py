@@ -19,6 +19,10 @@ def load_golden(name):
 def case_from_spec(spec):
     kw = dict(CASE_DEFAULTS)
     kw.update({k: v for k, v in spec.items() if k not in ("task", "seed")})
+    if isinstance(kw.get("shape"), (list, tuple)):
+        kw["shape"] = synth.ScanShape(*kw["shape"])
+    if "obj_range" in kw:
+        kw["obj_range"] = tuple(kw["obj_range"])
     return synth.make_case(spec["task"], spec["seed"], **kw)
 
 

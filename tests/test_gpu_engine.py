@@ -12,7 +12,12 @@ from tests.helpers import GOLDEN_SHAPE, case_from_golden, load_golden, parse_ins
 
 pytestmark = pytest.mark.gpu
 
-E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c"]
+E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c",
+       # BASELINE-size scans through the unmodified reference (120 000 / 124 992 points, 112 x 1440) and a class of very
+       # large, very close cut objects (7 880 - 15 709 points: global-scratch branches of the candidate selection)
+       "e2e_od_full", "e2e_ss_full", "e2e_ss_big"]
+# execution models of the engine: the per-scan persistent walker (default) and the staged round kernels
+MODES = [pytest.param(False, id="walker"), pytest.param(True, id="staged")]
 
 
 def make_engine(case, n_scans=1, max_points=None, **kw):
@@ -42,14 +47,17 @@ def assert_matches_oracle(case, got, ref, want, exact_tail=False):
         assert got.lines == ref["lines"]
 
 
+@pytest.mark.parametrize("staged", MODES)
 @pytest.mark.parametrize("name", E2E)
-def test_engine_matches_reference_run(name):
+def test_engine_matches_reference_run(name, staged):
     """Same seeded inputs and pre-drawn shuffles as the reference's own insertion.py run."""
     g = load_golden(name)
     spec, case = case_from_golden(g)
     pose = g["used_pose"] if "used_pose" in g.files else None
-    eng = make_engine(case)
+    eng = make_engine(case, staged_rounds=staged)
     got = eng.augment_batch([scan_input_from_case(case, pose)])[0]
+    if name == "e2e_ss_big":                       # > 4096 points and a pixel rectangle wider than the shared-memory tile
+        assert eng.stats()["select_global"] > 0
     eng.close()
     assert [(n, r) for n, r, _ in got.inserted] == parse_inserted(str(g["inserted"]))          # placement choices
     n0 = len(case.pcl5)
@@ -69,9 +77,10 @@ def test_engine_matches_reference_run(name):
 
 @pytest.mark.parametrize("task,seed,counts", [("od", 101, [2, 1]), ("od", 102, [0, 3]), ("ss", 201, [1, 1, 0, 1, 0, 1]),
                                               ("ss", 202, [0, 0, 1, 2, 0, 0])])
-def test_engine_vs_oracle_fresh_seeds(task, seed, counts):
+@pytest.mark.parametrize("staged", MODES)
+def test_engine_vs_oracle_fresh_seeds(task, seed, counts, staged):
     case = synth.make_case(task, seed, shape=GOLDEN_SHAPE, counts=counts, obj_range=(4.0, 16.0))
-    eng = make_engine(case)
+    eng = make_engine(case, staged_rounds=staged)
     got = eng.augment_batch([scan_input_from_case(case)])[0]
     eng.close()
     ref, want = oracle_run(case)
@@ -142,17 +151,20 @@ def test_candidate_flags_match_oracle_first_try():
         assert feasible == last[2]
 
 
+@pytest.mark.parametrize("staged", MODES)
 @pytest.mark.parametrize("task,seed,counts", [("od", 701, [2, 2]), ("ss", 702, [1, 1, 1, 1, 0, 0])])
-def test_in_place_image_patch_equals_full_reprojection(task, seed, counts):
+def test_in_place_image_patch_equals_full_reprojection(task, seed, counts, staged):
     """The incremental slot update (window mask + z-buffer patch + windowed close/fill) must give exactly what a full
     re-projection of every slot gives."""
     case = synth.make_case(task, seed, shape=GOLDEN_SHAPE, counts=counts, obj_range=(4.0, 16.0))
     outs = []
     for force in (False, True):
-        eng = make_engine(case, force_full_projection=force)
+        eng = make_engine(case, force_full_projection=force, staged_rounds=staged)
         outs.append(eng.augment_batch([scan_input_from_case(case)])[0])
         st = eng.stats()
         assert (st["patched_scans"] == 0) == force
+        if not staged:
+            assert (st["walker_full_reprojections"] > 0) == force
         eng.close()
     a, b = outs
     assert a.inserted == b.inserted and len(a.inserted) >= 2
@@ -169,16 +181,16 @@ def test_execution_modes_give_identical_results():
     inputs = [scan_input_from_case(c) for c in cases]
     n_pts = max(len(c.pcl5) for c in cases)
     ref = None
-    for graphs, subs in ((False, 1), (True, 1), (True, 5), (True, 16), (False, 16)):
+    for graphs, subs in ((None, 0), (False, 1), (True, 1), (True, 5), (True, 16), (False, 16)):      # None: the walker
         eng = Real3DEngine("od", cases[0].config, cases[0].db, max_scans=len(cases), max_points=n_pts,
-                           sub_batches=subs, round_graphs=graphs)
+                           sub_batches=subs, round_graphs=bool(graphs), staged_rounds=graphs is not None)
         staged = eng.stage(inputs)
         eng.load(staged)
         runs = []
         for _ in range(2):                                        # second pass: re-armed resident batch, cached graphs
             eng.run()
             runs.append(eng.unpack(eng.fetch_raw()))
-            eng.reset()
+            eng.reset(from_raw_points=len(runs) == 1 and graphs is None)      # the walker also re-arms from the raw points
         eng.close()
         for res in runs:
             assert all(r.status == 0 for r in res) and sum(len(r.inserted) for r in res) >= 37
@@ -251,8 +263,9 @@ def test_error_conventions_index_capacity_and_arguments():
     eng.close()
 
 
+@pytest.mark.parametrize("staged", MODES)
 @pytest.mark.parametrize("task,counts", [("od", [2, 2]), ("ss", [1, 1, 1, 1, 0, 0])])
-def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts):
+def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts, staged):
     """16 seeded scans per pipeline with 8 - 15 scene boxes each (the collision pruning — bounding circles, the
     separating-axis test on the object's point extents — and the ring-skipping road-level search see many near
     misses), one batch, every scan against the oracle: placement choices and keep-masks exact, xyz within 1e-6 m."""
@@ -262,7 +275,7 @@ def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts):
         for c in cases[1:]:
             c.pose, c.map_data = cases[0].pose, cases[0].map_data
     eng = Real3DEngine(task, cases[0].config, cases[0].db, max_scans=len(cases), max_points=max(len(c.pcl5) for c in cases),
-                       map_data=cases[0].map_data, sub_batches=3)
+                       map_data=cases[0].map_data, sub_batches=3, staged_rounds=staged)
     res = eng.augment_batch([scan_input_from_case(c) for c in cases])
     eng.close()
     placed = 0

@@ -110,7 +110,9 @@ def test_find_possible_places_matches_reference(task, mode, fast):
     assert total > 100
 
 
-E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c"]
+E2E = ["e2e_od_a", "e2e_od_b", "e2e_od_c", "e2e_ss_a", "e2e_ss_b", "e2e_ss_c",
+       # BASELINE-size scans (120 000 / 124 992 points) and the very large, very close cut objects (> 4096 points)
+       "e2e_od_full", "e2e_ss_full", "e2e_ss_big"]
 
 
 def run_oracle_e2e(g, case, mode="cumulative", fast=True):
