@@ -20,7 +20,7 @@ namespace {
 
 enum KernelId {
     KID_INGEST, KID_CTRL, KID_UPDATE, KID_CLEAR, KID_PROJECT, KID_CLOSEFILL, KID_ADJUST, KID_ONMAP, KID_HEIGHT, KID_COLLIDE,
-    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_PROJECT0, KID_CLOSEFILL0, KID_CLEAR0, KID_MINMAX0, KID_WALK, KID_PREP,
+    KID_GRID, KID_OCCL, KID_SELECT, KID_OUT, KID_MINMAX, KID_PROJECT0, KID_CLOSEFILL0, KID_CLEAR0, KID_MINMAX0, KID_WALK, KID_PREP, KID_SCATTER,
     KID_COUNT
 };
 const char* kKernelNames[KID_COUNT] = {
@@ -29,7 +29,10 @@ const char* kKernelNames[KID_COUNT] = {
     // round 0 of a run re-projects every scan in full; later rounds only the scans whose elevation range moved
     "project_zbuffer_full", "close_fill_full", "clear_images_full", "minmax_elevation_full",
     // the per-scan persistent walker (one CTA per scan runs all the slots / tries of its scan) and its set-up
-    "scan_walk", "walk_prepare"};
+    "scan_walk", "walk_prepare",
+    // fused streaming passes: ingest_spherical = A1 + A2 + index counts + z-buffer clear, index_build = scans + distance
+    // transform, scatter_project = CSR scatter of the three indices + A3 (pix ids, z-buffer)
+    "scatter_project"};
 
 template <class T>
 struct DevBuf {
@@ -70,6 +73,7 @@ struct r3d_engine {
     struct RoundGraph { cudaGraphExec_t exec = nullptr; EngineDev d; int ns = 0, chunks_all = 0, task_ctas = 0, sel_pts = 0, kernels = 0; };
     RoundGraph round_graph[R3D_MAX_SUB];
     bool use_graphs = true, capturing = false;
+    bool fresh = false;                          // ingest just ran: z-buffer / pix ids / elevation range of the originals are valid
     bool walked = false;                         // the last run used the walker (its step count is in h_offsets)
     bool staged = false;                         // true: the staged round kernels (debug / probe path); false: the per-scan walker
     bool run_active = false;
@@ -416,6 +420,9 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occl_smem_bytes(d)));
     if (onmap_smem_bytes(d.K) > 100 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: too many yaw steps for the placement kernel's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_onmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onmap_smem_bytes(d.K)));
+    if (2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G > 48 * 1024)
+        R3D_CUDA(cudaFuncSetAttribute(k_grid_near_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G)));
     if (walk_smem_layout(d.K, d.dwords).total > 200 * 1024)
         return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: range image / yaw steps too large for the walker's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_layout(d.K, d.dwords).total));
@@ -440,24 +447,26 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
     const int n = eng->n_scans;
     cudaStream_t st = eng->stream;
     k_reset_state<<<(n + 127) / 128, 128, 0, st>>>(d, n, eng->n0_arr.p, eng->nbox0_arr.p); r3d_count_launch();
+    R3D_CUDA(cudaMemsetAsync(eng->dmask.p, 0, (size_t)n * d.dwords * sizeof(unsigned), st));   // vis_px masks: cleared lazily afterwards
     const int chunks = (eng->max_n0 + CHUNK - 1) / CHUNK;
     if (ingest) {
-        { Launcher l(eng, KID_INGEST); k_ingest<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
-        Launcher l(eng, KID_GRID);
         R3D_CUDA(cudaMemsetAsync(eng->gcell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
         R3D_CUDA(cudaMemsetAsync(eng->col_off.p, 0, (size_t)n * (d.cols + 1) * sizeof(int), st));
         R3D_CUDA(cudaMemsetAsync(eng->acell.p, 0, (size_t)n * d.G * d.G * sizeof(int), st));
-        k_grid_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        k_index_build<1><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        k_bucket_scan<<<n, 1024, 0, st>>>(eng->gcell.p, (size_t)d.G * d.G, d.G * d.G, n);
-        k_bucket_scan<<<n, 1024, 0, st>>>(eng->col_off.p, (size_t)d.cols + 1, d.cols, n);
-        k_bucket_scan<<<n, 1024, 0, st>>>(eng->acell.p, (size_t)d.G * d.G, d.G * d.G, n);
-        k_grid_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        k_index_build<2><<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n);
-        k_grid_near<1><<<dim3((d.G * d.G + 255) / 256, n), 256, 0, st>>>(d, n);
-        k_grid_near<2><<<dim3((d.G * d.G + 255) / 256, n), 256, 0, st>>>(d, n);
-        r3d_count_launch(8);
+        { Launcher l(eng, KID_INGEST); k_ingest_count<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
+        {
+            Launcher l(eng, KID_GRID);
+            k_bucket_scan3<<<dim3(n, 3), 1024, 0, st>>>(d, n);
+        }
+        { Launcher l(eng, KID_SCATTER); k_scatter_project<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
+        {
+            Launcher l(eng, KID_GRID);
+            const size_t near_smem = 2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G;
+            k_grid_near_tiled<<<dim3((d.G + NEAR_BAND - 1) / NEAR_BAND, n), 256, near_smem, st>>>(d, n);
+        }
+        eng->fresh = true;                       // the first range image of every scan is already projected
     } else {
+        eng->fresh = false;
         k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
         // scene boxes: drop the boxes appended by the previous run
         R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, st));
@@ -618,10 +627,14 @@ static int run_walker(r3d_engine* eng) {
 #define R3D_FULL_Y 32
 #endif
     const int full_y = std::min(n, R3D_FULL_Y);
-    { Launcher l(eng, KID_PREP); k_walk_prepare<<<std::min((n * d.cf_tiles + 255) / 256, eng->n_sms * 4), 256, 0, st>>>(d, n); }
-    { Launcher l(eng, KID_MINMAX0); k_minmax<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
-    { Launcher l(eng, KID_CLEAR0); k_clear_images<<<dim3(32, full_y), STREAM_THREADS, 0, st>>>(d, n); }
-    { Launcher l(eng, KID_PROJECT0); k_project<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+    const bool fresh = eng->fresh;
+    eng->fresh = false;
+    { Launcher l(eng, KID_PREP); k_walk_prepare<<<std::min((n * d.cf_tiles + 255) / 256, eng->n_sms * 4), 256, 0, st>>>(d, n, fresh ? 0 : 1); }
+    if (!fresh) {                                // re-armed without ingest: rebuild the first range image from the caches
+        { Launcher l(eng, KID_MINMAX0); k_minmax<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_CLEAR0); k_clear_images<<<dim3(32, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+        { Launcher l(eng, KID_PROJECT0); k_project<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
+    }
     {
         Launcher l(eng, KID_CLOSEFILL0);
         const int cf_grid = std::min(n * d.cf_tiles, eng->n_sms * 4);

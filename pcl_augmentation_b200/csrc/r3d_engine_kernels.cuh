@@ -19,6 +19,7 @@ __device__ __forceinline__ void set_error(ScanState& s, int code) {
 #include "r3d_k_ctrl.cuh"
 #include "r3d_k_update_project.cuh"
 #include "r3d_k_grid.cuh"
+#include "r3d_k_prepass.cuh"
 #include "r3d_k_placement.cuh"
 #include "r3d_k_occlusion.cuh"
 #include "r3d_k_output.cuh"

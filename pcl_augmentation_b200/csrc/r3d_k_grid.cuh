@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int
 
 // exclusive prefix sum of the per-cell counts (one CTA per scan, four cells per thread and step); after the scatter
 // pass cell[c] = END of cell c
-__global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
+__device__ __forceinline__ void bucket_scan_body(int* arr, size_t stride, int n, int n_scans) {
     const int b = blockIdx.x;
     if (b >= n_scans) return;
     int* cell = arr + (size_t)b * stride;
@@ -140,4 +140,7 @@ __global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, i
         if (threadIdx.x == 0) s_run += tot;
         __syncthreads();
     }
+}
+__global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
+    bucket_scan_body(arr, stride, n, n_scans);
 }

@@ -194,7 +194,7 @@ __device__ __forceinline__ SelScratch sel_scratch(unsigned long long* dyn, int k
 }
 
 // every thread of the CTA (any size) calls it; k = rotation of the chosen candidate, `accepted` = it keeps min_points
-__device__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k, bool accepted, SelScratch q) {
+__device__ __noinline__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k, bool accepted, SelScratch q) {
     unsigned long long* s_keys = q.keys;
     double* s_r = q.r;
     unsigned long long* s_tile = q.tile;
@@ -224,7 +224,16 @@ __device__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k,
     unsigned* dm = e.dmask + (size_t)b * e.dwords;
     const double* smooth = e.smooth + (size_t)b * e.hw;
     const int t0 = s.n_tail, chk0 = s.n_check, nbox0 = s.n_boxes, nins0 = s.n_inserted, n0 = s.n0;
-    for (int i = threadIdx.x; i < e.dwords; i += blockDim.x) dm[i] = 0u;
+    // vis_px of the previous candidate lies inside the rectangle recorded with it: only those words are cleared (the
+    // mask is all zero after a (re-)arm)
+    if (s.d_r1 >= s.d_r0 && s.d_c1 >= s.d_c0) {
+        const int nw = (s.d_c1 >> 5) - (s.d_c0 >> 5) + 2, nrow = s.d_r1 - s.d_r0 + 1;
+        for (int i = threadIdx.x; i < nrow * nw; i += blockDim.x) {
+            const int r = s.d_r0 + i / nw;
+            const int w = ((r * e.cols + s.d_c0) >> 5) + i % nw;
+            if (w <= ((r * e.cols + s.d_c1) >> 5)) dm[w] = 0u;
+        }
+    }
     __syncthreads();
     // project every object point once (od/ins:474-478); pixel rectangle of the object
     {
@@ -340,11 +349,25 @@ __device__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k,
     // visible object points, ordered by (pix_id, original index) as the reference's per-pixel loop emits them
     const int nvis = s_nvis;
     if (accepted) {
-        int np2 = 1;
-        while (np2 < nvis) np2 <<= 1;
-        for (int i = nvis + threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = R3D_EMPTY_U64;
-        __syncthreads();
-        bitonic_sort_u64(s_keys, np2);
+        if (e.try_obj[b].count <= q.pts) {
+            // keys in shared memory: rank sort (the keys are distinct; one barrier instead of the log^2 barriers of the
+            // bitonic network), the ordered keys go to the range scratch, which is free by now
+            unsigned long long* sorted = reinterpret_cast<unsigned long long*>(s_r);
+            for (int j = threadIdx.x; j < nvis; j += blockDim.x) {
+                const unsigned long long key = s_keys[j];
+                int rank = 0;
+                for (int i = 0; i < nvis; ++i) rank += s_keys[i] < key;
+                sorted[rank] = key;
+            }
+            __syncthreads();
+            s_keys = sorted;
+        } else {
+            int np2 = 1;
+            while (np2 < nvis) np2 <<= 1;
+            for (int i = nvis + threadIdx.x; i < np2; i += blockDim.x) s_keys[i] = R3D_EMPTY_U64;
+            __syncthreads();
+            bitonic_sort_u64(s_keys, np2);
+        }
         if (t0 + nvis > e.max_inserted || nbox0 + 1 > e.max_boxes || nins0 + 1 > e.max_events) {
             __syncthreads();
             if (threadIdx.x == 0) { set_error(s, R3D_ERR_CAPACITY); s.phase = PH_ERROR; }

@@ -51,7 +51,10 @@ __device__ __forceinline__ bool in_surface(const SurfaceSet& s, unsigned lab) {
     return ok;
 }
 
-__device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x & 31) & ~(GRP - 1)); }
+template <int NL = GRP>           // lane mask of the calling thread's NL-lane group (NL = 8 or 32)
+__device__ __forceinline__ unsigned group_mask() {
+    return NL == 32 ? 0xFFFFFFFFu : ((1u << (NL & 31)) - 1u) << ((threadIdx.x & 31) & ~(NL - 1));
+}
 
 // Visit every point stored in the grid cells [x0, x1] x [y0, y1] MINUS the cells of the hole [hx0, hx1] x [hy0, hy1]
 // (a rectangle inside the first one; hx1 < hx0 = no hole) with the 8 lanes of a group.  The lanes fetch the CSR
@@ -60,11 +63,11 @@ __device__ __forceinline__ unsigned group_mask() { return 0xFFu << ((threadIdx.x
 // chain of L2 latencies, so memory-level parallelism is what counts.  `f(v)` is called per point; `stop()` is polled
 // after every row (group-uniform early exit).
 struct CellRect { int x0, x1, y0, y1; };
-template <class F, class S>
+template <int NL = GRP, class F, class S>
 __device__ __forceinline__ void group_visit(const int* __restrict__ cell, const float4* __restrict__ pts, int G, CellRect rc,
                                             CellRect hole, int gl, unsigned gm, F f, S stop) {
-    for (int yb = rc.y0; yb <= rc.y1; yb += GRP) {
-        const int nrows = min(GRP, rc.y1 - yb + 1);
+    for (int yb = rc.y0; yb <= rc.y1; yb += NL) {
+        const int nrows = min(NL, rc.y1 - yb + 1);
         int beg_a = 0, end_a = 0, beg_b = 0, end_b = 0;
         if (gl < nrows) {
             const int y = yb + gl, row = y * G;
@@ -83,13 +86,13 @@ __device__ __forceinline__ void group_visit(const int* __restrict__ cell, const 
         for (int r = 0; r < nrows; ++r) {
 #pragma unroll
             for (int seg = 0; seg < 2; ++seg) {
-                const int rb = __shfl_sync(gm, seg ? beg_b : beg_a, r, GRP), re = __shfl_sync(gm, seg ? end_b : end_a, r, GRP);
-                for (int p = rb + gl; p < re; p += 4 * GRP) {
+                const int rb = __shfl_sync(gm, seg ? beg_b : beg_a, r, NL), re = __shfl_sync(gm, seg ? end_b : end_a, r, NL);
+                for (int p = rb + gl; p < re; p += 4 * NL) {
                     float4 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int q = p + u * GRP; if (q < re) v[u] = __ldg(&pts[q]); }
+                    for (int u = 0; u < 4; ++u) { const int q = p + u * NL; if (q < re) v[u] = __ldg(&pts[q]); }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (p + u * GRP < re) f(v[u]);
+                    for (int u = 0; u < 4; ++u) if (p + u * NL < re) f(v[u]);
                 }
             }
             if (stop()) return;
@@ -112,6 +115,7 @@ __device__ __forceinline__ CellRect cells_within(const EngineDev& e, double cx, 
 // by scanning the grid cells around the centre in growing square rings (each ring only visits the cells the smaller
 // squares did not cover); the level is the mean z of the points inside that disc, summed in 2^-40 fixed point (order
 // independent; exact for float32 z, so equal to numpy's sequential float64 sum).
+template <int NL = GRP>
 __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& surf, double cx, double cy, int gl, unsigned gm,
                                  double& level) {
     const int G = e.G;
@@ -130,12 +134,12 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     }
     for (;; R = fmin(R < step ? step : R + step, 5.0)) {
         const CellRect rc = cells_within(e, cx, cy, R);
-        group_visit(cell, pts, G, rc, hole, gl, gm, [&](const float4& v) {
+        group_visit<NL>(cell, pts, G, rc, hole, gl, gm, [&](const float4& v) {
             if (!in_surface(surf, __float_as_uint(v.w))) return;
             const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
             best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                           // od/fs:153
         }, [] { return false; });
-        for (int o = GRP / 2; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(gm, best, o));
+        for (int o = NL / 2; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(gm, best, o));
         if (best <= R * R || R >= 5.0) break;          // every point outside the scanned cells is farther than R
         hole = rc;
     }
@@ -145,12 +149,12 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     const double r2 = e.radii_sq[j];
     long long zsum = 0;
     int cnt = 0;
-    group_visit(cell, pts, G, cells_within(e, cx, cy, sqrt(r2)), CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
+    group_visit<NL>(cell, pts, G, cells_within(e, cx, cy, sqrt(r2)), CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
         if (!in_surface(surf, __float_as_uint(v.w))) return;
         const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
         if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
     }, [] { return false; });
-    for (int o = GRP / 2; o > 0; o >>= 1) {
+    for (int o = NL / 2; o > 0; o >>= 1) {
         zsum += __shfl_xor_sync(gm, zsum, o);
         cnt += __shfl_xor_sync(gm, cnt, o);
     }
@@ -211,11 +215,12 @@ __device__ __forceinline__ bool inside_yaw(const YawTest& t, double x, double y,
 
 // rare paths of the collision test, kept out of line so the common path stays small (per-lane results):
 // obstacle points among the points of one already inserted object (its tail slice)
+template <int NL = GRP>
 __device__ __noinline__ bool tail_hits_candidate(const EngineDev& e, int b, const ScanState& s, const ClassCfg& cc,
                                                  const YawTest& yt, double zmin_ped, int t0, int cnt, int gl) {
     const size_t base = (size_t)b * e.P;
     const bool ped = cc.pedestrian != 0;
-    for (int i = gl; i < cnt; i += GRP) {
+    for (int i = gl; i < cnt; i += NL) {
         const size_t t = (size_t)b * e.max_inserted + t0 + i;
         const double x = e.tail_x[t], y = e.tail_y[t], z = e.tail_z[t];
         if ((!ped || z >= zmin_ped) && inside_yaw(yt, x, y, z) && obstacle_point(e, b, s, cc, base, s.n0 + t0 + i))
@@ -224,11 +229,12 @@ __device__ __noinline__ bool tail_hits_candidate(const EngineDev& e, int b, cons
     return false;
 }
 // any object point of the candidate strictly inside a scene box (od/fs:129-134)
+template <int NL = GRP>
 __device__ __noinline__ bool object_in_scene_box(const BoxTest* box_test, const double* ox, const double* oy, const double* oz,
                                                  int count, double c, double sn, double dz, int gl) {
     const BoxTest sbt = *box_test;
-    for (int i = gl; i < count; i += 2 * GRP) {
-        const int i1 = i + GRP;
+    for (int i = gl; i < count; i += 2 * NL) {
+        const int i1 = i + NL;
         const double x0 = ox[i], y0 = oy[i], z0 = oz[i];
         const double x1 = i1 < count ? ox[i1] : x0, y1 = i1 < count ? oy[i1] : y0, z1 = i1 < count ? oz[i1] : z0;
         if (inside_box(sbt, sub(mul(c, x0), mul(sn, y0)), add(mul(sn, x0), mul(c, y0)), add(z0, dz))) return true;
@@ -268,6 +274,7 @@ __device__ __forceinline__ bool extent_may_touch_box(const ObjBox& ob, const Yaw
 //  (ii) object points strictly inside an existing / already inserted box.
 // The exact cut_bounding_box test (strict inequalities in the reference's expression order) decides; grid cells and
 // bounding circles only prune.
+template <int NL = GRP>
 __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c,
                                double sn, double level, int gl, unsigned gm) {
     const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
@@ -275,14 +282,14 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
     const double zmin_ped = add(level, 0.1);                                      // od/fs:123-124
     const bool ped = cc.pedestrian != 0;
     const size_t base = (size_t)b * e.P;
-    const int gshift = (threadIdx.x & 31) & ~(GRP - 1);
+    const int gshift = (threadIdx.x & 31) & ~(NL - 1);
     bool hit = false;
     {
         const int G = e.G;
         const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
         const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
         const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
-        group_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, CellRect{0, -1, 0, -1}, gl, gm,
+        group_visit<NL>(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, CellRect{0, -1, 0, -1}, gl, gm,
                     [&](const float4& v) {
             if (hit) return;
             const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
@@ -297,7 +304,7 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
     // the lanes look at 8 boxes at a time; only the boxes whose bounding circle reaches the candidate's are tested
     const int nbox0 = s.n_boxes - s.n_inserted;
     int t_run = 0;
-    for (int j0 = 0; j0 < s.n_inserted; j0 += GRP) {                     // the tail of placed object j lies inside its box
+    for (int j0 = 0; j0 < s.n_inserted; j0 += NL) {                     // the tail of placed object j lies inside its box
         const int j = j0 + gl;
         int cnt = 0;
         bool near = false;
@@ -308,19 +315,19 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
             near = ddx * ddx + ddy * ddy <= rr * rr;
         }
         int inc = cnt;                                                   // tail offsets: prefix sum of the point counts
-        for (int o = 1; o < GRP; o <<= 1) { const int t = __shfl_up_sync(gm, inc, o, GRP); if (gl >= o) inc += t; }
+        for (int o = 1; o < NL; o <<= 1) { const int t = __shfl_up_sync(gm, inc, o, NL); if (gl >= o) inc += t; }
         unsigned m = (__ballot_sync(gm, near) & gm) >> gshift;
         while (m) {
             const int q = __ffs(m) - 1; m &= m - 1;
-            const int qcnt = __shfl_sync(gm, cnt, q, GRP), qt0 = t_run + __shfl_sync(gm, inc, q, GRP) - qcnt;
-            hit = tail_hits_candidate(e, b, s, cc, yt, zmin_ped, qt0, qcnt, gl);
+            const int qcnt = __shfl_sync(gm, cnt, q, NL), qt0 = t_run + __shfl_sync(gm, inc, q, NL) - qcnt;
+            hit = tail_hits_candidate<NL>(e, b, s, cc, yt, zmin_ped, qt0, qcnt, gl);
             if (__ballot_sync(gm, hit) & gm) return true;
         }
-        t_run += __shfl_sync(gm, inc, GRP - 1, GRP);
+        t_run += __shfl_sync(gm, inc, NL - 1, NL);
     }
     const double dz = sub(level, ob.cz);
     const double *ox = e.obj_x + ob.first, *oy = e.obj_y + ob.first, *oz = e.obj_z + ob.first;
-    for (int b0 = 0; b0 < s.n_boxes; b0 += GRP) {                        // (ii) od/fs:129-134
+    for (int b0 = 0; b0 < s.n_boxes; b0 += NL) {                        // (ii) od/fs:129-134
         const int bi = b0 + gl;
         bool near = false;
         if (bi < s.n_boxes) {
@@ -331,7 +338,7 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
         unsigned m = (__ballot_sync(gm, near) & gm) >> gshift;
         while (m) {
             const int q = __ffs(m) - 1; m &= m - 1;
-            hit = object_in_scene_box(&e.box_tests[(size_t)b * e.max_boxes + b0 + q], ox, oy, oz, ob.count, c, sn, dz, gl);
+            hit = object_in_scene_box<NL>(&e.box_tests[(size_t)b * e.max_boxes + b0 + q], ox, oy, oz, ob.count, c, sn, dz, gl);
             if (__ballot_sync(gm, hit) & gm) return true;
         }
     }

@@ -1,0 +1,183 @@
+// Kernels of the batched Real3D-Aug engine, part: the fused once-per-scan streaming passes.
+// Included by r3d_engine_kernels.cuh (inside namespace r3d, after r3d_k_grid.cuh); not a standalone header.
+// ------------------------------------------------------------------------------------------------ prepass
+// Two passes over the float4 points instead of the seven of the first version (ingest, grid count, index count, grid
+// scatter, index scatter, min/max, projection):
+//   k_ingest_count     A1 + A2 (r, elevation, azimuth bin cached), min / max elevation of the scan, per-cell /
+//                      per-column COUNTS of the three CSR indices, z-buffer cleared on the side
+//   k_bucket_scan3     exclusive scans of the three count arrays (one launch)
+//   k_scatter_project  CSR scatter of the three indices + A3 (pix ids, 64-bit atomicMin z-buffer)
+// Consecutive points of a spinning LiDAR fall into the same 0.5 m cell / image column, so the histogram atomics are
+// aggregated per warp with __match_any_sync: one atomic per distinct key of the warp instead of one per point.
+__device__ __forceinline__ void agg_count(int* arr, int key, bool active) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) return;
+    const unsigned peers = __match_any_sync(act, key);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&arr[key], __popc(peers));
+}
+__device__ __forceinline__ int agg_slot(int* arr, int key, bool active) {
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (!active) return -1;
+    const unsigned peers = __match_any_sync(act, key);
+    const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&arr[key], __popc(peers));
+    base = __shfl_sync(peers, base, leader);
+    return base + __popc(peers & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS) k_ingest_count(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    const int n0 = s.n0;
+    const int p0 = blockIdx.x * CHUNK;
+    {   // this CTA's share of the scan's z-buffer (od/ins:99: train = 500 everywhere = "empty")
+        unsigned long long* z = e.zraw + (size_t)b * e.hw;
+        const int per = (e.hw + gridDim.x - 1) / gridDim.x;
+        for (int i = blockIdx.x * per + threadIdx.x; i < min((int)(blockIdx.x + 1) * per, e.hw); i += STREAM_THREADS) z[i] = R3D_EMPTY_U64;
+    }
+    if (p0 >= n0) return;
+    const double d_az = kTwoPi / (double)e.cols;
+    const size_t base = (size_t)b * e.P;
+    int* cell = e.gcell + (size_t)b * e.G * e.G;
+    int* acell = e.acell + (size_t)b * e.G * e.G;
+    int* coff = e.col_off + (size_t)b * (e.cols + 1);
+    unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
+    for (int q = p0; q < min(p0 + CHUNK, n0); q += STREAM_THREADS) {       // whole warps stay in the loop (aggregated atomics)
+        const int p = q + threadIdx.x;
+        const bool in = p < n0;
+        float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+        unsigned lab = 0u;
+        if (in) { v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]); lab = e.label[base + p]; }
+        const double x = v.x, y = v.y, z = v.z;
+        const double r = range3(x, y, z);
+        const double el = elevation(z, r);
+        const int c = trunc_to_int(__ddiv_rn(az_mod(azimuth(x, y)), d_az));
+        const int cc = max(0, min(c, e.cols - 1));
+        if (in) {
+            if (!(r > 0.0) || c < 0 || c >= e.cols) set_error(s, R3D_ERR_ASSERT);      // od/ins:113 / nan elevation
+            e.r[base + p] = r;
+            e.el[base + p] = el;
+            e.col[base + p] = (unsigned short)cc;
+            e.alive[base + p] = 1;
+            const unsigned long long bits = dbl_bits(el);
+            lmin = min(lmin, bits); lmax = max(lmax, bits);
+        }
+        const int gc = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
+        agg_count(acell, gc, in && !(e.task == 0 && lab == (unsigned)e.road_label));     // od/ins:353-355
+        agg_count(cell, gc, in && (double)v.z > -3.0 && any_surface_label(e, lab));      // od/fs:154-155
+        agg_count(coff, cc, in);
+    }
+    __shared__ unsigned long long s_min[STREAM_THREADS / 32], s_max[STREAM_THREADS / 32];
+    for (int o = 16; o > 0; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) { s_min[threadIdx.x >> 5] = lmin; s_max[threadIdx.x >> 5] = lmax; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < STREAM_THREADS / 32; ++w) { lmin = min(lmin, s_min[w]); lmax = max(lmax, s_max[w]); }
+        // A2 (od/ins:79-80): every original point is live at this time (k_reset_state armed the two words)
+        if (lmax >= lmin) { atomicMin(&s.min_el_bits, lmin); atomicMax(&s.max_el_bits, lmax); }
+    }
+}
+
+// the three exclusive scans (surface grid, all-points grid, image columns) in one launch: blockIdx.y selects the array
+__global__ void __launch_bounds__(1024) k_bucket_scan3(EngineDev e, int n_scans) {
+    const size_t gg = (size_t)e.G * e.G;
+    if (blockIdx.y == 0) bucket_scan_body(e.gcell, gg, (int)gg, n_scans);
+    else if (blockIdx.y == 1) bucket_scan_body(e.acell, gg, (int)gg, n_scans);
+    else bucket_scan_body(e.col_off, (size_t)e.cols + 1, e.cols, n_scans);
+}
+
+__global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e, int n_scans) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    ScanState& s = e.st[b];
+    const int n0 = s.n0;
+    const int p0 = blockIdx.x * CHUNK;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {           // what k_clear_images does for a full projection
+        e.far_arr[b] = 0;
+        if (s.min_el_bits == R3D_EMPTY_U64) set_error(s, R3D_ERR_ASSERT);
+        s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+    }
+    if (p0 >= n0) return;
+    const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(s.max_el_bits), bits_dbl(s.min_el_bits));
+    const size_t base = (size_t)b * e.P;
+    int* cell = e.gcell + (size_t)b * e.G * e.G;
+    int* acell = e.acell + (size_t)b * e.G * e.G;
+    int* coff = e.col_off + (size_t)b * (e.cols + 1);
+    float4* out = e.gpts + (size_t)b * e.max_points;
+    float4* aout = e.apts + (size_t)b * e.max_points;
+    int* cidx = e.col_idx + (size_t)b * e.max_points;
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    for (int q = p0; q < min(p0 + CHUNK, n0); q += STREAM_THREADS) {
+        const int p = q + threadIdx.x;
+        const bool in = p < n0;
+        float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
+        unsigned lab = 0u;
+        int col = 0;
+        double el = 0.0, r = 0.0;
+        if (in) {
+            v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]); lab = e.label[base + p]; col = e.col[base + p];
+            el = e.el[base + p]; r = e.r[base + p];
+        }
+        const int gc = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
+        const int sa = agg_slot(acell, gc, in && !(e.task == 0 && lab == (unsigned)e.road_label));
+        if (sa >= 0) aout[sa] = make_float4(v.x, v.y, v.z, __int_as_float(p));
+        const int sg = agg_slot(cell, gc, in && (double)v.z > -3.0 && any_surface_label(e, lab));
+        if (sg >= 0) out[sg] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
+        const int sc = agg_slot(coff, col, in);
+        if (sc >= 0) cidx[sc] = p;
+        if (in) {                                        // A3 (od/ins:85-130)
+            int pix = -1;
+            const int row = bin_row(g, el);
+            if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);                 // od/ins:111
+            else { pix = row * g.cols + col; atomicMin(&z[pix], dbl_bits(r)); }
+            e.pix[base + p] = pix;
+        }
+    }
+}
+
+// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell of the surface grid to the nearest non-empty one,
+// one CTA per band of NEAR_BAND rows of one scan: occupancy and the row-pass result of the band (+ halo rows) live in
+// shared memory, both passes stop at the first hit.
+constexpr int NEAR_BAND = 32;
+__global__ void __launch_bounds__(256) k_grid_near_tiled(EngineDev e, int n_scans) {
+    const int b = blockIdx.y, G = e.G;
+    if (b >= n_scans) return;
+    extern __shared__ unsigned char s_near[];
+    constexpr int HALO = NEAR_CAP - 1, ROWS = NEAR_BAND + 2 * HALO;
+    unsigned char* s_occ = s_near;                  // [ROWS][G]
+    unsigned char* s_row = s_near + (size_t)ROWS * G;
+    const int y0 = blockIdx.x * NEAR_BAND - HALO;
+    const int* cell = e.gcell + (size_t)b * G * G;
+    for (int i = threadIdx.x; i < ROWS * G; i += blockDim.x) {
+        const int y = y0 + i / G, x = i % G;
+        unsigned char o = 0;
+        if (y >= 0 && y < G) { const int q = y * G + x; o = cell[q] > (q > 0 ? cell[q - 1] : 0); }
+        s_occ[i] = o;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ROWS * G; i += blockDim.x) {
+        const int x = i % G;
+        const unsigned char* row = s_occ + (i - x);
+        int best = NEAR_CAP;
+        for (int d = 0; d < NEAR_CAP; ++d) {
+            if ((x - d >= 0 && row[x - d]) || (x + d < G && row[x + d])) { best = d; break; }
+        }
+        s_row[i] = (unsigned char)best;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NEAR_BAND * G; i += blockDim.x) {
+        const int ly = HALO + i / G, x = i % G, y = y0 + ly;
+        if (y >= G) continue;
+        int best = NEAR_CAP;
+        for (int d = 0; d < best; ++d) {                // rows outside the grid hold NEAR_CAP (no occupancy): no effect
+            const int a = s_row[(ly - d) * G + x], c = s_row[(ly + d) * G + x];
+            best = min(best, max(d, min(a, c)));
+        }
+        e.gnear[(size_t)b * G * G + (size_t)y * G + x] = (unsigned char)best;
+    }
+}

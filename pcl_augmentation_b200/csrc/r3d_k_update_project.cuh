@@ -44,13 +44,20 @@ __device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, const 
     const unsigned long long lo = s.min_el_bits, hi = s.max_el_bits;
     if (c1 >= c0) {
         const int beg = c0 > 0 ? off[c0 - 1] : 0, end = off[c1];           // off[c] = END of column c's bucket
-        for (int i = beg + tid; i < end; i += nthr) {
-            const int p = idx[i];
-            if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
-                e.alive[base + p] = 0;
-                const unsigned long long bits = dbl_bits(e.el[base + p]);
-                extreme |= bits == lo || bits == hi;
-            }
+        // index -> alive / pix -> mask word is a chain of dependent loads: four points per thread in flight
+        for (int i = beg + tid; i < end; i += 4 * nthr) {
+            int p[4], px[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) p[u] = i + u * nthr < end ? idx[i + u * nthr] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) px[u] = (p[u] >= 0 && e.alive[base + p[u]]) ? e.pix[base + p[u]] : -1;
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (px[u] >= 0 && pix_removed(e, b, s, px[u])) {
+                    e.alive[base + p[u]] = 0;
+                    const unsigned long long bits = dbl_bits(e.el[base + p[u]]);
+                    extreme |= bits == lo || bits == hi;
+                }
         }
     }
     for (int t = tid; t < s.tail_before; t += nthr) {

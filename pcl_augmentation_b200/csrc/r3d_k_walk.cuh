@@ -48,6 +48,17 @@ __host__ __device__ __forceinline__ WalkSmem walk_smem_layout(int K, int dwords)
     return L;
 }
 
+// phase clocks (SM cycles, summed over all scans by thread 0 of each CTA) -> e.stats[WALK_T0 + phase]
+enum : int { WT_CTRL = 0, WT_UPDATE, WT_SETUP, WT_PLACE, WT_OCCL, WT_SELECT, WT_TOTAL, WT_COUNT };
+constexpr int WALK_T0 = 16;
+struct WalkClock {
+    long long t;
+    __device__ __forceinline__ void start() { if (threadIdx.x == 0) t = clock64(); }
+    __device__ __forceinline__ void lap(const EngineDev& e, int phase) {
+        if (threadIdx.x == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + phase], (unsigned long long)(n - t)); t = n; }
+    }
+};
+
 struct WalkCtl {                 // control block of the CTA (static shared memory)
     int apply, project, tryact;
     int n_list, nfw, n_feas, found;
@@ -61,6 +72,8 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     unsigned char wflag[WALK_W];
     double wlevel[WALK_W];
     int wfeas[WALK_W];           // window-local indices of the feasible candidates, in rotation order
+    int won[WALK_W];             // window-local indices of the candidates the next sub-stage works on
+    int next;                    // dynamic task counter of a sub-stage
     double wdz[WALK_W];          // semseg fixed point: the shift candidate i was (or must be) tested under
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
@@ -71,7 +84,7 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
 
 // ---- A4 on a pixel rectangle, any CTA size (the batch-wide kernel is r3d_closefill.cuh): tiles of CF_TH x CF_TW
 // outputs staged with their halo in shared memory, bit-row morphology, ordered fp64 neighbour mean
-__device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsigned char* scratch) {
+__device__ __noinline__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsigned char* scratch) {
     unsigned long long (*s_raw)[CF_SW] = reinterpret_cast<unsigned long long (*)[CF_SW]>(scratch);
     unsigned (*s_one)[CF_WORDS] = reinterpret_cast<unsigned (*)[CF_WORDS]>(scratch + (size_t)CF_SH * CF_SW * 8);
     unsigned (*s_in)[CF_WORDS] = s_one + CF_SH;
@@ -85,23 +98,27 @@ __device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsi
     bool far = false;
     for (int r0 = rect[0]; r0 <= rect[1]; r0 += CF_TH)
         for (int c0 = rect[2]; c0 <= rect[3]; c0 += CF_TW) {
-            for (int i = tid; i < CF_SH * CF_SW; i += nt) {
-                const int lr = i / CF_SW, lc = i % CF_SW;
+            // only the rows / columns of the rectangle (+ halo) are staged and computed: a typical object covers a few
+            // hundred pixels, not a whole 32 x 64 tile
+            const int th = min(CF_TH, rect[1] - r0 + 1), tw = min(CF_TW, rect[3] - c0 + 1);
+            const int sh = th + 2 * CF_HR, sw = tw + 2 * CF_HC;
+            for (int i = tid; i < sh * sw; i += nt) {
+                const int lr = i / sw, lc = i % sw;
                 const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
                 s_raw[lr][lc] = (r >= 0 && r < H && c >= 0 && c < W) ? raw[(size_t)r * W + c] : R3D_EMPTY_U64;
             }
-            if (tid < CF_SH) { s_one[tid][3] = 0u; s_in[tid][3] = 0u; s_dil[tid][3] = ~0u; }
+            if (tid < sh) { s_one[tid][3] = 0u; s_in[tid][3] = 0u; s_dil[tid][3] = ~0u; }
             __syncthreads();
-            for (int u = warp; u < CF_SH * 3; u += nwarps) {          // bit rows of the staged tile
+            for (int u = warp; u < sh * 3; u += nwarps) {             // bit rows of the staged tile
                 const int lr = u / 3, w = u % 3, lc = w * 32 + lane;
                 const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
-                const bool inside = lc < CF_SW && r >= 0 && r < H && c >= 0 && c < W;
-                const bool hit = inside && s_raw[lr][min(lc, CF_SW - 1)] != R3D_EMPTY_U64;
+                const bool inside = lc < sw && r >= 0 && r < H && c >= 0 && c < W;
+                const bool hit = inside && s_raw[lr][min(lc, sw - 1)] != R3D_EMPTY_U64;
                 const unsigned b_one = __ballot_sync(0xffffffffu, hit), b_in = __ballot_sync(0xffffffffu, inside);
                 if (lane == 0) { s_one[lr][w] = b_one; s_in[lr][w] = b_in; }
             }
             __syncthreads();
-            for (int t = tid; t < (CF_SH - 4) * 3; t += nt) {
+            for (int t = tid; t < (sh - 4) * 3; t += nt) {
                 const int lr = 2 + t / 3, w = t % 3;
                 unsigned d = 0u;
 #pragma unroll
@@ -109,7 +126,7 @@ __device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsi
                 s_dil[lr][w] = d | ~s_in[lr][w];
             }
             __syncthreads();
-            for (int t = tid; t < CF_TH * 3; t += nt) {
+            for (int t = tid; t < th * 3; t += nt) {
                 const int lr = CF_HR + t / 3, w = t % 3;
                 unsigned er = ~0u;
 #pragma unroll
@@ -117,8 +134,8 @@ __device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsi
                 s_ero[lr][w] = er;
             }
             __syncthreads();
-            for (int i = tid; i < CF_TH * CF_TW; i += nt) {
-                const int lr = i / CF_TW, lc = i % CF_TW;
+            for (int i = tid; i < th * tw; i += nt) {
+                const int lr = i / tw, lc = i % tw;
                 const int r = r0 + lr, c = c0 + lc;
                 if (r >= H || c >= W) continue;
                 const int sr = lr + CF_HR, sc = lc + CF_HC;
@@ -148,7 +165,7 @@ __device__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsi
 
 // ---- A2 + A3 for the whole scan inside the CTA: the rare slot whose elevation range moved (the first projection of
 // every scan is done batch-wide by k_minmax / k_clear_images / k_project before the walker starts)
-__device__ void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
+__device__ __noinline__ void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t base = (size_t)b * e.P;
     const int n = s.n0 + s.n_tail;
@@ -187,14 +204,14 @@ __device__ void walk_full_reproject(const EngineDev& e, int b, ScanState& s, Wal
 }
 
 // ---- semseg addjust_map_2 (ss/ins:202-224) for the scan's live points (same rule as k_adjust_map)
-__device__ void walk_adjust_map(const EngineDev& e, int b, ScanState& s) {
+__device__ __noinline__ void walk_adjust_map(const EngineDev& e, int b, ScanState& s) {
     const int n = s.n0 + s.n_tail;
     const double* T = e.poses + (size_t)b * 16;
     for (int p = threadIdx.x; p < n; p += blockDim.x) adjust_map_point(e, b, s, T, p);
 }
 
 // ---- slot update: what k_update + the refresh kernels of a staged round do for one scan
-__device__ void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
+__device__ __noinline__ void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
                             unsigned char* scratch) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t base = (size_t)b * e.P;
@@ -255,11 +272,32 @@ __device__ void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c,
     __syncthreads();
 }
 
-// ---- A5 + A6a + A7 + A8/A9 for ONE yaw candidate of an OD try, one 8-lane group (the chain the staged kernels
-// k_onmap_full -> k_road_level -> k_collide run as three launches)
-__device__ __noinline__ unsigned walk_candidate_od(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const double* ox,
-                                                   const double* oy, int k, int gl, unsigned gm, double& level) {
-    const ClassCfg& cc = e.classes[ob.cls];
+// ---- ordered list of the window entries i < nw with pred(i) -> out[]; every thread calls it (two barriers); also
+// re-arms the dynamic task counter of the next sub-stage
+template <class P>
+__device__ __forceinline__ int walk_window_list(WalkCtl& c, int nw, int* out, P pred) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NWW = (WALK_W + 31) / 32;
+    bool on = false;
+    unsigned m = 0u;
+    if (w < NWW) {
+        on = tid < nw && pred(tid);
+        m = __ballot_sync(0xffffffffu, on);
+        if (lane == 0) c.s_warp[w] = __popc(m);
+    }
+    __syncthreads();
+    int off = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < NWW; ++i) { if (i < w) off += c.s_warp[i]; tot += c.s_warp[i]; }
+    if (on) out[off + __popc(m & ((1u << lane) - 1u))] = tid;
+    if (tid == 0) c.next = 0;
+    __syncthreads();
+    return tot;
+}
+
+// ---- A5 + A6a (od/fs:263-279) on EVERY object point for one yaw candidate, one 8-lane group
+__device__ __forceinline__ bool walk_onmap_od(const EngineDev& e, int b, const ObjBox& ob, const ClassCfg& cc, const double* ox,
+                                              const double* oy, int k, int gl, unsigned gm) {
     const int count = ob.count, msel = cc.map_sel;
     const int* dims = e.od_map_dims + ((size_t)b * 2 + msel) * 4;
     const int sx = dims[0], sy = dims[1];
@@ -267,7 +305,7 @@ __device__ __noinline__ unsigned walk_candidate_od(const EngineDev& e, int b, co
     const unsigned char* map = e.od_maps + e.od_map_off[(size_t)b * 2 + msel];
     const double c = e.cos_k[k], sn = e.sin_k[k];
     bool any_in = false, bad = false;
-    for (int i0 = 0; i0 < count; i0 += 4 * GRP) {                      // od/fs:267-279 on every object point
+    for (int i0 = 0; i0 < count; i0 += 4 * GRP) {
         double x[4], y[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -286,18 +324,38 @@ __device__ __noinline__ unsigned walk_candidate_od(const EngineDev& e, int b, co
         bad = v[0] != 1 || v[1] != 1 || v[2] != 1 || v[3] != 1;
         if (__ballot_sync(gm, bad) & gm) { bad = true; break; }       // od/fs:277-279
     }
-    const bool on = (__ballot_sync(gm, any_in) & gm) != 0u && !bad;
-    if (!on) return 0u;
+    return (__ballot_sync(gm, any_in) & gm) != 0u && !bad;
+}
+
+// ---- A7 (+ A8 / A9) for the window candidates listed in c.won[0 .. n), ONE WARP per candidate, dealt dynamically: the
+// road-level ring search and the collision test are chains of dependent cell / point loads, so a candidate gets 32
+// lanes (four times shorter chains than the 8-lane groups of the staged kernels) and a free warp takes the next one.
+// with_level: search the road level first (OD); otherwise the level is already in c.wlevel (semseg).
+__device__ __noinline__ void walk_level_collide(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, int n, bool with_level) {
+    const int lane = threadIdx.x & 31;
+    const ObjBox& ob = c.ob;
+    const ClassCfg& cc = e.classes[ob.cls];
     const SurfaceSet surf = load_surface(cc);
-    if (!group_road_level(e, b, surf, sub(mul(c, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(c, ob.cy)), gl, gm, level))
-        return CF_ONMAP;                                               // od/fs:281-285
-    if (group_collides(e, b, s, ob, cc, c, sn, level, gl, gm)) return CF_ONMAP | CF_HOK | CF_COLLIDE;
-    return CF_ONMAP | CF_HOK;
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&c.next, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n) break;
+        const int i = c.won[t], k = c.wk[i];
+        const double cs = e.cos_k[k], sn = e.sin_k[k];
+        double level = c.wlevel[i];
+        unsigned f = CF_ONMAP | CF_HOK;
+        if (with_level && !group_road_level<32>(e, b, surf, sub(mul(cs, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(cs, ob.cy)), lane,
+                                                0xffffffffu, level))
+            f = CF_ONMAP;                                              // od/fs:281-285
+        if ((f & CF_HOK) && group_collides<32>(e, b, s, ob, cc, cs, sn, level, lane, 0xffffffffu)) f |= CF_COLLIDE;
+        if (lane == 0) { c.wflag[i] = (unsigned char)f; c.wlevel[i] = level; }
+    }
 }
 
 // ---- semseg window: A6b with the carried z shift as a fixed-point iteration over the window's yaws (see k_onmap_ss),
 // the road level searched only for the yaws that pass the map test, then A8/A9
-__device__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
+__device__ __noinline__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
                                const double* oz, int base, int nw) {
     const int tid = threadIdx.x, g = tid / GRP, gl = tid % GRP;
     const unsigned gm = group_mask();
@@ -320,9 +378,13 @@ __device__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl&
         if (g < nw && c.wtodo[g]) {                               // ss/fs:231-248 under the assumed shift
             const double dz = c.wdz[g];
             bool bad = false;
-            for (int i0 = 0; i0 < ob.count && !bad; i0 += GRP) {
-                const int i = i0 + gl;
-                const bool off = i < ob.count && ss_point_off_map(e, s, m, ox[i], oy[i], oz[i], cs, sn, dz);
+            for (int i0 = 0; i0 < ob.count && !bad; i0 += 4 * GRP) {   // 4 points per lane in flight
+                bool off = false;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + u * GRP + gl, ob.count - 1);                 // the clamped repeats change nothing
+                    off |= ss_point_off_map(e, s, m, ox[i], oy[i], oz[i], cs, sn, dz);
+                }
                 bad = (__ballot_sync(gm, off) & gm) != 0u;
             }
             if (gl == 0) c.wpass[g] = bad ? 0 : 1;
@@ -350,23 +412,15 @@ __device__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl&
         __syncthreads();
         if (!c.changed) break;
     }
-    if (g < nw) {
-        unsigned f = 0u;
-        if (c.wpass[g]) {
-            f = CF_ONMAP;
-            if (c.whok[g]) {
-                f |= CF_HOK;
-                if (group_collides(e, b, s, ob, cc, cs, sn, c.wlevel[g], gl, gm)) f |= CF_COLLIDE;
-            }
-        }
-        if (gl == 0) c.wflag[g] = (unsigned char)f;
-    }
+    if (tid < nw) c.wflag[tid] = c.wpass[tid] ? (c.whok[tid] ? (CF_ONMAP | CF_HOK) : CF_ONMAP) : 0;
     if (tid == 0) c.dz_run = c.dz_next;
+    const int n_h = walk_window_list(c, nw, c.won, [&](int i) { return c.wpass[i] && c.whok[i]; });
+    walk_level_collide(e, b, s, c, n_h, false);                   // ss/fs:256: check_bounding_box
 }
 
 // ---- exact A11 count of one candidate with the whole CTA (visible-pixel bit image in shared memory), for the
 // candidates the two-sided bound of walk_try cannot decide
-__device__ int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int k, double level, unsigned* bits) {
+__device__ __noinline__ int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int k, double level, unsigned* bits) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const ObjBox& ob = c.ob;
     const ImageGeom g = s.geom;
@@ -396,7 +450,7 @@ __device__ int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkC
 }
 
 // ---- one tried cut object (od/ins:430-561)
-__device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, unsigned char* dyn, const WalkSmem& L) {
+__device__ __noinline__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, unsigned char* dyn, const WalkSmem& L, WalkClock& clk) {
     const int K = e.K, tid = threadIdx.x, nt = blockDim.x;
     double* s_ox = reinterpret_cast<double*>(dyn);
     double* s_oy = s_ox + OBJ_SMEM_PTS;
@@ -441,6 +495,7 @@ __device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, un
     } else {
         __syncthreads();
     }
+    clk.lap(e, WT_SETUP);
     const int g = tid / GRP, gl = tid % GRP;
     const unsigned gm = group_mask();
     const int min_pts = max(cc.min_points, 1);                     // od/ins:530: V == 0 or V < min_points -> rejected
@@ -448,29 +503,35 @@ __device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, un
     const double* smooth = e.smooth + (size_t)b * e.hw;
     for (int base = 0; base < n_list; base += WALK_W) {
         const int nw = min(WALK_W, n_list - base);
-        // stage A: placement tests of the window's candidates, one 8-lane group each
+        // stage A: placement tests of the window's candidates.  OD: on-map test on every object point (an 8-lane group
+        // per candidate), then road level + collision for the survivors (a warp per candidate, dealt dynamically)
         if (e.task == 0) {
             if (g < nw) {
                 const int k = s_list[base + g];
-                double level = 0.0;
-                const unsigned f = walk_candidate_od(e, b, s, ob, ox, oy, k, gl, gm, level);
-                if (gl == 0) { c.wk[g] = k; c.wflag[g] = (unsigned char)f; c.wlevel[g] = level; }
+                const bool on = walk_onmap_od(e, b, ob, cc, ox, oy, k, gl, gm);
+                if (gl == 0) { c.wk[g] = k; c.wflag[g] = on ? CF_ONMAP : 0; c.wlevel[g] = 0.0; }
             }
+            __syncthreads();
+            const int n_on = walk_window_list(c, nw, c.won, [&](int i) { return (c.wflag[i] & CF_ONMAP) != 0; });
+            if (tid == 0) atomicAdd(&e.stats[7], (unsigned long long)n_on);
+            walk_level_collide(e, b, s, c, n_on, true);
         } else {
             walk_window_ss(e, b, s, c, ox, oy, oz, base, nw);
         }
         __syncthreads();
+        clk.lap(e, WT_PLACE);
         // stage B: the window's feasible candidates in rotation order (od/fs:288-296)
-        if (tid == 0) {
-            int nfw = 0;
-            for (int i = 0; i < nw; ++i)
-                if ((c.wflag[i] & (CF_ONMAP | CF_HOK | CF_COLLIDE)) == (CF_ONMAP | CF_HOK)) c.wfeas[nfw++] = i;
-            c.nfw = nfw;
-            if (nfw) { c.last_k = c.wk[c.wfeas[nfw - 1]]; c.last_level = c.wlevel[c.wfeas[nfw - 1]]; }
-            c.n_feas += nfw;
-            atomicAdd(&e.stats[9], 1ull);
+        {
+            const int n = walk_window_list(c, nw, c.wfeas, [&](int i) {
+                return (c.wflag[i] & (CF_ONMAP | CF_HOK | CF_COLLIDE)) == (CF_ONMAP | CF_HOK); });
+            if (tid == 0) {
+                c.nfw = n;
+                if (n) { c.last_k = c.wk[c.wfeas[n - 1]]; c.last_level = c.wlevel[c.wfeas[n - 1]]; }
+                c.n_feas += n;
+                atomicAdd(&e.stats[9], 1ull);
+            }
+            __syncthreads();
         }
-        __syncthreads();
         // stage C: A11 in rotation order with an early exit.  lo = points that are individually closer than the
         // scene, hi = points that fall into the image: lo <= V <= hi, and lo == 0 <=> V == 0, so most candidates are
         // decided without building the visible-pixel image
@@ -508,6 +569,7 @@ __device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, un
             }
             __syncthreads();
         }
+        clk.lap(e, WT_OCCL);
         if (c.found >= 0) break;
     }
     // A11 + A12 for the chosen candidate: the first one that keeps min_points, else the last feasible one (its
@@ -523,6 +585,7 @@ __device__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, un
                          sel_scratch(reinterpret_cast<unsigned long long*>(dyn), WALK_SEL_KEYS, WALK_SEL_PTS, WALK_SEL_TILE));
     }
     __syncthreads();
+    clk.lap(e, WT_SELECT);
 }
 
 __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(const __grid_constant__ EngineDev e, int n_scans) {
@@ -530,9 +593,20 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(co
     if (b >= n_scans) return;
     extern __shared__ __align__(16) unsigned char w_dyn[];
     __shared__ WalkCtl c;
-    ScanState& s = e.st[b];
+    // the scan's scheduling state lives in shared memory while its CTA runs: the serial scheduling step and every stage
+    // read and write it dozens of times
+    __shared__ ScanState s;
+    {
+        const int* src = reinterpret_cast<const int*>(&e.st[b]);
+        int* dst = reinterpret_cast<int*>(&s);
+        for (int i = threadIdx.x; i < (int)(sizeof(ScanState) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
     const WalkSmem L = walk_smem_layout(e.K, e.dwords);
     int steps = 0;
+    WalkClock clk;
+    clk.start();
+    const long long t_begin = clk.t;
     for (;;) {
         if (threadIdx.x == 0) {
             int apply = 0, project = 0, tryact = 0;
@@ -542,17 +616,26 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(co
         }
         __syncthreads();
         const int apply = c.apply, project = c.project, tryact = c.tryact;
+        clk.lap(e, WT_CTRL);
         if (apply || project) walk_update(e, b, s, c, apply, project, w_dyn + L.scratch_off);
+        clk.lap(e, WT_UPDATE);
         if (!tryact) break;                              // PH_DONE or PH_ERROR
-        walk_try(e, b, s, c, w_dyn, L);
+        walk_try(e, b, s, c, w_dyn, L, clk);
         ++steps;
+    }
+    if (threadIdx.x == 0) atomicAdd(&e.stats[WALK_T0 + WT_TOTAL], (unsigned long long)(clock64() - t_begin));
+    __syncthreads();
+    {
+        const int* src = reinterpret_cast<const int*>(&s);
+        int* dst = reinterpret_cast<int*>(&e.st[b]);
+        for (int i = threadIdx.x; i < (int)(sizeof(ScanState) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
     if (threadIdx.x == 0) atomicMax(&e.stats[8], (unsigned long long)steps);
 }
 
 // what the first round of the staged engine sets up, for the walker: every scan is listed for the batch-wide full
 // projection and every tile for close/fill; the state machine starts with its first range image already built
-__global__ void k_walk_prepare(EngineDev e, int n_scans) {
+__global__ void k_walk_prepare(EngineDev e, int n_scans, int reset_range) {
     const int tiles = e.cf_tiles;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_scans * tiles; i += gridDim.x * blockDim.x) e.cf_tasks[i] = i;
     for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_scans; b += gridDim.x * blockDim.x) {
@@ -561,7 +644,7 @@ __global__ void k_walk_prepare(EngineDev e, int n_scans) {
         if (e.task == 1) for (int i = 0; i <= OCC_FAR_CAP; ++i) occ_far_clear(e, b, i);
         ScanState& s = e.st[b];
         s.first = 0; s.scene_changed = 0;
-        s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull;
+        if (reset_range) { s.min_el_bits = R3D_EMPTY_U64; s.max_el_bits = 0ull; }      // k_minmax follows
         atomicAdd(&e.stats[0], 1ull);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) { e.work_cnt[0] = n_scans; e.work_cnt[1] = n_scans * tiles; e.stats[8] = 0ull; }

@@ -398,13 +398,15 @@ class Real3DEngine:
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
     def stats(self):
-        out = np.zeros(16, dtype=np.uint64)
-        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 16), "stats")
+        out = np.zeros(24, dtype=np.uint64)
+        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 24), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
                 'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5]),
                 'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7]), 'max_steps_per_scan': int(out[8]),
                 'candidate_windows': int(out[9]), 'exact_occlusion_counts': int(out[10]),
-                'walker_full_reprojections': int(out[11])}
+                'walker_full_reprojections': int(out[11]),
+                'walker_cycles': {k: int(out[16 + i]) for i, k in enumerate(
+                    ('schedule', 'update', 'setup_prefilter', 'placement', 'occlusion', 'select_insert', 'total'))}}
 
     def cuda_stream(self):
         import torch
