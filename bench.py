@@ -2,18 +2,26 @@
 
   python bench.py --gpus N --steps K --warmup W            (N > 1: launched by torchrun, one rank per GPU)
   python bench.py --impl reference --gpus N --steps K --warmup W
+  python bench.py --config c2|c4|c5 ...                     (the other BASELINE.json configurations as the headline)
 
-Workload (BASELINE.json configs[2], the one the metric is quoted on): a batch of 256 synthetic KITTI-shape HDL-64
-scans (120 000 points each, 112 x 1440 range image), 10 cut pedestrians / cyclists to insert per scan, 1024 yaw
-candidates per cut object, sharded by scan: every rank owns its own batch of 256 (weak scaling, no collective on
-the data path).  One step = one pass of the whole hot path (placement search + occlusion + insertion + output
-compaction) over the rank's batch.
+Headline workload (BASELINE.json configs[2], "c3", the one the metric is quoted on): a batch of 256 synthetic
+KITTI-shape HDL-64 scans (120 000 points each, 112 x 1440 range image), 10 cut pedestrians / cyclists to insert per
+scan, 1024 yaw candidates per cut object, sharded by scan: every rank owns its own batch of 256 (weak scaling, no
+collective on the data path).  One step = one pass of the WHOLE device path over the rank's batch, starting from the
+raw float4 points: spherical ingest + spatial indices + first range image (streaming kernels), the per-scan walker
+(placement search + occlusion + insertion for every slot of every scan), output compaction.
 
-  value  : scans/s with the batch already resident in HBM (device re-arm + run, CUDA events on the engine stream)
-  e2e    : scans/s through the public API (ScanPipeline) with HOST (pinned) buffers: H2D of every scan + run + D2H of
-           the results, consecutive batches overlapped on 3 engines / streams
-  roofline: the kernel with the largest share of device time; achieved = algorithmic bytes / measured time
+  value   : scans/s with the raw points already resident in HBM (CUDA events on the engine streams); the K steps
+            are dealt to `--resident-depth` engines so that one engine's streaming kernels overlap another's walker
+  serial  : the same step alone on ONE engine (`single_batch_ms`), and the per-kernel CUDA-event times of exactly
+            that mode (`kernels`): they add up to the serial step
+  e2e     : scans/s through the public API (ScanPipeline) with HOST (pinned) buffers: H2D of every scan + the step +
+            D2H of the augmented clouds inside the timed region; `copy_only` = the same bytes moved with no kernels
+  roofline: the kernel with the largest share of the serial step.  Streaming kernels: algorithmic bytes
+            / measured time.  The walker is latency / issue bound and has no streaming model: its `achieved` is the
+            ncu-measured DRAM traffic of one launch over the measured duration, with ncu's sm / issue utilisation
   cpu_baseline: the numpy oracle port of the reference timed on one host core on a bounded sample (rank 0, N = 1)
+  configs : short runs of the other BASELINE.json configurations (c2 semseg, c4 128-beam, c5 4541-scan stream)
 """
 from __future__ import annotations
 
@@ -21,7 +29,6 @@ import argparse
 import json
 import os
 import statistics
-import subprocess
 import sys
 import threading
 import time
@@ -32,34 +39,65 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-SCANS_PER_GPU = 256
-DISTINCT_SCANS = 32
-N_OBJECTS = 10
-YAW_STEPS = 1024
-ROWS, COLS = 112, 1440
 METRIC = "augmented scans/sec (120k-pt KITTI scan, placement + occlusion + insertion)"
 
+# name -> workload (BASELINE.json `configs`, in order c1 .. c5)
+WORKLOADS = {
+    "c1": dict(task="od", shape="KITTI", scans=1, objects=10, yaw=360, rows=112, cols=1440, distinct=1,
+               text="one KITTI-shape HDL-64 scan (120000 pts, 112x1440 range image), 10 cut pedestrians/cyclists, 360 yaw "
+                    "candidates per object"),
+    "c2": dict(task="ss", shape="SEMKITTI", scans=256, objects=20, yaw=360, rows=64, cols=2048, distinct=8,
+               text="batch of 256 SemanticKITTI-shape scans per GPU (124992 pts, 64x2048 range image), 20 rare-class objects "
+                    "per scan placed on the rich_map road / sidewalk, 360 yaw candidates per object"),
+    "c3": dict(task="od", shape="KITTI", scans=256, objects=10, yaw=1024, rows=112, cols=1440, distinct=32,
+               text="batch of 256 KITTI-shape scans per GPU (120000 pts, 112x1440 range image), 10 cut "
+                    "pedestrians/cyclists per scan, 1024 yaw candidates per object, sharded by scan"),
+    "c4": dict(task="od", shape="OS128", scans=128, objects=50, yaw=360, rows=128, cols=2048, distinct=4,
+               text="batch of 128 OS1-128-shape scans per GPU (262144 pts, 128x2048 range image), 50 inserted objects per "
+                    "scan, 360 yaw candidates per object"),
+    "c5": dict(task="ss", shape="SEMKITTI", scans=256, objects=10, yaw=360, rows=112, cols=1440, distinct=8, stream=4541,
+               text="SemanticKITTI-sequence-sized stream of 4541 scans (124992 pts, 112x1440 range image, 10 objects per "
+                    "scan) in batches of 256, sharded by scan over the GPUs, end to end incl. host<->device transfer"),
+}
 
-def workload_config(n_gpus):
-    return {"workload": "batch of 256 KITTI-shape scans per GPU (120000 pts, 112x1440 range image), 10 cut "
-                        "pedestrians/cyclists per scan, 1024 yaw candidates per object, sharded by scan",
-            "scans_per_gpu": SCANS_PER_GPU, "points_per_scan": 120000, "objects_per_scan": N_OBJECTS,
-            "yaw_candidates": YAW_STEPS, "range_image": [ROWS, COLS], "parallelism": f"scan-sharded x{n_gpus}",
-            "l2": "inputs larger than L2 (614 MB of points per batch, no flush needed)",
-            "distinct_scans": DISTINCT_SCANS}
 
-
-def build_cases(rank, n_scans=SCANS_PER_GPU, distinct=DISTINCT_SCANS):
-    """`distinct` different synthetic scans per rank, tiled to `n_scans` with different schedules / object draws."""
+def workload_config(name, n_gpus):
+    w = WORKLOADS[name]
     from pcl_augmentation_b200 import synth
-    base = [synth.make_case("od", 9000 + rank * 1000 + i, number_of_object=N_OBJECTS) for i in range(distinct)]
+    shape = getattr(synth, w["shape"] + "_SHAPE")
+    pts = shape.beams * shape.az_steps
+    return {"workload": w["text"], "name": name, "task": w["task"], "scans_per_gpu": w["scans"], "points_per_scan": pts,
+            "objects_per_scan": w["objects"], "yaw_candidates": w["yaw"], "range_image": [w["rows"], w["cols"]],
+            "parallelism": f"scan-sharded x{n_gpus}", "distinct_scans": w["distinct"],
+            "l2": f"inputs larger than L2 ({w['scans'] * pts * 20 / 1e6:.0f} MB of points per batch, no flush needed)"
+                  if w["scans"] * pts * 20 > 200e6 else "L2 flushed by the other resident engines' batches between steps"}
+
+
+def build_cases(name, rank):
+    """`distinct` different synthetic scans per rank, tiled to `scans` with different schedules / object draws."""
+    from pcl_augmentation_b200 import synth
+    w = WORKLOADS[name]
+    shape = getattr(synth, w["shape"] + "_SHAPE")
+    seed0 = {"c1": 9000, "c2": 7300, "c3": 9000, "c4": 7600, "c5": 7900}[name] + rank * 1000
+    base = [synth.make_case(w["task"], seed0 + i, shape=shape, number_of_object=w["objects"]) for i in range(w["distinct"])]
+    if w["task"] == "ss":                    # one engine = one sequence map: every scan uses the first pose / map
+        for c in base[1:]:
+            c.pose, c.map_data = base[0].pose, base[0].map_data
     cases = []
-    for j in range(n_scans):
-        c = base[j % distinct]
-        sched = synth.make_schedule(50000 + rank * 10000 + j, len(c.config["insertion"]["classes"]), N_OBJECTS,
-                                    [len(c.db[k]) for k in c.config["insertion"]["classes"]])
-        cases.append(synth.Case(c.task, c.config, c.pcl5, c.box_lines, c.db, sched, maps=c.maps, cars=c.cars))
+    for j in range(w["scans"]):
+        c = base[j % w["distinct"]]
+        classes = c.config["insertion"]["classes"]
+        sched = synth.make_schedule(50000 + seed0 + j, len(classes), w["objects"], [len(c.db[k]) for k in classes])
+        cc = synth.Case(c.task, c.config, c.pcl5, c.box_lines, c.db, sched, maps=c.maps, cars=c.cars)
+        cc.pose, cc.map_data = c.pose, c.map_data
+        cases.append(cc)
     return cases
+
+
+def engine_kwargs(name, cases):
+    w = WORKLOADS[name]
+    return dict(max_scans=w["scans"], max_points=max(len(c.pcl5) for c in cases), rows=w["rows"], cols=w["cols"],
+                yaw_steps=w["yaw"], max_events=w["objects"] + 1, max_boxes=128, map_data=cases[0].map_data)
 
 
 class ClockSampler:
@@ -127,42 +165,10 @@ class ClockSampler:
                "sm_min_mhz": min(s[1] for s in timed) if timed else None,
                "power_w_max": round(max(s[3] for s in timed), 1) if timed else None,
                "reasons": sorted(reasons), "samples": len(timed), "samples_total": len(self.samples),
-               "source": "NVML, 10 ms period, samples inside the two timed regions (device-resident + e2e)"}
+               "source": "NVML, 10 ms period, samples inside the timed regions (device-resident + e2e)"}
         if self.error:
             out["error"] = self.error
         return out
-
-
-# algorithmic bytes per unit: N points, HW pixels, 20 B point record.  "units" = how many scans /
-# tries the kernel really processed in the timed region (engine counters), so gated-off launches add time but no bytes.
-PLACEMENT_STAGES = ("onmap", "road_level", "collide", "place_try")
-
-
-def algorithmic_bytes(kernel, n_points, hw, stats, n_scans, steps):
-    per_project = stats["projected_scans"]
-    per_try = stats["tried_objects"]
-    per_mask = stats["masked_scans"]
-    table = {
-        "project_zbuffer_full": (20 * n_points + 8 * hw, per_project), # z-buffer pass, round 0 of every run
-        "clear_images_full": (8 * hw, per_project),
-        "close_fill_full": (16 * hw, per_project),
-        "update_mask_patch": (5 * n_points, per_mask),                 # occlusion mask
-        "placement": (20 * n_points, per_try),                         # placement pass over the scene, all stages
-        "compact_output": (40 * n_points, n_scans * steps),
-        "ingest_spherical": (20 * n_points, 0),
-    }
-    per_unit, units = table.get(kernel, (0, 0))
-    return per_unit, units
-
-
-def measured_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed `ncu --set full` capture of this
-    workload (profiles/ncu_traffic.json, written by tools/ncu_summary.py), or None."""
-    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        return json.load(f).get(kernel)
 
 
 def peaks():
@@ -173,30 +179,107 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def cpu_baseline_sample(yaw_steps=YAW_STEPS, budget_s=25.0):
+def ncu_record(kernel):
+    """What the committed `ncu --set full` capture of this workload says about a bench kernel (profiles/ncu_traffic.json,
+    written by tools/ncu_summary.py): DRAM bytes per launch, sm / issue utilisation; or None."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(kernel)
+
+
+def index_fractions(cases, eng):
+    """Fractions of the points that go into the all-points (collision) grid and into the surface (road-level) grid."""
+    fa, fg, n = 0.0, 0.0, 0
+    surface = eng.surface_labels()
+    for c in cases[:8]:
+        lab = c.pcl5[:, 4].astype(np.int64)
+        fa += float(np.sum(lab != eng.road_label)) if eng.task == "od" else float(len(lab))
+        fg += float(np.sum(np.isin(lab, surface) & (c.pcl5[:, 2] > -3.0)))
+        n += len(lab)
+    return fa / n, fg / n
+
+
+def algorithmic_bytes_per_scan(kernel, cases, eng):
+    """Bytes ONE scan's share of a streaming kernel's launch has to move by its own formulation.
+    None for kernels without a streaming model (the walker)."""
+    n = float(np.mean([len(c.pcl5) for c in cases]))
+    hw = eng.rows * eng.cols
+    g2 = (2 * eng.grid_half) ** 2
+    if kernel == "ingest_spherical":          # xyzi 16 + label 4 in; r 8 + el 8 + col 2 + alive 1 out; z-buffer clear
+        return 39 * n + 8 * hw
+    if kernel == "scatter_project":           # xyzi, label, col, el, r in; pix + column index out; 16 B per grid entry; z atomics
+        fa, fg = index_fractions(cases, eng)
+        return (38 + 8 + 16 * (fa + fg)) * n + 8 * hw
+    if kernel == "index_build":               # three exclusive scans (read + write) + the distance transform
+        return 8 * (2 * g2 + eng.cols + 1) + 5 * g2
+    if kernel == "close_fill_full":           # SURVEY 8d: 16 B per pixel
+        return 16 * hw
+    if kernel == "compact_output":            # SURVEY 8d: 40 B per point
+        return 40 * n
+    if kernel == "project_zbuffer_full":
+        return 20 * n + 8 * hw
+    if kernel == "clear_images_full":
+        return 8 * hw
+    return None
+
+
+def copy_only_probe(h2d_bytes, d2h_bytes, steps, barrier):
+    """The PCIe ceiling of the e2e leg: the same bytes per step, pinned host <-> device on two streams, no kernels."""
+    import torch
+    src_h = torch.empty(int(h2d_bytes), dtype=torch.uint8, pin_memory=True)
+    dst_d = torch.empty(int(h2d_bytes), dtype=torch.uint8, device="cuda")
+    src_d = torch.empty(int(d2h_bytes), dtype=torch.uint8, device="cuda")
+    dst_h = torch.empty(int(d2h_bytes), dtype=torch.uint8, pin_memory=True)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(2):
+        with torch.cuda.stream(s1):
+            dst_d.copy_(src_h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dst_h.copy_(src_d, non_blocking=True)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        with torch.cuda.stream(s1):
+            dst_d.copy_(src_h, non_blocking=True)
+        with torch.cuda.stream(s2):
+            dst_h.copy_(src_d, non_blocking=True)
+    barrier()
+    return time.perf_counter() - t0
+
+
+def oracle_scan_seconds(case, w):
+    from oracle import real3d_oracle as orc            # checker / baseline only
+    t0 = time.perf_counter()
+    orc.augment_scan(case.task, case.pcl5, case.box_lines, case.db, case.schedule.counts, case.schedule.perms, case.config,
+                     maps=case.maps, map_data=case.map_data, transform_matrix=case.pose, mode="closed",
+                     yaw_steps=w["yaw"], num_row=w["rows"], num_column=w["cols"])
+    return time.perf_counter() - t0
+
+
+def cpu_baseline_sample(name, budget_s):
     """The numpy oracle port of the reference (oracle/real3d_oracle.py) on ONE host core on whole scans of the same
     workload until ~budget_s of CPU work is spent (at least one scan)."""
-    from oracle import real3d_oracle as orc            # checker / baseline only
     from pcl_augmentation_b200 import synth
+    w = WORKLOADS[name]
+    shape = getattr(synth, w["shape"] + "_SHAPE")
     t_total, n = 0.0, 0
     while t_total < budget_s and n < 4:
-        case = synth.make_case("od", 9000 + n, number_of_object=N_OBJECTS)
-        t0 = time.perf_counter()
-        orc.augment_scan("od", case.pcl5, case.box_lines, case.db, case.schedule.counts, case.schedule.perms,
-                         case.config, maps=case.maps, mode="closed", yaw_steps=yaw_steps, num_row=ROWS, num_column=COLS)
-        t_total += time.perf_counter() - t0
+        case = synth.make_case(w["task"], 9000 + n, shape=shape, number_of_object=w["objects"])
+        t_total += oracle_scan_seconds(case, w)
         n += 1
-    return n / t_total, n, t_total
+    return {"value": n / t_total, "unit": "scans/s", "cores": 1, "kind": "port",
+            "sample": f"{n} whole scan(s) of the {name} workload through oracle/real3d_oracle.py, {t_total:.1f} s",
+            "host_cpus": os.cpu_count()}
 
 
-def _ref_worker(seed):
-    from oracle import real3d_oracle as orc
+def _ref_worker(arg):
+    name, seed = arg
     from pcl_augmentation_b200 import synth
-    case = synth.make_case("od", seed, number_of_object=N_OBJECTS)
-    t0 = time.perf_counter()
-    orc.augment_scan("od", case.pcl5, case.box_lines, case.db, case.schedule.counts, case.schedule.perms, case.config,
-                     maps=case.maps, mode="closed", yaw_steps=YAW_STEPS, num_row=ROWS, num_column=COLS)
-    return time.perf_counter() - t0
+    w = WORKLOADS[name]
+    case = synth.make_case(w["task"], seed, shape=getattr(synth, w["shape"] + "_SHAPE"), number_of_object=w["objects"])
+    return oracle_scan_seconds(case, w)
 
 
 def run_reference(args, json_out):
@@ -209,13 +292,12 @@ def run_reference(args, json_out):
     cores = max(1, min(os.cpu_count() or 1, 32))
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        for w in range(args.warmup):
-            pool.map(_ref_worker, [9000 + i for i in range(cores)])
-            break                                            # one warm-up wave is enough for a CPU path
+        if args.warmup:
+            pool.map(_ref_worker, [(args.config, 9000 + i) for i in range(cores)])      # one warm-up wave is enough for a CPU path
         t0 = time.perf_counter()
         done = 0
         for s in range(args.steps):
-            pool.map(_ref_worker, [9100 + s * cores + i for i in range(cores)])
+            pool.map(_ref_worker, [(args.config, 9100 + s * cores + i) for i in range(cores)])
             done += cores
         dt = time.perf_counter() - t0
     value = done / dt
@@ -224,7 +306,7 @@ def run_reference(args, json_out):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus),
+        "config": workload_config(args.config, args.gpus),
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})])
@@ -263,6 +345,197 @@ def run_side(args, json_out):
     print(json.dumps(res), file=json_out, flush=True)
 
 
+class Bench:
+    """One workload on this rank's GPU: engines, the staged (pinned) batch and the three measurements."""
+
+    def __init__(self, name, rank, world, args, barrier, max_over_ranks):
+        from pcl_augmentation_b200.engine import Real3DEngine, scan_input_from_case
+        from pcl_augmentation_b200.pipeline import ScanPipeline
+        self.name, self.rank, self.world, self.args = name, rank, world, args
+        self.barrier, self.max_over_ranks = barrier, max_over_ranks
+        self.w = WORKLOADS[name]
+        self.cases = build_cases(name, rank)
+        self.n_scans = len(self.cases)
+        kw = engine_kwargs(name, self.cases)
+        c0 = self.cases[0]
+        self.pipe = ScanPipeline(self.w["task"], c0.config, c0.db, depth=args.depth, **kw)
+        self.res_depth = max(1, args.resident_depth)
+        self.extra = [Real3DEngine(self.w["task"], c0.config, c0.db, **kw) for _ in range(self.res_depth - args.depth)]
+        self.res_engines = (self.pipe.engines + self.extra)[:self.res_depth]
+        self.eng = self.pipe.engines[0]
+        self.staged = self.eng.stage([scan_input_from_case(c) for c in self.cases])
+
+    def close(self):
+        self.pipe.close()
+        for e in self.extra:
+            e.close()
+
+    # ---- device-resident: K steps dealt round-robin to the resident engines (own host thread, own stream) --------
+    def _resident_steps(self, n_steps):
+        errors = []
+        engines = self.res_engines
+
+        def worker(w):
+            try:
+                for _ in range(w, n_steps, len(engines)):
+                    engines[w].reset(from_raw_points=True)      # the WHOLE device path: ingest + indices included
+                    engines[w].run()
+            except BaseException as exc:
+                errors.append(exc)
+        threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(len(engines))]
+        for t in threads:
+            t.start()
+        for t in threads:
+            t.join()
+        if errors:
+            raise errors[0]
+
+    def resident(self, steps, warmup, sampler=None):
+        import torch
+        for e in self.res_engines:
+            e.load(self.staged)
+            e.sync()
+        self._resident_steps(max(warmup, len(self.res_engines)))
+        for e in self.res_engines:
+            e.sync()
+        streams = [e.cuda_stream() for e in self.res_engines]
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev_end = [torch.cuda.Event(enable_timing=True) for _ in streams]
+        self.barrier()
+        launches0 = self.eng.launch_count()
+        if sampler:
+            sampler.mark(True)
+        ev0.record(streams[0])              # every engine stream is idle here (barrier = device synchronize)
+        self._resident_steps(steps)
+        for ev, es in zip(ev_end, streams):
+            ev.record(es)
+        for e in self.res_engines:
+            e.sync()
+        if sampler:
+            sampler.mark(False)
+        self.barrier()
+        dev_ms = self.max_over_ranks(max(ev0.elapsed_time(ev) for ev in ev_end))
+        return dev_ms, self.eng.launch_count() - launches0
+
+    # ---- one step alone on one engine + the per-kernel CUDA-event times of exactly that mode -------------------
+    def serial(self, steps):
+        import torch
+        eng, stream = self.eng, self.eng.cuda_stream()
+        eng.load(self.staged)
+        eng.reset(from_raw_points=True); eng.run(); eng.sync()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(stream)
+        for _ in range(steps):
+            eng.reset(from_raw_points=True); eng.run()
+        ev1.record(stream)
+        eng.sync()
+        serial_ms = ev0.elapsed_time(ev1) / steps
+        eng.profile(True)                       # CUDA events around every launch; same engine, same serial order
+        for _ in range(steps):
+            eng.reset(from_raw_points=True); eng.run()
+        eng.sync()
+        prof, stats = eng.profile_read(), eng.stats()
+        eng.profile(False)
+        results = eng.unpack(eng.fetch_raw())
+        return serial_ms, prof, stats, results
+
+    # ---- end to end through the public API with host buffers ----------------------------------------------------
+    def e2e(self, steps, sampler=None, stream_scans=None):
+        st = self.staged
+        self.pipe.warmup(st)
+        self.pipe.warmup(st)
+        if stream_scans is None:
+            n_batches = steps
+        else:                                   # the stream is sharded by scan over the ranks, batches of n_scans
+            per_rank = -(-stream_scans // self.world)
+            n_batches = -(-per_rank // self.n_scans)
+        self.barrier()
+        if sampler:
+            sampler.mark(True)
+        t0 = time.perf_counter()
+        out_bytes = self.pipe.process([st] * n_batches)
+        self.barrier()
+        secs = self.max_over_ranks(time.perf_counter() - t0)
+        if sampler:
+            sampler.mark(False)
+        h2d = sum(st[k].nbytes for k in ("xyzi", "labels", "boxes", "perms", "counts") if k in st)
+        h2d += st["maps"].nbytes if "maps" in st else st["poses"].nbytes
+        d2h = sum(out_bytes) / n_batches
+        return {"seconds": secs, "batches": n_batches, "h2d": int(h2d), "d2h": int(d2h)}
+
+
+def kernel_table(bench, prof, steps, peak):
+    total = sum(v["ms"] for v in prof.values())
+    table = {}
+    for name, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"]):
+        if not v["launches"]:
+            continue
+        ms_step = v["ms"] / steps
+        entry = {"ms_per_step": round(ms_step, 4), "launches_per_step": v["launches"] / steps,
+                 "share": round(v["ms"] / max(total, 1e-9), 4)}
+        per_scan = algorithmic_bytes_per_scan(name, bench.cases, bench.eng)
+        rec = ncu_record(name) if bench.name == "c3" else None
+        if per_scan is not None:
+            gbs = per_scan * bench.n_scans / (ms_step / 1e3) / 1e9
+            entry.update(bound="hbm", algorithmic_bytes_per_scan=int(per_scan), achieved_gbs=round(gbs, 1), frac=round(gbs / peak, 4))
+        else:
+            entry.update(bound="latency / issue (no streaming model)")
+        if rec:
+            entry["ncu"] = rec
+        table[name] = entry
+    return table, total / steps
+
+
+def roofline_of(name, entry, bench, peak, peak_src):
+    """The JSON `roofline` object of one kernel-table entry."""
+    rec = entry.get("ncu")
+    launch_ms = entry["ms_per_step"] / max(entry["launches_per_step"], 1)
+    out = {"kernel": name, "bound": "hbm", "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+           "avg_launch_ms": round(launch_ms, 4), "share_of_serial_step": entry["share"],
+           "traffic": rec["bytes_per_launch"] if rec else None, "traffic_source": rec["source"] if rec else None}
+    if "achieved_gbs" in entry:
+        out.update(achieved=entry["achieved_gbs"], frac=entry["frac"],
+                   bytes_per_launch=int(entry["algorithmic_bytes_per_scan"] * bench.n_scans / max(entry["launches_per_step"], 1)),
+                   bytes_source="algorithmic (DESIGN.md section 4)")
+    elif rec:
+        # latency-bound kernel without a streaming model: the DRAM bytes ncu measured for one launch of this workload
+        gbs = rec["bytes_per_launch"] / (launch_ms / 1e3) / 1e9
+        out.update(achieved=round(gbs, 1), frac=round(gbs / peak, 4), bytes_per_launch=rec["bytes_per_launch"],
+                   bytes_source="ncu dram__bytes_read.sum + dram__bytes_write.sum (no streaming model: the kernel is "
+                                "latency / issue bound)",
+                   limiter={k: rec[k] for k in ("sm_throughput_pct", "issue_active_pct", "warps_active_pct") if k in rec})
+    else:
+        out.update(achieved=None, frac=None, bytes_source="no ncu capture committed for this kernel")
+    return out
+
+
+def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_over_ranks, peak):
+    """A short run of another BASELINE.json configuration: device-resident value, serial step + dominant kernel, e2e."""
+    b = Bench(name, rank, world, args, barrier, max_over_ranks)
+    try:
+        steps = max(4, args.steps // 4)
+        dev_ms, _ = b.resident(steps, 2)
+        serial_ms, prof, stats, results = b.serial(3)
+        table, _ = kernel_table(b, prof, 3, peak)
+        top = next(iter(table))
+        e = b.e2e(steps, stream_scans=b.w.get("stream"))
+        scans_e2e = world * b.n_scans * e["batches"]
+        out = {"config": workload_config(name, world), "value": world * b.n_scans * steps / (dev_ms / 1e3), "unit": "scans/s",
+               "ms_per_step": dev_ms / steps, "steps": steps, "single_batch_ms": serial_ms,
+               "e2e": {"value": scans_e2e / e["seconds"], "unit": "scans/s", "h2d_bytes_per_step": e["h2d"],
+                       "d2h_bytes_per_step": e["d2h"], "batches": e["batches"],
+                       "pcie_gbs_each_way": round(max(e["h2d"], e["d2h"]) * e["batches"] / e["seconds"] / 1e9, 1)},
+               "dominant_kernel": {top: table[top]},
+               "streaming_kernels": {k: {"ms_per_step": v["ms_per_step"], "frac": v["frac"]} for k, v in table.items() if "frac" in v},
+               "objects_inserted_per_scan": sum_over_ranks(sum(len(r.inserted) for r in results)) / (world * b.n_scans),
+               "steps_per_scan_max": stats["max_steps_per_scan"]}
+        if b.w.get("stream"):
+            out["stream_scans"] = scans_e2e
+        return out
+    finally:
+        b.close()
+
+
 def main():
     # Libraries (NCCL's version banner, for one) write to fd 1: keep the real stdout for the ONE JSON line and send
     # everything else written to fd 1 during the run to stderr
@@ -273,15 +546,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scans", type=int, default=SCANS_PER_GPU)
+    ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS), help="headline workload (default: the one the metric is quoted on)")
+    ap.add_argument("--side-configs", default="c2,c4,c5",
+                    help="comma-separated other configurations measured briefly into the `configs` block ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--sub-batches", type=int, default=1,
-                    help="sub-batches the engine advances concurrently (own streams) in the device-resident leg")
-    ap.add_argument("--resident-depth", type=int, default=8,
-                    help="engines (each with its own HBM-resident batch) the device-resident leg deals the steps to: "
-                         "the thinning last rounds of one step overlap the busy first rounds of the next")
-    ap.add_argument("--e2e-sub-batches", type=int, default=2, help="same, per engine of the e2e pipeline")
-    ap.add_argument("--depth", type=int, default=4, help="engines (streams) the e2e leg pipelines batches through")
+    ap.add_argument("--resident-depth", type=int, default=3,
+                    help="engines (each with its own HBM-resident batch) the device-resident leg deals the steps to: one "
+                         "engine's streaming kernels overlap another's walker")
+    ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
     ap.add_argument("--side", default=None, choices=["rich_map_od", "rich_map_ss", "cut_objects"],
                     help="instead of the headline bench: one of the offline tools either side of the path (SURVEY 8f rows "
                          "3-4), GPU numbers from tools/bench_*.py plus the CPU baseline (numpy oracle port, one host core)")
@@ -300,10 +572,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    from pcl_augmentation_b200 import sharding as _sh
-    numa_cpus = _sh.bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("R3D_NUMA_BIND", "1") != "0") else None
+    from pcl_augmentation_b200 import sharding
+    numa_cpus = sharding.bind_to_gpu_numa_node(local_rank) if (world > 1 and os.environ.get("R3D_NUMA_BIND", "1") != "0") else None
     if world > 1:
-        # NCCL_DEBUG output goes to fd 1, which main() redirected to stderr: the JSON line keeps the real stdout
+        # NCCL_DEBUG output goes to fd 1, which was redirected to stderr above: the JSON line keeps the real stdout
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -311,193 +583,95 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    from pcl_augmentation_b200 import sharding
-
     def max_over_ranks(x):
         return sharding.all_reduce_scalar(x, "max", "cuda")
 
     def sum_over_ranks(x):
         return sharding.all_reduce_scalar(x, "sum", "cuda")
 
-    from pcl_augmentation_b200.engine import scan_input_from_case
-    from pcl_augmentation_b200.pipeline import ScanPipeline
-    n_scans = args.scans
-    cases = build_cases(rank, n_scans, min(DISTINCT_SCANS, n_scans))
-    n_points = len(cases[0].pcl5)
-    # PIPE_DEPTH engines (own stream, own device-resident batch, own host thread): the e2e leg streams batches through
-    # all of them so H2D, compute and D2H of consecutive batches overlap; the device-resident leg uses the first one
-    pipe = ScanPipeline("od", cases[0].config, cases[0].db, depth=args.depth, max_scans=n_scans, max_points=n_points,
-                        rows=ROWS, cols=COLS, yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1, sub_batches=args.sub_batches)
-    eng = pipe.engines[0]
-    staged = eng.stage([scan_input_from_case(c) for c in cases])
-    stream = eng.cuda_stream()
-    res_depth = max(1, args.resident_depth)
-    from pcl_augmentation_b200.engine import Real3DEngine
-    extra_engines = [Real3DEngine("od", cases[0].config, cases[0].db, max_scans=n_scans, max_points=n_points, rows=ROWS,
-                                  cols=COLS, yaw_steps=YAW_STEPS, max_events=N_OBJECTS + 1, sub_batches=args.sub_batches)
-                     for _ in range(res_depth - args.depth)]
-    res_engines = (pipe.engines + extra_engines)[:res_depth]
-
-    # ---- device-resident throughput ("value") --------------------------------------------------------
-    # Every resident engine holds the batch in HBM before the timed region starts.  A step = re-arm + all rounds +
-    # output compaction of one 256-scan batch; the K steps are dealt round-robin to `res_depth` engines (own host
-    # thread, own streams), so consecutive steps overlap: a step alone is bound by the chain of dependent kernels of
-    # its longest-running scan (rounds x kernel latency), not by the device.
-    for e in res_engines:
-        e.set_sub_batches(args.sub_batches)
-        e.load(staged)
-        e.sync()
-
-    def resident_steps(n_steps):
-        errors = []
-
-        def worker(w):
-            try:
-                for _ in range(w, n_steps, res_depth):
-                    res_engines[w].reset(from_raw_points=True)      # the whole device path: ingest + indices included
-                    res_engines[w].run()
-            except BaseException as exc:
-                errors.append(exc)
-        threads = [threading.Thread(target=worker, args=(w,), daemon=True) for w in range(res_depth)]
-        for t in threads:
-            t.start()
-        for t in threads:
-            t.join()
-        if errors:
-            raise errors[0]
-
-    resident_steps(max(args.warmup, res_depth))
-    for e in res_engines:
-        e.sync()
-    # one step alone (no overlap between steps): the latency of a batch
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    for _ in range(3):
-        eng.reset(from_raw_points=True); eng.run()
-    ev1.record(stream)
-    eng.sync()
-    single_batch_ms = ev0.elapsed_time(ev1) / 3
+    peak, peak_src = peaks()
+    name = args.config
+    b = Bench(name, rank, world, args, barrier, max_over_ranks)
+    n_scans = b.n_scans
     sampler = ClockSampler(local_rank)
     sampler.start()
-    barrier()
-    launches0 = eng.launch_count()
-    ext_streams = [e.cuda_stream() for e in res_engines]
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev_end = [torch.cuda.Event(enable_timing=True) for _ in res_engines]
-    barrier()
-    sampler.mark(True)
-    ev0.record(ext_streams[0])              # every engine stream is idle here (barrier = device synchronize)
-    resident_steps(args.steps)
-    for ev, es in zip(ev_end, ext_streams):
-        ev.record(es)
-    for e in res_engines:
-        e.sync()
-    sampler.mark(False)
-    barrier()
-    dev_ms = max(ev0.elapsed_time(ev) for ev in ev_end)
-    launches = eng.launch_count() - launches0
-    # per-kernel CUDA-event times: a second, untimed pass over the same steps with the engine's event profiling on
-    # (two event records per launch would otherwise sit inside the timed region)
-    # and ONE sub-batch, so that kernels run strictly one after the other and an event pair times one kernel alone
-    eng.set_sub_batches(1)
-    eng.profile(True)
-    for _ in range(args.steps):
-        eng.reset(from_raw_points=True)
-        eng.run()
-    eng.sync()
-    prof = eng.profile_read()
-    stats = eng.stats()
-    eng.profile(False)
-    eng.set_sub_batches(args.sub_batches)
-    dev_ms = max_over_ranks(dev_ms)
+
+    # ---- device-resident throughput ("value"): the whole device path from the raw points, steps overlapped ----------
+    dev_ms, launches = b.resident(args.steps, args.warmup, sampler)
     value = world * n_scans * args.steps / (dev_ms / 1000.0)
+    # ---- the same step alone on one engine, and the per-kernel times of exactly that mode ---------------------------
+    prof_steps = max(3, min(args.steps, 10))
+    serial_ms, prof, stats, results = b.serial(prof_steps)
+    table, kernel_sum_ms = kernel_table(b, prof, prof_steps, peak)
+    dominant = next(iter(table))
+    roofline = roofline_of(dominant, table[dominant], b, peak, peak_src)
+    streaming = [k for k, v in table.items() if "achieved_gbs" in v]
+    roofline_streaming = roofline_of(streaming[0], table[streaming[0]], b, peak, peak_src) if streaming else None
+    # consistency of the serial mode: the kernels add up to the step and none is longer than it
+    consistency = {"serial_step_ms": round(serial_ms, 4), "sum_of_kernels_ms": round(kernel_sum_ms, 4),
+                   "dominant_kernel_ms": table[dominant]["ms_per_step"],
+                   "ok": bool(table[dominant]["ms_per_step"] <= serial_ms * 1.02 and 0.85 * serial_ms <= kernel_sum_ms <= 1.1 * serial_ms)}
+    # measured DRAM traffic of one whole step (ncu, profiles/r2_step_traffic.json) over the timed step
+    step_traffic = None
+    tp = os.path.join(ROOT, "profiles", "r2_step_traffic.json")
+    if name == "c3" and os.path.exists(tp):
+        with open(tp) as f:
+            t = json.load(f)
+        gbs = t["dram_bytes_per_step"] / (dev_ms / args.steps / 1e3) / 1e9
+        step_traffic = {"dram_bytes_per_step": t["dram_bytes_per_step"], "source": t["source"],
+                        "achieved_gbs": round(gbs, 1), "frac_of_peak": round(gbs / peak, 4)}
 
-    # ---- end to end through the public API with host buffers ("e2e") -----------------------------------
-    # every step = one staged batch in pinned host memory: H2D of all points / labels / maps / schedules, the
-    # spherical ingest, the augmentation rounds, D2H of the augmented clouds into pinned host buffers
-    for e in pipe.engines:
-        e.set_sub_batches(args.e2e_sub_batches)
-    pipe.warmup(staged)
-    pipe.warmup(staged)
-    barrier()
-    sampler.mark(True)
-    t0 = time.perf_counter()
-    out_bytes = pipe.process([staged] * args.steps)
-    barrier()
-    e2e_s = max_over_ranks(time.perf_counter() - t0)
-    sampler.mark(False)
+    # ---- end to end through the public API with host buffers ("e2e") ------------------------------------------------
+    e = b.e2e(args.steps, sampler, stream_scans=b.w.get("stream"))
+    e2e_value = world * n_scans * e["batches"] / e["seconds"]
+    copy_s = max_over_ranks(copy_only_probe(e["h2d"], e["d2h"], args.steps, barrier))
+    copy_only = {"scans_per_s": world * n_scans * args.steps / copy_s,
+                 "gbs_each_way_per_gpu": round(max(e["h2d"], e["d2h"]) * args.steps / copy_s / 1e9, 1),
+                 "what": "the same H2D + D2H bytes per step from / to pinned host memory on two streams, no kernels, all ranks "
+                         "at once: the PCIe / host-memory ceiling of the e2e leg"}
     clocks = sampler.stop()
-    d2h = sum(out_bytes)
-    e2e_value = world * n_scans * args.steps / e2e_s
-    h2d = staged["xyzi"].nbytes + staged["labels"].nbytes + staged["boxes"].nbytes + staged["maps"].nbytes + staged["perms"].nbytes
-    results = eng.unpack(pipe._buffers[0])
-    inserted_total = sum(len(r.inserted) for r in results)
+    inserted_all = sum_over_ranks(sum(len(r.inserted) for r in results))
 
-    # ---- roofline of the dominant kernel ------------------------------------------------------------------
-    peak, peak_src = peaks()
-    hw = ROWS * COLS
-    total_kernel_ms = sum(v["ms"] for v in prof.values())
-    # the three placement stages (A5-A10) share ONE figure in SURVEY §8d (20 N bytes per tried object): one group
-    group = {"ms": sum(v["ms"] for k, v in prof.items() if k in PLACEMENT_STAGES),
-             "launches": max([v["launches"] for k, v in prof.items() if k in PLACEMENT_STAGES] or [0])}
-    entries = dict(prof)
-    entries["placement"] = group
-    kernel_table = {}
-    for name, v in sorted(entries.items(), key=lambda kv: -kv[1]["ms"]):
-        per_unit, units = algorithmic_bytes(name, n_points, hw, stats, n_scans, args.steps)
-        entry = {"ms": round(v["ms"], 3), "launches": v["launches"], "share": round(v["ms"] / max(total_kernel_ms, 1e-9), 4)}
-        if name == "placement":
-            entry["stages"] = [k for k in PLACEMENT_STAGES if k in prof and prof[k]["launches"]]
-        if per_unit and units and v["ms"] > 0:
-            gbs = per_unit * units / (v["ms"] / 1000.0) / 1e9
-            entry.update(algorithmic_bytes_per_unit=per_unit, units=units, achieved_gbs=round(gbs, 1),
-                         frac=round(gbs / peak, 4))
-        kernel_table[name] = entry
-    roofline = None
-    for name, e in kernel_table.items():        # dominant kernel (stage) = largest share of device time with a bytes model
-        if "achieved_gbs" in e:
-            traffic = measured_traffic(name)
-            roofline = {"kernel": name, "bound": "hbm", "achieved": e["achieved_gbs"], "peak": peak, "unit": "GB/s",
-                        "frac": e["frac"], "traffic": traffic["bytes_per_launch"] if traffic else None,
-                        "traffic_source": traffic["source"] if traffic else None, "peak_source": peak_src,
-                        "bytes_per_launch": e["algorithmic_bytes_per_unit"] * e["units"] / max(e["launches"], 1),
-                        "avg_launch_ms": e["ms"] / max(e["launches"], 1), "share_of_kernel_time": e["share"]}
-            break
-    b_scan = N_OBJECTS * (45 * n_points + 24 * hw) + 40 * n_points
-    step_roofline = {"algorithmic_bytes_per_scan": b_scan, "achieved_gbs": round(value / world * b_scan / 1e9, 1),
-                     "frac_of_peak": round(value / world * b_scan / 1e9 / peak, 4)}
-
-    # ---- CPU baseline (rank 0, N = 1 only) ----------------------------------------------------------------
+    # ---- CPU baseline (rank 0, N = 1 only) and the other configurations -----------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, n_done, secs = cpu_baseline_sample()
-        cpu = {"value": v, "unit": "scans/s", "cores": 1, "kind": "port",
-               "sample": f"{n_done} whole scan(s) of the same workload through oracle/real3d_oracle.py, {secs:.1f} s",
-               "host_cpus": os.cpu_count()}
-    inserted_all = sum_over_ranks(inserted_total)
+        cpu = cpu_baseline_sample(name, 20.0)
+    res_depth = b.res_depth
+    b.close()
+    configs = {}
+    for side in [s for s in args.side_configs.split(",") if s and s != name]:
+        configs[side] = measure_side_config(side, rank, world, args, barrier, max_over_ranks, sum_over_ranks, peak)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            configs[side]["cpu_baseline"] = cpu_baseline_sample(side, 6.0)
     if rank == 0:
+        cyc = stats.get("walker_cycles", {})
         print(file=json_out, flush=True, *[json.dumps({
             "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(world), steps_in_flight=f"{res_depth} (one 256-scan step per resident engine; "
-                           f"`single_batch_ms` is a step alone)"),
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h / args.steps), "pipeline_depth": args.depth,
-                    "sub_batches_per_engine": args.e2e_sub_batches,
-                    "ms_per_step": 1000.0 * e2e_s / args.steps,
-                    "pcie_gbs_each_way": round(max(h2d, d2h / args.steps) / (e2e_s / args.steps) / 1e9, 1)},
-            "gpu_launches": int(launches), "clocks": clocks, "sub_batches": args.sub_batches,
-            "resident_engines": res_depth, "single_batch_ms": single_batch_ms, "numa_bound_cpus": numa_cpus,
-            "single_batch_scans_per_s": world * n_scans / (single_batch_ms / 1000.0),
-            "kernel_times": "CUDA events around every launch in a separate pass with one sub-batch (serial)",
-            "step_roofline": step_roofline, "kernels": kernel_table,
-            "rounds_per_step": results[0].extra["rounds"], "objects_inserted_per_scan": inserted_all / (world * n_scans),
-            "engine_stats": stats})])
-    pipe.close()
-    for e in extra_engines:
-        e.close()
+            "config": dict(workload_config(name, world),
+                           steps_in_flight=f"{res_depth} resident engines, one {n_scans}-scan step each (`single_batch_ms` is a step alone)"),
+            "roofline": roofline, "roofline_streaming": roofline_streaming, "step_traffic": step_traffic,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
+                    "pipeline_depth": args.depth, "ms_per_step": 1000.0 * e["seconds"] / e["batches"],
+                    "pcie_gbs_each_way": round(max(e["h2d"], e["d2h"]) * e["batches"] / e["seconds"] / 1e9, 1),
+                    "copy_only": copy_only, "of_copy_only": round(e2e_value / copy_only["scans_per_s"], 3),
+                    "timed": "H2D of the staged batch (pinned), ingest + walker + compaction, D2H of the augmented clouds into "
+                             "pinned buffers; packing scans into the staged batch (the dataset reader's job) is outside"},
+            "gpu_launches": int(launches), "clocks": clocks, "resident_engines": res_depth,
+            "single_batch_ms": serial_ms, "single_batch_scans_per_s": n_scans / (serial_ms / 1000.0),
+            "numa_bound_cpus": numa_cpus,
+            "kernel_times": "CUDA events around every launch of the serial mode (one engine, one step at a time); `share` = of "
+                            "the sum of kernel times",
+            "kernels": table, "consistency": consistency,
+            "walker": {"steps_per_scan_max": stats["max_steps_per_scan"],
+                       "tries_per_scan": stats["tried_objects"] / max(prof_steps * n_scans, 1),
+                       "candidate_windows_per_try": stats["candidate_windows"] / max(stats["tried_objects"], 1),
+                       "exact_occlusion_counts_per_try": stats["exact_occlusion_counts"] / max(stats["tried_objects"], 1),
+                       "phase_share_of_cta_time": {k: round(v / max(cyc.get("total", 1), 1), 4) for k, v in cyc.items() if k != "total"}},
+            "objects_inserted_per_scan": inserted_all / (world * n_scans),
+            "configs": configs, "engine_stats": {k: v for k, v in stats.items() if k != "walker_cycles"}})])
     if world > 1:
         dist.destroy_process_group()
 

@@ -291,10 +291,12 @@ int r3d_engine_probe_places(r3d_engine* eng, int scan, int object_id, const doub
  * objects tried, vis_px masks applied, scans patched in place, selections in the shared-memory tile, selections in
  * the global scratch image, 0, 0} — the "units one launch processes" of the roofline arithmetic */
 int r3d_engine_stats(r3d_engine* eng, uint64_t* out8);
-/* the first n (<= 24) counters: the 8 above, then {max steps of one scan in the last run, candidate windows evaluated,
+/* the first n (<= 32) counters: the 8 above, then {max steps of one scan in the last run, candidate windows evaluated,
  * exact occlusion counts (candidates the two-sided bound could not decide), full re-projections inside the walker,
  * 4 unused}, then the walker's phase clocks in SM cycles summed over all scans: {scheduling step, slot update, try
- * set-up + prefilter, placement windows, occlusion counts, selection + insertion, whole walk, unused} */
+ * set-up + prefilter, placement windows, occlusion counts, selection + insertion, whole walk}, then finer clocks:
+ * {on-map stage, road-level warps, collision warps, road-level searches, collision tests, mask apply, z-buffer patch,
+ * close/fill} */
 int r3d_engine_stats_ex(r3d_engine* eng, uint64_t* out, int n);
 /* the engine's cudaStream_t (so callers can bracket work with their own CUDA events) */
 void* r3d_engine_stream(r3d_engine* eng);

@@ -96,7 +96,7 @@ struct r3d_engine {
     DevBuf<unsigned long long> zraw, obj_raw, stats;
     DevBuf<long long> od_map_off, out_count, out_off, check_off;
     DevBuf<ScanState> st;
-    DevBuf<Box> boxes;
+    DevBuf<Box> boxes, boxes0;                   // boxes0: the scene boxes as loaded (re-arm drops the inserted ones, device to device)
     DevBuf<BoxTest> box_tests;
     DevBuf<ObjBox> obj, try_obj;
     DevBuf<ClassCfg> classes;
@@ -264,6 +264,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     if (const char* env = getenv("R3D_WINDOW")) d.cand_window = std::max(0, atoi(env));
     if (d.task != 0) d.cand_window = 0;          // semseg walks the yaws with a carried z shift (ss/fs:146-147): no window
     TRY(eng->far_arr.alloc(B)); TRY(eng->boxes.alloc(B * d.max_boxes)); TRY(eng->box_tests.alloc(B * d.max_boxes));
+    TRY(eng->boxes0.alloc(B * d.max_boxes));
     TRY(eng->poses.alloc(B * 16)); TRY(eng->occ_win.alloc(B * ((size_t)d.map_window * d.map_window / 32)));
     TRY(eng->counts.alloc(B * d.n_classes)); TRY(eng->cos_k.alloc(K1)); TRY(eng->sin_k.alloc(K1));
     TRY(eng->radii_sq.alloc(R3D_NUM_RADII)); TRY(eng->radii_ok.alloc(R3D_NUM_RADII)); TRY(eng->classes.alloc(R3D_MAX_CLASSES));
@@ -420,9 +421,8 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     R3D_CUDA(cudaFuncSetAttribute(k_occl_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)occl_smem_bytes(d)));
     if (onmap_smem_bytes(d.K) > 100 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: too many yaw steps for the placement kernel's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_onmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onmap_smem_bytes(d.K)));
-    if (2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G > 48 * 1024)
-        R3D_CUDA(cudaFuncSetAttribute(k_grid_near_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G)));
+    if (grid_near_smem(d.G) > 200 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: road-level grid too large for shared memory");
+    R3D_CUDA(cudaFuncSetAttribute(k_grid_near_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_near_smem(d.G)));
     if (walk_smem_layout(d.K, d.dwords).total > 200 * 1024)
         return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: range image / yaw steps too large for the walker's shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_layout(d.K, d.dwords).total));
@@ -461,15 +461,14 @@ static int arm_batch(r3d_engine* eng, bool ingest) {
         { Launcher l(eng, KID_SCATTER); k_scatter_project<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(d, n); }
         {
             Launcher l(eng, KID_GRID);
-            const size_t near_smem = 2 * (size_t)(NEAR_BAND + 2 * (NEAR_CAP - 1)) * d.G;
-            k_grid_near_tiled<<<dim3((d.G + NEAR_BAND - 1) / NEAR_BAND, n), 256, near_smem, st>>>(d, n);
+            k_grid_near_bits<<<n, NEAR_THREADS, grid_near_smem(d.G), st>>>(d, n);
         }
         eng->fresh = true;                       // the first range image of every scan is already projected
     } else {
         eng->fresh = false;
         k_reset_alive<<<dim3(std::max(chunks, 1), n), 256, 0, st>>>(d, n); r3d_count_launch();
         // scene boxes: drop the boxes appended by the previous run
-        R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, st));
+        R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->boxes0.p, eng->h_boxes.size() * sizeof(Box), cudaMemcpyDeviceToDevice, st));
         k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, st>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
         r3d_count_launch();
     }
@@ -511,6 +510,7 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
         }
     eng->h_nbox0 = nb;
     R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, st));
+    R3D_CUDA(cudaMemcpyAsync(eng->boxes0.p, eng->boxes.p, eng->h_boxes.size() * sizeof(Box), cudaMemcpyDeviceToDevice, st));
     k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, st>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
     r3d_count_launch();
     R3D_CUDA(cudaMemcpyAsync(eng->n0_arr.p, n0.data(), n * sizeof(int), cudaMemcpyHostToDevice, st));
@@ -576,7 +576,7 @@ extern "C" int r3d_engine_rearm_batch(r3d_engine* eng, int from_raw_points) {
     if (!eng || !eng->batch_loaded) return r3d_fail(R3D_ERR_ARG, "r3d_engine_rearm_batch: no batch loaded");
     if (!from_raw_points) return arm_batch(eng, false);
     // the whole device path from the resident float4 points again: scene boxes, spherical ingest, spatial indices
-    R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->h_boxes.data(), eng->h_boxes.size() * sizeof(Box), cudaMemcpyHostToDevice, eng->stream));
+    R3D_CUDA(cudaMemcpyAsync(eng->boxes.p, eng->boxes0.p, eng->h_boxes.size() * sizeof(Box), cudaMemcpyDeviceToDevice, eng->stream));
     k_box_tests<<<(int)((eng->h_boxes.size() + 127) / 128), 128, 0, eng->stream>>>(eng->boxes.p, eng->box_tests.p, (int)eng->h_boxes.size());
     r3d_count_launch();
     return arm_batch(eng, true);

@@ -173,7 +173,7 @@ struct EngineDev {       // passed by value to kernels
     float* out_check;
 };
 
-#define R3D_N_STATS 24
+#define R3D_N_STATS 32
 #ifndef R3D_OCC_G
 #define R3D_OCC_G 8
 #endif

@@ -22,7 +22,7 @@ __device__ int list_entry(const EngineDev& e, int b, int ev, int ci, int sidx, i
 // one step of the state machine for scan b (ONE thread): what the scan needs next — apply the last vis_px mask,
 // refresh the range image (new slot after a scene change), try a cut object.  Shared by the staged round kernel k_ctrl
 // and the per-scan persistent walker (r3d_k_walk.cuh).
-__device__ __noinline__ void ctrl_advance(const EngineDev& e, int b, ScanState& s, int& apply, int& project, int& tryact) {
+__device__ void ctrl_advance(const EngineDev& e, int b, ScanState& s, int& apply, int& project, int& tryact) {
     apply = 0; project = 0; tryact = 0;
     if (s.phase != PH_DONE && s.phase != PH_ERROR) {
         const int uw = (e.n_objects + 31) / 32;

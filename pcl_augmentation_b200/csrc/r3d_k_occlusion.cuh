@@ -194,7 +194,7 @@ __device__ __forceinline__ SelScratch sel_scratch(unsigned long long* dyn, int k
 }
 
 // every thread of the CTA (any size) calls it; k = rotation of the chosen candidate, `accepted` = it keeps min_points
-__device__ __noinline__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k, bool accepted, SelScratch q) {
+__device__ void select_emit_body(const EngineDev& e, int b, ScanState& s, int k, bool accepted, SelScratch q) {
     unsigned long long* s_keys = q.keys;
     double* s_r = q.r;
     unsigned long long* s_tile = q.tile;

@@ -140,44 +140,68 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e,
     }
 }
 
-// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell of the surface grid to the nearest non-empty one,
-// one CTA per band of NEAR_BAND rows of one scan: occupancy and the row-pass result of the band (+ halo rows) live in
-// shared memory, both passes stop at the first hit.
-constexpr int NEAR_BAND = 32;
-__global__ void __launch_bounds__(256) k_grid_near_tiled(EngineDev e, int n_scans) {
-    const int b = blockIdx.y, G = e.G;
+// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell of the surface grid to the nearest non-empty one.
+// One CTA per scan, bit-parallel: the occupancy of the grid is a bit image in shared memory (a row of G cells = a few
+// 32-bit words); dilating it by a 3 x 3 square d times gives the cells within Chebyshev distance d, so the distance of a
+// cell is the first d at which its bit turns on — a dozen sweeps of shifts and ORs over ~2k words instead of a 23-tap
+// min filter per cell in each direction.
+constexpr int NEAR_THREADS = 1024;
+__host__ __device__ __forceinline__ size_t grid_near_smem(int G) {
+    const int wpr = (G + 31) / 32;
+    return (size_t)G * G + 2 * (size_t)(G + 2) * wpr * 4;           // distance bytes + two bit images with a zero row above / below
+}
+__global__ void __launch_bounds__(NEAR_THREADS) k_grid_near_bits(EngineDev e, int n_scans) {
+    const int b = blockIdx.x, G = e.G;
     if (b >= n_scans) return;
-    extern __shared__ unsigned char s_near[];
-    constexpr int HALO = NEAR_CAP - 1, ROWS = NEAR_BAND + 2 * HALO;
-    unsigned char* s_occ = s_near;                  // [ROWS][G]
-    unsigned char* s_row = s_near + (size_t)ROWS * G;
-    const int y0 = blockIdx.x * NEAR_BAND - HALO;
+    extern __shared__ __align__(16) unsigned char s_near[];
+    const int wpr = (G + 31) / 32, nwords = G * wpr;
+    unsigned char* s_dist = s_near;                                              // [G][G]
+    unsigned* s_a = reinterpret_cast<unsigned*>(s_near + (((size_t)G * G + 15) & ~(size_t)15));   // [(G + 2)][wpr], row 0 and G + 1 stay zero
+    unsigned* s_b = s_a + (size_t)(G + 2) * wpr;
     const int* cell = e.gcell + (size_t)b * G * G;
-    for (int i = threadIdx.x; i < ROWS * G; i += blockDim.x) {
-        const int y = y0 + i / G, x = i % G;
-        unsigned char o = 0;
-        if (y >= 0 && y < G) { const int q = y * G + x; o = cell[q] > (q > 0 ? cell[q - 1] : 0); }
-        s_occ[i] = o;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = NEAR_THREADS / 32;
+    for (int i = tid; i < (G + 2) * wpr; i += NEAR_THREADS) { s_a[i] = 0u; s_b[i] = 0u; }
+    for (int i = tid; i < G * G / 4; i += NEAR_THREADS) reinterpret_cast<unsigned*>(s_dist)[i] = 0x01010101u * (unsigned)NEAR_CAP;
+    for (int i = (G * G / 4) * 4 + tid; i < G * G; i += NEAR_THREADS) s_dist[i] = (unsigned char)NEAR_CAP;
+    __syncthreads();
+    for (int u = warp; u < nwords; u += nwarps) {                                // occupancy bits, one ballot per word
+        const int y = u / wpr, x = (u % wpr) * 32 + lane;
+        bool occ = false;
+        if (x < G) { const int q = y * G + x; occ = cell[q] > (q > 0 ? cell[q - 1] : 0); }
+        const unsigned m = __ballot_sync(0xffffffffu, occ);
+        if (lane == 0) s_a[(size_t)(y + 1) * wpr + u % wpr] = m;
+        if (occ) s_dist[y * G + x] = 0;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ROWS * G; i += blockDim.x) {
-        const int x = i % G;
-        const unsigned char* row = s_occ + (i - x);
-        int best = NEAR_CAP;
-        for (int d = 0; d < NEAR_CAP; ++d) {
-            if ((x - d >= 0 && row[x - d]) || (x + d < G && row[x + d])) { best = d; break; }
+    unsigned* cur = s_a;
+    unsigned* nxt = s_b;
+    for (int d = 1; d < NEAR_CAP; ++d) {
+        for (int u = tid; u < nwords; u += NEAR_THREADS) {
+            const int y = u / wpr, w = u % wpr;
+            unsigned acc = 0u;
+#pragma unroll
+            for (int dy = 0; dy <= 2; ++dy) {                                    // rows y - 1, y, y + 1 (padded image)
+                const unsigned* row = cur + (size_t)(y + dy) * wpr;
+                const unsigned m = row[w];
+                acc |= m | (m << 1) | (m >> 1) | (w > 0 ? row[w - 1] >> 31 : 0u) | (w + 1 < wpr ? row[w + 1] << 31 : 0u);
+            }
+            if (w == wpr - 1 && (G & 31)) acc &= (1u << (G & 31)) - 1u;            // no cells beyond column G - 1
+            const unsigned old = cur[(size_t)(y + 1) * wpr + w];
+            nxt[(size_t)(y + 1) * wpr + w] = acc;
+            unsigned fresh = acc & ~old;                                          // cells first reached at distance d
+            while (fresh) {
+                const int bit = __ffs(fresh) - 1; fresh &= fresh - 1;
+                const int x = w * 32 + bit;
+                if (x < G) s_dist[y * G + x] = (unsigned char)d;
+            }
         }
-        s_row[i] = (unsigned char)best;
+        __syncthreads();
+        unsigned* t = cur; cur = nxt; nxt = t;
     }
-    __syncthreads();
-    for (int i = threadIdx.x; i < NEAR_BAND * G; i += blockDim.x) {
-        const int ly = HALO + i / G, x = i % G, y = y0 + ly;
-        if (y >= G) continue;
-        int best = NEAR_CAP;
-        for (int d = 0; d < best; ++d) {                // rows outside the grid hold NEAR_CAP (no occupancy): no effect
-            const int a = s_row[(ly - d) * G + x], c = s_row[(ly + d) * G + x];
-            best = min(best, max(d, min(a, c)));
-        }
-        e.gnear[(size_t)b * G * G + (size_t)y * G + x] = (unsigned char)best;
+    unsigned char* out = e.gnear + (size_t)b * G * G;
+    if ((((size_t)b * G * G) & 15) == 0 && (G * G) % 16 == 0) {
+        for (int i = tid; i < G * G / 16; i += NEAR_THREADS) reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(s_dist)[i];
+    } else {
+        for (int i = tid; i < G * G; i += NEAR_THREADS) out[i] = s_dist[i];
     }
 }

@@ -10,6 +10,11 @@
 // in ORDERED WINDOWS with a real early exit at the first candidate that keeps min_points (od/ins:530-561).
 // The once-per-scan streaming work (spherical ingest, indices, first full projection + close/fill, output
 // compaction) stays in batch-wide HBM-bound kernels before / after this one.
+#ifdef R3D_WALK_NOINLINE
+#define R3D_WALK_FN __noinline__
+#else
+#define R3D_WALK_FN
+#endif
 #ifndef R3D_WALK_THREADS
 #define R3D_WALK_THREADS 512
 #endif
@@ -49,7 +54,8 @@ __host__ __device__ __forceinline__ WalkSmem walk_smem_layout(int K, int dwords)
 }
 
 // phase clocks (SM cycles, summed over all scans by thread 0 of each CTA) -> e.stats[WALK_T0 + phase]
-enum : int { WT_CTRL = 0, WT_UPDATE, WT_SETUP, WT_PLACE, WT_OCCL, WT_SELECT, WT_TOTAL, WT_COUNT };
+enum : int { WT_CTRL = 0, WT_UPDATE, WT_SETUP, WT_PLACE, WT_OCCL, WT_SELECT, WT_TOTAL, WT_ONMAP, WT_LEVEL_WARP, WT_COLLIDE_WARP,
+              WT_N_LEVEL, WT_N_COLLIDE, WT_APPLY, WT_PATCH, WT_CLOSEFILL, WT_COUNT };
 constexpr int WALK_T0 = 16;
 struct WalkClock {
     long long t;
@@ -84,7 +90,7 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
 
 // ---- A4 on a pixel rectangle, any CTA size (the batch-wide kernel is r3d_closefill.cuh): tiles of CF_TH x CF_TW
 // outputs staged with their halo in shared memory, bit-row morphology, ordered fp64 neighbour mean
-__device__ __noinline__ void walk_close_fill(const EngineDev& e, int b, const int* rect, unsigned char* scratch) {
+__device__ R3D_WALK_FN void walk_close_fill(const EngineDev& e, int b, const int* rect, unsigned char* scratch) {
     unsigned long long (*s_raw)[CF_SW] = reinterpret_cast<unsigned long long (*)[CF_SW]>(scratch);
     unsigned (*s_one)[CF_WORDS] = reinterpret_cast<unsigned (*)[CF_WORDS]>(scratch + (size_t)CF_SH * CF_SW * 8);
     unsigned (*s_in)[CF_WORDS] = s_one + CF_SH;
@@ -165,7 +171,7 @@ __device__ __noinline__ void walk_close_fill(const EngineDev& e, int b, const in
 
 // ---- A2 + A3 for the whole scan inside the CTA: the rare slot whose elevation range moved (the first projection of
 // every scan is done batch-wide by k_minmax / k_clear_images / k_project before the walker starts)
-__device__ __noinline__ void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
+__device__ R3D_WALK_FN void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t base = (size_t)b * e.P;
     const int n = s.n0 + s.n_tail;
@@ -204,19 +210,24 @@ __device__ __noinline__ void walk_full_reproject(const EngineDev& e, int b, Scan
 }
 
 // ---- semseg addjust_map_2 (ss/ins:202-224) for the scan's live points (same rule as k_adjust_map)
-__device__ __noinline__ void walk_adjust_map(const EngineDev& e, int b, ScanState& s) {
+__device__ R3D_WALK_FN void walk_adjust_map(const EngineDev& e, int b, ScanState& s) {
     const int n = s.n0 + s.n_tail;
     const double* T = e.poses + (size_t)b * 16;
     for (int p = threadIdx.x; p < n; p += blockDim.x) adjust_map_point(e, b, s, T, p);
 }
 
 // ---- slot update: what k_update + the refresh kernels of a staged round do for one scan
-__device__ __noinline__ void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
+__device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
                             unsigned char* scratch) {
+    long long ut = clock64();
+    auto ulap = [&](int phase) {
+        if (threadIdx.x == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + phase], (unsigned long long)(n - ut)); ut = n; }
+    };
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t base = (size_t)b * e.P;
     const bool ext = do_apply && apply_vis_mask(e, b, s, tid, nt);
     const int extreme = __syncthreads_or(ext);
+    ulap(WT_APPLY);
     if (tid == 0) {
         int full = 0, patch = 0;
         int* rect = c.rect;
@@ -267,7 +278,9 @@ __device__ __noinline__ void walk_update(const EngineDev& e, int b, ScanState& s
         walk_full_reproject(e, b, s, c);
     }
     __syncthreads();
+    ulap(WT_PATCH);
     if (c.rect[1] >= c.rect[0] && c.rect[3] >= c.rect[2]) walk_close_fill(e, b, c.rect, scratch);
+    ulap(WT_CLOSEFILL);
     if (do_update && e.task == 1) { __syncthreads(); walk_adjust_map(e, b, s); }
     __syncthreads();
 }
@@ -331,7 +344,7 @@ __device__ __forceinline__ bool walk_onmap_od(const EngineDev& e, int b, const O
 // road-level ring search and the collision test are chains of dependent cell / point loads, so a candidate gets 32
 // lanes (four times shorter chains than the 8-lane groups of the staged kernels) and a free warp takes the next one.
 // with_level: search the road level first (OD); otherwise the level is already in c.wlevel (semseg).
-__device__ __noinline__ void walk_level_collide(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, int n, bool with_level) {
+__device__ R3D_WALK_FN void walk_level_collide(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, int n, bool with_level) {
     const int lane = threadIdx.x & 31;
     const ObjBox& ob = c.ob;
     const ClassCfg& cc = e.classes[ob.cls];
@@ -345,17 +358,26 @@ __device__ __noinline__ void walk_level_collide(const EngineDev& e, int b, const
         const double cs = e.cos_k[k], sn = e.sin_k[k];
         double level = c.wlevel[i];
         unsigned f = CF_ONMAP | CF_HOK;
+        const long long t0 = clock64();
         if (with_level && !group_road_level<32>(e, b, surf, sub(mul(cs, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(cs, ob.cy)), lane,
                                                 0xffffffffu, level))
             f = CF_ONMAP;                                              // od/fs:281-285
+        const long long t1 = clock64();
         if ((f & CF_HOK) && group_collides<32>(e, b, s, ob, cc, cs, sn, level, lane, 0xffffffffu)) f |= CF_COLLIDE;
-        if (lane == 0) { c.wflag[i] = (unsigned char)f; c.wlevel[i] = level; }
+        if (lane == 0) {
+            c.wflag[i] = (unsigned char)f; c.wlevel[i] = level;
+            atomicAdd(&e.stats[WALK_T0 + WT_LEVEL_WARP], (unsigned long long)(t1 - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_LEVEL], 1ull);
+            if (f & CF_HOK) {
+                atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t1));
+                atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull);
+            }
+        }
     }
 }
 
 // ---- semseg window: A6b with the carried z shift as a fixed-point iteration over the window's yaws (see k_onmap_ss),
 // the road level searched only for the yaws that pass the map test, then A8/A9
-__device__ __noinline__ void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
+__device__ R3D_WALK_FN void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
                                const double* oz, int base, int nw) {
     const int tid = threadIdx.x, g = tid / GRP, gl = tid % GRP;
     const unsigned gm = group_mask();
@@ -420,7 +442,7 @@ __device__ __noinline__ void walk_window_ss(const EngineDev& e, int b, ScanState
 
 // ---- exact A11 count of one candidate with the whole CTA (visible-pixel bit image in shared memory), for the
 // candidates the two-sided bound of walk_try cannot decide
-__device__ __noinline__ int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int k, double level, unsigned* bits) {
+__device__ R3D_WALK_FN int walk_exact_visible(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int k, double level, unsigned* bits) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const ObjBox& ob = c.ob;
     const ImageGeom g = s.geom;
@@ -450,7 +472,7 @@ __device__ __noinline__ int walk_exact_visible(const EngineDev& e, int b, ScanSt
 }
 
 // ---- one tried cut object (od/ins:430-561)
-__device__ __noinline__ void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, unsigned char* dyn, const WalkSmem& L, WalkClock& clk) {
+__device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, WalkCtl& c, unsigned char* dyn, const WalkSmem& L, WalkClock& clk) {
     const int K = e.K, tid = threadIdx.x, nt = blockDim.x;
     double* s_ox = reinterpret_cast<double*>(dyn);
     double* s_oy = s_ox + OBJ_SMEM_PTS;
@@ -512,6 +534,7 @@ __device__ __noinline__ void walk_try(const EngineDev& e, int b, ScanState& s, W
                 if (gl == 0) { c.wk[g] = k; c.wflag[g] = on ? CF_ONMAP : 0; c.wlevel[g] = 0.0; }
             }
             __syncthreads();
+            if (tid == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_ONMAP], (unsigned long long)(n - clk.t)); }
             const int n_on = walk_window_list(c, nw, c.won, [&](int i) { return (c.wflag[i] & CF_ONMAP) != 0; });
             if (tid == 0) atomicAdd(&e.stats[7], (unsigned long long)n_on);
             walk_level_collide(e, b, s, c, n_on, true);

@@ -70,7 +70,11 @@ class Real3DEngine:
         self.classes = list(config['insertion']['classes'])
         self.rows, self.cols, self.yaw_steps, self.max_tries = rows, cols, yaw_steps, max_tries
         self.max_scans, self.max_points = int(max_scans), int(max_points)
-        nobj = int(config['insertion'].get('number_of_object', 10))
+        self.grid_half, self.grid_cell = int(grid_half), float(grid_cell)
+        self.road_label = int(config['labels']['Road']) if task == 'od' else 0
+        ins = config['insertion']
+        # slots per scan: the pre-drawn class counts sum to number_of_object (random) or to sum(number_of_classes)
+        nobj = int(ins.get('number_of_object', 10)) if ins.get('random', True) else int(np.sum(ins['number_of_classes']))
         self.max_events = int(max_events if max_events is not None else nobj + 1)
         self._prepare_db(db)
         if max_inserted is None:
@@ -192,6 +196,11 @@ class Real3DEngine:
         box_off = np.zeros(n + 1, dtype=np.int32)
         box_rows = []
         n_events = max(int(np.asarray(s.perms).shape[0]) for s in scans)
+        most = max(int(np.sum(s.counts)) for s in scans)
+        if most + 1 > self.max_events:
+            raise _lib.Real3DError(f"a scan asks for {most} insertions but the engine was built with max_events = "
+                                   f"{self.max_events} (insertion.number_of_object / number_of_classes of the config, or "
+                                   f"pass max_events)")
         nc = len(self.classes)
         counts = _pinned((n, nc), np.int32)
         counts[:] = 0
@@ -398,15 +407,29 @@ class Real3DEngine:
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
     def stats(self):
-        out = np.zeros(24, dtype=np.uint64)
-        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 24), "stats")
+        out = np.zeros(32, dtype=np.uint64)
+        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 32), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
                 'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5]),
                 'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7]), 'max_steps_per_scan': int(out[8]),
                 'candidate_windows': int(out[9]), 'exact_occlusion_counts': int(out[10]),
                 'walker_full_reprojections': int(out[11]),
                 'walker_cycles': {k: int(out[16 + i]) for i, k in enumerate(
-                    ('schedule', 'update', 'setup_prefilter', 'placement', 'occlusion', 'select_insert', 'total'))}}
+                    ('schedule', 'update', 'setup_prefilter', 'placement', 'occlusion', 'select_insert', 'total'))},
+                'walker_detail': {k: int(out[16 + 7 + i]) for i, k in enumerate(
+                    ('onmap_cycles', 'level_warp_cycles', 'collide_warp_cycles', 'n_level', 'n_collide', 'apply_cycles',
+                     'patch_cycles', 'closefill_cycles'))}}
+
+    def surface_labels(self):
+        """Semantic labels the road-level search of any class accepts (what the surface grid indexes)."""
+        if self.task == 'od':
+            return [int(self.config['labels']['Road'])]
+        ins = self.config['insertion']
+        out = set()
+        for cls in self.classes:
+            for v in ins['placement'][cls]:
+                out.update(int(x) for x in ins['placement_labels'][v])
+        return sorted(out)
 
     def cuda_stream(self):
         import torch
