@@ -91,6 +91,7 @@ struct r3d_engine {
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks, need2, occ_far;
+    DevBuf<unsigned> occ_cnt;
     DevBuf<unsigned> round_ctl;
     DevBuf<unsigned char> alive, od_maps, ss_map, cand_flags, gnear, gscratch;
     DevBuf<unsigned long long> zraw, obj_raw, stats;
@@ -286,6 +287,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->od_map_off.alloc(B * 2 + 1)); TRY(eng->od_map_dims.alloc(B * 8)); TRY(eng->stats.alloc(R3D_N_STATS));
     R3D_CUDA(cudaMemset(eng->stats.p, 0, R3D_N_STATS * sizeof(unsigned long long)));
     TRY(eng->occ_far.alloc(B * (OCC_FAR_CAP + 1)));
+    if (cfg->task == 1) TRY(eng->occ_cnt.alloc(B * (size_t)d.map_window * d.map_window));
     R3D_CUDA(cudaMemset(eng->occ_far.p, 0xFF, B * (OCC_FAR_CAP + 1) * sizeof(int)));
     R3D_CUDA(cudaHostAlloc((void**)&eng->h_words, R3D_MAX_SUB * 64 * sizeof(unsigned long long), cudaHostAllocMapped));
     memset(eng->h_words, 0, R3D_MAX_SUB * 64 * sizeof(unsigned long long));
@@ -321,7 +323,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     d.gcell = eng->gcell.p; d.gpts = eng->gpts.p; d.gnear = eng->gnear.p; d.gscratch = eng->gscratch.p;
     d.col_off = eng->col_off.p; d.col_idx = eng->col_idx.p; d.acell = eng->acell.p; d.apts = eng->apts.p;
     d.try_obj = eng->try_obj.p; d.chunk_cnt = eng->chunk_cnt.p;
-    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p; d.occ_far = eng->occ_far.p;
+    d.od_map_off = eng->od_map_off.p; d.od_map_dims = eng->od_map_dims.p; d.stats = eng->stats.p; d.occ_far = eng->occ_far.p; d.occ_cnt = eng->occ_cnt.p;
     *out = eng;
     return R3D_OK;
 }
@@ -605,7 +607,7 @@ static EngineDev sub_view(const EngineDev& d, int b0) {
     R3D_OFF(occ_pix, (size_t)OCC_G * d.max_obj_points); R3D_OFF(sel_pix, d.max_obj_points);
     R3D_OFF(sel_keys, d.sel_key_cap); R3D_OFF(sel_r, d.max_obj_points); R3D_OFF(inserted, (size_t)d.max_events * 4);
     R3D_OFF(inserted_box, (size_t)d.max_events * 8); R3D_OFF(check, (size_t)d.max_inserted * 5); R3D_OFF(chunk_cnt, d.max_chunks);
-    R3D_OFF(out_count, 1); R3D_OFF(occ_far, OCC_FAR_CAP + 1);
+    R3D_OFF(out_count, 1); R3D_OFF(occ_far, OCC_FAR_CAP + 1); R3D_OFF(occ_cnt, (size_t)d.map_window * d.map_window);
 #undef R3D_OFF
     return v;
 }
@@ -649,7 +651,8 @@ static int run_walker(r3d_engine* eng) {
     }
     if (d.task == 1) {
         R3D_CUDA(cudaMemsetAsync(eng->occ_win.p, 0, (size_t)n * ((size_t)d.map_window * d.map_window / 32) * sizeof(unsigned), st));
-        Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n);
+        R3D_CUDA(cudaMemsetAsync(eng->occ_cnt.p, 0, (size_t)n * (size_t)d.map_window * d.map_window * sizeof(unsigned), st));
+        Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n, 1);
     }
     { Launcher l(eng, KID_WALK); k_scan_walk<<<n, WALK_THREADS, walk_smem_layout(d.K, d.dwords).total, st>>>(d, n); }
     {

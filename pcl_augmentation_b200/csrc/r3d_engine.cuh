@@ -129,6 +129,7 @@ struct EngineDev {       // passed by value to kernels
     long long ss_move_x, ss_move_y;
     const double* poses;              // [B][16]
     unsigned* occ_win;                // [B][map_window*map_window/32]
+    unsigned* occ_cnt;                // [B][map_window^2] scene points per marked cell of the window (walker: incremental marks)
     int* occ_far;                     // [B][64]: count + cells marked occupied outside the window (numpy-wrapped indices)
     // schedule
     const int* counts;                // [B][C]

@@ -63,41 +63,73 @@ __device__ __forceinline__ unsigned group_mask() {
 // chain of L2 latencies, so memory-level parallelism is what counts.  `f(v)` is called per point; `stop()` is polled
 // after every row (group-uniform early exit).
 struct CellRect { int x0, x1, y0, y1; };
-template <int NL = GRP, class F, class S>
-__device__ __forceinline__ void group_visit(const int* __restrict__ cell, const float4* __restrict__ pts, int G, CellRect rc,
-                                            CellRect hole, int gl, unsigned gm, F f, S stop) {
+// A CSR grid to walk: the scan's whole grid in global memory, or a window of it staged in shared memory by the walker
+// (cell table of the window's rows with one extra leading entry per row = the row's begin; offsets index the staged
+// points).  Cell coordinates are the global ones in both cases.
+struct GridView {
+    const int* cell;
+    const float4* pts;
+    int stride, ybase, bias;        // entry of cell (x, y) = cell[(y - ybase) * stride + bias + x]
+    CellRect win;                   // cells the view holds
+};
+__device__ __forceinline__ GridView global_view(const int* cell, const float4* pts, int G) {
+    return GridView{cell, pts, G, 0, 0, CellRect{0, G - 1, 0, G - 1}};
+}
+__device__ __forceinline__ bool view_holds(const GridView& v, const CellRect& rc) {
+    return rc.x0 >= v.win.x0 && rc.x1 <= v.win.x1 && rc.y0 >= v.win.y0 && rc.y1 <= v.win.y1;
+}
+template <int NL = GRP, bool STAGED = false, class F, class S>
+__device__ __forceinline__ void group_visit(const GridView& gv, CellRect rc, CellRect hole, int gl, unsigned gm, F f, S stop) {
+    const int* __restrict__ cell = gv.cell;
+    const float4* __restrict__ pts = gv.pts;
+    auto ldc = [&](int i) { return STAGED ? cell[i] : __ldg(&cell[i]); };
     for (int yb = rc.y0; yb <= rc.y1; yb += NL) {
         const int nrows = min(NL, rc.y1 - yb + 1);
         int beg_a = 0, end_a = 0, beg_b = 0, end_b = 0;
         if (gl < nrows) {
-            const int y = yb + gl, row = y * G;
+            const int y = yb + gl, row = (y - gv.ybase) * gv.stride + gv.bias;
             const bool split = hole.x1 >= hole.x0 && y >= hole.y0 && y <= hole.y1;
             const int xa1 = split ? hole.x0 - 1 : rc.x1;                 // segment A: [x0, xa1], B: [hole.x1 + 1, x1]
             if (xa1 >= rc.x0) {
                 const int c0 = row + rc.x0;
-                beg_a = c0 > 0 ? __ldg(&cell[c0 - 1]) : 0;
-                end_a = __ldg(&cell[row + xa1]);
+                beg_a = (STAGED || c0 > 0) ? ldc(c0 - 1) : 0;
+                end_a = ldc(row + xa1);
             }
             if (split && hole.x1 < rc.x1) {
-                beg_b = __ldg(&cell[row + hole.x1]);
-                end_b = __ldg(&cell[row + rc.x1]);
+                beg_b = ldc(row + hole.x1);
+                end_b = ldc(row + rc.x1);
             }
         }
-        for (int r = 0; r < nrows; ++r) {
+        // rows are dealt to sub-groups of 8 lanes (one for the 8-lane groups of the staged kernels, four for a warp): the
+        // point loads of NSUB rows are in flight together instead of one dependent round trip per row
+        constexpr int SL = 8, NSUB = NL / SL;
+        const int sub = gl / SL, sl = gl % SL;
+        for (int r0 = 0; r0 < nrows; r0 += NSUB) {
+            const int r = r0 + sub;
+            const bool valid = r < nrows;
 #pragma unroll
             for (int seg = 0; seg < 2; ++seg) {
-                const int rb = __shfl_sync(gm, seg ? beg_b : beg_a, r, NL), re = __shfl_sync(gm, seg ? end_b : end_a, r, NL);
-                for (int p = rb + gl; p < re; p += 4 * NL) {
+                const int rb = __shfl_sync(gm, seg ? beg_b : beg_a, valid ? r : 0, NL);
+                int re = __shfl_sync(gm, seg ? end_b : end_a, valid ? r : 0, NL);
+                if (!valid) re = rb;
+                for (int p = rb + sl; p < re; p += 4 * SL) {
                     float4 v[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) { const int q = p + u * NL; if (q < re) v[u] = __ldg(&pts[q]); }
+                    for (int u = 0; u < 4; ++u) { const int q = p + u * SL; if (q < re) v[u] = STAGED ? pts[q] : __ldg(&pts[q]); }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) if (p + u * NL < re) f(v[u]);
+                    for (int u = 0; u < 4; ++u) if (p + u * SL < re) f(v[u]);
                 }
             }
             if (stop()) return;
         }
     }
+}
+// the same walk on the staged window when it holds the whole rectangle, else on the global grid
+template <int NL = GRP, class F, class S>
+__device__ __forceinline__ void group_visit_any(const GridView& global, const GridView* staged, CellRect rc, CellRect hole, int gl,
+                                                unsigned gm, F f, S stop) {
+    if (staged != nullptr && view_holds(*staged, rc)) group_visit<NL, true>(*staged, rc, hole, gl, gm, f, stop);
+    else group_visit<NL, false>(global, rc, hole, gl, gm, f, stop);
 }
 
 // grid cells that hold every point within distance R of (cx, cy): grid_coord is monotone and the float conversions
@@ -117,14 +149,13 @@ __device__ __forceinline__ CellRect cells_within(const EngineDev& e, double cx, 
 // independent; exact for float32 z, so equal to numpy's sequential float64 sum).
 template <int NL = GRP>
 __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& surf, double cx, double cy, int gl, unsigned gm,
-                                 double& level) {
+                                 double& level, const GridView* staged = nullptr) {
     const int G = e.G;
-    const int* __restrict__ cell = e.gcell + (size_t)b * G * G;
-    const float4* __restrict__ pts = e.gpts + (size_t)b * e.max_points;
+    const GridView gv = global_view(e.gcell + (size_t)b * G * G, e.gpts + (size_t)b * e.max_points, G);
     double best = 1e300;
     CellRect hole{0, -1, 0, -1};
     const double step = e.grid_cell;
-    double R = 0.5 * step;
+    double R = 1.5 * step;          // first square: the cells within 0.75 m (most candidates find their nearest surface point there)
     // every cell closer than `ring` cells (Chebyshev) to the centre's cell is empty: start at the radius whose square
     // of cells still lies inside that empty block and treat the block as already visited
     const int ring = e.gnear[(size_t)b * G * G + (size_t)grid_coord(e, (float)cy) * G + grid_coord(e, (float)cx)];
@@ -134,7 +165,7 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     }
     for (;; R = fmin(R < step ? step : R + step, 5.0)) {
         const CellRect rc = cells_within(e, cx, cy, R);
-        group_visit<NL>(cell, pts, G, rc, hole, gl, gm, [&](const float4& v) {
+        group_visit_any<NL>(gv, staged, rc, hole, gl, gm, [&](const float4& v) {
             if (!in_surface(surf, __float_as_uint(v.w))) return;
             const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
             best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                           // od/fs:153
@@ -149,7 +180,7 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     const double r2 = e.radii_sq[j];
     long long zsum = 0;
     int cnt = 0;
-    group_visit<NL>(cell, pts, G, cells_within(e, cx, cy, sqrt(r2)), CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
+    group_visit_any<NL>(gv, staged, cells_within(e, cx, cy, sqrt(r2)), CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
         if (!in_surface(surf, __float_as_uint(v.w))) return;
         const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
         if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
@@ -157,6 +188,81 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
     for (int o = NL / 2; o > 0; o >>= 1) {
         zsum += __shfl_xor_sync(gm, zsum, o);
         cnt += __shfl_xor_sync(gm, cnt, o);
+    }
+    if (cnt == 0) return false;
+    level = __ddiv_rn(__ddiv_rn((double)zsum, kFix), (double)cnt);    // od/fs:164 np.mean
+    return true;
+}
+
+// ---- lean warp-wide grid walks for the per-scan walker (64 registers per thread: the generic group_visit keeps its
+// four float4 loads per lane in local memory there, which serialises them).  The four 8-lane sub-groups of the warp take
+// rows y0 + sub, y0 + sub + 4, ...; every sub-group fetches its own row's CSR range (no shuffles, no hole logic: a ring
+// search re-visits the inner cells, which costs two loads per row), two 16-byte point loads in flight per lane.
+template <class F, class S>
+__device__ __forceinline__ void warp_visit(const int* __restrict__ cell, const float4* __restrict__ pts, int G, const CellRect& rc,
+                                           int lane, F f, S stop) {
+    const int sub = lane >> 3, sl = lane & 7;
+    for (int y0 = rc.y0; y0 <= rc.y1; y0 += 4) {                  // four rows of cells in flight, then the (warp-uniform) exit test
+        const int y = y0 + sub;
+        if (y <= rc.y1) {
+            const int c0 = y * G + rc.x0;
+            const int rb = c0 > 0 ? __ldg(&cell[c0 - 1]) : 0, re = __ldg(&cell[y * G + rc.x1]);
+            for (int p = rb + sl; p < re; p += 16) {
+                const float4 a = __ldg(&pts[p]);
+                const bool two = p + 8 < re;
+                float4 bq = a;
+                if (two) bq = __ldg(&pts[p + 8]);
+                f(a);
+                if (two) f(bq);
+            }
+        }
+        if (stop()) return;
+    }
+}
+
+// A7 for one candidate centre, one warp (same result as group_road_level: the nearest surface point decides the radius
+// index whatever sequence of growing squares finds it).  CHECK_LABEL = false when the surface grid holds one label only (OD).
+template <bool CHECK_LABEL>
+__device__ bool warp_road_level(const EngineDev& e, int b, const unsigned* __restrict__ surf, int n_surf, double cx, double cy, int lane,
+                                double& level) {
+    const int G = e.G;
+    const int* __restrict__ cell = e.gcell + (size_t)b * G * G;
+    const float4* __restrict__ pts = e.gpts + (size_t)b * e.max_points;
+    auto on_surface = [&](unsigned lab) {
+        if (!CHECK_LABEL) return true;
+        bool ok = false;
+        for (int i = 0; i < n_surf; ++i) ok |= lab == surf[i];
+        return ok;
+    };
+    const double step = e.grid_cell;
+    double R = 1.5 * step;
+    const int ring = e.gnear[(size_t)b * G * G + (size_t)grid_coord(e, (float)cy) * G + grid_coord(e, (float)cx)];
+    if (ring >= 3) R = fmin((ring - 1) * step, 5.0);       // every cell closer than `ring` cells is empty
+    double best = 1e300;
+    for (;; R = fmin(R + step, 5.0)) {
+        const CellRect rc = cells_within(e, cx, cy, R);
+        warp_visit(cell, pts, G, rc, lane, [&](const float4& v) {
+            if (!on_surface(__float_as_uint(v.w))) return;
+            const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+            best = fmin(best, add(mul(dx, dx), mul(dy, dy)));                           // od/fs:153
+        }, [] { return false; });
+        for (int o = 16; o > 0; o >>= 1) best = fmin(best, __shfl_xor_sync(0xffffffffu, best, o));
+        if (best <= R * R || R >= 5.0) break;              // every point outside the scanned cells is farther than R
+    }
+    if (!(best <= e.radii_sq[R3D_NUM_RADII - 1])) return false;
+    const int j = radius_index(e.radii_sq, best);          // smallest j with best <= r_j^2
+    if (!e.radii_ok[j]) return false;                      // od/fs:156-160: no surface within reach
+    const double r2 = e.radii_sq[j];
+    long long zsum = 0;
+    int cnt = 0;
+    warp_visit(cell, pts, G, cells_within(e, cx, cy, sqrt(r2)), lane, [&](const float4& v) {
+        if (!on_surface(__float_as_uint(v.w))) return;
+        const double dx = sub((double)v.x, cx), dy = sub((double)v.y, cy);
+        if (add(mul(dx, dx), mul(dy, dy)) <= r2) { zsum += __double2ll_rn(mul((double)v.z, kFix)); ++cnt; }
+    }, [] { return false; });
+    for (int o = 16; o > 0; o >>= 1) {
+        zsum += __shfl_xor_sync(0xffffffffu, zsum, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
     }
     if (cnt == 0) return false;
     level = __ddiv_rn(__ddiv_rn((double)zsum, kFix), (double)cnt);    // od/fs:164 np.mean
@@ -274,23 +380,27 @@ __device__ __forceinline__ bool extent_may_touch_box(const ObjBox& ob, const Yaw
 //  (ii) object points strictly inside an existing / already inserted box.
 // The exact cut_bounding_box test (strict inequalities in the reference's expression order) decides; grid cells and
 // bounding circles only prune.
+// (part 2 of the collision test) obstacle points among the inserted objects' tails + object points inside scene boxes
+template <int NL = GRP>
+__device__ bool group_collides_rest(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
+                                    const YawBox& yb, const YawTest& yt, double c, double sn, double level, int gl, unsigned gm);
+
 template <int NL = GRP>
 __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c,
-                               double sn, double level, int gl, unsigned gm) {
+                               double sn, double level, int gl, unsigned gm, const GridView* staged = nullptr) {
     const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
     const YawTest yt = make_yaw_test(yb, level, ob.length, ob.width, ob.height);
     const double zmin_ped = add(level, 0.1);                                      // od/fs:123-124
     const bool ped = cc.pedestrian != 0;
     const size_t base = (size_t)b * e.P;
-    const int gshift = (threadIdx.x & 31) & ~(NL - 1);
     bool hit = false;
     {
         const int G = e.G;
         const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
         const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
         const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
-        group_visit<NL>(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, CellRect{0, -1, 0, -1}, gl, gm,
-                    [&](const float4& v) {
+        group_visit_any<NL>(global_view(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G), staged, rc,
+                            CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
             if (hit) return;
             const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
             if (dx * dx + dy * dy > fr2 || v.z < zlo || v.z > zhi) return;
@@ -301,6 +411,16 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
         }, [&] { return (__ballot_sync(gm, hit) & gm) != 0u; });
         if (__ballot_sync(gm, hit) & gm) return true;
     }
+    return group_collides_rest<NL>(e, b, s, ob, cc, yb, yt, c, sn, level, gl, gm);
+}
+
+template <int NL>
+__device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
+                                                 const YawBox& yb, const YawTest& yt, double c, double sn, double level, int gl,
+                                                 unsigned gm) {
+    const double zmin_ped = add(level, 0.1);
+    const int gshift = (threadIdx.x & 31) & ~(NL - 1);
+    bool hit = false;
     // the lanes look at 8 boxes at a time; only the boxes whose bounding circle reaches the candidate's are tested
     const int nbox0 = s.n_boxes - s.n_inserted;
     int t_run = 0;
@@ -343,6 +463,34 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
         }
     }
     return false;
+}
+
+// A8 + A9 for one candidate, one warp: part (i) on the lean walk, the rest shared with group_collides
+__device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c, double sn,
+                              double level, int lane) {
+    const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
+    const YawTest yt = make_yaw_test(yb, level, ob.length, ob.width, ob.height);
+    {
+        const double zmin_ped = add(level, 0.1);                                  // od/fs:123-124
+        const bool ped = cc.pedestrian != 0;
+        const size_t base = (size_t)b * e.P;
+        const int G = e.G;
+        const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
+        const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
+        const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
+        bool hit = false;
+        warp_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, lane, [&](const float4& v) {
+            if (hit) return;
+            const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
+            if (dx * dx + dy * dy > fr2 || v.z < zlo || v.z > zhi) return;
+            const double x = v.x, yy = v.y, z = v.z;
+            if (ped && !(z >= zmin_ped)) return;
+            if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
+            if (obstacle_point(e, b, s, cc, base, __float_as_int(v.w))) hit = true;
+        }, [&] { return __any_sync(0xffffffffu, hit) != 0; });
+        if (__any_sync(0xffffffffu, hit)) return true;
+    }
+    return group_collides_rest<32>(e, b, s, ob, cc, yb, yt, c, sn, level, lane, 0xffffffffu);
 }
 
 // ordered compaction of the rotations 1..K whose flag byte satisfies (f & mask) == want (all threads of the CTA);

@@ -34,7 +34,12 @@ __device__ __forceinline__ bool last_block_done(unsigned* ticket, unsigned n_blo
 
 // scene = scene[pix_id not in vis_px] (od/ins:488-501) for the calling thread's share (tid of nthr) of the points in
 // the column range of the recorded rectangle + the inserted tail; true if a removed point held the min / max elevation
-__device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, const ScanState& s, int tid, int nthr) {
+__device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, ScanState& s, const double* T, int p, int delta = 0,
+                                                 bool ignore_alive = false);
+
+template <bool OCC_COUNTS = false>      // OCC_COUNTS (walker, semseg): a removed point also leaves its map cell's count
+__device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, ScanState& s, int tid, int nthr) {
+    const double* T = e.poses + (size_t)b * 16;
     const size_t base = (size_t)b * e.P;
     bool extreme = false;
     const int* off = e.col_off + (size_t)b * (e.cols + 1);
@@ -55,6 +60,7 @@ __device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, const 
             for (int u = 0; u < 4; ++u)
                 if (px[u] >= 0 && pix_removed(e, b, s, px[u])) {
                     e.alive[base + p[u]] = 0;
+                    if (OCC_COUNTS) adjust_map_point(e, b, s, T, p[u], -1, true);
                     const unsigned long long bits = dbl_bits(e.el[base + p[u]]);
                     extreme |= bits == lo || bits == hi;
                 }
@@ -64,6 +70,7 @@ __device__ __forceinline__ bool apply_vis_mask(const EngineDev& e, int b, const 
         const int p = s.n0 + t;
         if (e.alive[base + p] && pix_removed(e, b, s, e.pix[base + p])) {
             e.alive[base + p] = 0;
+            if (OCC_COUNTS) adjust_map_point(e, b, s, T, p, -1, true);
             const unsigned long long bits = dbl_bits(e.el[base + p]);
             extreme |= bits == lo || bits == hi;
         }
@@ -256,9 +263,14 @@ struct RawImage {        // the engine's z-buffer as close/fill input
 // The reference indexes map[ix][iy] with the truncated world coordinates as they are: a negative index wraps around
 // like any numpy index (cell size + ix), an index past the end raises IndexError (-> R3D_ERR_INDEX).  Wrapped cells
 // lie far from the scan, outside the bit window: they go to a short per-scan list (occ_far).
-__device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, ScanState& s, const double* T, int p) {
+// delta = 0: set the bit (full rebuild from the live points); +1 / -1: the point joined / left the scene — the per-cell
+// COUNT of such points (occ_cnt) is kept, the bit follows count > 0 (incremental form used by the per-scan walker: the
+// reference rebuilds the marks from the whole current scene at every slot, which is the same set of cells).
+// `ignore_alive`: the caller knows the point qualifies as a scene point (it is being removed / was just appended).
+__device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, ScanState& s, const double* T, int p, int delta,
+                                                 bool ignore_alive) {
     const size_t base = (size_t)b * e.P;
-    if (!e.alive[base + p]) return;
+    if (!ignore_alive && !e.alive[base + p]) return;
     const unsigned lab = e.label[base + p];
     bool ground = false;
     for (int i = 0; i < e.n_road_indexes; ++i) ground |= lab == (unsigned)e.road_indexes[i];
@@ -270,12 +282,13 @@ __device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, Scan
     const double wy = add(add(add(mul(T[4], x), mul(T[5], y)), mul(T[6], z)), T[7]);
     int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
     int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
-    if (ix >= e.ss_sx || iy >= e.ss_sy || ix < -e.ss_sx || iy < -e.ss_sy) { set_error(s, R3D_ERR_INDEX); return; }   // IndexError
+    if (ix >= e.ss_sx || iy >= e.ss_sy || ix < -e.ss_sx || iy < -e.ss_sy) { if (delta >= 0) set_error(s, R3D_ERR_INDEX); return; }   // IndexError
     if (ix < 0) ix += e.ss_sx;                                   // numpy negative index
     if (iy < 0) iy += e.ss_sy;
     if (e.ss_map[(size_t)ix * e.ss_sy + iy] == 0) return;
     const int lx = ix - s.win_x0, ly = iy - s.win_y0;
     if (lx < 0 || ly < 0 || lx >= e.map_window || ly >= e.map_window) {
+        if (delta < 0) return;                                   // far cells are not counted: the walker rebuilds in full when any exists
         int* far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);        // small set: [0] = non-empty flag, then cells or -1
         const int cell = ix * e.ss_sy + iy;
         far[0] = 1;
@@ -287,10 +300,15 @@ __device__ __forceinline__ void adjust_map_point(const EngineDev& e, int b, Scan
         return;
     }
     const int bit = lx * e.map_window + ly;
-    atomicOr(&e.occ_win[(size_t)b * (e.map_window * e.map_window / 32) + (bit >> 5)], 1u << (bit & 31));
+    unsigned* word = &e.occ_win[(size_t)b * (e.map_window * e.map_window / 32) + (bit >> 5)];
+    if (delta == 0) { atomicOr(word, 1u << (bit & 31)); return; }
+    unsigned* cnt = &e.occ_cnt[(size_t)b * e.map_window * e.map_window + bit];
+    if (delta > 0) { atomicAdd(cnt, 1u); atomicOr(word, 1u << (bit & 31)); }
+    else if (atomicSub(cnt, 1u) == 1u) atomicAnd(word, ~(1u << (bit & 31)));
 }
 
-__global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int n_scans) {
+// count_too != 0: also build the per-cell counts (the walker keeps them up to date afterwards)
+__global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int n_scans, int count_too = 0) {
     const int b = blockIdx.y;
     if (b >= n_scans || !e.gate_update[b]) return;
     ScanState& s = e.st[b];
@@ -298,5 +316,5 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_adjust_map(EngineDev e, int 
     const int p0 = blockIdx.x * CHUNK;
     if (p0 >= n) return;
     const double* T = e.poses + (size_t)b * 16;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) adjust_map_point(e, b, s, T, p);
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n); p += STREAM_THREADS) adjust_map_point(e, b, s, T, p, count_too ? 1 : 0);
 }

@@ -31,6 +31,7 @@ constexpr int WALK_OCC_LANES = 64;                    // threads that count one 
 constexpr int WALK_OCC_PAR = WALK_THREADS / WALK_OCC_LANES;
 constexpr int WALK_NWARPS = WALK_THREADS / 32;
 
+
 // dynamic shared memory: [object x | y | z (fp64)] [ordered candidate list] [prefilter flags] [scratch]; the scratch
 // holds the visible-pixel bit image of the exact occlusion count or the close/fill tile; the selection (after the
 // last window of a try) reuses everything from offset 0
@@ -79,7 +80,12 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     double wlevel[WALK_W];
     int wfeas[WALK_W];           // window-local indices of the feasible candidates, in rotation order
     int won[WALK_W];             // window-local indices of the candidates the next sub-stage works on
+    int wsub[WALK_W];            // chunk-local list (candidates of the chunk that have a road level)
+    int n_sub;
     int next;                    // dynamic task counter of a sub-stage
+    double wcx[WALK_W], wcy[WALK_W];     // centre of the window's candidates (the box centre turned about the sensor)
+    unsigned surf[R3D_MAX_SURFACE];      // labels the tried class may stand on (road-level search)
+    int n_surf;
     double wdz[WALK_W];          // semseg fixed point: the shift candidate i was (or must be) tested under
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
@@ -225,7 +231,7 @@ __device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s,
     };
     const int tid = threadIdx.x, nt = blockDim.x;
     const size_t base = (size_t)b * e.P;
-    const bool ext = do_apply && apply_vis_mask(e, b, s, tid, nt);
+    const bool ext = do_apply && (e.task == 1 ? apply_vis_mask<true>(e, b, s, tid, nt) : apply_vis_mask<false>(e, b, s, tid, nt));
     const int extreme = __syncthreads_or(ext);
     ulap(WT_APPLY);
     if (tid == 0) {
@@ -250,7 +256,10 @@ __device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s,
         c.upd_full = full; c.upd_patch = patch;
     }
     __syncthreads();
-    if (do_update && e.task == 1) {
+    // semseg map marks (addjust_map_2): kept incrementally by the removals above and the insertions of walk_try; a
+    // scan with marked cells outside the bit window (numpy-wrapped indices) rebuilds them from all its live points
+    const bool rebuild_marks = do_update && e.task == 1 && s.far_flag;
+    if (rebuild_marks) {
         const int ww = e.map_window * e.map_window / 32;
         unsigned* o = e.occ_win + (size_t)b * ww;
         for (int i = tid; i < ww; i += nt) o[i] = 0u;
@@ -281,7 +290,7 @@ __device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s,
     ulap(WT_PATCH);
     if (c.rect[1] >= c.rect[0] && c.rect[3] >= c.rect[2]) walk_close_fill(e, b, c.rect, scratch);
     ulap(WT_CLOSEFILL);
-    if (do_update && e.task == 1) { __syncthreads(); walk_adjust_map(e, b, s); }
+    if (rebuild_marks) { __syncthreads(); walk_adjust_map(e, b, s); }
     __syncthreads();
 }
 
@@ -340,52 +349,62 @@ __device__ __forceinline__ bool walk_onmap_od(const EngineDev& e, int b, const O
     return (__ballot_sync(gm, any_in) & gm) != 0u && !bad;
 }
 
-// ---- A7 (+ A8 / A9) for the window candidates listed in c.won[0 .. n), ONE WARP per candidate, dealt dynamically: the
-// road-level ring search and the collision test are chains of dependent cell / point loads, so a candidate gets 32
-// lanes (four times shorter chains than the 8-lane groups of the staged kernels) and a free warp takes the next one.
-// with_level: search the road level first (OD); otherwise the level is already in c.wlevel (semseg).
-__device__ R3D_WALK_FN void walk_level_collide(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, int n, bool with_level) {
+// ---- A7 for the window candidates listed in c.won[0 .. n): ONE WARP per candidate, dealt dynamically (a free warp takes
+// the next one): the ring search is a chain of dependent cell / point loads, 32 lanes keep four rows of cells in flight
+__device__ R3D_WALK_FN void walk_levels(const EngineDev& e, int b, WalkCtl& c, const int* list, int n) {
     const int lane = threadIdx.x & 31;
-    const ObjBox& ob = c.ob;
-    const ClassCfg& cc = e.classes[ob.cls];
-    const SurfaceSet surf = load_surface(cc);
     for (;;) {
         int t = 0;
         if (lane == 0) t = atomicAdd(&c.next, 1);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= n) break;
-        const int i = c.won[t], k = c.wk[i];
-        const double cs = e.cos_k[k], sn = e.sin_k[k];
-        double level = c.wlevel[i];
-        unsigned f = CF_ONMAP | CF_HOK;
+        const int i = list[t];
+        double level = 0.0;
         const long long t0 = clock64();
-        if (with_level && !group_road_level<32>(e, b, surf, sub(mul(cs, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(cs, ob.cy)), lane,
-                                                0xffffffffu, level))
-            f = CF_ONMAP;                                              // od/fs:281-285
-        const long long t1 = clock64();
-        if ((f & CF_HOK) && group_collides<32>(e, b, s, ob, cc, cs, sn, level, lane, 0xffffffffu)) f |= CF_COLLIDE;
+        const bool ok = e.task == 0 ? warp_road_level<false>(e, b, c.surf, c.n_surf, c.wcx[i], c.wcy[i], lane, level)
+                                    : warp_road_level<true>(e, b, c.surf, c.n_surf, c.wcx[i], c.wcy[i], lane, level);
         if (lane == 0) {
-            c.wflag[i] = (unsigned char)f; c.wlevel[i] = level;
-            atomicAdd(&e.stats[WALK_T0 + WT_LEVEL_WARP], (unsigned long long)(t1 - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_LEVEL], 1ull);
-            if (f & CF_HOK) {
-                atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t1));
-                atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull);
-            }
+            c.wflag[i] = (unsigned char)(ok ? (CF_ONMAP | CF_HOK) : CF_ONMAP);           // od/fs:281-285
+            c.wlevel[i] = level;
+            atomicAdd(&e.stats[WALK_T0 + WT_LEVEL_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_LEVEL], 1ull);
+        }
+    }
+}
+
+// ---- A8 + A9 for the window candidates listed in c.won[0 .. n) (they have a road level), one warp per candidate
+__device__ R3D_WALK_FN void walk_collides(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, const int* list, int n) {
+    const int lane = threadIdx.x & 31;
+    const ObjBox& ob = c.ob;
+    const ClassCfg& cc = e.classes[ob.cls];
+    for (;;) {
+        int t = 0;
+        if (lane == 0) t = atomicAdd(&c.next, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= n) break;
+        const int i = list[t], k = c.wk[i];
+        const long long t0 = clock64();
+        const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane);
+        if (lane == 0) {
+            if (hit) c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE);
+            atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull);
         }
     }
 }
 
 // ---- semseg window: A6b with the carried z shift as a fixed-point iteration over the window's yaws (see k_onmap_ss),
 // the road level searched only for the yaws that pass the map test, then A8/A9
-__device__ R3D_WALK_FN void walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
-                               const double* oz, int base, int nw) {
+__device__ R3D_WALK_FN int walk_window_ss(const EngineDev& e, int b, ScanState& s, WalkCtl& c, const double* ox, const double* oy,
+                              const double* oz, int base, int nw) {
     const int tid = threadIdx.x, g = tid / GRP, gl = tid % GRP;
     const unsigned gm = group_mask();
     const ObjBox& ob = c.ob;
     const ClassCfg& cc = e.classes[ob.cls];
     if (tid < nw) {
-        c.wk[tid] = base + tid + 1; c.wdz[tid] = c.dz_run; c.wpass[tid] = 0; c.wtodo[tid] = 1; c.whas[tid] = 0; c.whok[tid] = 0;
-        c.wlevel[tid] = 0.0; c.wflag[tid] = 0;
+        const int kk = base + tid + 1;
+        const double ck = e.cos_k[kk], sk = e.sin_k[kk];
+        c.wk[tid] = kk; c.wdz[tid] = c.dz_run; c.wpass[tid] = 0; c.wtodo[tid] = 1; c.whas[tid] = 0; c.whok[tid] = 0;
+        c.wlevel[tid] = 0.0; c.wflag[tid] = 0; c.won[tid] = tid;
+        c.wcx[tid] = sub(mul(ck, c.ob.cx), mul(sk, c.ob.cy)); c.wcy[tid] = add(mul(sk, c.ob.cx), mul(ck, c.ob.cy));
     }
     __syncthreads();
     const double* T = e.poses + (size_t)b * 16;
@@ -415,8 +434,7 @@ __device__ R3D_WALK_FN void walk_window_ss(const EngineDev& e, int b, ScanState&
         if (g < nw && c.wpass[g] && !c.whas[g]) {                 // ss/fs:250: correct_height of a yaw on the map
             const SurfaceSet surf = load_surface(cc);
             double level = 0.0;
-            const bool ok = group_road_level(e, b, surf, sub(mul(cs, ob.cx), mul(sn, ob.cy)), add(mul(sn, ob.cx), mul(cs, ob.cy)), gl,
-                                             gm, level);
+            const bool ok = group_road_level(e, b, surf, c.wcx[g], c.wcy[g], gl, gm, level);
             if (gl == 0) { c.whas[g] = 1; c.whok[g] = ok ? 1 : 0; c.wlevel[g] = level; }
         }
         __syncthreads();
@@ -436,8 +454,7 @@ __device__ R3D_WALK_FN void walk_window_ss(const EngineDev& e, int b, ScanState&
     }
     if (tid < nw) c.wflag[tid] = c.wpass[tid] ? (c.whok[tid] ? (CF_ONMAP | CF_HOK) : CF_ONMAP) : 0;
     if (tid == 0) c.dz_run = c.dz_next;
-    const int n_h = walk_window_list(c, nw, c.won, [&](int i) { return c.wpass[i] && c.whok[i]; });
-    walk_level_collide(e, b, s, c, n_h, false);                   // ss/fs:256: check_bounding_box
+    return walk_window_list(c, nw, c.won, [&](int i) { return c.wpass[i] && c.whok[i]; });
 }
 
 // ---- exact A11 count of one candidate with the whole CTA (visible-pixel bit image in shared memory), for the
@@ -484,6 +501,9 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
         c.ob = e.obj[s.cur_obj];
         e.try_obj[b] = c.ob;
         c.n_feas = 0; c.found = -1; c.last_k = 0; c.last_level = 0.0; c.dz_run = 0.0;
+        const ClassCfg& tc = e.classes[c.ob.cls];
+        c.n_surf = tc.n_surface;
+        for (int i = 0; i < R3D_MAX_SURFACE; ++i) c.surf[i] = i < tc.n_surface ? (unsigned)tc.surface[i] : 0xFFFFFFFFu;
         atomicAdd(&e.stats[1], 1ull);
     }
     __syncthreads();
@@ -525,74 +545,95 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
     const double* smooth = e.smooth + (size_t)b * e.hw;
     for (int base = 0; base < n_list; base += WALK_W) {
         const int nw = min(WALK_W, n_list - base);
-        // stage A: placement tests of the window's candidates.  OD: on-map test on every object point (an 8-lane group
-        // per candidate), then road level + collision for the survivors (a warp per candidate, dealt dynamically)
+        // stage A: the map test of the window's candidates -> ordered list c.won of the ones that go on.  OD: on-map test
+        // on every object point (an 8-lane group per candidate); semseg: the fixed-point walk incl. the road levels
+        int n_on;
         if (e.task == 0) {
             if (g < nw) {
                 const int k = s_list[base + g];
                 const bool on = walk_onmap_od(e, b, ob, cc, ox, oy, k, gl, gm);
-                if (gl == 0) { c.wk[g] = k; c.wflag[g] = on ? CF_ONMAP : 0; c.wlevel[g] = 0.0; }
+                if (gl == 0) {
+                    const double ck = e.cos_k[k], sk = e.sin_k[k];
+                    c.wk[g] = k; c.wflag[g] = on ? CF_ONMAP : 0; c.wlevel[g] = 0.0;
+                    c.wcx[g] = sub(mul(ck, ob.cx), mul(sk, ob.cy)); c.wcy[g] = add(mul(sk, ob.cx), mul(ck, ob.cy));
+                }
             }
             __syncthreads();
             if (tid == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_ONMAP], (unsigned long long)(n - clk.t)); }
-            const int n_on = walk_window_list(c, nw, c.won, [&](int i) { return (c.wflag[i] & CF_ONMAP) != 0; });
+            n_on = walk_window_list(c, nw, c.won, [&](int i) { return (c.wflag[i] & CF_ONMAP) != 0; });
             if (tid == 0) atomicAdd(&e.stats[7], (unsigned long long)n_on);
-            walk_level_collide(e, b, s, c, n_on, true);
         } else {
-            walk_window_ss(e, b, s, c, ox, oy, oz, base, nw);
+            n_on = walk_window_ss(e, b, s, c, ox, oy, oz, base, nw);
         }
-        __syncthreads();
-        clk.lap(e, WT_PLACE);
-        // stage B: the window's feasible candidates in rotation order (od/fs:288-296)
-        {
-            const int n = walk_window_list(c, nw, c.wfeas, [&](int i) {
-                return (c.wflag[i] & (CF_ONMAP | CF_HOK | CF_COLLIDE)) == (CF_ONMAP | CF_HOK); });
-            if (tid == 0) {
-                c.nfw = n;
+        if (tid == 0) atomicAdd(&e.stats[9], 1ull);
+        // stages B + C in CHUNKS of the ordered list, one candidate per warp: road level (OD) -> collision test -> occlusion
+        // count of the chunk's feasible candidates, leaving at the first candidate that keeps min_points (od/ins:530-561).
+        // The first feasible candidates of a try are the likely winners: evaluating the whole window at once spent most
+        // of its road-level / collision work on candidates that are never looked at.
+        for (int c0 = 0; c0 < n_on && c.found < 0; c0 += WALK_NWARPS) {
+            const int nch = min(WALK_NWARPS, n_on - c0);
+            const int* chunk = c.won + c0;
+            if (e.task == 0) {
+                walk_levels(e, b, c, chunk, nch);
+                __syncthreads();
+            }
+            if (tid == 0) {                                   // the chunk's candidates with a road level, in order
+                int n = 0;
+                for (int t = 0; t < nch; ++t) if ((c.wflag[chunk[t]] & (CF_ONMAP | CF_HOK)) == (CF_ONMAP | CF_HOK)) c.wsub[n++] = chunk[t];
+                c.n_sub = n; c.next = 0;
+            }
+            __syncthreads();
+            walk_collides(e, b, s, c, c.wsub, c.n_sub);
+            __syncthreads();
+            clk.lap(e, WT_PLACE);
+            if (tid == 0) {                                   // feasible candidates of the chunk in rotation order (od/fs:288-296)
+                int n = 0;
+                for (int t = 0; t < c.n_sub; ++t)
+                    if ((c.wflag[c.wsub[t]] & (CF_ONMAP | CF_HOK | CF_COLLIDE)) == (CF_ONMAP | CF_HOK)) c.wfeas[n++] = c.wsub[t];
+                c.nfw = n; c.next = 0;
                 if (n) { c.last_k = c.wk[c.wfeas[n - 1]]; c.last_level = c.wlevel[c.wfeas[n - 1]]; }
                 c.n_feas += n;
-                atomicAdd(&e.stats[9], 1ull);
             }
             __syncthreads();
-        }
-        // stage C: A11 in rotation order with an early exit.  lo = points that are individually closer than the
-        // scene, hi = points that fall into the image: lo <= V <= hi, and lo == 0 <=> V == 0, so most candidates are
-        // decided without building the visible-pixel image
-        const int nfw = c.nfw;
-        const int sg = tid / WALK_OCC_LANES, sl = tid % WALK_OCC_LANES;
-        for (int j0 = 0; j0 < nfw && c.found < 0; j0 += WALK_OCC_PAR) {
-            if (tid < WALK_OCC_PAR) { c.cnt_lo[tid] = 0; c.cnt_hi[tid] = 0; }
-            __syncthreads();
-            const int j = j0 + sg;
-            if (j < nfw) {
-                const int i = c.wfeas[j], k = c.wk[i];
-                const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(c.wlevel[i], ob.cz);
-                int lo = 0, hi = 0;
-                for (int p = sl; p < ob.count; p += WALK_OCC_LANES) {
-                    const ObjProj o = project_obj_point(e, ob, geom, p, cs, sn, dz, s);
-                    if (o.pix >= 0) { ++hi; if (o.r < smooth[o.pix]) ++lo; }
+            // stage C: A11 in rotation order with an early exit.  lo = points that are individually closer than the
+            // scene, hi = points that fall into the image: lo <= V <= hi, and lo == 0 <=> V == 0, so most candidates are
+            // decided without building the visible-pixel image
+            const int nfw = c.nfw;
+            const int sg = tid / WALK_OCC_LANES, sl = tid % WALK_OCC_LANES;
+            for (int j0 = 0; j0 < nfw && c.found < 0; j0 += WALK_OCC_PAR) {
+                if (tid < WALK_OCC_PAR) { c.cnt_lo[tid] = 0; c.cnt_hi[tid] = 0; }
+                __syncthreads();
+                const int j = j0 + sg;
+                if (j < nfw) {
+                    const int i = c.wfeas[j], k = c.wk[i];
+                    const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(c.wlevel[i], ob.cz);
+                    int lo = 0, hi = 0;
+                    for (int p = sl; p < ob.count; p += WALK_OCC_LANES) {
+                        const ObjProj o = project_obj_point(e, ob, geom, p, cs, sn, dz, s);
+                        if (o.pix >= 0) { ++hi; if (o.r < smooth[o.pix]) ++lo; }
+                    }
+                    for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
+                    if ((tid & 31) == 0) { if (lo) atomicAdd(&c.cnt_lo[sg], lo); if (hi) atomicAdd(&c.cnt_hi[sg], hi); }
                 }
-                for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }
-                if ((tid & 31) == 0) { if (lo) atomicAdd(&c.cnt_lo[sg], lo); if (hi) atomicAdd(&c.cnt_hi[sg], hi); }
-            }
-            __syncthreads();
-            int found = -1;
-            for (int q = 0; q < WALK_OCC_PAR && j0 + q < nfw; ++q) {          // uniform over the CTA
-                const int lo = c.cnt_lo[q], hi = c.cnt_hi[q];
-                bool ok = lo >= min_pts;
-                if (!ok && lo > 0 && hi >= min_pts) {
-                    const int i = c.wfeas[j0 + q];
-                    ok = walk_exact_visible(e, b, s, c, c.wk[i], c.wlevel[i], reinterpret_cast<unsigned*>(scratch)) >= min_pts;
+                __syncthreads();
+                int found = -1;
+                for (int q = 0; q < WALK_OCC_PAR && j0 + q < nfw; ++q) {          // uniform over the CTA
+                    const int lo = c.cnt_lo[q], hi = c.cnt_hi[q];
+                    bool ok = lo >= min_pts;
+                    if (!ok && lo > 0 && hi >= min_pts) {
+                        const int i = c.wfeas[j0 + q];
+                        ok = walk_exact_visible(e, b, s, c, c.wk[i], c.wlevel[i], reinterpret_cast<unsigned*>(scratch)) >= min_pts;
+                    }
+                    if (ok) { found = j0 + q; break; }
                 }
-                if (ok) { found = j0 + q; break; }
+                if (found >= 0 && tid == 0) {
+                    const int i = c.wfeas[found];
+                    c.found = found; c.found_k = c.wk[i]; c.found_level = c.wlevel[i];
+                }
+                __syncthreads();
             }
-            if (found >= 0 && tid == 0) {
-                const int i = c.wfeas[found];
-                c.found = found; c.found_k = c.wk[i]; c.found_level = c.wlevel[i];
-            }
-            __syncthreads();
+            clk.lap(e, WT_OCCL);
         }
-        clk.lap(e, WT_OCCL);
         if (c.found >= 0) break;
     }
     // A11 + A12 for the chosen candidate: the first one that keeps min_points, else the last feasible one (its
@@ -608,6 +649,11 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
                          sel_scratch(reinterpret_cast<unsigned long long*>(dyn), WALK_SEL_KEYS, WALK_SEL_PTS, WALK_SEL_TILE));
     }
     __syncthreads();
+    if (e.task == 1 && n_feas > 0 && c.found >= 0) {               // the appended object points join the map marks (next slot)
+        const double* T = e.poses + (size_t)b * 16;
+        for (int p = s.n0 + s.tail_before + tid; p < s.n0 + s.n_tail; p += nt) adjust_map_point(e, b, s, T, p, 1, true);
+        __syncthreads();
+    }
     clk.lap(e, WT_SELECT);
 }
 
@@ -624,6 +670,7 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(co
         int* dst = reinterpret_cast<int*>(&s);
         for (int i = threadIdx.x; i < (int)(sizeof(ScanState) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
     }
+    if (threadIdx.x == 0) s.far_flag = e.task == 1 && e.occ_far[(size_t)b * (OCC_FAR_CAP + 1)] != 0;
     __syncthreads();
     const WalkSmem L = walk_smem_layout(e.K, e.dwords);
     int steps = 0;
