@@ -82,6 +82,52 @@ int r3d_adjust_map(const double* rows9, int64_t n, const double* pose16_host, in
                    const int32_t* ground_labels, int n_ground, double* map_dev, int size_x, int size_y,
                    r3d_stream stream);
 
+/* ------------------------------------------------------------------- stream-level placement / occlusion / insertion */
+/* The stages of find_possible_places and of the occlusion / insertion step as re-entrant calls on DEVICE pointers
+ * (caller-allocated outputs, no hidden state; the batched engine below is the fast path for many scans).
+ *
+ * r3d_place_candidates — A5 + A6 + A7 (od/fs:263-285, ss/fs:229-250) for the yaw_steps candidates of ONE cut object,
+ * visited in order (the semseg map test of candidate k sees the z shift of the last candidate that passed and found a
+ * road level, ss/fs:146-147).  obj_rows: m rows of row_stride doubles (x y z first); box8_host: cx cy cz(bottom) m00 m10
+ * length width height; cos_k / sin_k: yaw_steps + 1 doubles (device), candidate k turns the object by k steps about
+ * the sensor z axis.  task 0 (OD): map = uint8 {0, 1} size_x x size_y, move = (min_x, min_y), od/fs:267-279; task 1
+ * (semseg): map = uint8 values 0..4 (after r3d_adjust_map), move = map move, pose16_host = lidar -> world,
+ * map_ok_mask bit v = value v allowed (ss/fs:235-248).  ground_rows5: the ORIGINAL scan as n_ground x 5 float64
+ * (x y z intensity label) for correct_height (od/fs:138-172); surface_labels (host): labels it accepts.
+ * Outputs (device): flags_out[k] bit0 = on the map, bit1 = road level found; level_out[k] = road level. */
+int r3d_place_candidates(const double* obj_rows, int64_t m, int32_t row_stride, const double* box8_host, int32_t yaw_steps,
+                         const double* cos_k, const double* sin_k, int32_t task, const uint8_t* map, int32_t size_x,
+                         int32_t size_y, int64_t move_x, int64_t move_y, const double* pose16_host, uint32_t map_ok_mask,
+                         const double* ground_rows5, int64_t n_ground, const int32_t* surface_labels, int32_t n_surface,
+                         const double* radii_sq_host, const int32_t* radii_ok_host, uint8_t* flags_out, double* level_out,
+                         r3d_stream stream);
+
+/* r3d_obb_collide — check_bounding_box (od/fs:109-135, ss/fs:79-104) for n_cand candidate placements at once:
+ * collide_out[k] = 1 iff (i) an obstacle scene point lies strictly inside candidate k's box or (ii) one of candidate
+ * k's object points lies strictly inside a scene box.  scene_rows9: n x 9 working rows (label = column 7);
+ * scene_boxes / cand_boxes: R3D_BOX_DOUBLES each; obj_rows: the object's points BEFORE the candidate transform;
+ * cand4[k] = {cos, sin, dz, 0}: candidate k's points are (c x - s y, s x + c y, z + dz).
+ * mode 0 (OD): obstacle = label == 1 (od/fs:121), pedestrian != 0 keeps only points with z >= box bottom + 0.1
+ * (od/fs:123); mode 1 (semseg): obstacle = label not in ok_labels (host, ss/fs:92-93). */
+int r3d_obb_collide(const double* scene_rows9, int64_t n, const double* scene_boxes, int32_t n_boxes, const double* obj_rows,
+                    int64_t m, int32_t row_stride, const double* cand4, const double* cand_boxes, int32_t n_cand, int32_t mode,
+                    int32_t pedestrian, const int32_t* ok_labels, int32_t n_ok, uint8_t* collide_out, r3d_stream stream);
+
+/* r3d_occlude_mask — od/ins:486-501: vis_px = obj_smooth < scene_smooth (strict; both num_pix float64 images as
+ * r3d_close_fill returns them); scene_keep[i] = 0 iff the scene row's pix_id (column 8) is in vis_px; obj_keep[j] = 1
+ * iff the object row's pix_id is >= 0 and in vis_px; counts_out (device int32[2]) = {scene rows removed, object rows
+ * kept}; vis_px: num_pix uint8 (device, output). */
+int r3d_occlude_mask(const double* scene_rows9, int64_t n, const double* obj_rows9, int64_t m, const double* scene_smooth,
+                     const double* obj_smooth, int32_t num_pix, uint8_t* scene_keep, uint8_t* obj_keep, uint8_t* vis_px,
+                     int32_t* counts_out, r3d_stream stream);
+
+/* r3d_compact_insert — od/ins:545: out = the kept scene rows in order, then the kept object rows in (pix_id, index)
+ * order (the order the reference's per-pixel loop appends them).  out_rows9: capacity n + m rows; n_out (device
+ * int64[2]) = {rows written, of which scene rows}; sort_scratch: device uint64[scratch_len >= next_pow2(m)]. */
+int r3d_compact_insert(const double* scene_rows9, const uint8_t* scene_keep, int64_t n, const double* obj_rows9,
+                       const uint8_t* obj_keep, int64_t m, double* out_rows9, int64_t* n_out, uint64_t* sort_scratch,
+                       int64_t scratch_len, r3d_stream stream);
+
 /* ------------------------------------------------------------------------------------------------- rich maps */
 /* object_detection/rich_map/single_drivable_area_map.py:123-194, batched over frames (all pointers: device).
  * xyzi: total x 4 float32, labels: total uint32 (semantic label & 0xFFFF), point_offsets: n_scans + 1.

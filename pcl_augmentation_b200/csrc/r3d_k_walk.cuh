@@ -431,7 +431,9 @@ __device__ R3D_WALK_FN int walk_window_ss(const EngineDev& e, int b, ScanState& 
             if (gl == 0) c.wpass[g] = bad ? 0 : 1;
         }
         __syncthreads();
-        if (g < nw && c.wpass[g] && !c.whas[g]) {                 // ss/fs:250: correct_height of a yaw on the map
+        const bool need_level = g < nw && c.wpass[g] && !c.whas[g];
+        __syncwarp();                                             // every lane has read the flags its group's lane 0 rewrites below
+        if (need_level) {                                         // ss/fs:250: correct_height of a yaw on the map
             const SurfaceSet surf = load_surface(cc);
             double level = 0.0;
             const bool ok = group_road_level(e, b, surf, c.wcx[g], c.wcy[g], gl, gm, level);

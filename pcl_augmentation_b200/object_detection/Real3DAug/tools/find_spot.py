@@ -69,17 +69,11 @@ def rotate_bounding_box(bbox_pcl, annotation, rotation=1):
 
 
 def check_bounding_box(scene_pcl, scene_anno, sample_pcl, sample_anno):
-    """True iff the candidate collides with nothing (od/fs:109-135)."""
-    inside = cut_bounding_box_mask(scene_pcl, sample_anno)
-    inside &= scene_pcl[:, 7] == 1
-    if sample_anno['class'] == 'Pedestrian':
-        inside &= scene_pcl[:, 2] >= sample_anno['center']['z'] + 0.1
-    if inside.any():
-        return False
-    for anno in scene_anno:
-        if cut_bounding_box_mask(sample_pcl, anno).any():
-            return False
-    return True
+    """True iff the candidate collides with nothing (od/fs:109-135): one device call (r3d_obb_collide) tests the obstacle
+    scene points against the candidate box and the object points against every scene box."""
+    from ....ops import obb_collide
+    return not bool(obb_collide(scene_pcl, scene_anno, sample_pcl, [(1.0, 0.0, 0.0, sample_anno)], mode='od',
+                                pedestrian=sample_anno['class'] == 'Pedestrian')[0])
 
 
 def _road_level(scene_pcl, labels, cx, cy):

@@ -118,3 +118,89 @@ def cut_bounding_box_mask(point_cloud, annotation, annotation_move=(0, 0, 0)):
 def cut_bounding_box(point_cloud, annotation, annotation_move=[0, 0, 0]):
     """Rows of ``point_cloud`` strictly inside the oriented box, z measured from the box bottom (cb:7-68)."""
     return point_cloud[cut_bounding_box_mask(point_cloud, annotation, annotation_move)]
+
+
+# ----------------------------------------------------------------------- stream-level placement / occlusion / insertion
+def obb_collide(scene_pcl, scene_annos, sample_pcl, candidates, mode='od', pedestrian=False, ok_surface=()):
+    """check_bounding_box (od/fs:109-135, ss/fs:79-104) for several candidate placements of one object in ONE call.
+
+    ``candidates``: list of ``(cos, sin, dz, annotation)`` — candidate k's points are ``sample_pcl`` turned by
+    (cos, sin) about the sensor z axis and lifted by dz, its box is ``annotation``.  Returns a bool array: True = the
+    candidate collides (with an obstacle scene point inside its box, or with a scene box around one of its points)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    k = len(candidates)
+    if k == 0:
+        return np.zeros(0, dtype=bool)
+    scene = _dev(scene_pcl, np.float64)
+    obj = _dev(sample_pcl, np.float64)
+    sboxes = _dev(np.array([box_record(a) for a in scene_annos], dtype=np.float64).reshape(-1, 16), np.float64)
+    cand4 = _dev(np.array([[c, s, dz, 0.0] for c, s, dz, _ in candidates], dtype=np.float64), np.float64)
+    cboxes = _dev(np.array([box_record(a) for _, _, _, a in candidates], dtype=np.float64), np.float64)
+    ok = np.asarray(list(ok_surface), dtype=np.int32)
+    out = torch.empty(k, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.r3d_obb_collide(scene.data_ptr(), len(scene_pcl), sboxes.data_ptr() if len(scene_annos) else None,
+                                   len(scene_annos), obj.data_ptr(), len(sample_pcl), sample_pcl.shape[1], cand4.data_ptr(),
+                                   cboxes.data_ptr(), k, 0 if mode == 'od' else 1, 1 if pedestrian else 0,
+                                   ok.ctypes.data if len(ok) else None, len(ok), out.data_ptr(), _stream()), "obb_collide")
+    return out.cpu().numpy().astype(bool)
+
+
+def occlude_and_insert(scene_pcl, scene_train, sample_pcl9, sample_train):
+    """The occlusion step of insertion.py (od/ins:486-501, 545) on already projected and smoothed inputs:
+    ``scene_pcl`` / ``sample_pcl9`` are N x 9 / M x 9 working rows with their pix ids in column 8, ``scene_train`` /
+    ``sample_train`` the smoothed range images.  Returns (new scene rows = kept scene rows + visible object rows in
+    (pix_id, index) order, number of visible object rows, vis_px bool image)."""
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    h, w = scene_train.shape
+    n, m = len(scene_pcl), len(sample_pcl9)
+    scene = _dev(scene_pcl, np.float64)
+    obj = _dev(sample_pcl9, np.float64)
+    st, ot = _dev(scene_train, np.float64), _dev(sample_train, np.float64)
+    skeep = torch.empty(max(n, 1), dtype=torch.uint8, device="cuda")
+    okeep = torch.empty(max(m, 1), dtype=torch.uint8, device="cuda")
+    vis = torch.empty(h * w, dtype=torch.uint8, device="cuda")
+    counts = torch.zeros(2, dtype=torch.int32, device="cuda")
+    _lib.check(lib.r3d_occlude_mask(scene.data_ptr(), n, obj.data_ptr(), m, st.data_ptr(), ot.data_ptr(), h * w,
+                                    skeep.data_ptr(), okeep.data_ptr(), vis.data_ptr(), counts.data_ptr(), _stream()),
+               "occlude_mask")
+    out = torch.empty((n + m, 9), dtype=torch.float64, device="cuda")
+    n_out = torch.zeros(2, dtype=torch.int64, device="cuda")
+    cap = 1
+    while cap < max(m, 1):
+        cap <<= 1
+    scratch = torch.empty(cap, dtype=torch.int64, device="cuda")
+    _lib.check(lib.r3d_compact_insert(scene.data_ptr(), skeep.data_ptr(), n, obj.data_ptr(), okeep.data_ptr(), m,
+                                      out.data_ptr(), n_out.data_ptr(), scratch.data_ptr(), cap, _stream()), "compact_insert")
+    rows, kept = (int(v) for v in n_out.cpu().numpy())
+    return out[:rows].cpu().numpy(), rows - kept, vis.cpu().numpy().reshape(h, w).astype(bool)
+
+
+def place_candidates(sample_pcl, sample_anno, yaw_steps, task, map_u8, map_move, original_pcl5, surface_labels, pose=None,
+                     ok_map_values=()):
+    """A5 + A6 + A7 of find_possible_places (od/fs:263-285, ss/fs:229-250) for all yaw candidates of one cut object.
+    Returns (flags uint8 [yaw_steps + 1]: bit0 on the map, bit1 road level found; road level float64 [yaw_steps + 1])."""
+    from . import boxes as bx
+    torch = _lib.require_cuda()
+    lib = _lib.load()
+    obj = _dev(sample_pcl, np.float64)
+    ground = _dev(np.ascontiguousarray(original_pcl5[:, :5]), np.float64)
+    cos_k, sin_k = bx.yaw_tables(yaw_steps)
+    ck, sk = _dev(cos_k, np.float64), _dev(sin_k, np.float64)
+    m8 = _dev(np.ascontiguousarray(map_u8, dtype=np.uint8), np.uint8)
+    box8 = np.ascontiguousarray(bx.object_box_record(sample_anno), dtype=np.float64)
+    r2, ok = bx.search_radii()
+    lab = np.asarray(list(surface_labels), dtype=np.int32)
+    mask = 0
+    for v in ok_map_values:
+        mask |= 1 << int(v)
+    flags = torch.zeros(yaw_steps + 1, dtype=torch.uint8, device="cuda")
+    level = torch.zeros(yaw_steps + 1, dtype=torch.float64, device="cuda")
+    p16 = np.ascontiguousarray(pose, dtype=np.float64) if pose is not None else None
+    _lib.check(lib.r3d_place_candidates(obj.data_ptr(), len(sample_pcl), sample_pcl.shape[1], box8.ctypes.data, yaw_steps,
+                                        ck.data_ptr(), sk.data_ptr(), 0 if task == 'od' else 1, m8.data_ptr(), map_u8.shape[0],
+                                        map_u8.shape[1], int(map_move[0]), int(map_move[1]), p16.ctypes.data if p16 is not None else None,
+                                        mask, ground.data_ptr(), len(original_pcl5), lab.ctypes.data, len(lab), r2.ctypes.data,
+                                        ok.ctypes.data, flags.data_ptr(), level.data_ptr(), _stream()), "place_candidates")
+    return flags.cpu().numpy(), level.cpu().numpy()

@@ -35,15 +35,13 @@ def rotate_bounding_box_2(bbox_pcl, annotation, rotation=1):
 
 def check_bounding_box(scene_pcl, scene_anno, sample_pcl, sample_anno, ok_surface):
     """True iff no scene point with a label outside ``ok_surface`` lies in the candidate box and no object point lies
-    in an existing box (ss/fs:79-104)."""
-    inside = cut_bounding_box_mask(scene_pcl, sample_anno)
-    inside &= ~np.isin(scene_pcl[:, 7], ok_surface)
-    if inside.any():
-        return False
-    for anno in scene_anno:
-        if cut_bounding_box_mask(sample_pcl, anno).any():
-            return False
-    return True
+    in an existing box (ss/fs:79-104); one device call (r3d_obb_collide)."""
+    from ....ops import obb_collide
+    if len(ok_surface) > 8:                      # more surface labels than the primitive's label set holds
+        inside = cut_bounding_box_mask(scene_pcl, sample_anno) & ~np.isin(scene_pcl[:, 7], ok_surface)
+        return not inside.any() and not any(cut_bounding_box_mask(sample_pcl, anno).any() for anno in scene_anno)
+    return not bool(obb_collide(scene_pcl, scene_anno, sample_pcl, [(1.0, 0.0, 0.0, sample_anno)], mode='ss',
+                                ok_surface=[int(v) for v in ok_surface])[0])
 
 
 def correct_height(scene_pcl, sample_pcl, sample_anno, ok_surface):

@@ -109,3 +109,26 @@ def test_driver_removes_marker_when_nothing_was_inserted(tmp_path):
     assert (written, skipped) == (0, 1)
     assert not os.path.exists(os.path.join(out, "added_objects/000000.txt"))                   # od/ins:616-620
     assert not os.path.exists(os.path.join(out, "velodyne/000000.bin"))
+
+
+def test_failed_frame_is_given_back_and_the_others_are_written(tmp_path):
+    """A scan that ends with a non-zero status (what the reference raises as an exception) must not take the rest of
+    its batch with it: the other frames are written, the failed frame's marker is removed (so a later run retries it)
+    and the failure is reported after the run."""
+    ga, gb = load_golden("e2e_od_a"), load_golden("e2e_od_b")
+    (_, ca), (_, cb) = case_from_golden(ga), case_from_golden(gb)
+    _, out, cfg = synth_io.write_od_dataset([ca, cb, ca], str(tmp_path), fixed_counts=ca.schedule.counts)
+
+    class FailingSecond(OracleEngine):
+        def augment_batch(self, scans):
+            res = super().augment_batch(scans)
+            res[1].status = -4                      # e.g. IndexError: class list shorter than a window (od/ins:410)
+            return res
+
+    with PredrawnShuffle([ca.schedule.perms, ca.schedule.perms, ca.schedule.perms], len(cfg["insertion"]["classes"])):
+        with pytest.raises(drv.FrameError) as err:
+            drv.augment_kitti(cfg, batch_size=8, engine_cls=FailingSecond, log=lambda *a: None)
+    assert err.value.failures == [("000001", -4)]
+    assert os.path.exists(os.path.join(out, "velodyne/000000.bin")) and os.path.exists(os.path.join(out, "velodyne/000002.bin"))
+    assert not os.path.exists(os.path.join(out, "added_objects/000001.txt"))
+    assert not os.path.exists(os.path.join(out, "velodyne/000001.bin"))
