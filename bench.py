@@ -282,32 +282,96 @@ def _ref_worker(arg):
     return oracle_scan_seconds(case, w)
 
 
+REF_OBJECTS_PER_SAMPLE = 1           # objects the reference inserts into each sampled scan (the workload asks for w["objects"])
+
+
+def _ref_real_worker(arg):
+    """One bounded sample of the workload through the UNMODIFIED reference (oracle/_ref, `oracle/build_ref.py`): its own
+    `insertion.py` executed as `__main__` on a one-frame dataset written in its on-disk formats, inserting
+    REF_OBJECTS_PER_SAMPLE objects instead of the workload's w["objects"] (a whole 120k-point scan takes the
+    reference 1-2 minutes).  Returns (seconds inside the reference, objects it inserted)."""
+    name, seed = arg
+    import random
+    import shutil
+    import tempfile
+    os.environ["R3D_REFERENCE_ROOT"] = os.path.join(ROOT, "oracle", "_ref")
+    from oracle import shim                                       # baseline leg only
+    from pcl_augmentation_b200 import synth, synth_io
+    shim.REFERENCE_ROOT = os.environ["R3D_REFERENCE_ROOT"]
+    w = WORKLOADS[name]
+    case = synth.make_case(w["task"], seed, shape=getattr(synth, w["shape"] + "_SHAPE"), number_of_object=w["objects"])
+    classes = case.config["insertion"]["classes"]
+    counts = [0] * len(classes)
+    counts[seed % len(classes)] = REF_OBJECTS_PER_SAMPLE
+    root = tempfile.mkdtemp(prefix="r3d_refarm_")
+    try:
+        if w["task"] == "od":
+            cwd, out, _ = synth_io.write_od_dataset([case], root, fixed_counts=counts)
+            inputs = []
+        else:
+            cwd, out, _ = synth_io.write_ss_dataset([case], root, fixed_counts=counts)
+            inputs = ["1", "0", "no"]
+        random.seed(seed)
+        np.random.seed(seed % (2 ** 31))
+        t0 = time.perf_counter()
+        shim.run_main(w["task"], cwd, inputs=inputs)
+        dt = time.perf_counter() - t0
+        added = os.path.join(out, "added_objects", "000000.txt")
+        inserted = len([l for l in open(added).read().splitlines() if l.strip()]) if os.path.exists(added) else 0
+        return dt, inserted
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
 def run_reference(args, json_out):
-    """--impl reference: the CPU implementation of the path (the oracle port: the Python reference itself cannot
-    travel to the GPU box) on all host cores, one scan per worker process per step."""
+    """--impl reference: the reference's own CPU implementation of the path on all host cores.  With `oracle/_ref`
+    present (the unmodified reference files, copied there by `oracle/build_ref.py` in the build container) every step runs
+    the reference's `insertion.py` itself on one scan per worker process, bounded to REF_OBJECTS_PER_SAMPLE inserted
+    objects per scan (`kind: "reference"`); the per-scan figure scales that by the workload's objects per scan — the
+    reference's cost is per object slot (projection + closing of the scene, the yaw loop, the occlusion loop), nothing
+    of it is per scan.  Without `oracle/_ref`: the numpy oracle port on whole scans (`kind: "port"`, ~20x faster than
+    the reference)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from oracle import build_ref                                   # baseline leg only
+    real = build_ref.available() and os.environ.get("R3D_REFERENCE_ARM", "reference") != "port"
+    w = WORKLOADS[args.config]
     cores = max(1, min(os.cpu_count() or 1, 32))
+    worker = _ref_real_worker if real else _ref_worker
     ctx = mp.get_context("fork")
+    inserted = 0
     with ctx.Pool(cores) as pool:
         if args.warmup:
-            pool.map(_ref_worker, [(args.config, 9000 + i) for i in range(cores)])      # one warm-up wave is enough for a CPU path
+            pool.map(worker, [(args.config, 9000 + i) for i in range(cores)])      # one warm-up wave is enough for a CPU path
         t0 = time.perf_counter()
-        done = 0
+        done = 0.0
         for s in range(args.steps):
-            pool.map(_ref_worker, [(args.config, 9100 + s * cores + i) for i in range(cores)])
-            done += cores
+            res = pool.map(worker, [(args.config, 9100 + s * cores + i) for i in range(cores)])
+            if real:
+                inserted += sum(r[1] for r in res)
+                done += cores * REF_OBJECTS_PER_SAMPLE / w["objects"]
+            else:
+                done += cores
         dt = time.perf_counter() - t0
     value = done / dt
-    sample = f"{cores} whole scans per step (one per worker process), {args.steps} steps"
+    if real:
+        kind = "reference"
+        sample = (f"{cores} scans per step (one per worker process) through the unmodified reference insertion.py (oracle/_ref), "
+                  f"{REF_OBJECTS_PER_SAMPLE} of the {w['objects']} objects per scan each = {REF_OBJECTS_PER_SAMPLE}/{w['objects']} scan; "
+                  f"{args.steps} steps, {inserted} objects inserted; the reference's yaw loop is fixed at 360 candidates "
+                  f"(find_spot.py:263) whatever the workload's yaw_candidates")
+    else:
+        kind = "port"
+        sample = f"{cores} whole scans per step (one per worker process) through oracle/real3d_oracle.py, {args.steps} steps"
     print(file=json_out, flush=True, *[json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": "scans/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * dt / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.config, args.gpus),
-        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0})])
 
@@ -669,6 +733,7 @@ def main():
                        "tries_per_scan": stats["tried_objects"] / max(prof_steps * n_scans, 1),
                        "candidate_windows_per_try": stats["candidate_windows"] / max(stats["tried_objects"], 1),
                        "exact_occlusion_counts_per_try": stats["exact_occlusion_counts"] / max(stats["tried_objects"], 1),
+                       "cta_ms_mean": round(cyc.get("total", 0) / max(prof_steps * n_scans, 1) / ((clocks.get("sm_mhz") or 1965.0) * 1e3), 4),
                        "phase_share_of_cta_time": {k: round(v / max(cyc.get("total", 1), 1), 4) for k, v in cyc.items() if k != "total"}},
             "objects_inserted_per_scan": inserted_all / (world * n_scans),
             "configs": configs, "engine_stats": {k: v for k, v in stats.items() if k != "walker_cycles"}})])

@@ -147,84 +147,87 @@ static __device__ __forceinline__ void cf_async_copy16(void* smem, const void* g
     const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sa), "l"(gmem) : "memory");
 }
-static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_raw_pipelined(const unsigned long long* __restrict__ raw, int H, int W,
-                                                                           int64_t img_stride, double* __restrict__ out_train,
-                                                                           int* __restrict__ far_flag, const int* __restrict__ tasks,
-                                                                           const int* __restrict__ n_tasks) {
-    __shared__ __align__(16) unsigned long long s_raw[2][CF_SH][CF_SW];
-    __shared__ unsigned s_one[CF_SH][CF_WORDS], s_in[CF_SH][CF_WORDS], s_dil[CF_SH][CF_WORDS], s_ero[CF_SH][CF_WORDS];
+// shared memory of the pipelined walk: two raw tiles + four bit-row images
+struct CfPipeSmem {
+    unsigned long long raw[2][CF_SH][CF_SW];
+    unsigned one[CF_SH][CF_WORDS], in[CF_SH][CF_WORDS], dil[CF_SH][CF_WORDS], ero[CF_SH][CF_WORDS];
+};
+// tasks t0, t0 + tstep, ... < n of a CTA of NT threads; task_of(t) = image * tiles_per_image + tile
+template <int NT, class TaskOf>
+static __device__ __forceinline__ void cf_pipelined_tiles(CfPipeSmem& sm, const unsigned long long* __restrict__ raw, int H, int W,
+                                                          int64_t img_stride, double* __restrict__ out_train, int* __restrict__ far_flag,
+                                                          int t0, int n, int tstep, TaskOf task_of) {
     const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles = tiles_x * ((H + CF_TH - 1) / CF_TH);
-    const int n = *n_tasks;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     constexpr int CHUNKS = CF_SW / 2;                  // 16-byte requests per staged row
     auto issue = [&](int t, int buf) {
-        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        const int task = task_of(t), z = task / tiles, tile = task % tiles;
         const int r0 = (tile / tiles_x) * CF_TH, c0 = (tile % tiles_x) * CF_TW;
         const unsigned long long* img = raw + (int64_t)z * img_stride;
-        for (int i = threadIdx.x; i < CF_SH * CHUNKS; i += CF_THREADS) {
+        for (int i = threadIdx.x; i < CF_SH * CHUNKS; i += NT) {
             const int lr = i / CHUNKS, ch = i % CHUNKS;
             const int r = r0 - CF_HR + lr, c = c0 - CF_HC + 2 * ch;
-            if (r >= 0 && r < H && c >= 0 && c + 1 < W) cf_async_copy16(&s_raw[buf][lr][2 * ch], img + (int64_t)r * W + c);
+            if (r >= 0 && r < H && c >= 0 && c + 1 < W) cf_async_copy16(&sm.raw[buf][lr][2 * ch], img + (int64_t)r * W + c);
         }
     };
     auto left = [](const unsigned* a, int w) { return (a[w] << 1) | (w > 0 ? a[w - 1] >> 31 : 0u); };
     auto right = [](const unsigned* a, int w) { return (a[w] >> 1) | (a[w + 1] << 31); };
-    int t = blockIdx.x;
+    int t = t0;
     if (t < n) issue(t, 0);
     asm volatile("cp.async.commit_group;" ::: "memory");
-    if (threadIdx.x < CF_SH) { s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; s_dil[threadIdx.x][3] = ~0u; }
-    for (int buf = 0; t < n; t += gridDim.x, buf ^= 1) {
-        if (t + (int)gridDim.x < n) issue(t + gridDim.x, buf ^ 1);
+    if (threadIdx.x < CF_SH) { sm.one[threadIdx.x][3] = 0u; sm.in[threadIdx.x][3] = 0u; sm.dil[threadIdx.x][3] = ~0u; }
+    for (int buf = 0; t < n; t += tstep, buf ^= 1) {
+        if (t + tstep < n) issue(t + tstep, buf ^ 1);
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_group 1;" ::: "memory");          // everything but the newest group has landed
         __syncthreads();
-        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        const int task = task_of(t), z = task / tiles, tile = task % tiles;
         const int r0 = (tile / tiles_x) * CF_TH, c0 = (tile % tiles_x) * CF_TW;
         const int64_t base = (int64_t)z * img_stride;
-        for (int u = warp; u < CF_SH * 3; u += CF_THREADS / 32) {     // bit rows of the staged tile
+        for (int u = warp; u < CF_SH * 3; u += NT / 32) {             // bit rows of the staged tile
             const int lr = u / 3, w = u % 3, lc = w * 32 + lane;
             const int r = r0 - CF_HR + lr, c = c0 - CF_HC + lc;
             const bool inside = lc < CF_SW && r >= 0 && r < H && c >= 0 && c < W;
-            const bool hit = inside && s_raw[buf][lr][min(lc, CF_SW - 1)] != R3D_EMPTY_U64;
+            const bool hit = inside && sm.raw[buf][lr][min(lc, CF_SW - 1)] != R3D_EMPTY_U64;
             const unsigned b_one = __ballot_sync(0xffffffffu, hit), b_in = __ballot_sync(0xffffffffu, inside);
-            if (lane == 0) { s_one[lr][w] = b_one; s_in[lr][w] = b_in; }
+            if (lane == 0) { sm.one[lr][w] = b_one; sm.in[lr][w] = b_in; }
         }
         __syncthreads();
         if (threadIdx.x < (CF_SH - 4) * 3) {
             const int lr = 2 + threadIdx.x / 3, w = threadIdx.x % 3;
             unsigned d = 0u;
 #pragma unroll
-            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_one[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
-            s_dil[lr][w] = d | ~s_in[lr][w];
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = sm.one[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
+            sm.dil[lr][w] = d | ~sm.in[lr][w];
         }
         __syncthreads();
         if (threadIdx.x < CF_TH * 3) {
             const int lr = CF_HR + threadIdx.x / 3, w = threadIdx.x % 3;
             unsigned e = ~0u;
 #pragma unroll
-            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_dil[lr + dr]; e &= a[w] & left(a, w) & right(a, w); }
-            s_ero[lr][w] = e;
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = sm.dil[lr + dr]; e &= a[w] & left(a, w) & right(a, w); }
+            sm.ero[lr][w] = e;
         }
         __syncthreads();
         bool far = false;
-        for (int i = threadIdx.x; i < CF_TH * CF_TW; i += CF_THREADS) {
+        for (int i = threadIdx.x; i < CF_TH * CF_TW; i += NT) {
             const int lr = i / CF_TW, lc = i % CF_TW;
             const int r = r0 + lr, c = c0 + lc;
             if (r >= H || c >= W) continue;
             const int sr = lr + CF_HR, sc = lc + CF_HC;
-            const bool e = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
-            const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
-            double tv = one ? r3d::bits_dbl(s_raw[buf][sr][sc]) : r3d::kEmptyRange;      // od/ins:100: empty = 500
+            const bool e = (sm.ero[sr][sc >> 5] >> (sc & 31)) & 1u;
+            const bool one = (sm.one[sr][sc >> 5] >> (sc & 31)) & 1u;
+            double tv = one ? r3d::bits_dbl(sm.raw[buf][sr][sc]) : r3d::kEmptyRange;      // od/ins:100: empty = 500
             if (e && !one) {                                  // cl:41-43
                 int neighbors = 0;
                 double sum = 0.0;
                 const int q = sc - 1, qw = q >> 5, qb = q & 31;
 #pragma unroll
                 for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51, (drow, dcol) order
-                    const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
-                    if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc - 1])); }
-                    if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc])); }
-                    if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + 1])); }
+                    const unsigned m = __funnelshift_r(sm.one[sr + dr][qw], sm.one[sr + dr][qw + 1], qb) & 7u;
+                    if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(sm.raw[buf][sr + dr][sc - 1])); }
+                    if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(sm.raw[buf][sr + dr][sc])); }
+                    if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(sm.raw[buf][sr + dr][sc + 1])); }
                 }
                 if (neighbors > 0) tv = __ddiv_rn(sum, (double)neighbors);       // cl:57
             }
@@ -232,7 +235,15 @@ static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_raw_pipelin
             far |= tv > r3d::kEmptyRange;
         }
         if (far) atomicOr(&far_flag[z], 1);
-        __syncthreads();                                  // s_raw[buf] is the target of the loads issued two tasks ahead
+        __syncthreads();                                  // sm.raw[buf] is the target of the loads issued two tasks ahead
     }
+}
+static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_raw_pipelined(const unsigned long long* __restrict__ raw, int H, int W,
+                                                                           int64_t img_stride, double* __restrict__ out_train,
+                                                                           int* __restrict__ far_flag, const int* __restrict__ tasks,
+                                                                           const int* __restrict__ n_tasks) {
+    __shared__ __align__(16) CfPipeSmem sm;
+    cf_pipelined_tiles<CF_THREADS>(sm, raw, H, W, img_stride, out_train, far_flag, (int)blockIdx.x, *n_tasks, (int)gridDim.x,
+                                   [&](int t) { return tasks[t]; });
 }
 

@@ -299,7 +299,20 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
         cls[c].min_points = s.min_points; cls[c].map_sel = s.map_sel; cls[c].map_ok_mask = s.map_ok_mask;
         cls[c].pedestrian = s.pedestrian; cls[c].n_surface = std::min(std::max(s.n_surface, 0), R3D_MAX_SURFACE);
         for (int i = 0; i < R3D_MAX_SURFACE; ++i) cls[c].surface[i] = s.surface[i];
+        cls[c].ok_slots = 0u;
     }
+    d.n_surf_all = 0;
+    for (int c = 0; c < cfg->n_classes; ++c)
+        for (int i = 0; i < cls[c].n_surface; ++i) {
+            int slot = -1;
+            for (int j = 0; j < d.n_surf_all; ++j) if (d.surf_all[j] == cls[c].surface[i]) slot = j;
+            if (slot < 0) {
+                if (d.n_surf_all >= 15) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_create: more than 15 distinct surface labels");
+                slot = d.n_surf_all; d.surf_all[d.n_surf_all++] = cls[c].surface[i];
+            }
+            cls[c].ok_slots |= 1u << slot;
+        }
+    if (d.max_points + d.max_inserted > (1 << APT_IDX_BITS)) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_create: more than 2^27 points per scan");
     R3D_CUDA(cudaMemcpy(eng->classes.p, cls.data(), cls.size() * sizeof(ClassCfg), cudaMemcpyHostToDevice));
     R3D_CUDA(cudaMemcpy(eng->radii_sq.p, cfg->radii_sq, sizeof(cfg->radii_sq), cudaMemcpyHostToDevice));
     R3D_CUDA(cudaMemcpy(eng->radii_ok.p, cfg->radii_ok, sizeof(cfg->radii_ok), cudaMemcpyHostToDevice));

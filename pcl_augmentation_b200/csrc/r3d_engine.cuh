@@ -22,12 +22,15 @@ namespace r3d {
 
 enum : int { PH_INIT = 0, PH_AFTER_TRY = 1, PH_DONE = 2, PH_ERROR = 3 };
 enum : unsigned { CF_ONMAP = 1u, CF_HOK = 2u };
+constexpr int APT_IDX_BITS = 27;                       // apts.w = (surface slot << 27) | point index
+constexpr unsigned APT_IDX_MASK = (1u << APT_IDX_BITS) - 1u, APT_SLOT_NONE = 15u;
 
 struct ClassCfg {
     int min_points, map_sel;
     unsigned map_ok_mask;
     int pedestrian, n_surface;
     int surface[R3D_MAX_SURFACE];
+    unsigned ok_slots;   // bit i: EngineDev::surf_all[i] is one of this class's surface labels
 };
 
 struct ObjBox {          // one cut object: box from read_label_line (od/fs:175-224, ss/fs:155-189), host-prepared
@@ -68,6 +71,10 @@ struct EngineDev {       // passed by value to kernels
     int B, max_points, max_inserted, P, max_boxes, max_events, max_obj_points;
     int road_label, n_road_indexes, map_window, dwords, n_objects, n_perm_events;
     int road_indexes[R3D_MAX_SURFACE];
+    // semseg: the distinct labels some class may stand on (ss/fs:92-93).  Entries of the all-points grid carry the slot of
+    // their label (APT_SLOT_NONE = none of them) above the point index, so the collision test drops the ground points
+    // a class accepts before any arithmetic
+    int n_surf_all, surf_all[15];
     double step_rad;
     int G;                            // road-level grid side in cells
     float grid_inv_cell;
@@ -174,7 +181,7 @@ struct EngineDev {       // passed by value to kernels
     float* out_check;
 };
 
-#define R3D_N_STATS 32
+#define R3D_N_STATS 40
 #ifndef R3D_OCC_G
 #define R3D_OCC_G 8
 #endif

@@ -26,6 +26,16 @@ __device__ __forceinline__ bool any_surface_label(const EngineDev& e, unsigned l
     }
     return false;
 }
+// apts.w of original point p with label lab: the point index, and for semseg the slot of the label among the labels
+// some class may stand on (EngineDev::surf_all)
+__device__ __forceinline__ float apt_tag(const EngineDev& e, unsigned lab, int p) {
+    unsigned slot = 0u;
+    if (e.task == 1) {
+        slot = APT_SLOT_NONE;
+        for (int j = 0; j < e.n_surf_all; ++j) if (lab == (unsigned)e.surf_all[j]) slot = (unsigned)j;
+    }
+    return __uint_as_float((slot << APT_IDX_BITS) | (unsigned)p);
+}
 __device__ __forceinline__ int grid_coord(const EngineDev& e, float v) {
     const int i = (int)floorf(v * e.grid_inv_cell) + (e.G >> 1);
     return max(0, min(i, e.G - 1));
@@ -49,7 +59,7 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int 
         const int c = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
         if (!(e.task == 0 && lab == (unsigned)e.road_label)) {      // OD: Road points are never obstacles (od/ins:353-355)
             if (PASS == 1) atomicAdd(&acell[c], 1);
-            else aout[atomicAdd(&acell[c], 1)] = make_float4(v.x, v.y, v.z, __int_as_float(p));
+            else aout[atomicAdd(&acell[c], 1)] = make_float4(v.x, v.y, v.z, apt_tag(e, lab, p));
         }
         if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
         if (PASS == 1) atomicAdd(&cell[c], 1);

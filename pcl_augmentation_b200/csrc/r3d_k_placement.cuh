@@ -399,15 +399,18 @@ __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, co
         const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
         const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
         const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
+        const unsigned ok_slots = e.task == 1 ? cc.ok_slots : 0u;       // OD tags carry slot 0 and no class accepts it here
         group_visit_any<NL>(global_view(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G), staged, rc,
                             CellRect{0, -1, 0, -1}, gl, gm, [&](const float4& v) {
             if (hit) return;
+            const unsigned tag = __float_as_uint(v.w);
+            if ((ok_slots >> (tag >> APT_IDX_BITS)) & 1u) return;        // semseg: ground the class may stand on (ss/fs:92-93)
             const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
             if (dx * dx + dy * dy > fr2 || v.z < zlo || v.z > zhi) return;
             const double x = v.x, yy = v.y, z = v.z;
             if (ped && !(z >= zmin_ped)) return;
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
-            if (obstacle_point(e, b, s, cc, base, __float_as_int(v.w))) hit = true;
+            if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) hit = true;
         }, [&] { return (__ballot_sync(gm, hit) & gm) != 0u; });
         if (__ballot_sync(gm, hit) & gm) return true;
     }
@@ -478,15 +481,18 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
         const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
         const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
         const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
+        const unsigned ok_slots = e.task == 1 ? cc.ok_slots : 0u;       // OD tags carry slot 0 and no class accepts it here
         bool hit = false;
         warp_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, lane, [&](const float4& v) {
             if (hit) return;
+            const unsigned tag = __float_as_uint(v.w);
+            if ((ok_slots >> (tag >> APT_IDX_BITS)) & 1u) return;        // semseg: ground the class may stand on (ss/fs:92-93)
             const float dx = v.x - fcx, dy = v.y - fcy;                  // cheap conservative pruning first
             if (dx * dx + dy * dy > fr2 || v.z < zlo || v.z > zhi) return;
             const double x = v.x, yy = v.y, z = v.z;
             if (ped && !(z >= zmin_ped)) return;
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
-            if (obstacle_point(e, b, s, cc, base, __float_as_int(v.w))) hit = true;
+            if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) hit = true;
         }, [&] { return __any_sync(0xffffffffu, hit) != 0; });
         if (__any_sync(0xffffffffu, hit)) return true;
     }
@@ -687,15 +693,26 @@ struct SsMapTest {          // everything the map test of one object point needs
     unsigned okmask;
     const unsigned* occ;
     const int* far;         // occupied cells outside the bit window (numpy-wrapped indices of addjust_map_2), [0] = count
+    double inv02, inv12;    // 1 / |t02|, 1 / |t12| (1e300 for a zero term): cell-edge distance -> tolerated change of the z shift
 };
-__device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanState& s, const SsMapTest& m, double x0, double y0,
-                                                 double z0, double c, double sn, double dz) {
+// `tol` (when asked for): how far the carried z shift may move from `dz` before this point can reach another map cell.
+// dz enters the cell indices only through t02 * z and t12 * z (the pitch / roll terms of the pose), so a point that is
+// `dx` away from the nearest integer of (wx - move_x) keeps its cell while |shift| * |t02| < dx (1e-9 m covers the rounding
+// of the expression, ~1e-13 m); same for y.  The walker retests a yaw only when the carried shift left this interval.
+template <bool TOL>
+__device__ __forceinline__ bool ss_point_off_map_t(const EngineDev& e, const ScanState& s, const SsMapTest& m, double x0, double y0,
+                                                   double z0, double c, double sn, double dz, double& tol) {
     const double x = sub(mul(c, x0), mul(sn, y0)), y = add(mul(sn, x0), mul(c, y0));
     const double z = add(z0, dz);
     const double wx = add(add(add(mul(m.t00, x), mul(m.t01, y)), mul(m.t02, z)), m.t03);
     const double wy = add(add(add(mul(m.t10, x), mul(m.t11, y)), mul(m.t12, z)), m.t13);
-    const int ix = trunc_to_int(sub(wx, (double)e.ss_move_x));
-    const int iy = trunc_to_int(sub(wy, (double)e.ss_move_y));
+    const double vx = sub(wx, (double)e.ss_move_x), vy = sub(wy, (double)e.ss_move_y);
+    if (TOL) {
+        const double dx = fabs(vx - rint(vx)) - 1e-9, dy = fabs(vy - rint(vy)) - 1e-9;
+        tol = fmin(dx * m.inv02, dy * m.inv12);
+    }
+    const int ix = trunc_to_int(vx);
+    const int iy = trunc_to_int(vy);
     if (ix < e.ss_sx && ix > -1 && iy < e.ss_sy && iy > -1) {
         unsigned v = e.ss_map[(size_t)ix * e.ss_sy + iy];
         const int lx = ix - s.win_x0, ly = iy - s.win_y0;
@@ -709,6 +726,11 @@ __device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanS
         if (!((m.okmask >> v) & 1u)) return true;
     }
     return false;
+}
+__device__ __forceinline__ bool ss_point_off_map(const EngineDev& e, const ScanState& s, const SsMapTest& m, double x0, double y0,
+                                                 double z0, double c, double sn, double dz) {
+    double tol;
+    return ss_point_off_map_t<false>(e, s, m, x0, y0, z0, c, sn, dz, tol);
 }
 
 __global__ void __launch_bounds__(1024) k_onmap_ss_seq(EngineDev e, int n_scans);

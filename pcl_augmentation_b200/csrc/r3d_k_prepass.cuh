@@ -26,6 +26,24 @@ __device__ __forceinline__ int agg_slot(int* arr, int key, bool active) {
     return base + __popc(peers & ((1u << lane) - 1u));
 }
 
+// the same in two halves: the returning atomic of the group's leader is issued at once, its result is only waited for
+// when the slot is needed — so the round trips of several indices / points overlap
+struct AggTicket { unsigned peers; int base; };
+__device__ __forceinline__ AggTicket agg_issue(int* arr, int key, bool active) {
+    AggTicket t{0u, 0};
+    const unsigned act = __ballot_sync(0xffffffffu, active);
+    if (active) {
+        t.peers = __match_any_sync(act, key);
+        if ((int)(threadIdx.x & 31) == __ffs(t.peers) - 1) t.base = atomicAdd(&arr[key], __popc(t.peers));
+    }
+    return t;
+}
+__device__ __forceinline__ int agg_finish(const AggTicket& t) {
+    if (!t.peers) return -1;
+    const int base = __shfl_sync(t.peers, t.base, __ffs(t.peers) - 1);
+    return base + __popc(t.peers & ((1u << (threadIdx.x & 31)) - 1u));
+}
+
 __global__ void __launch_bounds__(STREAM_THREADS) k_ingest_count(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans) return;
@@ -112,30 +130,50 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e,
     float4* aout = e.apts + (size_t)b * e.max_points;
     int* cidx = e.col_idx + (size_t)b * e.max_points;
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    for (int q = p0; q < min(p0 + CHUNK, n0); q += STREAM_THREADS) {
-        const int p = q + threadIdx.x;
-        const bool in = p < n0;
-        float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
-        unsigned lab = 0u;
-        int col = 0;
-        double el = 0.0, r = 0.0;
-        if (in) {
-            v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]); lab = e.label[base + p]; col = e.col[base + p];
-            el = e.el[base + p]; r = e.r[base + p];
+    static_assert(CHUNK % (2 * STREAM_THREADS) == 0, "two points per thread and iteration");
+    for (int q = p0; q < min(p0 + CHUNK, n0); q += 2 * STREAM_THREADS) {
+        // two points per thread: all loads first, then the six slot atomics back to back, then the stores
+        int p[2], col[2], gc[2];
+        bool in[2];
+        float4 v[2];
+        unsigned lab[2];
+        double el[2], r[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            p[u] = q + u * STREAM_THREADS + threadIdx.x;
+            in[u] = p[u] < n0;
+            v[u] = make_float4(1.f, 0.f, 0.f, 0.f); lab[u] = 0u; col[u] = 0; el[u] = 0.0; r[u] = 0.0;
+            if (in[u]) {
+                v[u] = __ldg(&e.xyzi[(size_t)b * e.max_points + p[u]]); lab[u] = e.label[base + p[u]]; col[u] = e.col[base + p[u]];
+                el[u] = e.el[base + p[u]]; r[u] = e.r[base + p[u]];
+            }
         }
-        const int gc = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
-        const int sa = agg_slot(acell, gc, in && !(e.task == 0 && lab == (unsigned)e.road_label));
-        if (sa >= 0) aout[sa] = make_float4(v.x, v.y, v.z, __int_as_float(p));
-        const int sg = agg_slot(cell, gc, in && (double)v.z > -3.0 && any_surface_label(e, lab));
-        if (sg >= 0) out[sg] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
-        const int sc = agg_slot(coff, col, in);
-        if (sc >= 0) cidx[sc] = p;
-        if (in) {                                        // A3 (od/ins:85-130)
+        AggTicket ta[2], tg[2], tc[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            gc[u] = grid_coord(e, v[u].y) * e.G + grid_coord(e, v[u].x);
+            ta[u] = agg_issue(acell, gc[u], in[u] && !(e.task == 0 && lab[u] == (unsigned)e.road_label));
+            tg[u] = agg_issue(cell, gc[u], in[u] && (double)v[u].z > -3.0 && any_surface_label(e, lab[u]));
+            tc[u] = agg_issue(coff, col[u], in[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
             int pix = -1;
-            const int row = bin_row(g, el);
-            if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);                 // od/ins:111
-            else { pix = row * g.cols + col; atomicMin(&z[pix], dbl_bits(r)); }
-            e.pix[base + p] = pix;
+            if (in[u]) {                                 // A3 (od/ins:85-130)
+                const int row = bin_row(g, el[u]);
+                if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);             // od/ins:111
+                else { pix = row * g.cols + col[u]; atomicMin(&z[pix], dbl_bits(r[u])); }
+                e.pix[base + p[u]] = pix;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int sa = agg_finish(ta[u]);
+            if (sa >= 0) aout[sa] = make_float4(v[u].x, v[u].y, v[u].z, apt_tag(e, lab[u], p[u]));
+            const int sg = agg_finish(tg[u]);
+            if (sg >= 0) out[sg] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float(lab[u]));
+            const int sc = agg_finish(tc[u]);
+            if (sc >= 0) cidx[sc] = p[u];
         }
     }
 }

@@ -51,12 +51,13 @@ __host__ __device__ __forceinline__ WalkSmem walk_smem_layout(int K, int dwords)
     o += occ > cf ? occ : cf;
     const size_t sel = walk_sel_bytes();
     L.total = o > sel ? o : sel;
+    if (L.total < sizeof(CfPipeSmem)) L.total = sizeof(CfPipeSmem);
     return L;
 }
 
 // phase clocks (SM cycles, summed over all scans by thread 0 of each CTA) -> e.stats[WALK_T0 + phase]
 enum : int { WT_CTRL = 0, WT_UPDATE, WT_SETUP, WT_PLACE, WT_OCCL, WT_SELECT, WT_TOTAL, WT_ONMAP, WT_LEVEL_WARP, WT_COLLIDE_WARP,
-              WT_N_LEVEL, WT_N_COLLIDE, WT_APPLY, WT_PATCH, WT_CLOSEFILL, WT_COUNT };
+              WT_N_LEVEL, WT_N_COLLIDE, WT_APPLY, WT_PATCH, WT_CLOSEFILL, WT_SS_RESWEEP, WT_SS_LEVEL, WT_COUNT };
 constexpr int WALK_T0 = 16;
 struct WalkClock {
     long long t;
@@ -87,6 +88,9 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     unsigned surf[R3D_MAX_SURFACE];      // labels the tried class may stand on (road-level search)
     int n_surf;
     double wdz[WALK_W];          // semseg fixed point: the shift candidate i was (or must be) tested under
+    double wtol[WALK_W];         // ... and how far the shift may move from it without changing the verdict of the map test
+    unsigned long long wtolp[WALK_W], wtolb[WALK_W];   // its parts while the map test runs: min over on-map points, max over off-map points
+    int wbad[WALK_W];
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
     int s_warp[WALK_NWARPS];
@@ -179,13 +183,29 @@ __device__ R3D_WALK_FN void walk_close_fill(const EngineDev& e, int b, const int
 // every scan is done batch-wide by k_minmax / k_clear_images / k_project before the walker starts)
 __device__ R3D_WALK_FN void walk_full_reproject(const EngineDev& e, int b, ScanState& s, WalkCtl& c) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    const size_t base = (size_t)b * e.P;
-    const int n = s.n0 + s.n_tail;
+    const size_t base = (size_t)b * e.P;                 // rows are padded to a multiple of 16 points: 4-point vectors
+    const int n = s.n0 + s.n_tail, n4 = (n + 3) >> 2;
+    const unsigned* __restrict__ alive4 = reinterpret_cast<const unsigned*>(e.alive + base);
+    const double2* __restrict__ el2 = reinterpret_cast<const double2*>(e.el + base);
     if (tid == 0) { c.el_min = R3D_EMPTY_U64; c.el_max = 0ull; }
+    unsigned long long* z = e.zraw + (size_t)b * e.hw;
+    {
+        ulonglong2* z2 = reinterpret_cast<ulonglong2*>(z);
+        for (int i = tid; i < e.hw / 2; i += nt) z2[i] = make_ulonglong2(R3D_EMPTY_U64, R3D_EMPTY_U64);
+        if ((e.hw & 1) && tid == 0) z[e.hw - 1] = R3D_EMPTY_U64;
+    }
     __syncthreads();
     unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
-    for (int p = tid; p < n; p += nt)
-        if (e.alive[base + p]) { const unsigned long long bits = dbl_bits(e.el[base + p]); lmin = min(lmin, bits); lmax = max(lmax, bits); }
+#pragma unroll 2
+    for (int q = tid; q < n4; q += nt) {
+        const unsigned a = alive4[q];
+        if (!a) continue;
+        const double2 lo = el2[2 * q], hi = el2[2 * q + 1];
+        const double ev[4] = {lo.x, lo.y, hi.x, hi.y};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (((a >> (8 * u)) & 0xFFu) && 4 * q + u < n) { const unsigned long long bits = dbl_bits(ev[u]); lmin = min(lmin, bits); lmax = max(lmax, bits); }
+    }
     for (int o = 16; o > 0; o >>= 1) {
         lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
         lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
@@ -200,18 +220,28 @@ __device__ R3D_WALK_FN void walk_full_reproject(const EngineDev& e, int b, ScanS
         s.geom = make_geom(e.rows, e.cols, e.cols, bits_dbl(mx), bits_dbl(mn));
         atomicAdd(&e.stats[11], 1ull);
     }
-    unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    for (int i = tid; i < e.hw; i += nt) z[i] = R3D_EMPTY_U64;
-    __syncthreads();
     const ImageGeom g = make_geom(e.rows, e.cols, e.cols, bits_dbl(mx), bits_dbl(mn));
-    for (int p = tid; p < n; p += nt) {
-        int pix = -1;
-        if (e.alive[base + p]) {
-            const int row = bin_row(g, e.el[base + p]);
-            if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);                          // od/ins:111
-            else { pix = row * g.cols + (int)e.col[base + p]; atomicMin(&z[pix], dbl_bits(e.r[base + p])); }
+    const double2* __restrict__ r2 = reinterpret_cast<const double2*>(e.r + base);
+    const ushort4* __restrict__ col4 = reinterpret_cast<const ushort4*>(e.col + base);
+    int4* pix4 = reinterpret_cast<int4*>(e.pix + base);
+#pragma unroll 2
+    for (int q = tid; q < n4; q += nt) {
+        const unsigned a = alive4[q];
+        int px[4] = {-1, -1, -1, -1};
+        if (a) {
+            const double2 lo = el2[2 * q], hi = el2[2 * q + 1], rl = r2[2 * q], rh = r2[2 * q + 1];
+            const ushort4 cc = col4[q];
+            const double ev[4] = {lo.x, lo.y, hi.x, hi.y}, rv[4] = {rl.x, rl.y, rh.x, rh.y};
+            const int cv[4] = {cc.x, cc.y, cc.z, cc.w};
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (((a >> (8 * u)) & 0xFFu) && 4 * q + u < n) {
+                    const int row = bin_row(g, ev[u]);
+                    if (row < 0 || row >= g.rows) set_error(s, R3D_ERR_ASSERT);                  // od/ins:111
+                    else { px[u] = row * g.cols + cv[u]; atomicMin(&z[px[u]], dbl_bits(rv[u])); }
+                }
         }
-        e.pix[base + p] = pix;
+        pix4[q] = make_int4(px[0], px[1], px[2], px[3]);
     }
 }
 
@@ -224,7 +254,7 @@ __device__ R3D_WALK_FN void walk_adjust_map(const EngineDev& e, int b, ScanState
 
 // ---- slot update: what k_update + the refresh kernels of a staged round do for one scan
 __device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s, WalkCtl& c, int do_apply, int do_update,
-                            unsigned char* scratch) {
+                            unsigned char* scratch, unsigned char* dyn) {
     long long ut = clock64();
     auto ulap = [&](int phase) {
         if (threadIdx.x == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + phase], (unsigned long long)(n - ut)); ut = n; }
@@ -288,7 +318,13 @@ __device__ R3D_WALK_FN void walk_update(const EngineDev& e, int b, ScanState& s,
     }
     __syncthreads();
     ulap(WT_PATCH);
-    if (c.rect[1] >= c.rect[0] && c.rect[3] >= c.rect[2]) walk_close_fill(e, b, c.rect, scratch);
+    if (c.upd_full && !(e.cols & 1)) {
+        // the whole image: the tiles stream through two shared-memory buffers (cp.async), as in the batch-wide kernel;
+        // the object staging area of the dynamic shared memory is free between two tries
+        const int tiles = e.cf_tiles;
+        cf_pipelined_tiles<WALK_THREADS>(*reinterpret_cast<CfPipeSmem*>(dyn), e.zraw, e.rows, e.cols, (int64_t)e.hw, e.smooth, e.far_arr,
+                                         0, tiles, 1, [&](int t) { return b * tiles + t; });
+    } else if (c.rect[1] >= c.rect[0] && c.rect[3] >= c.rect[2]) walk_close_fill(e, b, c.rect, scratch);
     ulap(WT_CLOSEFILL);
     if (rebuild_marks) { __syncthreads(); walk_adjust_map(e, b, s); }
     __syncthreads();
@@ -413,43 +449,108 @@ __device__ R3D_WALK_FN int walk_window_ss(const EngineDev& e, int b, ScanState& 
     m.okmask = cc.map_ok_mask;
     m.occ = e.occ_win + (size_t)b * (e.map_window * e.map_window / 32);
     m.far = e.occ_far + (size_t)b * (OCC_FAR_CAP + 1);
+    m.inv02 = m.t02 != 0.0 ? 1.0 / fabs(m.t02) : 1e300;
+    m.inv12 = m.t12 != 0.0 ? 1.0 / fabs(m.t12) : 1e300;
     const int k = base + g + 1;
     const double cs = g < nw ? e.cos_k[k] : 1.0, sn = g < nw ? e.sin_k[k] : 0.0;
+    const int warp = tid >> 5, lane = tid & 31;
+    constexpr int ITEM_PTS = 128;                                 // object points per work item of the full map test
+    const int n_items_per = ob.count > 4 * GRP ? (ob.count - 4 * GRP + ITEM_PTS - 1) / ITEM_PTS : 0;
     for (int sweep = 0; sweep <= nw; ++sweep) {
-        if (g < nw && c.wtodo[g]) {                               // ss/fs:231-248 under the assumed shift
+        long long t_ph = clock64();
+        // (1) ss/fs:231-248 under the assumed shift, first on the first 32 object points (an 8-lane group per yaw: most
+        // off-map yaws end here).  tolerated change of the shift: a yaw that passes keeps its verdict while EVERY point
+        // keeps its map cell, a yaw that fails while ONE of its off-map points does
+        if (g < nw && c.wtodo[g]) {
             const double dz = c.wdz[g];
-            bool bad = false;
-            for (int i0 = 0; i0 < ob.count && !bad; i0 += 4 * GRP) {   // 4 points per lane in flight
-                bool off = false;
+            bool off = false;
+            double tol_pass = 1e300, tol_bad = 0.0;
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = min(i0 + u * GRP + gl, ob.count - 1);                 // the clamped repeats change nothing
-                    off |= ss_point_off_map(e, s, m, ox[i], oy[i], oz[i], cs, sn, dz);
-                }
-                bad = (__ballot_sync(gm, off) & gm) != 0u;
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(u * GRP + gl, ob.count - 1);                          // the clamped repeats change nothing
+                double tol;
+                const bool o = ss_point_off_map_t<true>(e, s, m, ox[i], oy[i], oz[i], cs, sn, dz, tol);
+                tol = fmax(tol, 0.0);
+                off |= o;
+                if (o) tol_bad = fmax(tol_bad, tol); else tol_pass = fmin(tol_pass, tol);
             }
-            if (gl == 0) c.wpass[g] = bad ? 0 : 1;
+            const bool bad = (__ballot_sync(gm, off) & gm) != 0u;
+            double tol = bad ? tol_bad : tol_pass;
+#pragma unroll
+            for (int o = GRP / 2; o > 0; o >>= 1) {
+                const double other = __shfl_xor_sync(gm, tol, o);
+                tol = bad ? fmax(tol, other) : fmin(tol, other);
+            }
+            if (gl == 0) {
+                c.wbad[g] = bad ? 1 : 0;
+                c.wtolp[g] = dbl_bits(bad ? 1e300 : tol); c.wtolb[g] = dbl_bits(bad ? tol : 0.0);
+            }
         }
         __syncthreads();
-        const bool need_level = g < nw && c.wpass[g] && !c.whas[g];
-        __syncwarp();                                             // every lane has read the flags its group's lane 0 rewrites below
-        if (need_level) {                                         // ss/fs:250: correct_height of a yaw on the map
-            const SurfaceSet surf = load_surface(cc);
-            double level = 0.0;
-            const bool ok = group_road_level(e, b, surf, c.wcx[g], c.wcy[g], gl, gm, level);
-            if (gl == 0) { c.whas[g] = 1; c.whok[g] = ok ? 1 : 0; c.wlevel[g] = level; }
+        // (2) the rest of the points of the yaws that are still on the map: (yaw, 128-point chunk) items dealt to the warps
+        // of the whole CTA (a big object on a few surviving yaws would otherwise keep 8 lanes busy and 500 waiting)
+        const int n_live = n_items_per ? walk_window_list(c, nw, c.wsub, [&](int i) { return c.wtodo[i] && !c.wbad[i]; }) : 0;
+        for (int t = warp; t < n_live * n_items_per; t += WALK_NWARPS) {
+            const int i = c.wsub[t / n_items_per], q = t % n_items_per;
+            if (*(volatile int*)&c.wbad[i]) continue;                                   // another chunk already found an off-map point
+            const int kk = base + i + 1;
+            const double ci = e.cos_k[kk], si = e.sin_k[kk], dz = c.wdz[i];
+            bool off = false;
+            double tol_pass = 1e300, tol_bad = 0.0;
+#pragma unroll
+            for (int u = 0; u < ITEM_PTS / 32; ++u) {
+                const int p = 4 * GRP + q * ITEM_PTS + u * 32 + lane;
+                if (p < ob.count) {
+                    double tol;
+                    const bool o = ss_point_off_map_t<true>(e, s, m, ox[p], oy[p], oz[p], ci, si, dz, tol);
+                    tol = fmax(tol, 0.0);
+                    off |= o;
+                    if (o) tol_bad = fmax(tol_bad, tol); else tol_pass = fmin(tol_pass, tol);
+                }
+            }
+            const bool bad = __any_sync(0xffffffffu, off);
+            double tol = bad ? tol_bad : tol_pass;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double other = __shfl_xor_sync(0xffffffffu, tol, o);
+                tol = bad ? fmax(tol, other) : fmin(tol, other);
+            }
+            if (lane == 0) {
+                if (bad) { atomicMax(&c.wtolb[i], dbl_bits(tol)); atomicExch(&c.wbad[i], 1); }
+                else atomicMin(&c.wtolp[i], dbl_bits(tol));
+            }
+        }
+        __syncthreads();
+        if (tid < nw && c.wtodo[tid]) {
+            const bool bad = c.wbad[tid] != 0;
+            c.wpass[tid] = bad ? 0 : 1;
+            c.wtol[tid] = bits_dbl(bad ? c.wtolb[tid] : c.wtolp[tid]);
+        }
+        __syncthreads();
+        if (tid == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_ONMAP], (unsigned long long)(n - t_ph)); t_ph = n; }
+        // (3) ss/fs:250: correct_height of the yaws on the map that have no road level yet, one warp per yaw
+        const int n_lvl = walk_window_list(c, nw, c.wsub, [&](int i) { return c.wpass[i] && !c.whas[i]; });
+        walk_levels(e, b, c, c.wsub, n_lvl);
+        __syncthreads();
+        if (tid < n_lvl) {
+            const int i = c.wsub[tid];
+            c.whas[i] = 1; c.whok[i] = (c.wflag[i] & CF_HOK) ? 1 : 0;
         }
         __syncthreads();
         if (tid == 0) {                                           // the ordered walk over the flags (ss/fs:144-148)
+            const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_SS_LEVEL], (unsigned long long)(n - t_ph));
             double run = c.dz_run;
             int changed = 0;
             for (int i = 0; i < nw; ++i) {
-                const bool redo = run != c.wdz[i];
+                // yaw i was tested under another shift: test it again unless the shift stayed within the interval in
+                // which none of the deciding points can change its map cell
+                const bool redo = run != c.wdz[i] && !(fabs(run - c.wdz[i]) < c.wtol[i]);
                 c.wtodo[i] = redo;
                 if (redo) { c.wdz[i] = run; changed = 1; }
                 if (c.wpass[i] && c.whok[i]) run = sub(c.wlevel[i], ob.cz);
             }
             c.changed = changed; c.dz_next = run;
+            if (changed) atomicAdd(&e.stats[WALK_T0 + WT_SS_RESWEEP], 1ull);
         }
         __syncthreads();
         if (!c.changed) break;
@@ -689,7 +790,7 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(co
         __syncthreads();
         const int apply = c.apply, project = c.project, tryact = c.tryact;
         clk.lap(e, WT_CTRL);
-        if (apply || project) walk_update(e, b, s, c, apply, project, w_dyn + L.scratch_off);
+        if (apply || project) walk_update(e, b, s, c, apply, project, w_dyn + L.scratch_off, w_dyn);
         clk.lap(e, WT_UPDATE);
         if (!tryact) break;                              // PH_DONE or PH_ERROR
         walk_try(e, b, s, c, w_dyn, L, clk);

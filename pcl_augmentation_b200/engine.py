@@ -61,7 +61,7 @@ class Real3DEngine:
 
     def __init__(self, task, config, db, *, max_scans, max_points, rows=112, cols=1440, yaw_steps=360,
                  max_tries=MAX_NUM_TRIES, max_inserted=None, max_boxes=64, max_events=None, map_data=None,
-                 map_window=512, road_indexes=ROAD_INDEXES, grid_cell=0.5, grid_half=120, force_full_projection=False,
+                 map_window=512, road_indexes=None, grid_cell=0.5, grid_half=120, force_full_projection=False,
                  sub_batches=0, fetch_labels=None, round_graphs=True, candidate_window=True, staged_rounds=False):
         _lib.require_cuda()
         self.lib = _lib.load()
@@ -87,6 +87,9 @@ class Real3DEngine:
         cfg.max_scans, cfg.max_points, cfg.max_inserted = self.max_scans, self.max_points, self.max_inserted
         cfg.max_boxes, cfg.max_events = self.max_boxes, self.max_events
         cfg.road_label = int(config['labels']['Road']) if task == 'od' else 0
+        if road_indexes is None:         # config key (shipped waymo.yaml), else the reference's constant (od/fs:14)
+            road_indexes = config['insertion'].get('road_indexes', ROAD_INDEXES)
+        self.road_indexes = [int(v) for v in road_indexes]
         cfg.n_road_indexes = len(road_indexes)
         for i, v in enumerate(road_indexes):
             cfg.road_indexes[i] = int(v)
@@ -407,8 +410,8 @@ class Real3DEngine:
         return {ks[i]: {'ms': ms[i], 'launches': int(launches[i])} for i in range(n.value)}
 
     def stats(self):
-        out = np.zeros(32, dtype=np.uint64)
-        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 32), "stats")
+        out = np.zeros(40, dtype=np.uint64)
+        _lib.check(self.lib.r3d_engine_stats_ex(self.handle, out.ctypes.data, 40), "stats")
         return {'projected_scans': int(out[0]), 'tried_objects': int(out[1]), 'masked_scans': int(out[2]),
                 'patched_scans': int(out[3]), 'select_tile': int(out[4]), 'select_global': int(out[5]),
                 'prefilter_survivors': int(out[6]), 'onmap_rotations': int(out[7]), 'max_steps_per_scan': int(out[8]),
@@ -418,7 +421,7 @@ class Real3DEngine:
                     ('schedule', 'update', 'setup_prefilter', 'placement', 'occlusion', 'select_insert', 'total'))},
                 'walker_detail': {k: int(out[16 + 7 + i]) for i, k in enumerate(
                     ('onmap_cycles', 'level_warp_cycles', 'collide_warp_cycles', 'n_level', 'n_collide', 'apply_cycles',
-                     'patch_cycles', 'closefill_cycles'))}}
+                     'patch_cycles', 'closefill_cycles', 'ss_resweeps', 'ss_level_cycles'))}}
 
     def surface_labels(self):
         """Semantic labels the road-level search of any class accepts (what the surface grid indexes)."""

@@ -132,3 +132,45 @@ def test_failed_frame_is_given_back_and_the_others_are_written(tmp_path):
     assert os.path.exists(os.path.join(out, "velodyne/000000.bin")) and os.path.exists(os.path.join(out, "velodyne/000002.bin"))
     assert not os.path.exists(os.path.join(out, "added_objects/000001.txt"))
     assert not os.path.exists(os.path.join(out, "velodyne/000001.bin"))
+
+
+def test_waymo_adapter_and_config(tmp_path):
+    """The `Waymo` adapter on frames in the reference's converted layout (ss/ds:218-410) and the shipped waymo.yaml:
+    LiDAR mounting shift in / out, pose correction, per-sequence frame lists, ground labels for addjust_map_2."""
+    import yaml
+    from pcl_augmentation_b200 import engine as eng_mod
+    from pcl_augmentation_b200.semantic_segmentation.Real3DAug.tools.datasets import Waymo
+    cfg_path = os.path.join(os.path.dirname(eng_mod.__file__), "config", "waymo.yaml")
+    with open(cfg_path) as f:
+        cfg = yaml.safe_load(f)
+    assert cfg["insertion"]["classes"] == [5, 6, 7] and cfg["insertion"]["placement_labels"] == {1: [18, 19], 2: [22], 3: [20]}
+    assert cfg["insertion"]["road_indexes"] == [18, 19, 20, 22] and cfg["labels"][22] == "sidewalk"
+    rng = np.random.default_rng(5)
+    data, out = tmp_path / "data", tmp_path / "out"
+    frames = {}
+    for seq, names in (("seg_a", ["0000", "0001"]), ("seg_b", ["0000"])):
+        for sub in ("lidar", "labels_v3_2", "poses"):
+            os.makedirs(data / seq / sub)
+        for n in names:
+            pts = rng.uniform(-20, 20, (50, 6)).astype(np.float32)
+            lab = np.stack((rng.integers(0, 9, 50), rng.integers(0, 23, 50)), axis=1).astype(np.int32)
+            pose = np.eye(4); pose[:3, 3] = rng.uniform(-5, 5, 3)
+            np.save(data / seq / "lidar" / f"{n}.npy", pts); np.save(data / seq / "labels_v3_2" / f"{n}.npy", lab)
+            np.save(data / seq / "poses" / f"{n}.npy", pose)
+            frames[(seq, n)] = (pts, lab, pose)
+    cfg["path"].update(dataset_path=str(data), annotation_path=str(tmp_path / "anno"), output_path=str(out))
+    ds = Waymo(cfg)
+    assert ds.sequence_names == ["seg_a", "seg_b"] and len(ds) == 3 and ds.sequence == "seg_a"
+    xyzi, labels, pose, anno, name = ds.read_frame(2)
+    pts, lab, p0 = frames[("seg_b", "0000")]
+    np.testing.assert_array_equal(xyzi[:, :3], (pts[:, :3].astype(np.float64) - Waymo.LiDAR_location).astype(np.float32))   # ss/ds:262-267
+    np.testing.assert_array_equal(labels, lab[:, 1].astype(np.uint32))
+    corr = np.eye(4); corr[:3, 3] = Waymo.LiDAR_location
+    np.testing.assert_array_equal(pose, p0 @ corr)
+    assert anno == f"{tmp_path}/anno/seg_b/bbox/0000.txt" and name == "0000"
+    folder, number = ds.create_directories("chosen")
+    assert (folder, number) == ("chosen/00", 0) and os.path.isdir(out / folder / "seg_a" / "labels_v3_2")
+    ds._write(f"{folder}/seg_a", "0000", xyzi, labels, np.hstack((xyzi[:2], [[5.0], [6.0]])).astype(np.float32))
+    back = np.load(out / folder / "seg_a" / "lidar" / "0000.npy")
+    np.testing.assert_allclose(back[:, :3], pts[:, :3], rtol=0, atol=4e-6)                     # shifted back (ss/ds:286-287)
+    assert np.load(out / folder / "seg_a" / "labels_v3_2" / "0000.npy").shape == (50, 1)

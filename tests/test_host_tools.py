@@ -1,6 +1,8 @@
 """CPU tier: host-side logic of the offline-tool drop-ins — label parsing, label -> map class
 precedence, camera record, filter_objects bookkeeping — against the oracle restatement and the reference goldens.
 No CUDA call is made here."""
+import os
+import pytest
 import json
 
 import numpy as np
@@ -79,3 +81,17 @@ def test_filter_objects_bookkeeping_matches_reference_run():
         assert sorted(kept) == json.loads(str(g[folder + "_kept"]))
         removed += len(samples) - len(kept)
     assert removed >= 10
+
+
+def test_reference_arm_recipe_lists_existing_reference_files():
+    """oracle/build_ref.py (the recipe behind `bench.py --impl reference`, kind "reference"): every file it names exists
+    in the reference tree, and the copy under oracle/_ref is byte-identical (skipped where /root/reference is absent)."""
+    import filecmp
+    from oracle import build_ref
+    if not os.path.isdir(build_ref.SRC):
+        pytest.skip("no /root/reference here")
+    assert build_ref.build(verbose=False)
+    for rel in build_ref.FILES:
+        src = os.path.join(build_ref.SRC, rel)
+        assert os.path.isfile(src), rel
+        assert filecmp.cmp(src, os.path.join(build_ref.DST, rel), shallow=False), rel
