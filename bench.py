@@ -46,7 +46,7 @@ WORKLOADS = {
     "c1": dict(task="od", shape="KITTI", scans=1, objects=10, yaw=360, rows=112, cols=1440, distinct=1,
                text="one KITTI-shape HDL-64 scan (120000 pts, 112x1440 range image), 10 cut pedestrians/cyclists, 360 yaw "
                     "candidates per object"),
-    "c2": dict(task="ss", shape="SEMKITTI", scans=256, objects=20, yaw=360, rows=64, cols=2048, distinct=8,
+    "c2": dict(task="ss", shape="SEMKITTI", scans=256, objects=20, yaw=360, rows=64, cols=2048, distinct=8, resident=8,
                text="batch of 256 SemanticKITTI-shape scans per GPU (124992 pts, 64x2048 range image), 20 rare-class objects "
                     "per scan placed on the rich_map road / sidewalk, 360 yaw candidates per object"),
     "c3": dict(task="od", shape="KITTI", scans=256, objects=10, yaw=1024, rows=112, cols=1440, distinct=32,
@@ -55,7 +55,7 @@ WORKLOADS = {
     "c4": dict(task="od", shape="OS128", scans=128, objects=50, yaw=360, rows=128, cols=2048, distinct=4,
                text="batch of 128 OS1-128-shape scans per GPU (262144 pts, 128x2048 range image), 50 inserted objects per "
                     "scan, 360 yaw candidates per object"),
-    "c5": dict(task="ss", shape="SEMKITTI", scans=256, objects=10, yaw=360, rows=112, cols=1440, distinct=8, stream=4541,
+    "c5": dict(task="ss", shape="SEMKITTI", scans=256, objects=10, yaw=360, rows=112, cols=1440, distinct=8, stream=4541, resident=6,
                text="SemanticKITTI-sequence-sized stream of 4541 scans (124992 pts, 112x1440 range image, 10 objects per "
                     "scan) in batches of 256, sharded by scan over the GPUs, end to end incl. host<->device transfer"),
 }
@@ -423,7 +423,10 @@ class Bench:
         kw = engine_kwargs(name, self.cases)
         c0 = self.cases[0]
         self.pipe = ScanPipeline(self.w["task"], c0.config, c0.db, depth=args.depth, **kw)
-        self.res_depth = max(1, args.resident_depth)
+        # engines the device-resident leg deals its steps to: --resident-depth, or the workload's own figure when the
+        # flag is left at its default (semseg scans differ a lot in the tries they need — the walker of one batch ends
+        # with a few long scans, which more resident batches fill)
+        self.res_depth = max(1, args.resident_depth if args.resident_depth > 0 else self.w.get("resident", 3))
         self.extra = [Real3DEngine(self.w["task"], c0.config, c0.db, **kw) for _ in range(self.res_depth - args.depth)]
         self.res_engines = (self.pipe.engines + self.extra)[:self.res_depth]
         self.eng = self.pipe.engines[0]
@@ -577,7 +580,7 @@ def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_ov
     """A short run of another BASELINE.json configuration: device-resident value, serial step + dominant kernel, e2e."""
     b = Bench(name, rank, world, args, barrier, max_over_ranks)
     try:
-        steps = max(4, args.steps // 4)
+        steps = max(4, args.steps // 4, 2 * b.res_depth)
         dev_ms, _ = b.resident(steps, 2)
         serial_ms, prof, stats, results = b.serial(3)
         table, _ = kernel_table(b, prof, 3, peak)
@@ -614,9 +617,9 @@ def main():
     ap.add_argument("--side-configs", default="c2,c4,c5",
                     help="comma-separated other configurations measured briefly into the `configs` block ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--resident-depth", type=int, default=3,
+    ap.add_argument("--resident-depth", type=int, default=0,
                     help="engines (each with its own HBM-resident batch) the device-resident leg deals the steps to: one "
-                         "engine's streaming kernels overlap another's walker")
+                         "engine's streaming kernels overlap another's walker (0 = the workload's default: 3, semseg 6-8)")
     ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
     ap.add_argument("--side", default=None, choices=["rich_map_od", "rich_map_ss", "cut_objects"],
                     help="instead of the headline bench: one of the offline tools either side of the path (SURVEY 8f rows "

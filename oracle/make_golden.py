@@ -242,6 +242,28 @@ def gen_fn_projection():
         ref.set_image_size(112, 1440)
 
 
+def gen_fn_projection_full():
+    """A1-A4 at BASELINE size: a 120 000-point KITTI-shape scan on the reference's own 112 x 1440 image.  The images are
+    1.3 MB each, so the fixture keeps the pix ids and the elevation range, and sha256 digests of the fp64 images (the
+    bar is bit-exactness) plus the positions / values of the filled pixels for diagnosis."""
+    ref = shim.load("od")
+    ref.set_image_size(112, 1440)
+    pcl, labels = synth.make_scan(6, synth.KITTI_SHAPE)
+    pcl5 = np.hstack((pcl, labels.reshape(-1, 1))).astype(np.float64)
+    t0 = time.time()
+    pc = ref.insertion.add_space_for_spherical(pcl5)
+    pc, mx, mn = ref.insertion.fill_spherical(pc)
+    train, label, pc = ref.insertion.geometrical_front_view(pc, 112, 1440, mx, mn)
+    s_train, s_label = ref.closing.smooth_out(train, label)
+    filled = np.flatnonzero((s_label == 1) & (label != 1)).astype(np.int32)
+    np.savez_compressed(
+        os.path.join(GOLDEN_DIR, "fn_projection_full.npz"), in_digest=synth.array_digest(pcl5), max_el=mx, min_el=mn,
+        pix=pc[:, 8].astype(np.int32), r_sha=sha(pc[:, 3]), train_sha=sha(train), label_sha=sha(label.astype(np.int8)),
+        s_train_sha=sha(s_train), s_label_sha=sha(s_label.astype(np.int8)), filled=filled,
+        filled_values=s_train.ravel()[filled], occupied=int((label == 1).sum()))
+    print(f"fn_projection_full: {time.time() - t0:.1f}s occupied px {int((label == 1).sum())} filled px {len(filled)}")
+
+
 def gen_fn_cut_bbox():
     ref = shim.load("od")
     rng = np.random.default_rng(99)
@@ -468,6 +490,7 @@ GENERATORS = {
     "rich_map_od": gen_rich_map_od,
     "rich_map_ss": gen_rich_map_ss,
     "fn_projection": gen_fn_projection,
+    "fn_projection_full": gen_fn_projection_full,
     "fn_cut_bbox": gen_fn_cut_bbox,
     "fn_places_od": lambda: gen_fn_places("od"),
     "fn_places_ss": lambda: gen_fn_places("ss"),

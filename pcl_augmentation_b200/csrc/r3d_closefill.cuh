@@ -7,6 +7,7 @@
 // coalesced row reads; dilation, erosion and the hole fill then run out of shared memory, so HBM sees one read of
 // the input (x1.33 for the halo, mostly L2 hits) and one write of the output: 16 B/pixel for the engine variant.
 #pragma once
+#include <cuda.h>            // CUtensorMap (the TMA descriptor of the z-buffer; encoded through the driver entry point)
 #include "r3d_common.cuh"
 
 constexpr int CF_TH = 32;       // output rows per CTA
@@ -247,3 +248,124 @@ static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_raw_pipelin
                                    [&](int t) { return tasks[t]; });
 }
 
+
+// ---- the same walk with the tile loads done by the TMA unit (sm_90+; here sm_100a): ONE thread arms an mbarrier with
+// the byte count of a staged tile and issues one `cp.async.bulk.tensor.3d` for the 68 x 40 x 1 box at
+// (c0 - 2, r0 - 4, image) of the [B][H][W] u64 z-buffer; the unit does the address arithmetic and fills whatever lies
+// outside the image with zeros.  A range of 0.0 cannot occur (r > 0 is asserted at ingest), so "0" doubles as the
+// outside marker and the per-pixel border tests of the cp.async variant disappear; the CTA waits on the mbarrier phase
+// instead of `cp.async.wait_group` + barrier.  Double buffered like the variant above.
+static __device__ __forceinline__ unsigned cf_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+static __device__ __forceinline__ void cf_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cf_smem_u32(bar)), "r"(count) : "memory");
+}
+static __device__ __forceinline__ void cf_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(cf_smem_u32(bar)), "r"(bytes) : "memory");
+}
+static __device__ __forceinline__ void cf_mbar_wait(unsigned long long* bar, unsigned phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "CF_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra CF_DONE;\n"
+        "bra CF_WAIT;\n"
+        "CF_DONE:\n"
+        "}" ::"r"(cf_smem_u32(bar)), "r"(phase) : "memory");
+}
+static __device__ __forceinline__ void cf_tma_load_3d(void* dst, const CUtensorMap* tm, unsigned long long* bar, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(cf_smem_u32(dst)), "l"(tm), "r"(cf_smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_tma(const __grid_constant__ CUtensorMap tmap, int H, int W, int64_t img_stride,
+                                                                         double* __restrict__ out_train, int* __restrict__ far_flag,
+                                                                         const int* __restrict__ tasks, const int* __restrict__ n_tasks) {
+    __shared__ __align__(128) unsigned long long s_raw[2][CF_SH][CF_SW];
+    __shared__ unsigned s_one[CF_SH][CF_WORDS], s_in[CF_SH][CF_WORDS], s_dil[CF_SH][CF_WORDS], s_ero[CF_SH][CF_WORDS];
+    __shared__ __align__(8) unsigned long long s_bar[2];
+    const int tiles_x = (W + CF_TW - 1) / CF_TW, tiles = tiles_x * ((H + CF_TH - 1) / CF_TH);
+    const int n = *n_tasks;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) {
+        cf_mbar_init(&s_bar[0], 1); cf_mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (threadIdx.x < CF_SH) { s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; s_dil[threadIdx.x][3] = ~0u; }
+    __syncthreads();
+    auto issue = [&](int t, int buf) {                 // one thread
+        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        cf_mbar_expect_tx(&s_bar[buf], (unsigned)(CF_SH * CF_SW * sizeof(unsigned long long)));
+        cf_tma_load_3d(&s_raw[buf][0][0], &tmap, &s_bar[buf], (tile % tiles_x) * CF_TW - CF_HC, (tile / tiles_x) * CF_TH - CF_HR, z);
+    };
+    auto left = [](const unsigned* a, int w) { return (a[w] << 1) | (w > 0 ? a[w - 1] >> 31 : 0u); };
+    auto right = [](const unsigned* a, int w) { return (a[w] >> 1) | (a[w + 1] << 31); };
+    int t = blockIdx.x;
+    unsigned phases = 0u;                              // bit b = parity the next wait on buffer b looks for
+    if (t < n && threadIdx.x == 0) issue(t, 0);
+    for (int buf = 0; t < n; t += gridDim.x, buf ^= 1) {
+        if (threadIdx.x == 0 && t + (int)gridDim.x < n) issue(t + gridDim.x, buf ^ 1);
+        cf_mbar_wait(&s_bar[buf], (phases >> buf) & 1u);
+        phases ^= 1u << buf;
+        const int task = tasks[t], z = task / tiles, tile = task % tiles;
+        const int r0 = (tile / tiles_x) * CF_TH, c0 = (tile % tiles_x) * CF_TW;
+        const int64_t base = (int64_t)z * img_stride;
+        for (int lr = warp; lr < CF_SH; lr += CF_THREADS / 32) {      // bit rows of the staged tile, one staged row per warp
+            const unsigned long long v0 = s_raw[buf][lr][lane], v1 = s_raw[buf][lr][32 + lane];
+            const unsigned long long v2 = lane < CF_SW - 64 ? s_raw[buf][lr][64 + lane] : 0ull;
+            const unsigned i0 = __ballot_sync(0xffffffffu, v0 != 0ull), i1 = __ballot_sync(0xffffffffu, v1 != 0ull);
+            const unsigned i2 = __ballot_sync(0xffffffffu, v2 != 0ull);
+            const unsigned o0 = __ballot_sync(0xffffffffu, v0 != 0ull && v0 != R3D_EMPTY_U64);
+            const unsigned o1 = __ballot_sync(0xffffffffu, v1 != 0ull && v1 != R3D_EMPTY_U64);
+            const unsigned o2 = __ballot_sync(0xffffffffu, v2 != 0ull && v2 != R3D_EMPTY_U64);
+            if (lane < 3) {
+                s_one[lr][lane] = lane == 0 ? o0 : (lane == 1 ? o1 : o2);
+                s_in[lr][lane] = lane == 0 ? i0 : (lane == 1 ? i1 : i2);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < (CF_SH - 4) * 3) {
+            const int lr = 2 + threadIdx.x / 3, w = threadIdx.x % 3;
+            unsigned d = 0u;
+#pragma unroll
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_one[lr + dr]; d |= a[w] | left(a, w) | right(a, w); }
+            s_dil[lr][w] = d | ~s_in[lr][w];
+        }
+        __syncthreads();
+        if (threadIdx.x < CF_TH * 3) {
+            const int lr = CF_HR + threadIdx.x / 3, w = threadIdx.x % 3;
+            unsigned e = ~0u;
+#pragma unroll
+            for (int dr = -2; dr <= 2; ++dr) { const unsigned* a = s_dil[lr + dr]; e &= a[w] & left(a, w) & right(a, w); }
+            s_ero[lr][w] = e;
+        }
+        __syncthreads();
+        bool far = false;
+        for (int i = threadIdx.x; i < CF_TH * CF_TW; i += CF_THREADS) {
+            const int lr = i / CF_TW, lc = i % CF_TW;
+            const int r = r0 + lr, c = c0 + lc;
+            if (r >= H || c >= W) continue;
+            const int sr = lr + CF_HR, sc = lc + CF_HC;
+            const bool e = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
+            const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
+            double tv = one ? r3d::bits_dbl(s_raw[buf][sr][sc]) : r3d::kEmptyRange;      // od/ins:100: empty = 500
+            if (e && !one) {                                  // cl:41-43
+                int neighbors = 0;
+                double sum = 0.0;
+                const int q = sc - 1, qw = q >> 5, qb = q & 31;
+#pragma unroll
+                for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51, (drow, dcol) order
+                    const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
+                    if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc - 1])); }
+                    if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc])); }
+                    if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + 1])); }
+                }
+                if (neighbors > 0) tv = __ddiv_rn(sum, (double)neighbors);       // cl:57
+            }
+            out_train[base + (int64_t)r * W + c] = tv;
+            far |= tv > r3d::kEmptyRange;
+        }
+        if (far) atomicOr(&far_flag[z], 1);
+        __syncthreads();                                  // s_raw[buf] is the target of the TMA load issued two tasks ahead
+    }
+}

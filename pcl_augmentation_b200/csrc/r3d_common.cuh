@@ -63,6 +63,41 @@ __device__ __forceinline__ int bin_col(const ImageGeom& g, double az) {
     return trunc_to_int(__ddiv_rn(az_mod(az), g.d_az));
 }
 
+// ---- fast binning.  A bin index only needs the transcendental to ~1e-6 rad unless the point sits next to a bin edge:
+// float atan2f / acosf (CUDA: <= 3 / 2 ulp) give the position in bin units with a known error bound; if that position
+// is at least the bound away from both edges of its bin (and from both ends of the image), floor() of it IS the index
+// the fp64 expression of the reference yields; otherwise the caller evaluates the exact fp64 path.  Error budget in
+// radians: arguments rounded to float 2e-7, function 7e-7 (azimuth near 2 pi) resp. 2.4e-7 / sqrt(1 - t^2) (elevation,
+// |t| <= 0.9 only), offsets 2.4e-7 -> < 1.5e-6 rad, taken as 6e-6; the product with the float reciprocal of the bin
+// width adds 2.4e-7 relative to the position (<= nbins).
+struct FastGeom { float inv_d_az, inv_d_el, el0, err_az, err_el; };
+__device__ __forceinline__ FastGeom make_fast_geom(const ImageGeom& g) {
+    FastGeom f;
+    f.inv_d_az = (float)(1.0 / g.d_az); f.inv_d_el = (float)(1.0 / g.d_el);
+    f.el0 = (float)(g.min_el + 0.00001);
+    f.err_az = 6e-6f * f.inv_d_az + 5e-7f * (float)g.cols + 1e-5f;
+    f.err_el = 6e-6f * f.inv_d_el + 5e-7f * (float)g.rows + 1e-5f;
+    if (!(f.err_az < 0.25f)) f.err_az = 2.0f;            // hopeless geometry: the test below never passes
+    if (!(f.err_el < 0.25f)) f.err_el = 2.0f;
+    return f;
+}
+__device__ __forceinline__ bool fast_bin(float t, float err, int nbins, int& bin) {
+    const float f = floorf(t), fr = t - f;
+    if (!(fr > err && fr < 1.0f - err && t > err && t < (float)nbins - err)) return false;      // also NaN
+    bin = (int)f;
+    return true;
+}
+// od/ins:106 without the fp64 arctan2 where the azimuth is clear of the bin edges
+__device__ __forceinline__ bool fast_col(float inv_d_az, float err_az, int cols, float x, float y, int& col) {
+    return fast_bin((atan2f(y, x) + 3.14159274f) * inv_d_az, err_az, cols, col);
+}
+// od/ins:105 without the fp64 arccos where the elevation is clear of the bin edges
+__device__ __forceinline__ bool fast_row(const FastGeom& f, int rows, float z, float r, int& row) {
+    const float t = z / r;
+    if (!(fabsf(t) <= 0.9f)) return false;
+    return fast_bin((acosf(t) - f.el0) * f.inv_d_el, f.err_el, rows, row);
+}
+
 // ---------------------------------------------------------------------------------------------- boxes
 // Host-prepared oriented box: centre (z = box BOTTOM, cb:56-66), rotation matrix (row-major) and extents.
 struct Box {

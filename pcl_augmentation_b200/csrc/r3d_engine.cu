@@ -101,6 +101,8 @@ struct r3d_engine {
     DevBuf<BoxTest> box_tests;
     DevBuf<ObjBox> obj, try_obj;
     DevBuf<ClassCfg> classes;
+    CUtensorMap zraw_tmap;            // [B][H][W] u64 z-buffer as a 3-D tiled tensor, box = one staged close/fill tile
+    bool zraw_tmap_ok = false;
     // host copies needed for re-arming
     std::vector<Box> h_boxes;
     std::vector<int> h_nbox0;
@@ -200,6 +202,27 @@ static cudaError_t engine_wait(r3d_engine* eng) {
     return cudaEventSynchronize(eng->ev_wait);
 }
 
+// TMA descriptor of the z-buffer for k_close_fill_tma (r3d_closefill.cuh).  cuTensorMapEncodeTiled is a driver API entry:
+// fetched through the runtime so that the library does not link against libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static bool make_zraw_tensor_map(CUtensorMap* tm, void* base, int W, int H, int B) {
+    if (getenv("R3D_NO_TMA") || (W & 1) || ((uintptr_t)base & 15)) return false;       // row pitch must be a multiple of 16 bytes
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !fn) {
+        cudaGetLastError();
+        return false;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)W * 8, (cuuint64_t)W * H * 8};
+    const cuuint32_t box[3] = {(cuuint32_t)CF_SW, (cuuint32_t)CF_SH, 1u};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    return ((EncodeTiledFn)fn)(tm, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     if (!cfg || !out) return r3d_fail(R3D_ERR_ARG, "r3d_engine_create: null argument");
     if (cfg->rows <= 0 || cfg->cols <= 0 || cfg->cols > 65535 || cfg->yaw_steps <= 0 || cfg->n_classes <= 0 ||
@@ -251,6 +274,7 @@ extern "C" int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out) {
     TRY(eng->tail_z.alloc(B * d.max_inserted)); TRY(eng->tail_i.alloc(B * d.max_inserted)); TRY(eng->label.alloc(B * P));
     TRY(eng->r.alloc(B * P)); TRY(eng->el.alloc(B * P)); TRY(eng->col.alloc(B * P)); TRY(eng->pix.alloc(B * P));
     TRY(eng->alive.alloc(B * P)); TRY(eng->zraw.alloc(B * HW)); TRY(eng->obj_raw.alloc(B * HW)); TRY(eng->smooth.alloc(B * HW));
+    eng->zraw_tmap_ok = make_zraw_tensor_map(&eng->zraw_tmap, eng->zraw.p, d.cols, d.rows, (int)B);
     TRY(eng->dmask.alloc(B * d.dwords)); TRY(eng->vmask.alloc(B * d.dwords)); TRY(eng->st.alloc(B));
     TRY(eng->gate_update.alloc(B)); TRY(eng->gate_try.alloc(B)); TRY(eng->gate_apply.alloc(B)); TRY(eng->gate_full.alloc(B));
     TRY(eng->gate_patch.alloc(B)); TRY(eng->cf_rect.alloc(B * 4)); TRY(eng->active_count.alloc(R3D_MAX_SUB * 64 * 2));
@@ -653,7 +677,10 @@ static int run_walker(r3d_engine* eng) {
     {
         Launcher l(eng, KID_CLOSEFILL0);
         const int cf_grid = std::min(n * d.cf_tiles, eng->n_sms * 4);
-        if ((d.cols & 1) == 0 && ((uintptr_t)d.zraw & 15) == 0) {
+        if (eng->zraw_tmap_ok) {                 // tile loads by the TMA unit
+            k_close_fill_tma<<<cf_grid, CF_THREADS, 0, st>>>(eng->zraw_tmap, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr, d.cf_tasks,
+                                                              d.work_cnt + 1);
+        } else if ((d.cols & 1) == 0 && ((uintptr_t)d.zraw & 15) == 0) {
             k_close_fill_raw_pipelined<<<cf_grid, CF_THREADS, 0, st>>>(d.zraw, d.rows, d.cols, (int64_t)d.hw, d.smooth, d.far_arr, d.cf_tasks,
                                                                         d.work_cnt + 1);
         } else {

@@ -20,11 +20,9 @@ __device__ __forceinline__ int radius_index(const double* r2, double d2) {
 // Points outside the grid extent are clamped into border cells: distances are always computed from the coordinates,
 // and clamping never increases a cell-index difference, so the square searches below stay exact.
 __device__ __forceinline__ bool any_surface_label(const EngineDev& e, unsigned lab) {
-    for (int c = 0; c < e.n_classes; ++c) {
-        const ClassCfg& cc = e.classes[c];
-        for (int i = 0; i < cc.n_surface; ++i) if (lab == (unsigned)cc.surface[i]) return true;
-    }
-    return false;
+    bool ok = false;                                  // the distinct surface labels of all classes (kernel parameter space)
+    for (int j = 0; j < e.n_surf_all; ++j) ok |= lab == (unsigned)e.surf_all[j];
+    return ok;
 }
 // apts.w of original point p with label lab: the point index, and for semseg the slot of the label among the labels
 // some class may stand on (EngineDev::surf_all)

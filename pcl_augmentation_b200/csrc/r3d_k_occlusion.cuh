@@ -22,6 +22,26 @@ __device__ __forceinline__ ObjProj project_obj_point(const EngineDev& e, const O
     return o;
 }
 
+// the same for the occlusion counts, which need the pixel and the range only: the bins come from the float estimate of
+// the angles where that is safe (r3d_common.cuh, fast binning), else from the exact path above
+struct ObjPix { double r; int pix; };
+__device__ __forceinline__ ObjPix project_obj_pix(const EngineDev& e, const ObjBox& ob, const ImageGeom& g, const FastGeom& fg, int i,
+                                                  double c, double sn, double dz, ScanState& s) {
+    ObjPix o;
+    const double x0 = e.obj_x[ob.first + i], y0 = e.obj_y[ob.first + i];
+    const double x = sub(mul(c, x0), mul(sn, y0)), y = add(mul(sn, x0), mul(c, y0)), z = add(e.obj_z[ob.first + i], dz);
+    o.r = range3(x, y, z);
+    int row, col;
+    if (!fast_row(fg, g.rows, (float)z, (float)o.r, row)) row = bin_row(g, elevation(z, o.r));
+    if (!fast_col(fg.inv_d_az, fg.err_az, g.cols, (float)x, (float)y, col)) col = bin_col(g, azimuth(x, y));
+    o.pix = -1;
+    if (row >= 0 && row < g.rows) {                                    // od/ins:108-109
+        if (col < 0 || col >= g.cols) set_error(s, R3D_ERR_ASSERT);      // od/ins:113
+        else o.pix = row * g.cols + col;
+    }
+    return o;
+}
+
 // A11 (od/ins:486-501) for every feasible candidate: V = number of object points whose pixel is visible.  A pixel
 // that holds object points keeps its own min range through smooth_out, and min_r < scene <=> some point of the pixel
 // has r < scene, so no z-buffer is needed for the count: pass 1 marks visible pixels in a shared-memory bit image,

@@ -44,6 +44,27 @@ __device__ __forceinline__ int agg_finish(const AggTicket& t) {
     return base + __popc(t.peers & ((1u << (threadIdx.x & 31)) - 1u));
 }
 
+// OD: a point goes to the all-points grid (not Road) or to the surface grid (Road, z > -3), never to both, so ONE
+// aggregated atomic serves the two grids: which = 0 (all-points), 1 (surface), -1 (neither)
+__device__ __forceinline__ bool grids_exclusive(const EngineDev& e) {
+    return e.task == 0 && e.n_surf_all == 1 && e.surf_all[0] == e.road_label;
+}
+__device__ __forceinline__ void agg_count2(int* arr_a, int* arr_g, int gc, int which) {
+    const unsigned act = __ballot_sync(0xffffffffu, which >= 0);
+    if (which < 0) return;
+    const unsigned peers = __match_any_sync(act, gc * 2 + which);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&(which ? arr_g : arr_a)[gc], __popc(peers));
+}
+__device__ __forceinline__ AggTicket agg_issue2(int* arr_a, int* arr_g, int gc, int which) {
+    AggTicket t{0u, 0};
+    const unsigned act = __ballot_sync(0xffffffffu, which >= 0);
+    if (which >= 0) {
+        t.peers = __match_any_sync(act, gc * 2 + which);
+        if ((int)(threadIdx.x & 31) == __ffs(t.peers) - 1) t.base = atomicAdd(&(which ? arr_g : arr_a)[gc], __popc(t.peers));
+    }
+    return t;
+}
+
 __global__ void __launch_bounds__(STREAM_THREADS) k_ingest_count(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans) return;
@@ -57,21 +78,36 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_ingest_count(EngineDev e, in
     }
     if (p0 >= n0) return;
     const double d_az = kTwoPi / (double)e.cols;
+    const float inv_d_az = (float)(1.0 / d_az);
+    float err_az = 6e-6f * inv_d_az + 5e-7f * (float)e.cols + 1e-5f;       // r3d_common.cuh, fast binning
+    if (!(err_az < 0.25f)) err_az = 2.0f;
     const size_t base = (size_t)b * e.P;
     int* cell = e.gcell + (size_t)b * e.G * e.G;
     int* acell = e.acell + (size_t)b * e.G * e.G;
     int* coff = e.col_off + (size_t)b * (e.cols + 1);
     unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;
-    for (int q = p0; q < min(p0 + CHUNK, n0); q += STREAM_THREADS) {       // whole warps stay in the loop (aggregated atomics)
+    const bool excl = grids_exclusive(e);
+    const float4* __restrict__ src = e.xyzi + (size_t)b * e.max_points;
+    const int q_end = min(p0 + CHUNK, n0);
+    // the next point's loads are issued before the arithmetic of the current one (~500 instructions) starts
+    float4 vn = make_float4(1.f, 0.f, 0.f, 0.f);
+    unsigned labn = 0u;
+    if (p0 + (int)threadIdx.x < n0) { vn = __ldg(&src[p0 + threadIdx.x]); labn = e.label[base + p0 + threadIdx.x]; }
+    for (int q = p0; q < q_end; q += STREAM_THREADS) {       // whole warps stay in the loop (aggregated atomics)
         const int p = q + threadIdx.x;
         const bool in = p < n0;
-        float4 v = make_float4(1.f, 0.f, 0.f, 0.f);
-        unsigned lab = 0u;
-        if (in) { v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]); lab = e.label[base + p]; }
+        const float4 v = vn;
+        const unsigned lab = labn;
+        {
+            const int pn = p + STREAM_THREADS;
+            vn = make_float4(1.f, 0.f, 0.f, 0.f); labn = 0u;
+            if (q + STREAM_THREADS < q_end && pn < n0) { vn = __ldg(&src[pn]); labn = e.label[base + pn]; }
+        }
         const double x = v.x, y = v.y, z = v.z;
         const double r = range3(x, y, z);
         const double el = elevation(z, r);
-        const int c = trunc_to_int(__ddiv_rn(az_mod(azimuth(x, y)), d_az));
+        int c;
+        if (!fast_col(inv_d_az, err_az, e.cols, v.x, v.y, c)) c = trunc_to_int(__ddiv_rn(az_mod(azimuth(x, y)), d_az));
         const int cc = max(0, min(c, e.cols - 1));
         if (in) {
             if (!(r > 0.0) || c < 0 || c >= e.cols) set_error(s, R3D_ERR_ASSERT);      // od/ins:113 / nan elevation
@@ -83,8 +119,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_ingest_count(EngineDev e, in
             lmin = min(lmin, bits); lmax = max(lmax, bits);
         }
         const int gc = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
-        agg_count(acell, gc, in && !(e.task == 0 && lab == (unsigned)e.road_label));     // od/ins:353-355
-        agg_count(cell, gc, in && (double)v.z > -3.0 && any_surface_label(e, lab));      // od/fs:154-155
+        const bool in_a = in && !(e.task == 0 && lab == (unsigned)e.road_label);         // od/ins:353-355
+        const bool in_g = in && (double)v.z > -3.0 && any_surface_label(e, lab);         // od/fs:154-155
+        if (excl) agg_count2(acell, cell, gc, in_g ? 1 : (in_a ? 0 : -1));
+        else { agg_count(acell, gc, in_a); agg_count(cell, gc, in_g); }
         agg_count(coff, cc, in);
     }
     __shared__ unsigned long long s_min[STREAM_THREADS / 32], s_max[STREAM_THREADS / 32];
@@ -131,9 +169,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e,
     int* cidx = e.col_idx + (size_t)b * e.max_points;
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
     static_assert(CHUNK % (2 * STREAM_THREADS) == 0, "two points per thread and iteration");
+    const bool excl = grids_exclusive(e);
     for (int q = p0; q < min(p0 + CHUNK, n0); q += 2 * STREAM_THREADS) {
         // two points per thread: all loads first, then the six slot atomics back to back, then the stores
-        int p[2], col[2], gc[2];
+        int p[2], col[2], gc[2], which[2];
         bool in[2];
         float4 v[2];
         unsigned lab[2];
@@ -152,8 +191,17 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e,
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             gc[u] = grid_coord(e, v[u].y) * e.G + grid_coord(e, v[u].x);
-            ta[u] = agg_issue(acell, gc[u], in[u] && !(e.task == 0 && lab[u] == (unsigned)e.road_label));
-            tg[u] = agg_issue(cell, gc[u], in[u] && (double)v[u].z > -3.0 && any_surface_label(e, lab[u]));
+            const bool in_a = in[u] && !(e.task == 0 && lab[u] == (unsigned)e.road_label);
+            const bool in_g = in[u] && (double)v[u].z > -3.0 && any_surface_label(e, lab[u]);
+            if (excl) {                                  // one atomic for the two grids (see agg_count2)
+                which[u] = in_g ? 1 : (in_a ? 0 : -1);
+                ta[u] = agg_issue2(acell, cell, gc[u], which[u]);
+                tg[u] = AggTicket{0u, 0};
+            } else {
+                which[u] = -1;
+                ta[u] = agg_issue(acell, gc[u], in_a);
+                tg[u] = agg_issue(cell, gc[u], in_g);
+            }
             tc[u] = agg_issue(coff, col[u], in[u]);
         }
 #pragma unroll
@@ -169,7 +217,10 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_scatter_project(EngineDev e,
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int sa = agg_finish(ta[u]);
-            if (sa >= 0) aout[sa] = make_float4(v[u].x, v[u].y, v[u].z, apt_tag(e, lab[u], p[u]));
+            if (sa >= 0) {
+                if (which[u] == 1) out[sa] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float(lab[u]));
+                else aout[sa] = make_float4(v[u].x, v[u].y, v[u].z, apt_tag(e, lab[u], p[u]));
+            }
             const int sg = agg_finish(tg[u]);
             if (sg >= 0) out[sg] = make_float4(v[u].x, v[u].y, v[u].z, __uint_as_float(lab[u]));
             const int sc = agg_finish(tc[u]);

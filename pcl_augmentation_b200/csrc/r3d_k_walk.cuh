@@ -572,8 +572,9 @@ __device__ R3D_WALK_FN int walk_exact_visible(const EngineDev& e, int b, ScanSta
     if (tid == 0) { c.exact_cnt = 0; atomicAdd(&e.stats[10], 1ull); }
     __syncthreads();
     const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(level, ob.cz);
+    const FastGeom fg = make_fast_geom(g);
     for (int i = tid; i < ob.count; i += nt) {
-        const ObjProj o = project_obj_point(e, ob, g, i, cs, sn, dz, s);
+        const ObjPix o = project_obj_pix(e, ob, g, fg, i, cs, sn, dz, s);
         pixbuf[i] = o.pix;
         if (o.pix >= 0 && o.r < smooth[o.pix]) atomicOr(&bits[o.pix >> 5], 1u << (o.pix & 31));
     }
@@ -645,6 +646,7 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
     const unsigned gm = group_mask();
     const int min_pts = max(cc.min_points, 1);                     // od/ins:530: V == 0 or V < min_points -> rejected
     const ImageGeom geom = s.geom;
+    const FastGeom fgeom = make_fast_geom(geom);
     const double* smooth = e.smooth + (size_t)b * e.hw;
     for (int base = 0; base < n_list; base += WALK_W) {
         const int nw = min(WALK_W, n_list - base);
@@ -712,7 +714,7 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
                     const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(c.wlevel[i], ob.cz);
                     int lo = 0, hi = 0;
                     for (int p = sl; p < ob.count; p += WALK_OCC_LANES) {
-                        const ObjProj o = project_obj_point(e, ob, geom, p, cs, sn, dz, s);
+                        const ObjPix o = project_obj_pix(e, ob, geom, fgeom, p, cs, sn, dz, s);
                         if (o.pix >= 0) { ++hi; if (o.r < smooth[o.pix]) ++lo; }
                     }
                     for (int o = 16; o > 0; o >>= 1) { lo += __shfl_xor_sync(0xffffffffu, lo, o); hi += __shfl_xor_sync(0xffffffffu, hi, o); }

@@ -284,3 +284,27 @@ def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts, staged):
         assert_matches_oracle(case, got, ref, want)
         placed += len(got.inserted)
     assert placed >= 24
+
+
+@pytest.mark.parametrize("task,seed,counts", [("od", 811, [2, 2]), ("ss", 812, [1, 1, 1, 0, 1, 0])])
+def test_points_next_to_bin_edges_take_the_exact_path(task, seed, counts):
+    """The ingest and the occlusion counts bin with a float estimate of the angles where that is provably safe and fall
+    back to the reference's fp64 expression next to a bin edge (r3d_common.cuh, fast binning).  Scene points are moved
+    onto / next to azimuth-bin edges (offsets from 1e-9 to 1e-2 of a bin, both sides, after the float32 cast of the
+    scan): keep-masks, placement choices and counts must still equal the oracle's."""
+    case = synth.make_case(task, seed, shape=GOLDEN_SHAPE, counts=counts, n_cars=5, obj_range=(4.0, 16.0))
+    rng = np.random.default_rng(seed)
+    cols = 1440
+    idx = rng.choice(len(case.pcl5), size=len(case.pcl5) // 3, replace=False)
+    rho = np.hypot(case.pcl5[idx, 0], case.pcl5[idx, 1])
+    edge = rng.integers(0, cols + 1, len(idx))
+    off = rng.choice([0.0, 1e-9, 1e-7, 1e-5, 1e-4, 1e-3, 2e-3, 3e-3, 5e-3, 1e-2], len(idx)) * rng.choice([-1.0, 1.0], len(idx))
+    az = (edge + off) * (2 * np.pi / cols) - np.pi                         # od/ins:76: azimuth = arctan2(y, x) + pi
+    case.pcl5[idx, 0] = (rho * np.cos(az)).astype(np.float32)
+    case.pcl5[idx, 1] = (rho * np.sin(az)).astype(np.float32)
+    ref, want = oracle_run(case)
+    eng = make_engine(case)
+    got = eng.augment_batch([scan_input_from_case(case)])[0]
+    eng.close()
+    assert got.status == 0
+    assert_matches_oracle(case, got, ref, want)

@@ -6,7 +6,7 @@ import pytest
 from oracle import real3d_oracle as orc
 from pcl_augmentation_b200 import ops, synth
 from tests.helpers import load_golden
-from tests.test_oracle_golden import FN_IMG, _fn_projection_inputs
+from tests.test_oracle_golden import FN_IMG, _fn_projection_full_inputs, _fn_projection_inputs, check_projection_full
 
 pytestmark = pytest.mark.gpu
 
@@ -52,6 +52,20 @@ def test_fill_spherical_and_projection_vs_golden(monkeypatch):
     os_train, os_label = ops.smooth_out(o_train, o_label)
     np.testing.assert_array_equal(os_train, g["os_train"])
     np.testing.assert_array_equal(os_label.astype(np.int8), g["os_label"])
+
+
+def test_projection_at_baseline_size_vs_reference_golden(monkeypatch):
+    """120 000 points on the reference's 112 x 1440 image: pix ids, range image, closing and fp64 hole-fill means
+    bit-identical to what the unmodified reference produced (tests/golden/fn_projection_full.npz)."""
+    g = load_golden("fn_projection_full")
+    pcl5 = _fn_projection_full_inputs()
+    monkeypatch.setattr(ops, "NUMCOLUMN", 1440)
+    pc = ops.add_space_for_spherical(pcl5)
+    pc, mx, mn = ops.fill_spherical(pc)
+    assert abs(mx - float(g["max_el"])) < 1e-14 and abs(mn - float(g["min_el"])) < 1e-14
+    train, label, pc = ops.geometrical_front_view(pc, 112, 1440, mx, mn)
+    s_train, s_label = ops.smooth_out(train, label)
+    check_projection_full(g, pc, mx, mn, train, label, s_train, s_label, exact_elevation=False)
 
 
 def test_projection_assert_like_reference():

@@ -48,6 +48,41 @@ def test_projection_and_closing_match_reference():
     np.testing.assert_array_equal(os_label.astype(np.int8), g["os_label"])
 
 
+def _sha(a):
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def _fn_projection_full_inputs():
+    pcl, labels = synth.make_scan(6, synth.KITTI_SHAPE)
+    return np.hstack((pcl, labels.reshape(-1, 1))).astype(np.float64)
+
+
+def check_projection_full(g, pc, mx, mn, train, label, s_train, s_label, exact_elevation=True):
+    """A1-A4 results on the 120 000-point scan vs what the unmodified reference produced at 112 x 1440."""
+    if exact_elevation:
+        assert mx == float(g["max_el"]) and mn == float(g["min_el"])
+    assert _sha(pc[:, 3]) == str(g["r_sha"])
+    np.testing.assert_array_equal(pc[:, 8].astype(np.int32), g["pix"])
+    assert int((label == 1).sum()) == int(g["occupied"])
+    assert _sha(train) == str(g["train_sha"]) and _sha(label.astype(np.int8)) == str(g["label_sha"])
+    filled = np.flatnonzero((s_label == 1) & (label != 1)).astype(np.int32)
+    np.testing.assert_array_equal(filled, g["filled"])
+    np.testing.assert_array_equal(s_train.ravel()[filled], g["filled_values"])      # bit-exact fp64 neighbour means
+    assert _sha(s_train) == str(g["s_train_sha"]) and _sha(s_label.astype(np.int8)) == str(g["s_label_sha"])
+
+
+def test_projection_and_closing_match_reference_at_baseline_size():
+    g = load_golden("fn_projection_full")
+    pcl5 = _fn_projection_full_inputs()
+    assert synth.array_digest(pcl5) == str(g["in_digest"])
+    pc = orc.add_space_for_spherical(pcl5)
+    pc, mx, mn = orc.fill_spherical(pc)
+    train, label, pc = orc.geometrical_front_view(pc, 112, 1440, mx, mn)
+    s_train, s_label = orc.smooth_out(train, label)
+    check_projection_full(g, pc, mx, mn, train, label, s_train, s_label)
+
+
 def test_cut_bounding_box_matches_reference():
     g = load_golden("fn_cut_bbox")
     rng = np.random.default_rng(99)

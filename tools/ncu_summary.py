@@ -27,7 +27,9 @@ SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
 
 
 def main():
-    tag, reps = sys.argv[1], sys.argv[2:]
+    args = [a for a in sys.argv[1:] if a != "--no-traffic"]
+    keep_traffic = "--no-traffic" in sys.argv          # captures of another workload than the headline one: CSV only
+    tag, reps = args[0], args[1:]
     traffic_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     traffic = json.load(open(traffic_path)) if os.path.exists(traffic_path) else {}
     for rep in reps:
@@ -67,6 +69,8 @@ def main():
                           "source": f"profiles/{os.path.basename(dst)} (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, "
                                     f"all scans of the batch active in the captured launch)"}
         print("wrote", dst)
+    if keep_traffic:
+        return
     with open(traffic_path, "w") as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
     print("wrote", traffic_path)
