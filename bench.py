@@ -502,6 +502,7 @@ class Bench:
             eng.reset(from_raw_points=True); eng.run()
         eng.sync()
         prof, stats = eng.profile_read(), eng.stats()
+        stats["walk_profile"] = eng.walk_profile()           # (cycles, tries) per scan of the last step
         eng.profile(False)
         results = eng.unpack(eng.fetch_raw())
         return serial_ms, prof, stats, results
@@ -576,6 +577,16 @@ def roofline_of(name, entry, bench, peak, peak_src):
     return out
 
 
+def walk_spread(stats, clocks):
+    """Spread of the walker CTA lifetimes over the scans of one step (ms): what makes one batch alone tail bound."""
+    cyc, tries = stats["walk_profile"]
+    mhz = (clocks.get("sm_mhz") or 1965.0) * 1e3
+    ms = np.sort(cyc / mhz)
+    pick = lambda q: round(float(ms[min(len(ms) - 1, int(q * len(ms)))]), 3)
+    return {"p50": pick(0.5), "p90": pick(0.9), "p99": pick(0.99), "max": round(float(ms[-1]), 3),
+            "tries_p50": int(np.sort(tries)[len(tries) // 2]), "tries_max": int(tries.max())}
+
+
 def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_over_ranks, peak):
     """A short run of another BASELINE.json configuration: device-resident value, serial step + dominant kernel, e2e."""
     b = Bench(name, rank, world, args, barrier, max_over_ranks)
@@ -595,7 +606,7 @@ def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_ov
                "dominant_kernel": {top: table[top]},
                "streaming_kernels": {k: {"ms_per_step": v["ms_per_step"], "frac": v["frac"]} for k, v in table.items() if "frac" in v},
                "objects_inserted_per_scan": sum_over_ranks(sum(len(r.inserted) for r in results)) / (world * b.n_scans),
-               "steps_per_scan_max": stats["max_steps_per_scan"]}
+               "steps_per_scan_max": stats["max_steps_per_scan"], "walker_cta_ms": walk_spread(stats, {})}
         if b.w.get("stream"):
             out["stream_scans"] = scans_e2e
         return out
@@ -620,7 +631,7 @@ def main():
     ap.add_argument("--resident-depth", type=int, default=0,
                     help="engines (each with its own HBM-resident batch) the device-resident leg deals the steps to: one "
                          "engine's streaming kernels overlap another's walker (0 = the workload's default: 3, semseg 6-8)")
-    ap.add_argument("--depth", type=int, default=3, help="engines (streams) the e2e leg pipelines batches through")
+    ap.add_argument("--depth", type=int, default=4, help="engines (streams) the e2e leg pipelines batches through")
     ap.add_argument("--side", default=None, choices=["rich_map_od", "rich_map_ss", "cut_objects"],
                     help="instead of the headline bench: one of the offline tools either side of the path (SURVEY 8f rows "
                          "3-4), GPU numbers from tools/bench_*.py plus the CPU baseline (numpy oracle port, one host core)")
@@ -737,9 +748,10 @@ def main():
                        "candidate_windows_per_try": stats["candidate_windows"] / max(stats["tried_objects"], 1),
                        "exact_occlusion_counts_per_try": stats["exact_occlusion_counts"] / max(stats["tried_objects"], 1),
                        "cta_ms_mean": round(cyc.get("total", 0) / max(prof_steps * n_scans, 1) / ((clocks.get("sm_mhz") or 1965.0) * 1e3), 4),
+                       "cta_ms_percentiles": walk_spread(stats, clocks),
                        "phase_share_of_cta_time": {k: round(v / max(cyc.get("total", 1), 1), 4) for k, v in cyc.items() if k != "total"}},
             "objects_inserted_per_scan": inserted_all / (world * n_scans),
-            "configs": configs, "engine_stats": {k: v for k, v in stats.items() if k != "walker_cycles"}})])
+            "configs": configs, "engine_stats": {k: v for k, v in stats.items() if k not in ("walker_cycles", "walk_profile")}})])
     if world > 1:
         dist.destroy_process_group()
 

@@ -344,6 +344,9 @@ int r3d_engine_stats(r3d_engine* eng, uint64_t* out8);
  * {on-map stage, road-level warps, collision warps, road-level searches, collision tests, mask apply, z-buffer patch,
  * close/fill} */
 int r3d_engine_stats_ex(r3d_engine* eng, uint64_t* out, int n);
+/* per scan of the last run (walker execution model): SM cycles its CTA lived and the cut objects it tried — the spread
+ * between scans is what resident batches have to fill */
+int r3d_engine_walk_profile(r3d_engine* eng, int64_t* cycles, int32_t* tries, int n);
 /* the engine's cudaStream_t (so callers can bracket work with their own CUDA events) */
 void* r3d_engine_stream(r3d_engine* eng);
 

@@ -82,6 +82,7 @@ PROTOTYPES = {
                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "r3d_compact_insert": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_int64, C.c_void_p]),
+    "r3d_engine_walk_profile": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "r3d_engine_probe_places": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                           C.c_void_p, C.c_int, C.POINTER(C.c_int32)]),
     "r3d_engine_create": (C.c_int, [C.POINTER(EngineCfg), C.POINTER(C.c_void_p)]),

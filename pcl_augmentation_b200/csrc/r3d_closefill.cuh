@@ -291,7 +291,7 @@ static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_tma(const _
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (threadIdx.x < CF_SH) { s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; s_dil[threadIdx.x][3] = ~0u; }
+    if (threadIdx.x < CF_SH) { s_one[threadIdx.x][3] = 0u; s_in[threadIdx.x][3] = 0u; s_dil[threadIdx.x][3] = ~0u; s_ero[threadIdx.x][3] = 0u; }
     __syncthreads();
     auto issue = [&](int t, int buf) {                 // one thread
         const int task = tasks[t], z = task / tiles, tile = task % tiles;
@@ -341,29 +341,38 @@ static __global__ void __launch_bounds__(CF_THREADS, 4) k_close_fill_tma(const _
         }
         __syncthreads();
         bool far = false;
-        for (int i = threadIdx.x; i < CF_TH * CF_TW; i += CF_THREADS) {
-            const int lr = i / CF_TW, lc = i % CF_TW;
+        // two horizontally adjacent output pixels per thread: their 5 x 3 neighbourhoods share two of three columns, so one
+        // 4-bit window per row serves both, and the pair leaves as one 16-byte store (W is even with a tensor map)
+        for (int i = threadIdx.x; i < CF_TH * CF_TW / 2; i += CF_THREADS) {
+            const int lr = i / (CF_TW / 2), lc = (i % (CF_TW / 2)) * 2;
             const int r = r0 + lr, c = c0 + lc;
             if (r >= H || c >= W) continue;
             const int sr = lr + CF_HR, sc = lc + CF_HC;
-            const bool e = (s_ero[sr][sc >> 5] >> (sc & 31)) & 1u;
-            const bool one = (s_one[sr][sc >> 5] >> (sc & 31)) & 1u;
-            double tv = one ? r3d::bits_dbl(s_raw[buf][sr][sc]) : r3d::kEmptyRange;      // od/ins:100: empty = 500
-            if (e && !one) {                                  // cl:41-43
-                int neighbors = 0;
-                double sum = 0.0;
-                const int q = sc - 1, qw = q >> 5, qb = q & 31;
+            const int q = sc - 1, qw = q >> 5, qb = q & 31;                  // window bits: columns sc - 1 .. sc + 2
+            const unsigned e2 = __funnelshift_r(s_ero[sr][sc >> 5], s_ero[sr][(sc >> 5) + 1], sc & 31) & 3u;
+            unsigned win[5];
 #pragma unroll
-                for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51, (drow, dcol) order
-                    const unsigned m = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 7u;
-                    if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc - 1])); }
-                    if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc])); }
-                    if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + 1])); }
+            for (int dr = -2; dr <= 2; ++dr) win[dr + 2] = __funnelshift_r(s_one[sr + dr][qw], s_one[sr + dr][qw + 1], qb) & 15u;
+            double tv[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const bool one = (win[2] >> (1 + u)) & 1u, e = (e2 >> u) & 1u;
+                tv[u] = one ? r3d::bits_dbl(s_raw[buf][sr][sc + u]) : r3d::kEmptyRange;  // od/ins:100: empty = 500
+                if (e && !one) {                                  // cl:41-43
+                    int neighbors = 0;
+                    double sum = 0.0;
+#pragma unroll
+                    for (int dr = -2; dr <= 2; ++dr) {             // cl:46-51, (drow, dcol) order
+                        const unsigned m = (win[dr + 2] >> u) & 7u;
+                        if (m & 1u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + u - 1])); }
+                        if (m & 2u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + u])); }
+                        if (m & 4u) { neighbors += 1; sum = r3d::add(sum, r3d::bits_dbl(s_raw[buf][sr + dr][sc + u + 1])); }
+                    }
+                    if (neighbors > 0) tv[u] = __ddiv_rn(sum, (double)neighbors);    // cl:57
                 }
-                if (neighbors > 0) tv = __ddiv_rn(sum, (double)neighbors);       // cl:57
+                far |= tv[u] > r3d::kEmptyRange;
             }
-            out_train[base + (int64_t)r * W + c] = tv;
-            far |= tv > r3d::kEmptyRange;
+            *reinterpret_cast<double2*>(out_train + base + (int64_t)r * W + c) = make_double2(tv[0], tv[1]);
         }
         if (far) atomicOr(&far_flag[z], 1);
         __syncthreads();                                  // s_raw[buf] is the target of the TMA load issued two tasks ahead

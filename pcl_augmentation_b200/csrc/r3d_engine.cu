@@ -981,6 +981,16 @@ extern "C" int r3d_engine_stats_ex(r3d_engine* eng, uint64_t* out, int n) {
     return R3D_OK;
 }
 
+extern "C" int r3d_engine_walk_profile(r3d_engine* eng, int64_t* cycles, int32_t* tries, int n) {
+    if (eng) cudaSetDevice(eng->device);
+    if (!eng || !cycles || !tries || n < 0 || n > eng->dev.B) return r3d_fail(R3D_ERR_ARG, "r3d_engine_walk_profile: bad argument");
+    R3D_CUDA(cudaStreamSynchronize(eng->stream));
+    std::vector<ScanState> st((size_t)n);
+    R3D_CUDA(cudaMemcpy(st.data(), eng->dev.st, (size_t)n * sizeof(ScanState), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) { cycles[i] = st[i].walk_cycles; tries[i] = st[i].walk_tries; }
+    return R3D_OK;
+}
+
 extern "C" int r3d_engine_stats(r3d_engine* eng, uint64_t* out8) {
     if (eng) cudaSetDevice(eng->device);
     if (!eng || !out8) return r3d_fail(R3D_ERR_ARG, "r3d_engine_stats: null argument");

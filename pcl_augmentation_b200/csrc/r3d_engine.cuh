@@ -63,7 +63,8 @@ struct ScanState {
     int win_x0, win_y0;
     unsigned long long min_el_bits, max_el_bits;
     ImageGeom geom;
-    double dz_unused;
+    long long walk_cycles;               // SM cycles the scan's walker CTA lived in the last run (diagnostics)
+    int walk_tries, walk_pad;
 };
 
 struct EngineDev {       // passed by value to kernels

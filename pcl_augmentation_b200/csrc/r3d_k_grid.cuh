@@ -39,81 +39,10 @@ __device__ __forceinline__ int grid_coord(const EngineDev& e, float v) {
     return max(0, min(i, e.G - 1));
 }
 
-template <int PASS>     // 1: count per cell, 2: scatter (after the prefix scan)
-__global__ void __launch_bounds__(STREAM_THREADS) k_grid_build(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans) return;
-    const int n0 = e.st[b].n0;
-    const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n0) return;
-    const size_t base = (size_t)b * e.P;
-    int* cell = e.gcell + (size_t)b * e.G * e.G;
-    int* acell = e.acell + (size_t)b * e.G * e.G;
-    float4* out = e.gpts + (size_t)b * e.max_points;
-    float4* aout = e.apts + (size_t)b * e.max_points;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
-        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
-        const unsigned lab = e.label[base + p];
-        const int c = grid_coord(e, v.y) * e.G + grid_coord(e, v.x);
-        if (!(e.task == 0 && lab == (unsigned)e.road_label)) {      // OD: Road points are never obstacles (od/ins:353-355)
-            if (PASS == 1) atomicAdd(&acell[c], 1);
-            else aout[atomicAdd(&acell[c], 1)] = make_float4(v.x, v.y, v.z, apt_tag(e, lab, p));
-        }
-        if (!((double)v.z > -3.0) || !any_surface_label(e, lab)) continue;       // od/fs:154-155
-        if (PASS == 1) atomicAdd(&cell[c], 1);
-        else out[atomicAdd(&cell[c], 1)] = make_float4(v.x, v.y, v.z, __uint_as_float(lab));
-    }
-}
-
-// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell to the nearest cell that holds a surface point:
-// the road-level search of a candidate whose surroundings are empty starts at that ring instead of growing through
-// the empty ones.  Separable: row pass (min |dx| along the row), then column pass (min over dy of max(|dy|, row value)).
+// Chebyshev distance (in cells, capped at NEAR_CAP) from every cell to the nearest cell that holds a surface point
+// (k_grid_near_bits, r3d_k_prepass.cuh): the road-level search of a candidate whose surroundings are empty starts at
+// that ring instead of growing through the empty ones.
 constexpr int NEAR_CAP = 12;
-template <int PASS>
-__global__ void __launch_bounds__(256) k_grid_near(EngineDev e, int n_scans) {
-    const int b = blockIdx.y, G = e.G;
-    const int c = blockIdx.x * 256 + threadIdx.x;
-    if (b >= n_scans || c >= G * G) return;
-    const int y = c / G, x = c % G;
-    const size_t gb = (size_t)b * G * G;
-    int best = NEAR_CAP;
-    if (PASS == 1) {
-        const int* cell = e.gcell + gb;
-        for (int dx = -(NEAR_CAP - 1); dx <= NEAR_CAP - 1; ++dx) {
-            const int x1 = x + dx;
-            if (x1 < 0 || x1 >= G) continue;
-            const int q = y * G + x1;
-            if (cell[q] > (q > 0 ? cell[q - 1] : 0)) best = min(best, abs(dx));
-        }
-        e.gscratch[gb + c] = (unsigned char)best;
-    } else {
-        for (int dy = -(NEAR_CAP - 1); dy <= NEAR_CAP - 1; ++dy) {
-            const int y1 = y + dy;
-            if (y1 < 0 || y1 >= G) continue;
-            best = min(best, max(abs(dy), (int)e.gscratch[gb + (size_t)y1 * G + x]));
-        }
-        e.gnear[gb + c] = (unsigned char)best;
-    }
-}
-
-// One more once-per-scan CSR index over the ORIGINAL points (their azimuth bin never changes): by image column,
-// for k_apply_window.
-template <int PASS>     // 1: count, 2: scatter point indices
-__global__ void __launch_bounds__(STREAM_THREADS) k_index_build(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans) return;
-    const int n0 = e.st[b].n0;
-    const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n0) return;
-    const size_t base = (size_t)b * e.P;
-    int* coff = e.col_off + (size_t)b * (e.cols + 1);
-    int* cidx = e.col_idx + (size_t)b * e.max_points;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
-        const int c = e.col[base + p];
-        if (PASS == 1) atomicAdd(&coff[c], 1);
-        else cidx[atomicAdd(&coff[c], 1)] = p;
-    }
-}
 
 // exclusive prefix sum of the per-cell counts (one CTA per scan, four cells per thread and step); after the scatter
 // pass cell[c] = END of cell c
@@ -148,7 +77,4 @@ __device__ __forceinline__ void bucket_scan_body(int* arr, size_t stride, int n,
         if (threadIdx.x == 0) s_run += tot;
         __syncthreads();
     }
-}
-__global__ void __launch_bounds__(1024) k_bucket_scan(int* arr, size_t stride, int n, int n_scans) {
-    bucket_scan_body(arr, stride, n, n_scans);
 }

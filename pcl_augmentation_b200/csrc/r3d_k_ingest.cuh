@@ -1,30 +1,7 @@
 // Kernels of the batched Real3D-Aug engine, part: A1 + A2 once per original point.
 // Included by r3d_engine_kernels.cuh (inside namespace r3d, after the shared constants); not a standalone header.
 // ------------------------------------------------------------------------------------------------ ingest
-// A1 + A2 (od/ins:55-82) once per original point: r, elevation and the azimuth bin are cached in HBM.
-__global__ void __launch_bounds__(STREAM_THREADS) k_ingest(EngineDev e, int n_scans) {
-    const int b = blockIdx.y;
-    if (b >= n_scans) return;
-    ScanState& s = e.st[b];
-    const int n0 = s.n0;
-    const int p0 = blockIdx.x * CHUNK;
-    if (p0 >= n0) return;
-    const double d_az = kTwoPi / (double)e.cols;
-    const size_t base = (size_t)b * e.P;
-    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, n0); p += STREAM_THREADS) {
-        const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
-        const double x = v.x, y = v.y, z = v.z;
-        const double r = range3(x, y, z);
-        const double el = elevation(z, r);
-        const int c = trunc_to_int(__ddiv_rn(az_mod(azimuth(x, y)), d_az));
-        if (!(r > 0.0) || c < 0 || c >= e.cols) set_error(s, R3D_ERR_ASSERT);      // od/ins:113 / nan elevation
-        e.r[base + p] = r;
-        e.el[base + p] = el;
-        e.col[base + p] = (unsigned short)max(0, min(c, e.cols - 1));
-        e.alive[base + p] = 1;
-    }
-}
-
+// (the once-per-point ingest itself is k_ingest_count, r3d_k_prepass.cuh)
 __global__ void k_reset_alive(EngineDev e, int n_scans) {
     const int b = blockIdx.y;
     if (b >= n_scans) return;

@@ -798,7 +798,11 @@ __global__ void __launch_bounds__(WALK_THREADS, WALK_CTAS_PER_SM) k_scan_walk(co
         walk_try(e, b, s, c, w_dyn, L, clk);
         ++steps;
     }
-    if (threadIdx.x == 0) atomicAdd(&e.stats[WALK_T0 + WT_TOTAL], (unsigned long long)(clock64() - t_begin));
+    if (threadIdx.x == 0) {
+        const long long lived = clock64() - t_begin;
+        atomicAdd(&e.stats[WALK_T0 + WT_TOTAL], (unsigned long long)lived);
+        s.walk_cycles = lived; s.walk_tries = steps;
+    }
     __syncthreads();
     {
         const int* src = reinterpret_cast<const int*>(&s);

@@ -423,6 +423,13 @@ class Real3DEngine:
                     ('onmap_cycles', 'level_warp_cycles', 'collide_warp_cycles', 'n_level', 'n_collide', 'apply_cycles',
                      'patch_cycles', 'closefill_cycles', 'ss_resweeps', 'ss_level_cycles'))}}
 
+    def walk_profile(self):
+        """(SM cycles each scan's walker CTA lived, cut objects it tried) for the scans of the last run."""
+        n = self._n_scans
+        cycles, tries = np.zeros(n, dtype=np.int64), np.zeros(n, dtype=np.int32)
+        _lib.check(self.lib.r3d_engine_walk_profile(self.handle, cycles.ctypes.data, tries.ctypes.data, n), "walk_profile")
+        return cycles, tries
+
     def surface_labels(self):
         """Semantic labels the road-level search of any class accepts (what the surface grid indexes)."""
         if self.task == 'od':
