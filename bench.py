@@ -52,7 +52,7 @@ WORKLOADS = {
     "c3": dict(task="od", shape="KITTI", scans=256, objects=10, yaw=1024, rows=112, cols=1440, distinct=32,
                text="batch of 256 KITTI-shape scans per GPU (120000 pts, 112x1440 range image), 10 cut "
                     "pedestrians/cyclists per scan, 1024 yaw candidates per object, sharded by scan"),
-    "c4": dict(task="od", shape="OS128", scans=128, objects=50, yaw=360, rows=128, cols=2048, distinct=4,
+    "c4": dict(task="od", shape="OS128", scans=128, objects=50, yaw=360, rows=128, cols=2048, distinct=4, resident=6,
                text="batch of 128 OS1-128-shape scans per GPU (262144 pts, 128x2048 range image), 50 inserted objects per "
                     "scan, 360 yaw candidates per object"),
     "c5": dict(task="ss", shape="SEMKITTI", scans=256, objects=10, yaw=360, rows=112, cols=1440, distinct=8, stream=4541, resident=6,

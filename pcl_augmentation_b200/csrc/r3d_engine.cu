@@ -452,7 +452,7 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     d.unplaceable = eng->unplaceable.p; d.occ_pix = eng->occ_pix.p; d.sel_pix = eng->sel_pix.p;
     const size_t sel_smem = select_smem_bytes(std::min(max_pts, SEL_SMEM_PTS));
     d.sel_key_cap = next_pow2(max_pts);
-    if (max_pts > std::min(SEL_SMEM_PTS, WALK_SEL_PTS)) {        // objects the selection cannot keep in shared memory
+    if (max_pts > std::min(SEL_SMEM_PTS, walk_od::WALK_SEL_PTS)) {        // objects the selection cannot keep in shared memory
         TRY(eng->sel_keys.alloc((size_t)d.B * d.sel_key_cap)); TRY(eng->sel_r.alloc((size_t)d.B * max_pts));
     }
     d.sel_keys = eng->sel_keys.p; d.sel_r = eng->sel_r.p;
@@ -462,9 +462,10 @@ extern "C" int r3d_engine_set_objects(r3d_engine* eng, const r3d_object_db* db) 
     R3D_CUDA(cudaFuncSetAttribute(k_onmap, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)onmap_smem_bytes(d.K)));
     if (grid_near_smem(d.G) > 200 * 1024) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: road-level grid too large for shared memory");
     R3D_CUDA(cudaFuncSetAttribute(k_grid_near_bits, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)grid_near_smem(d.G)));
-    if (walk_smem_layout(d.K, d.dwords).total > 200 * 1024)
+    if (std::max(walk_od::walk_smem_layout(d.K, d.dwords).total, walk_ss::walk_smem_layout(d.K, d.dwords).total) > 200 * 1024)
         return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_set_objects: range image / yaw steps too large for the walker's shared memory");
-    R3D_CUDA(cudaFuncSetAttribute(k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_smem_layout(d.K, d.dwords).total));
+    R3D_CUDA(cudaFuncSetAttribute(walk_od::k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_od::walk_smem_layout(d.K, d.dwords).total));
+    R3D_CUDA(cudaFuncSetAttribute(walk_ss::k_scan_walk, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)walk_ss::walk_smem_layout(d.K, d.dwords).total));
     eng->objects_set = true;
     return R3D_OK;
 }
@@ -668,7 +669,7 @@ static int run_walker(r3d_engine* eng) {
     const int full_y = std::min(n, R3D_FULL_Y);
     const bool fresh = eng->fresh;
     eng->fresh = false;
-    { Launcher l(eng, KID_PREP); k_walk_prepare<<<std::min((n * d.cf_tiles + 255) / 256, eng->n_sms * 4), 256, 0, st>>>(d, n, fresh ? 0 : 1); }
+    { Launcher l(eng, KID_PREP); walk_od::k_walk_prepare<<<std::min((n * d.cf_tiles + 255) / 256, eng->n_sms * 4), 256, 0, st>>>(d, n, fresh ? 0 : 1); }
     if (!fresh) {                                // re-armed without ingest: rebuild the first range image from the caches
         { Launcher l(eng, KID_MINMAX0); k_minmax<<<dim3(chunks0, full_y), STREAM_THREADS, 0, st>>>(d, n); }
         { Launcher l(eng, KID_CLEAR0); k_clear_images<<<dim3(32, full_y), STREAM_THREADS, 0, st>>>(d, n); }
@@ -694,7 +695,11 @@ static int run_walker(r3d_engine* eng) {
         R3D_CUDA(cudaMemsetAsync(eng->occ_cnt.p, 0, (size_t)n * (size_t)d.map_window * d.map_window * sizeof(unsigned), st));
         Launcher l(eng, KID_ADJUST); k_adjust_map<<<dim3(chunks0, n), STREAM_THREADS, 0, st>>>(d, n, 1);
     }
-    { Launcher l(eng, KID_WALK); k_scan_walk<<<n, WALK_THREADS, walk_smem_layout(d.K, d.dwords).total, st>>>(d, n); }
+    {
+        Launcher l(eng, KID_WALK);               // CTA shape per task: see the head of r3d_k_walk.cuh
+        if (d.task == 1) walk_ss::k_scan_walk<<<n, walk_ss::WALK_THREADS, walk_ss::walk_smem_layout(d.K, d.dwords).total, st>>>(d, n);
+        else walk_od::k_scan_walk<<<n, walk_od::WALK_THREADS, walk_od::walk_smem_layout(d.K, d.dwords).total, st>>>(d, n);
+    }
     {
         Launcher l(eng, KID_OUT);
         k_out_count<<<dim3(chunks_all, n), STREAM_THREADS, 0, st>>>(d, n);

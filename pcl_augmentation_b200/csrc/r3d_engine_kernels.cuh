@@ -23,6 +23,20 @@ __device__ __forceinline__ void set_error(ScanState& s, int code) {
 #include "r3d_k_placement.cuh"
 #include "r3d_k_occlusion.cuh"
 #include "r3d_k_output.cuh"
+// the per-scan walker in its two CTA shapes (see the head of r3d_k_walk.cuh)
+namespace walk_od {
+#define R3D_WALK_THREADS 384
+#define R3D_WALK_CTAS_PER_SM 3
 #include "r3d_k_walk.cuh"
+#undef R3D_WALK_THREADS
+#undef R3D_WALK_CTAS_PER_SM
+}  // namespace walk_od
+namespace walk_ss {
+#define R3D_WALK_THREADS 512
+#define R3D_WALK_CTAS_PER_SM 2
+#include "r3d_k_walk.cuh"
+#undef R3D_WALK_THREADS
+#undef R3D_WALK_CTAS_PER_SM
+}  // namespace walk_ss
 
 }  // namespace r3d

@@ -10,22 +10,24 @@
 // in ORDERED WINDOWS with a real early exit at the first candidate that keeps min_points (od/ins:530-561).
 // The once-per-scan streaming work (spherical ingest, indices, first full projection + close/fill, output
 // compaction) stays in batch-wide HBM-bound kernels before / after this one.
+// This header is included TWICE by r3d_engine_kernels.cuh, each time inside its own namespace and with its own CTA shape
+// (R3D_WALK_THREADS x R3D_WALK_CTAS_PER_SM, both defined by the includer): `walk_od` = 384 threads x 3 CTAs per SM for
+// the object-detection workloads (short tries: narrower CTAs leave fewer lanes idle at the barriers and the SM holds
+// three scans; 256 x 3 gives +6 % more throughput but one batch alone takes 5.5 instead of 4.8 ms), `walk_ss` = 512 x 2
+// for semseg (big objects: the map test / collision work of a try is throughput bound inside the CTA).
 #ifdef R3D_WALK_NOINLINE
 #define R3D_WALK_FN __noinline__
 #else
 #define R3D_WALK_FN
 #endif
-#ifndef R3D_WALK_THREADS
-#define R3D_WALK_THREADS 512
-#endif
-#ifndef R3D_WALK_CTAS_PER_SM
-#define R3D_WALK_CTAS_PER_SM 2
-#endif
 constexpr int WALK_THREADS = R3D_WALK_THREADS;
 constexpr int WALK_CTAS_PER_SM = R3D_WALK_CTAS_PER_SM;
 constexpr int WALK_W = WALK_THREADS / GRP;            // candidates per window = 8-lane groups of the CTA
 constexpr int WALK_SEL_PTS = 1024;                    // object points / tile pixels the selection keeps in shared memory
-constexpr int WALK_SEL_TILE = 4096;
+#ifndef R3D_WALK_SEL_TILE
+#define R3D_WALK_SEL_TILE 4096
+#endif
+constexpr int WALK_SEL_TILE = R3D_WALK_SEL_TILE;
 constexpr int WALK_SEL_KEYS = 1024;                   // next_pow2(WALK_SEL_PTS)
 constexpr int WALK_OCC_LANES = 64;                    // threads that count one feasible candidate's visible points
 constexpr int WALK_OCC_PAR = WALK_THREADS / WALK_OCC_LANES;

@@ -1,0 +1,39 @@
+"""Disk-to-disk frames/s of the script-level drop-in: a synthetic KITTI-format dataset of N frames
+(120 000 points each) on a RAM-backed directory -> `dataset_driver.augment_kitti` (reader thread -> ScanPipeline ->
+writer thread) -> the reference's output tree.  usage (GPU box): python tools/bench_dataset_driver.py [frames] [batch]
+
+Reference loop: object_detection/Real3DAug/insertion.py:321-628 (read frame, augment, save_data)."""
+import json, os, shutil, sys, tempfile, time
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from pcl_augmentation_b200 import dataset_driver as drv, synth, synth_io
+
+
+def main():
+    frames = int(sys.argv[1]) if len(sys.argv) > 1 else 512
+    batch = int(sys.argv[2]) if len(sys.argv) > 2 else 128
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else None
+    root = tempfile.mkdtemp(prefix="r3d_ddrv_", dir=base)
+    try:
+        distinct = [synth.make_case("od", 9000 + i, shape=synth.KITTI_SHAPE, number_of_object=10) for i in range(16)]
+        cases = [distinct[i % len(distinct)] for i in range(frames)]
+        _, out, cfg = synth_io.write_od_dataset(cases, root)
+        in_bytes = sum(os.path.getsize(os.path.join(root, "data/velodyne", f)) for f in os.listdir(os.path.join(root, "data/velodyne")))
+        np.random.seed(1)
+        t0 = time.perf_counter()
+        folder, written, skipped = drv.augment_kitti(cfg, batch_size=batch, log=lambda *a: None)
+        dt = time.perf_counter() - t0
+        out_bytes = sum(os.path.getsize(os.path.join(out, "velodyne", f)) for f in os.listdir(os.path.join(out, "velodyne")))
+        print(json.dumps({"metric": "frames/s disk to disk (KITTI-format dataset on a RAM-backed directory, augment_kitti)",
+                          "value": round(written / dt, 1), "unit": "frames/s", "frames": frames, "written": written,
+                          "skipped": skipped, "batch_size": batch, "seconds": round(dt, 2),
+                          "read_mb": round(in_bytes / 1e6), "written_mb": round(out_bytes / 1e6), "directory": root,
+                          "includes": "engine creation, cut-object DB load, file reads (np.fromfile / np.load of two maps per "
+                                      "frame), staging, H2D, device path, D2H, unpack, np.tofile writes, marker files"}))
+    finally:
+        shutil.rmtree(root, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -8,7 +8,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
     --log-file gpurun_out/${TAG}_launches.csv $BENCH > /dev/null 2>&1
 wc -l gpurun_out/${TAG}_launches.csv
 timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:"k_scan_walk|k_ingest_count|k_scatter_project|k_bucket_scan3|k_grid_near_bits|k_close_fill_raw_pipelined|k_out_count|k_out_write" \
-    -s 10 -c 10 -f -o gpurun_out/${TAG}_full_step $BENCH > /dev/null 2> gpurun_out/${TAG}_ncu.err
+    -k regex:"k_scan_walk|k_ingest_count|k_scatter_project|k_bucket_scan3|k_grid_near_bits|k_close_fill|k_out_count|k_out_write" \
+    -s 11 -c 11 -f -o gpurun_out/${TAG}_full_step $BENCH > /dev/null 2> gpurun_out/${TAG}_ncu.err
 tail -2 gpurun_out/${TAG}_ncu.err
 ls -la gpurun_out/${TAG}_*.ncu-rep

@@ -17,7 +17,7 @@ METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.
 BENCH_NAME = {"k_project": "project_zbuffer_full", "k_close_fill": "close_fill_full", "k_clear_images": "clear_images_full",
               "k_minmax": "minmax_elevation_full", "k_ingest": "ingest_spherical", "k_update": "update_mask_patch",
               "k_out_write": "compact_output", "k_out_count": "compact_output", "k_onmap": "placement",
-              "k_close_fill_raw_pipelined": "close_fill_full", "k_close_fill_tasks": "close_fill_full",
+              "k_close_fill_raw_pipelined": "close_fill_full", "k_close_fill_tasks": "close_fill_full", "k_close_fill_tma": "close_fill_full",
               "k_onmap_full": "placement", "k_road_level": "placement", "k_collide": "placement",
               "k_occl_count": "occlusion_count", "k_select_emit": "select_emit",
               # round 2: the per-scan walker and the fused streaming passes
@@ -46,7 +46,7 @@ def main():
             w = csv.writer(f)
             w.writerow(["kernel"] + [f"{m} [{units[i]}]" for m, i in zip(metrics, idx)])
             for r in data:
-                k = r[kn].replace("(anonymous namespace)::", "").replace("<unnamed>::", "").replace("r3d::", "").split("(")[0].replace("void ", "").split("<")[0]
+                k = r[kn].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]        # kernel name without namespaces
                 w.writerow([k] + [r[i] for i in idx])
                 rd = float(r[idx[1]].replace(",", "")) * SCALE.get(units[idx[1]], 1.0)
                 wr = float(r[idx[2]].replace(",", "")) * SCALE.get(units[idx[2]], 1.0)

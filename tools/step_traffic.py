@@ -16,7 +16,7 @@ launches = {}
 for r in rows[hi + 1:]:
     if len(r) <= mv:
         continue
-    name = r[kn].split("(")[0].replace("r3d::", "").replace("<unnamed>::", "").replace("void ", "")
+    name = r[kn].split("(")[0].replace("void ", "").split("<")[0].split("::")[-1]              # kernel name without namespaces
     launches.setdefault(int(r[idc]), {"kernel": name})[r[mn]] = float(r[mv].replace(",", "")) * SCALE.get(r[mu], 1.0)
 seq = [launches[k] for k in sorted(launches)]
 starts = [i for i, l in enumerate(seq) if l["kernel"] == "k_reset_state"]
