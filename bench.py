@@ -599,7 +599,7 @@ def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_ov
         e = b.e2e(steps, stream_scans=b.w.get("stream"))
         scans_e2e = world * b.n_scans * e["batches"]
         out = {"config": workload_config(name, world), "value": world * b.n_scans * steps / (dev_ms / 1e3), "unit": "scans/s",
-               "ms_per_step": dev_ms / steps, "steps": steps, "single_batch_ms": serial_ms,
+               "ms_per_step": dev_ms / steps, "steps": steps, "resident_engines": b.res_depth, "single_batch_ms": serial_ms,
                "e2e": {"value": scans_e2e / e["seconds"], "unit": "scans/s", "h2d_bytes_per_step": e["h2d"],
                        "d2h_bytes_per_step": e["d2h"], "batches": e["batches"],
                        "pcie_gbs_each_way": round(max(e["h2d"], e["d2h"]) * e["batches"] / e["seconds"] / 1e9, 1)},
