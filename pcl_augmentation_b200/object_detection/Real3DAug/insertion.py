@@ -60,7 +60,22 @@ def main(argv=None):
     ap.add_argument("--batch", type=int, default=64, help="frames augmented per engine batch")
     ap.add_argument("--folder", type=int, default=None, help="run folder number 0-99 (default 00, od/ds:130)")
     ap.add_argument("--yaw-steps", type=int, default=360, help="yaw candidates per cut object (reference: 360)")
+    ap.add_argument("--processes", type=int, default=1,
+                    help="start this many copies of the script on the same output folder (the reference's own scale-out, "
+                         "object_detection/README.md:36: the frame markers of od/ins:335-347 keep them apart); the host "
+                         "side of a copy (file I/O, schedule draws) is one Python process, the GPU is shared")
     args = ap.parse_args(argv)
+    if args.processes > 1:
+        import subprocess
+        import sys
+        cmd = [sys.executable, "-m", __spec__.name if __spec__ else "pcl_augmentation_b200.object_detection.Real3DAug.insertion",
+               "--config", args.config, "--batch", str(args.batch), "--yaw-steps", str(args.yaw_steps), "--folder",
+               str(0 if args.folder is None else args.folder)]
+        procs = [subprocess.Popen(cmd) for _ in range(args.processes)]
+        rc = max(p.wait() for p in procs)
+        if rc:
+            raise SystemExit(rc)
+        return
     with open(args.config, "r") as f:
         config = yaml.safe_load(f)
     folder, written, skipped = augment_kitti(config, batch_size=args.batch, yaw_steps=args.yaw_steps,
