@@ -191,10 +191,12 @@ __device__ R3D_WALK_FN void walk_full_reproject(const EngineDev& e, int b, ScanS
     const double2* __restrict__ el2 = reinterpret_cast<const double2*>(e.el + base);
     if (tid == 0) { c.el_min = R3D_EMPTY_U64; c.el_max = 0ull; }
     unsigned long long* z = e.zraw + (size_t)b * e.hw;
-    {
+    if ((reinterpret_cast<size_t>(z) & 15) == 0) {
         ulonglong2* z2 = reinterpret_cast<ulonglong2*>(z);
         for (int i = tid; i < e.hw / 2; i += nt) z2[i] = make_ulonglong2(R3D_EMPTY_U64, R3D_EMPTY_U64);
         if ((e.hw & 1) && tid == 0) z[e.hw - 1] = R3D_EMPTY_U64;
+    } else {                                             // odd image size: the scan's z-buffer starts on an 8-byte boundary
+        for (int i = tid; i < e.hw; i += nt) z[i] = R3D_EMPTY_U64;
     }
     __syncthreads();
     unsigned long long lmin = R3D_EMPTY_U64, lmax = 0ull;

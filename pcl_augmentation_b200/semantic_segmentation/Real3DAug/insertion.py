@@ -66,7 +66,33 @@ def main(argv=None):
     ap.add_argument("--reverse", action="store_true", help="process the frames in reverse order (ss/ds:117-141)")
     ap.add_argument("--skip", type=int, default=0, help="skip the first frames of the sequence (ss/ds:117-141)")
     ap.add_argument("--yaw-steps", type=int, default=360)
+    ap.add_argument("--processes", type=int, default=1,
+                    help="start this many copies of the script on the same output folder (the reference's scale-out: the "
+                         "frame markers of ss/ins:327-339 keep them apart); the GPU is shared")
     args = ap.parse_args(argv)
+    if args.processes > 1:
+        import subprocess
+        import sys
+        passed = [a for a in (sys.argv[1:] if argv is None else list(argv))]
+        keep, skip = [], False
+        for a in passed:                                     # the same command line without --processes N
+            if skip:
+                skip = False
+                continue
+            if a == "--processes":
+                skip = True
+                continue
+            if a.startswith("--processes="):
+                continue
+            keep.append(a)
+        if "--folder" not in keep:
+            keep += ["--folder", "0"]
+        mod = __spec__.name if __spec__ else "pcl_augmentation_b200.semantic_segmentation.Real3DAug.insertion"
+        procs = [subprocess.Popen([sys.executable, "-m", mod] + keep) for _ in range(args.processes)]
+        rc = max(p.wait() for p in procs)
+        if rc:
+            raise SystemExit(rc)
+        return
     cfg_path = args.config or ("../config/semantic-kitti.yaml" if args.dataset == "semantic-kitti" else "../config/waymo.yaml")
     with open(cfg_path, "r") as f:
         config = yaml.safe_load(f)

@@ -308,3 +308,33 @@ def test_points_next_to_bin_edges_take_the_exact_path(task, seed, counts):
     eng.close()
     assert got.status == 0
     assert_matches_oracle(case, got, ref, want)
+
+
+@pytest.mark.parametrize("variant", ["no_tma", "odd_width"])
+def test_close_fill_fallback_paths_match_oracle(variant, monkeypatch):
+    """The batch-wide close / fill has three tile loaders: the TMA tensor map (default), `cp.async` (R3D_NO_TMA=1, or a
+    z-buffer the tensor map cannot describe) and plain loads for odd image widths (rows not 16-byte aligned).  The two
+    fallbacks must give the oracle's result too."""
+    case = synth.make_case("od", 821, shape=GOLDEN_SHAPE, counts=[2, 1], n_cars=5, obj_range=(4.0, 16.0))
+    kw = {}
+    if variant == "no_tma":
+        monkeypatch.setenv("R3D_NO_TMA", "1")
+    else:
+        kw = dict(rows=61, cols=1439)
+    eng = make_engine(case, **kw)
+    got = eng.augment_batch([scan_input_from_case(case)])[0]
+    eng.close()
+    ref, want = oracle_run(case, **({"num_row": 61, "num_column": 1439} if variant == "odd_width" else {}))
+    assert got.status == 0
+    assert_matches_oracle(case, got, ref, want)
+
+
+def test_walk_profile_reports_every_scan():
+    """r3d_engine_walk_profile: cycles > 0 and the number of tried cut objects per scan of the last run."""
+    cases = [synth.make_case("od", 830 + i, shape=GOLDEN_SHAPE, counts=[1, 1], n_cars=4, obj_range=(4.0, 16.0)) for i in range(3)]
+    eng = make_engine(cases[0], n_scans=3, max_points=max(len(c.pcl5) for c in cases))
+    res = eng.augment_batch([scan_input_from_case(c) for c in cases])
+    cycles, tries = eng.walk_profile()
+    eng.close()
+    assert len(cycles) == 3 and (cycles > 0).all()
+    assert all(t >= len(r.inserted) for t, r in zip(tries, res))
