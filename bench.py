@@ -70,7 +70,8 @@ def workload_config(name, n_gpus):
             "objects_per_scan": w["objects"], "yaw_candidates": w["yaw"], "range_image": [w["rows"], w["cols"]],
             "parallelism": f"scan-sharded x{n_gpus}", "distinct_scans": w["distinct"],
             "l2": f"inputs larger than L2 ({w['scans'] * pts * 20 / 1e6:.0f} MB of points per batch, no flush needed)"
-                  if w["scans"] * pts * 20 > 200e6 else "L2 flushed by the other resident engines' batches between steps"}
+                  if w["scans"] * pts * 20 > 200e6 else
+                  f"NOT flushed: the {w['scans'] * pts * 20 / 1e6:.1f} MB of a step stay L2-resident (single-scan latency case, not a throughput figure)"}
 
 
 def build_cases(name, rank):
@@ -625,7 +626,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c3", choices=sorted(WORKLOADS), help="headline workload (default: the one the metric is quoted on)")
-    ap.add_argument("--side-configs", default="c2,c4,c5",
+    ap.add_argument("--side-configs", default="c1,c2,c4,c5",
                     help="comma-separated other configurations measured briefly into the `configs` block ('' = none)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--resident-depth", type=int, default=0,

@@ -198,11 +198,12 @@ __device__ bool group_road_level(const EngineDev& e, int b, const SurfaceSet& su
 // four float4 loads per lane in local memory there, which serialises them).  The four 8-lane sub-groups of the warp take
 // rows y0 + sub, y0 + sub + 4, ...; every sub-group fetches its own row's CSR range (no shuffles, no hole logic: a ring
 // search re-visits the inner cells, which costs two loads per row), two 16-byte point loads in flight per lane.
+// `part` of `nparts`: several warps can share one rectangle, each taking every nparts-th block of four rows
 template <class F, class S>
 __device__ __forceinline__ void warp_visit(const int* __restrict__ cell, const float4* __restrict__ pts, int G, const CellRect& rc,
-                                           int lane, F f, S stop) {
+                                           int lane, F f, S stop, int part = 0, int nparts = 1) {
     const int sub = lane >> 3, sl = lane & 7;
-    for (int y0 = rc.y0; y0 <= rc.y1; y0 += 4) {                  // four rows of cells in flight, then the (warp-uniform) exit test
+    for (int y0 = rc.y0 + 4 * part; y0 <= rc.y1; y0 += 4 * nparts) {   // four rows of cells in flight, then the (warp-uniform) exit test
         const int y = y0 + sub;
         if (y <= rc.y1) {
             const int c0 = y * G + rc.x0;
@@ -469,8 +470,11 @@ __device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, cons
 }
 
 // A8 + A9 for one candidate, one warp: part (i) on the lean walk, the rest shared with group_collides
+// `part` of `nparts` warps work on the same candidate (the walker hands spare warps of a chunk to its candidates): the
+// rows of the obstacle grid are dealt to the parts, the tails / scene boxes are the last part's; `shared_hit` (shared
+// memory, zeroed by the caller) carries a hit to the other parts
 __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c, double sn,
-                              double level, int lane) {
+                              double level, int lane, int part = 0, int nparts = 1, volatile int* shared_hit = nullptr) {
     const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
     const YawTest yt = make_yaw_test(yb, level, ob.length, ob.width, ob.height);
     {
@@ -493,9 +497,10 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
             if (ped && !(z >= zmin_ped)) return;
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
             if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) hit = true;
-        }, [&] { return __any_sync(0xffffffffu, hit) != 0; });
+        }, [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && *shared_hit != 0); }, part, nparts);
         if (__any_sync(0xffffffffu, hit)) return true;
     }
+    if (part != nparts - 1 || (shared_hit != nullptr && *shared_hit != 0)) return false;
     return group_collides_rest<32>(e, b, s, ob, cc, yb, yt, c, sn, level, lane, 0xffffffffu);
 }
 

@@ -93,6 +93,7 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     double wtol[WALK_W];         // ... and how far the shift may move from it without changing the verdict of the map test
     unsigned long long wtolp[WALK_W], wtolb[WALK_W];   // its parts while the map test runs: min over on-map points, max over off-map points
     int wbad[WALK_W];
+    int whit[WALK_W];            // collision found by one of the warps that share a candidate
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
     int s_warp[WALK_NWARPS];
@@ -413,21 +414,22 @@ __device__ R3D_WALK_FN void walk_levels(const EngineDev& e, int b, WalkCtl& c, c
 
 // ---- A8 + A9 for the window candidates listed in c.won[0 .. n) (they have a road level), one warp per candidate
 __device__ R3D_WALK_FN void walk_collides(const EngineDev& e, int b, const ScanState& s, WalkCtl& c, const int* list, int n) {
-    const int lane = threadIdx.x & 31;
+    // n <= WALK_NWARPS candidates (a chunk): the warps are dealt statically, and when the chunk is short the spare warps
+    // join in — `wpc` warps per candidate share its obstacle-grid rows (semseg chunks hold ~6 candidates whose boxes cover
+    // thousands of grid points each)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const ObjBox& ob = c.ob;
     const ClassCfg& cc = e.classes[ob.cls];
-    for (;;) {
-        int t = 0;
-        if (lane == 0) t = atomicAdd(&c.next, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
-        if (t >= n) break;
-        const int i = list[t], k = c.wk[i];
-        const long long t0 = clock64();
-        const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane);
-        if (lane == 0) {
-            if (hit) c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE);
-            atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull);
-        }
+    if (n <= 0) return;
+    const int wpc = max(1, WALK_NWARPS / n);
+    const int t = warp / wpc, part = warp % wpc;
+    if (t >= n) return;
+    const int i = list[t], k = c.wk[i];
+    const long long t0 = clock64();
+    const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane, part, wpc, &c.whit[i]);
+    if (lane == 0) {
+        if (hit) { c.whit[i] = 1; c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE); }
+        if (part == 0) { atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull); }
     }
 }
 
@@ -688,7 +690,8 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
             }
             if (tid == 0) {                                   // the chunk's candidates with a road level, in order
                 int n = 0;
-                for (int t = 0; t < nch; ++t) if ((c.wflag[chunk[t]] & (CF_ONMAP | CF_HOK)) == (CF_ONMAP | CF_HOK)) c.wsub[n++] = chunk[t];
+                for (int t = 0; t < nch; ++t)
+                    if ((c.wflag[chunk[t]] & (CF_ONMAP | CF_HOK)) == (CF_ONMAP | CF_HOK)) { c.whit[chunk[t]] = 0; c.wsub[n++] = chunk[t]; }
                 c.n_sub = n; c.next = 0;
             }
             __syncthreads();
@@ -708,8 +711,12 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
             // scene, hi = points that fall into the image: lo <= V <= hi, and lo == 0 <=> V == 0, so most candidates are
             // decided without building the visible-pixel image
             const int nfw = c.nfw;
-            const int sg = tid / WALK_OCC_LANES, sl = tid % WALK_OCC_LANES;
-            for (int j0 = 0; j0 < nfw && c.found < 0; j0 += WALK_OCC_PAR) {
+            for (int j0 = 0, npar = 1; j0 < nfw && c.found < 0; j0 += npar) {
+                // candidates counted side by side: as many as are left (at most WALK_OCC_PAR), rounded up to a divisor of
+                // the warp count so that every candidate gets whole warps — a lone feasible candidate gets the whole CTA
+                npar = 1;
+                while (npar < min(nfw - j0, WALK_OCC_PAR) || WALK_NWARPS % npar != 0) ++npar;
+                const int lanes = WALK_THREADS / npar, sg = tid / lanes, sl = tid % lanes;
                 if (tid < WALK_OCC_PAR) { c.cnt_lo[tid] = 0; c.cnt_hi[tid] = 0; }
                 __syncthreads();
                 const int j = j0 + sg;
@@ -717,7 +724,7 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
                     const int i = c.wfeas[j], k = c.wk[i];
                     const double cs = e.cos_k[k], sn = e.sin_k[k], dz = sub(c.wlevel[i], ob.cz);
                     int lo = 0, hi = 0;
-                    for (int p = sl; p < ob.count; p += WALK_OCC_LANES) {
+                    for (int p = sl; p < ob.count; p += lanes) {
                         const ObjPix o = project_obj_pix(e, ob, geom, fgeom, p, cs, sn, dz, s);
                         if (o.pix >= 0) { ++hi; if (o.r < smooth[o.pix]) ++lo; }
                     }
@@ -726,7 +733,7 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
                 }
                 __syncthreads();
                 int found = -1;
-                for (int q = 0; q < WALK_OCC_PAR && j0 + q < nfw; ++q) {          // uniform over the CTA
+                for (int q = 0; q < npar && j0 + q < nfw; ++q) {                  // uniform over the CTA
                     const int lo = c.cnt_lo[q], hi = c.cnt_hi[q];
                     bool ok = lo >= min_pts;
                     if (!ok && lo > 0 && hi >= min_pts) {
