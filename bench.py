@@ -46,7 +46,7 @@ WORKLOADS = {
     "c1": dict(task="od", shape="KITTI", scans=1, objects=10, yaw=360, rows=112, cols=1440, distinct=1,
                text="one KITTI-shape HDL-64 scan (120000 pts, 112x1440 range image), 10 cut pedestrians/cyclists, 360 yaw "
                     "candidates per object"),
-    "c2": dict(task="ss", shape="SEMKITTI", scans=256, objects=20, yaw=360, rows=64, cols=2048, distinct=8, resident=8,
+    "c2": dict(task="ss", shape="SEMKITTI", scans=256, objects=20, yaw=360, rows=64, cols=2048, distinct=8, resident=10,
                text="batch of 256 SemanticKITTI-shape scans per GPU (124992 pts, 64x2048 range image), 20 rare-class objects "
                     "per scan placed on the rich_map road / sidewalk, 360 yaw candidates per object"),
     "c3": dict(task="od", shape="KITTI", scans=256, objects=10, yaw=1024, rows=112, cols=1440, distinct=32,
