@@ -84,18 +84,30 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_out_write(EngineDev e, int n
         const int* cc = e.chunk_cnt + (size_t)b * e.max_chunks;
         for (int c = 0; c < (int)blockIdx.x; ++c) o0 += cc[c];
     }
-    __shared__ int s_w[STREAM_THREADS / 32];
-    __shared__ int s_run;
-    if (threadIdx.x == 0) s_run = 0;
-    __syncthreads();
+    // every warp owns a contiguous slice of the chunk (CHUNK / warps points): the live counts of the slices give the
+    // warps their output offsets with ONE barrier, after which a warp compacts its slice 32 points at a time with
+    // ballots only
+    constexpr int NW = STREAM_THREADS / 32, SLICE = CHUNK / NW;
+    static_assert(SLICE % 32 == 0 && SLICE / 32 <= 32, "one alive word per lane covers the slice");
+    __shared__ int s_w[NW];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int q0 = p0; q0 < min(p0 + CHUNK, n); q0 += STREAM_THREADS) {
-        const int p = q0 + threadIdx.x;
-        const bool a = p < n && e.alive[base + p];
+    const int q0 = p0 + w * SLICE, q1 = min(q0 + SLICE, n);
+    int mine = 0;
+    for (int p = q0 + lane; p < q1; p += 32) mine += e.alive[base + p] ? 1 : 0;
+    for (int o = 16; o > 0; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0) s_w[w] = mine;
+    __syncthreads();
+    long long o = o0;
+    for (int i = 0; i < w; ++i) o += s_w[i];
+    const float4* __restrict__ src = e.xyzi + (size_t)b * e.max_points;
+#pragma unroll 2
+    for (int q = q0; q < q1; q += 32) {
+        const int p = q + lane;
+        const bool a = p < q1 && e.alive[base + p];
         float4 v;
         unsigned lab = 0;
-        if (a) {                                        // issue the loads before the scan's barriers
-            if (p < s.n0) v = __ldg(&e.xyzi[(size_t)b * e.max_points + p]);
+        if (a) {
+            if (p < s.n0) v = __ldg(&src[p]);
             else {
                 const size_t t = (size_t)b * e.max_inserted + (p - s.n0);
                 v = make_float4((float)e.tail_x[t], (float)e.tail_y[t], (float)e.tail_z[t], e.tail_i[t]);
@@ -103,16 +115,11 @@ __global__ void __launch_bounds__(STREAM_THREADS) k_out_write(EngineDev e, int n
             lab = e.label[base + p];
         }
         const unsigned m = __ballot_sync(0xffffffffu, a);
-        if (lane == 0) s_w[w] = __popc(m);
-        __syncthreads();
-        int off = s_run, tot = 0;
-        for (int i = 0; i < STREAM_THREADS / 32; ++i) { if (i < w) off += s_w[i]; tot += s_w[i]; }
         if (a) {
-            const long long o = o0 + off + __popc(m & ((1u << lane) - 1u));
-            e.out_xyzi[o] = v;
-            e.out_label[o] = lab;
+            const long long oo = o + __popc(m & ((1u << lane) - 1u));
+            e.out_xyzi[oo] = v;
+            e.out_label[oo] = lab;
         }
-        __syncthreads();
-        if (threadIdx.x == 0) s_run += tot;
+        o += __popc(m);
     }
 }
