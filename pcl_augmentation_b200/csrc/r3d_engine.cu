@@ -565,6 +565,13 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     } else {
         R3D_CUDA(cudaMemcpyAsync(eng->poses.p, bt->poses, (size_t)n * 16 * sizeof(double), cudaMemcpyHostToDevice, st));
     }
+    for (int sc = 0; sc < n; ++sc) {                  // a schedule must fit the per-scan event / insertion records
+        long long want = 0;
+        for (int c = 0; c < d.n_classes; ++c) want += std::max(bt->counts[(size_t)sc * d.n_classes + c], 0);
+        if (want + 1 > d.max_events)
+            return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: a scan's schedule asks for more objects than max_events - 1 "
+                                              "(create the engine with max_events = objects per scan + 1)");
+    }
     R3D_CUDA(cudaMemcpyAsync(eng->counts.p, bt->counts, (size_t)n * d.n_classes * sizeof(int), cudaMemcpyHostToDevice, st));
     const size_t nperm = (size_t)n * bt->n_events * d.n_classes * d.max_tries;
     if (nperm > eng->perms.n) TRY(eng->perms.alloc(nperm));

@@ -681,8 +681,14 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
         // count of the chunk's feasible candidates, leaving at the first candidate that keeps min_points (od/ins:530-561).
         // The first feasible candidates of a try are the likely winners: evaluating the whole window at once spent most
         // of its road-level / collision work on candidates that are never looked at.
-        for (int c0 = 0; c0 < n_on && c.found < 0; c0 += WALK_NWARPS) {
-            const int nch = min(WALK_NWARPS, n_on - c0);
+#ifndef R3D_WALK_FIRST_CHUNK
+#define R3D_WALK_FIRST_CHUNK 0                       // 0 = every chunk holds one candidate per warp
+#endif
+        for (int c0 = 0, nch = 0; c0 < n_on && c.found < 0; c0 += nch) {
+            // the very first chunk of a try may be shorter: its candidates are the likeliest winners, a full chunk spends
+            // road-level / collision work on candidates that are never looked at (the spare warps share the collisions)
+            const int cap = (R3D_WALK_FIRST_CHUNK > 0 && base == 0 && c0 == 0) ? min(R3D_WALK_FIRST_CHUNK, WALK_NWARPS) : WALK_NWARPS;
+            nch = min(cap, n_on - c0);
             const int* chunk = c.won + c0;
             if (e.task == 0) {
                 walk_levels(e, b, c, chunk, nch);

@@ -261,6 +261,11 @@ def test_error_conventions_index_capacity_and_arguments():
     with pytest.raises(Real3DError):
         eng.run()
     eng.close()
+    # (4) a schedule that asks for more objects than the engine's event records hold is refused at load time
+    tight = Real3DEngine("od", case2.config, case2.db, max_scans=1, max_points=len(case2.pcl5), max_events=2)
+    with pytest.raises(Real3DError, match="max_events"):
+        tight.load(tight.stage([scan_input_from_case(case2)]))          # counts [1, 1]: 2 objects + 1 > max_events 2
+    tight.close()
 
 
 @pytest.mark.parametrize("staged", MODES)
