@@ -262,6 +262,11 @@ typedef struct r3d_batch {
     int32_t n_events;
     const uint16_t* labels16;     /* total: the same labels packed to 16 bits (they are & 0xFFFF) — 2 instead of 4 bytes
                                      per point over PCIe; widened on the device */
+    const uint8_t* labels1;       /* object detection only, (total + 7) / 8 bytes, used when labels and labels16 are NULL:
+                                     bit i (little-endian bit order, i = index into the packed points of the batch) = point i
+                                     carries the Road label.  The reference collapses the labels to {Road, 1} itself before
+                                     the loop (od/ins:353-355), so one bit per point is all the OD path reads: 1/8 byte
+                                     instead of 2 bytes per point over PCIe; expanded to {road_label, other} on the device */
 } r3d_batch;
 
 typedef struct r3d_batch_result {

@@ -47,7 +47,7 @@ class Batch(C.Structure):
     _fields_ = [("n_scans", C.c_int32), ("point_offsets", C.c_void_p), ("xyzi", C.c_void_p), ("labels", C.c_void_p),
                 ("box_offsets", C.c_void_p), ("boxes", C.c_void_p), ("map_offsets", C.c_void_p), ("maps", C.c_void_p),
                 ("map_dims", C.c_void_p), ("poses", C.c_void_p), ("counts", C.c_void_p), ("perms", C.c_void_p),
-                ("n_events", C.c_int32), ("labels16", C.c_void_p)]
+                ("n_events", C.c_int32), ("labels16", C.c_void_p), ("labels1", C.c_void_p)]
 
 
 class BatchResult(C.Structure):

@@ -88,6 +88,7 @@ struct r3d_engine {
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
     DevBuf<unsigned short> col, cand_list, label16;
+    DevBuf<unsigned char> label1;
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
         class_list, radii_ok, cand_v, gcell, n_list, feas, occ_pix, sel_pix, inserted, n0_arr, nbox0_arr, work_cnt, full_list, cf_tasks, need2, occ_far;
@@ -132,6 +133,20 @@ __global__ void k_widen_labels(const unsigned short* src, const long long* pt_of
     const int cnt = (int)(pt_off[b + 1] - pt_off[b]);
     const int p0 = blockIdx.x * CHUNK;
     for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, cnt); p += blockDim.x) label[(size_t)b * P + p] = src[o + p];
+}
+// one "is Road" bit per point (object detection) -> {road_label, some other label}
+__global__ void k_expand_label_bits(const unsigned char* bits, const long long* pt_off, unsigned* label, int P, int n_scans,
+                                    unsigned road_label) {
+    const int b = blockIdx.y;
+    if (b >= n_scans) return;
+    const long long o = pt_off[b] - pt_off[0];
+    const int cnt = (int)(pt_off[b + 1] - pt_off[b]);
+    const int p0 = blockIdx.x * CHUNK;
+    const unsigned other = road_label == 1u ? 2u : 1u;       // od/ins:353-355 relabels every non-Road point to 1
+    for (int p = p0 + threadIdx.x; p < min(p0 + CHUNK, cnt); p += blockDim.x) {
+        const long long i = o + p;
+        label[(size_t)b * P + p] = ((bits[i >> 3] >> (i & 7)) & 1u) ? road_label : other;
+    }
 }
 __global__ void k_set_round(unsigned* round_ctl, unsigned seq_base) { round_ctl[0] = 0u; round_ctl[1] = seq_base; }
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
@@ -523,7 +538,7 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     EngineDev& d = eng->dev;
     const int n = bt->n_scans;
     if (n <= 0 || n > d.B) return r3d_fail(R3D_ERR_CAPACITY, "r3d_engine_load_batch: n_scans exceeds max_scans");
-    if (!bt->point_offsets || !bt->xyzi || (!bt->labels && !bt->labels16) || !bt->counts || !bt->perms || bt->n_events <= 0)
+    if (!bt->point_offsets || !bt->xyzi || (!bt->labels && !bt->labels16 && !bt->labels1) || !bt->counts || !bt->perms || bt->n_events <= 0)
         return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: missing arrays");
     if (d.task == 1 && (!bt->poses || !d.ss_map)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: semseg needs poses and the map");
     if (d.task == 0 && (!bt->maps || !bt->map_offsets || !bt->map_dims)) return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: OD needs maps");
@@ -580,12 +595,21 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     // points: packed host rows -> per-scan strided device rows (one pitched copy when every scan has the same size)
     bool uniform = true;
     for (int s = 1; s < n; ++s) uniform &= n0[s] == n0[0];
-    const bool packed = bt->labels == nullptr;         // 16-bit labels: staged contiguously, widened on the device
+    const bool packed = bt->labels == nullptr;         // 16-bit labels / Road bits: staged contiguously, expanded on the device
+    const bool bits = packed && bt->labels16 == nullptr;
+    if (bits && (d.task != 0 || bt->point_offsets[0] != 0))
+        return r3d_fail(R3D_ERR_ARG, "r3d_engine_load_batch: labels1 (one Road bit per point) is for object detection batches that start at point 0");
     if (packed) {
         const size_t total = (size_t)(bt->point_offsets[n] - bt->point_offsets[0]);
-        if (total > eng->label16.n) TRY(eng->label16.alloc(total));
         if ((size_t)n + 1 > eng->pt_off.n) TRY(eng->pt_off.alloc((size_t)d.B + 1));
-        R3D_CUDA(cudaMemcpyAsync(eng->label16.p, bt->labels16 + bt->point_offsets[0], total * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+        if (bits) {
+            const size_t nbytes = (total + 7) / 8;
+            if (nbytes > eng->label1.n) TRY(eng->label1.alloc(nbytes));
+            R3D_CUDA(cudaMemcpyAsync(eng->label1.p, bt->labels1, nbytes, cudaMemcpyHostToDevice, st));
+        } else {
+            if (total > eng->label16.n) TRY(eng->label16.alloc(total));
+            R3D_CUDA(cudaMemcpyAsync(eng->label16.p, bt->labels16 + bt->point_offsets[0], total * sizeof(unsigned short), cudaMemcpyHostToDevice, st));
+        }
         R3D_CUDA(cudaMemcpyAsync(eng->pt_off.p, bt->point_offsets, ((size_t)n + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
     }
     if (uniform) {
@@ -604,7 +628,8 @@ extern "C" int r3d_engine_load_batch(r3d_engine* eng, const r3d_batch* bt) {
     }
     if (packed) {
         const int chunks = (eng->max_n0 + CHUNK - 1) / CHUNK;
-        k_widen_labels<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(eng->label16.p, eng->pt_off.p, eng->label.p, d.P, n);
+        if (bits) k_expand_label_bits<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(eng->label1.p, eng->pt_off.p, eng->label.p, d.P, n, (unsigned)d.road_label);
+        else k_widen_labels<<<dim3(chunks, n), STREAM_THREADS, 0, st>>>(eng->label16.p, eng->pt_off.p, eng->label.p, d.P, n);
         r3d_count_launch();
     }
     // the std::vectors above are pageable: the copies from them completed before cudaMemcpyAsync returned

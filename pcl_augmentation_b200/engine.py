@@ -195,7 +195,10 @@ class Real3DEngine:
             pt_off[i + 1] = pt_off[i] + len(s.xyzi)
         total = int(pt_off[-1])
         xyzi = _pinned((total, 4), np.float32)
-        labels = _pinned((total,), np.int16)          # labels are & 0xFFFF (od/ds:65): 2 bytes per point over PCIe
+        # labels over PCIe: semseg 2 bytes per point (they are & 0xFFFF, od/ds:65); object detection ONE BIT per point —
+        # the reference collapses the labels to {Road, 1} before its loop (od/ins:353-355), "is Road" is all the path reads
+        road_bits = self.task == 'od'
+        labels = _pinned((total,), np.int16) if not road_bits else np.zeros(total, dtype=bool)
         box_off = np.zeros(n + 1, dtype=np.int32)
         box_rows = []
         n_events = max(int(np.asarray(s.perms).shape[0]) for s in scans)
@@ -213,7 +216,10 @@ class Real3DEngine:
             xyzi[pt_off[i]:pt_off[i + 1]] = s.xyzi
             lab = np.asarray(s.labels)
             assert lab.size == 0 or int(lab.max()) < 65536, "semantic labels must be masked with 0xFFFF (od/ds:65)"
-            labels[pt_off[i]:pt_off[i + 1]] = lab.astype(np.uint16).view(np.int16)
+            if road_bits:
+                labels[pt_off[i]:pt_off[i + 1]] = lab == self.road_label
+            else:
+                labels[pt_off[i]:pt_off[i + 1]] = lab.astype(np.uint16).view(np.int16)
             for anno in (s.box_dicts if s.box_dicts is not None else [read(line) for line in s.box_lines]):
                 box_rows.append(bx.box_record(anno))
             box_off[i + 1] = len(box_rows)
@@ -223,7 +229,11 @@ class Real3DEngine:
         boxes = _pinned((max(len(box_rows), 1), 16), np.float64)[:len(box_rows)]
         if box_rows:
             boxes[:] = np.array(box_rows, dtype=np.float64).reshape(-1, 16)
-        staged = {'n': n, 'pt_off': pt_off, 'xyzi': xyzi, 'labels': labels, 'box_off': box_off, 'boxes': boxes,
+        if road_bits:
+            packed = np.packbits(labels, bitorder='little')
+            labels = _pinned((max(len(packed), 1),), np.uint8)
+            labels[:len(packed)] = packed
+        staged = {'n': n, 'pt_off': pt_off, 'xyzi': xyzi, 'labels': labels, 'label_bits': road_bits, 'box_off': box_off, 'boxes': boxes,
                   'counts': counts, 'perms': perms, 'n_events': n_events, 'total': total}
         if self.task == 'od':
             blobs, moff, dims = [], [0], np.zeros((n, 2, 4), dtype=np.int32)
@@ -248,7 +258,8 @@ class Real3DEngine:
         b.point_offsets = staged['pt_off'].ctypes.data
         b.xyzi = staged['xyzi'].ctypes.data
         b.labels = None
-        b.labels16 = staged['labels'].ctypes.data
+        b.labels16 = None if staged.get('label_bits') else staged['labels'].ctypes.data
+        b.labels1 = staged['labels'].ctypes.data if staged.get('label_bits') else None
         b.box_offsets = staged['box_off'].ctypes.data
         b.boxes = staged['boxes'].ctypes.data if staged['boxes'].size else None
         if self.task == 'od':
