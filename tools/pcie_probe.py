@@ -1,5 +1,5 @@
 """The PCIe / host-memory ceiling of the end-to-end leg, on its own: the bytes one step of the headline workload moves
-(H2D 564 MB, D2H 504 MB) between pinned host memory and the device on two streams, no kernels, every rank at once.
+(H2D 506 MB, D2H 504 MB) between pinned host memory and the device on two streams, no kernels, every rank at once.
   python tools/pcie_probe.py                       (one GPU)
   torchrun --nproc-per-node N tools/pcie_probe.py  (N GPUs of one box: the aggregate is what the host side sustains)
 `bench.py` runs the same probe after its e2e leg and reports it as `e2e.copy_only`."""
@@ -9,7 +9,7 @@ sys.path.insert(0, ROOT)
 import torch
 import bench
 
-H2D, D2H, STEPS = 563873792, 503802292, 20
+H2D, D2H, STEPS = 506273792, 503802292, 20
 
 
 def main():
