@@ -423,12 +423,15 @@ class Bench:
         self.n_scans = len(self.cases)
         kw = engine_kwargs(name, self.cases)
         c0 = self.cases[0]
-        self.pipe = ScanPipeline(self.w["task"], c0.config, c0.db, depth=args.depth, **kw)
+        # engines of the e2e pipeline: --depth, more for the semseg workloads (a batch's walker ends with a few long scans:
+        # more batches in flight keep the device busy while the copies of the others run)
+        self.depth = max(args.depth, self.w.get("e2e_depth", 0))
+        self.pipe = ScanPipeline(self.w["task"], c0.config, c0.db, depth=self.depth, **kw)
         # engines the device-resident leg deals its steps to: --resident-depth, or the workload's own figure when the
         # flag is left at its default (semseg scans differ a lot in the tries they need — the walker of one batch ends
         # with a few long scans, which more resident batches fill)
         self.res_depth = max(1, args.resident_depth if args.resident_depth > 0 else self.w.get("resident", 3))
-        self.extra = [Real3DEngine(self.w["task"], c0.config, c0.db, **kw) for _ in range(self.res_depth - args.depth)]
+        self.extra = [Real3DEngine(self.w["task"], c0.config, c0.db, **kw) for _ in range(self.res_depth - self.depth)]
         self.res_engines = (self.pipe.engines + self.extra)[:self.res_depth]
         self.eng = self.pipe.engines[0]
         self.staged = self.eng.stage([scan_input_from_case(c) for c in self.cases])
@@ -602,7 +605,7 @@ def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_ov
         out = {"config": workload_config(name, world), "value": world * b.n_scans * steps / (dev_ms / 1e3), "unit": "scans/s",
                "ms_per_step": dev_ms / steps, "steps": steps, "resident_engines": b.res_depth, "single_batch_ms": serial_ms,
                "e2e": {"value": scans_e2e / e["seconds"], "unit": "scans/s", "h2d_bytes_per_step": e["h2d"],
-                       "d2h_bytes_per_step": e["d2h"], "batches": e["batches"],
+                       "d2h_bytes_per_step": e["d2h"], "batches": e["batches"], "pipeline_depth": b.depth,
                        "pcie_gbs_each_way": round(max(e["h2d"], e["d2h"]) * e["batches"] / e["seconds"] / 1e9, 1)},
                "dominant_kernel": {top: table[top]},
                "streaming_kernels": {k: {"ms_per_step": v["ms_per_step"], "frac": v["frac"]} for k, v in table.items() if "frac" in v},
@@ -715,7 +718,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(name, 20.0)
-    res_depth = b.res_depth
+    res_depth, b_depth = b.res_depth, b.depth
     b.close()
     configs = {}
     for side in [s for s in args.side_configs.split(",") if s and s != name]:
@@ -733,7 +736,7 @@ def main():
             "roofline": roofline, "roofline_streaming": roofline_streaming, "step_traffic": step_traffic,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": e["h2d"], "d2h_bytes_per_step": e["d2h"],
-                    "pipeline_depth": args.depth, "ms_per_step": 1000.0 * e["seconds"] / e["batches"],
+                    "pipeline_depth": b_depth, "ms_per_step": 1000.0 * e["seconds"] / e["batches"],
                     "pcie_gbs_each_way": round(max(e["h2d"], e["d2h"]) * e["batches"] / e["seconds"] / 1e9, 1),
                     "copy_only": copy_only, "of_copy_only": round(e2e_value / copy_only["scans_per_s"], 3),
                     "timed": "H2D of the staged batch (pinned), ingest + walker + compaction, D2H of the augmented clouds into "

@@ -283,6 +283,8 @@ typedef struct r3d_batch_result {
     double* inserted_box;   /* n_scans x max_events x 8: cx cy cz m00 m10 length width height of the placed box */
     int32_t* status;        /* n_scans: 0 or a negative R3D_ERR_* */
     int32_t* rounds;        /* 1: device rounds the batch took */
+    uint16_t* out_labels16; /* capacity_points, alternative to out_labels: the same labels as 16-bit values (they are & 0xFFFF,
+                               od/ds:65) — 2 instead of 4 bytes per point over PCIe; may be NULL */
 } r3d_batch_result;
 
 int r3d_engine_create(const r3d_engine_cfg* cfg, r3d_engine** out);

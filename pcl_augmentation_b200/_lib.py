@@ -54,7 +54,7 @@ class BatchResult(C.Structure):
     _fields_ = [("out_offsets", C.c_void_p), ("out_xyzi", C.c_void_p), ("out_labels", C.c_void_p),
                 ("capacity_points", C.c_int64), ("check_offsets", C.c_void_p), ("check_xyzil", C.c_void_p),
                 ("capacity_check", C.c_int64), ("n_inserted", C.c_void_p), ("inserted", C.c_void_p),
-                ("inserted_box", C.c_void_p), ("status", C.c_void_p), ("rounds", C.c_void_p)]
+                ("inserted_box", C.c_void_p), ("status", C.c_void_p), ("rounds", C.c_void_p), ("out_labels16", C.c_void_p)]
 
 
 # name -> (restype, argtypes); must list every symbol declared in include/real3d_b200.h

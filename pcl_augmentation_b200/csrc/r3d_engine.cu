@@ -87,7 +87,7 @@ struct r3d_engine {
         inserted_box;
     DevBuf<float> tail_i, obj_i, check, out_check;
     DevBuf<unsigned> label, dmask, vmask, occ_win, unplaceable, obj_label, out_label, tickets;
-    DevBuf<unsigned short> col, cand_list, label16;
+    DevBuf<unsigned short> col, cand_list, label16, out_label16;
     DevBuf<unsigned char> label1;
     DevBuf<long long> pt_off;
     DevBuf<int> chunk_cnt, pix, gate_update, gate_try, gate_apply, gate_full, gate_patch, cf_rect, col_off, col_idx, acell, active_count, far_arr, od_map_dims, counts, perms, class_list_off,
@@ -147,6 +147,9 @@ __global__ void k_expand_label_bits(const unsigned char* bits, const long long* 
         const long long i = o + p;
         label[(size_t)b * P + p] = ((bits[i >> 3] >> (i & 7)) & 1u) ? road_label : other;
     }
+}
+__global__ void k_narrow_labels(const unsigned* src, unsigned short* dst, long long n) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) dst[i] = (unsigned short)src[i];
 }
 __global__ void k_set_round(unsigned* round_ctl, unsigned seq_base) { round_ctl[0] = 0u; round_ctl[1] = seq_base; }
 __global__ void k_fill_u64(unsigned long long* p, size_t n, unsigned long long v) {
@@ -985,6 +988,11 @@ extern "C" int r3d_engine_fetch(r3d_engine* eng, r3d_batch_result* res) {
     if (res->check_offsets) memcpy(res->check_offsets, eng->h_offsets + d.B + 1, (n + 1) * sizeof(long long));
     if (res->out_xyzi && total) R3D_CUDA(cudaMemcpyAsync(res->out_xyzi, eng->out_xyzi.p, (size_t)total * sizeof(float4), cudaMemcpyDeviceToHost, st));
     if (res->out_labels && total) R3D_CUDA(cudaMemcpyAsync(res->out_labels, eng->out_label.p, (size_t)total * sizeof(unsigned), cudaMemcpyDeviceToHost, st));
+    if (res->out_labels16 && total) {                  // 16-bit labels over PCIe (widened again by the caller)
+        if ((size_t)total > eng->out_label16.n) TRY(eng->out_label16.alloc((size_t)d.B * d.P));
+        k_narrow_labels<<<eng->n_sms * 4, 256, 0, st>>>(eng->out_label.p, eng->out_label16.p, total); r3d_count_launch();
+        R3D_CUDA(cudaMemcpyAsync(res->out_labels16, eng->out_label16.p, (size_t)total * sizeof(unsigned short), cudaMemcpyDeviceToHost, st));
+    }
     if (res->check_xyzil && total_check) R3D_CUDA(cudaMemcpyAsync(res->check_xyzil, eng->out_check.p, (size_t)total_check * 5 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (res->inserted) R3D_CUDA(cudaMemcpyAsync(res->inserted, eng->inserted.p, (size_t)n * d.max_events * 4 * sizeof(int), cudaMemcpyDeviceToHost, st));
     if (res->inserted_box) R3D_CUDA(cudaMemcpyAsync(res->inserted_box, eng->inserted_box.p, (size_t)n * d.max_events * 8 * sizeof(double), cudaMemcpyDeviceToHost, st));

@@ -309,7 +309,7 @@ class Real3DEngine:
         if buffers is None or buffers['cap_points'] < rows or buffers['cap_check'] < chk:
             cap_p, cap_c = max(rows, 1), max(chk, 1)
             buffers = {'cap_points': cap_p, 'cap_check': cap_c, 'xyzi': _pinned((cap_p, 4), np.float32),
-                       'labels': _pinned((cap_p,), np.int32), 'check': _pinned((cap_c, 5), np.float32)}
+                       'labels': _pinned((cap_p,), np.int16), 'check': _pinned((cap_c, 5), np.float32)}   # labels: 16 bit over PCIe
         buffers.update(out_off=np.zeros(n + 1, dtype=np.int64), check_off=np.zeros(n + 1, dtype=np.int64),
                        n_inserted=np.zeros(n, dtype=np.int32), inserted=np.zeros((n, self.max_events, 4), dtype=np.int32),
                        inserted_box=np.zeros((n, self.max_events, 8), dtype=np.float64),
@@ -317,7 +317,8 @@ class Real3DEngine:
         r = _lib.BatchResult()
         r.out_offsets = buffers['out_off'].ctypes.data
         r.out_xyzi = buffers['xyzi'].ctypes.data
-        r.out_labels = buffers['labels'].ctypes.data if self.fetch_labels else None
+        r.out_labels = None
+        r.out_labels16 = buffers['labels'].ctypes.data if self.fetch_labels else None
         r.capacity_points = buffers['cap_points']
         r.check_offsets = buffers['check_off'].ctypes.data
         r.check_xyzil = buffers['check'].ctypes.data
@@ -328,7 +329,7 @@ class Real3DEngine:
         r.status = buffers['status'].ctypes.data
         r.rounds = buffers['rounds'].ctypes.data
         _lib.check(self.lib.r3d_engine_fetch(self.handle, C.byref(r)), "fetch")
-        buffers['out_bytes'] = rows * (20 if self.fetch_labels else 16) + chk * 20
+        buffers['out_bytes'] = rows * (18 if self.fetch_labels else 16) + chk * 20
         return buffers
 
     def outputs_on_device(self):
@@ -376,7 +377,7 @@ class Real3DEngine:
                     lines.append(bx.create_annotation_line(self.obj_strings[obj], box, rot * (360.0 / self.yaw_steps)))
             chk = np.array(buffers['check'][ca:cb])
             out.append(ScanResult(velodyne=np.array(buffers['xyzi'][a:b]),
-                                  labels=(np.array(buffers['labels'][a:b]).view(np.uint32) if self.fetch_labels
+                                  labels=(np.array(buffers['labels'][a:b]).view(np.uint16).astype(np.uint32) if self.fetch_labels
                                           else np.zeros(0, dtype=np.uint32)),
                                   check=chk if ss else chk[:, :4], inserted=inserted, lines=lines, boxes=boxes,
                                   visible=visible, status=st, extra={'rounds': int(buffers['rounds'][0])}))
