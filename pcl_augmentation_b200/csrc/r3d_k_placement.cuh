@@ -473,20 +473,34 @@ __device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, cons
 // `part` of `nparts` warps work on the same candidate (the walker hands spare warps of a chunk to its candidates): the
 // rows of the obstacle grid are dealt to the parts, the tails / scene boxes are the last part's; `shared_hit` (shared
 // memory, zeroed by the caller) carries a hit to the other parts
+// `witness` (shared memory, -1 = none): index of the original point that made an earlier candidate of this try collide.
+// Neighbouring yaws turn the box by a fraction of a degree, so the same obstacle usually sits in the next candidate's box
+// too: it is tested first (the same exact test as in the walk below, so a hit is a hit), and most colliding candidates of a
+// try that fails never walk the grid at all.
 __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c, double sn,
-                              double level, int lane, int part = 0, int nparts = 1, volatile int* shared_hit = nullptr) {
+                              double level, int lane, int part = 0, int nparts = 1, volatile int* shared_hit = nullptr,
+                              int* witness = nullptr) {
     const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
     const YawTest yt = make_yaw_test(yb, level, ob.length, ob.width, ob.height);
     {
         const double zmin_ped = add(level, 0.1);                                  // od/fs:123-124
         const bool ped = cc.pedestrian != 0;
         const size_t base = (size_t)b * e.P;
+        if (witness != nullptr) {
+            const int wp = *(volatile int*)witness;
+            if (wp >= 0) {
+                const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + wp]);
+                const double x = v.x, yy = v.y, z = v.z;
+                if ((!ped || z >= zmin_ped) && inside_yaw(yt, x, yy, z) && obstacle_point(e, b, s, cc, base, wp)) return true;
+            }
+        }
         const int G = e.G;
         const float fcx = (float)yb.cx, fcy = (float)yb.cy, fr = (float)ob.reach + 1e-3f, fr2 = fr * fr;
         const float zlo = (float)level - 1e-3f, zhi = (float)(level + ob.height) + 1e-3f;
         const CellRect rc{grid_coord(e, fcx - fr), grid_coord(e, fcx + fr), grid_coord(e, fcy - fr), grid_coord(e, fcy + fr)};
         const unsigned ok_slots = e.task == 1 ? cc.ok_slots : 0u;       // OD tags carry slot 0 and no class accepts it here
         bool hit = false;
+        int hit_p = -1;
         warp_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, lane, [&](const float4& v) {
             if (hit) return;
             const unsigned tag = __float_as_uint(v.w);
@@ -496,9 +510,13 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
             const double x = v.x, yy = v.y, z = v.z;
             if (ped && !(z >= zmin_ped)) return;
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
-            if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) hit = true;
+            if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) { hit = true; hit_p = (int)(tag & APT_IDX_MASK); }
         }, [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && *shared_hit != 0); }, part, nparts);
-        if (__any_sync(0xffffffffu, hit)) return true;
+        const unsigned hm = __ballot_sync(0xffffffffu, hit);
+        if (hm) {
+            if (witness != nullptr && lane == __ffs(hm) - 1) *witness = hit_p;         // one word: no torn witness
+            return true;
+        }
     }
     if (part != nparts - 1 || (shared_hit != nullptr && *shared_hit != 0)) return false;
     return group_collides_rest<32>(e, b, s, ob, cc, yb, yt, c, sn, level, lane, 0xffffffffu);

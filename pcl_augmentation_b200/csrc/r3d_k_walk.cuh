@@ -94,6 +94,7 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     unsigned long long wtolp[WALK_W], wtolb[WALK_W];   // its parts while the map test runs: min over on-map points, max over off-map points
     int wbad[WALK_W];
     int whit[WALK_W];            // collision found by one of the warps that share a candidate
+    int witness;                 // original point that made an earlier candidate of the try collide (-1: none yet)
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
     int s_warp[WALK_NWARPS];
@@ -426,7 +427,7 @@ __device__ R3D_WALK_FN void walk_collides(const EngineDev& e, int b, const ScanS
     if (t >= n) return;
     const int i = list[t], k = c.wk[i];
     const long long t0 = clock64();
-    const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane, part, wpc, &c.whit[i]);
+    const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane, part, wpc, &c.whit[i], &c.witness);
     if (lane == 0) {
         if (hit) { c.whit[i] = 1; c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE); }
         if (part == 0) { atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull); }
@@ -610,7 +611,7 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
     if (tid == 0) {
         c.ob = e.obj[s.cur_obj];
         e.try_obj[b] = c.ob;
-        c.n_feas = 0; c.found = -1; c.last_k = 0; c.last_level = 0.0; c.dz_run = 0.0;
+        c.n_feas = 0; c.found = -1; c.last_k = 0; c.last_level = 0.0; c.dz_run = 0.0; c.witness = -1;
         const ClassCfg& tc = e.classes[c.ob.cls];
         c.n_surf = tc.n_surface;
         for (int i = 0; i < R3D_MAX_SURFACE; ++i) c.surf[i] = i < tc.n_surface ? (unsigned)tc.surface[i] : 0xFFFFFFFFu;
