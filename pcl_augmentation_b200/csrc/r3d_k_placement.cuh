@@ -383,8 +383,9 @@ __device__ __forceinline__ bool extent_may_touch_box(const ObjBox& ob, const Yaw
 // bounding circles only prune.
 // (part 2 of the collision test) obstacle points among the inserted objects' tails + object points inside scene boxes
 template <int NL = GRP>
-__device__ bool group_collides_rest(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
-                                    const YawBox& yb, const YawTest& yt, double c, double sn, double level, int gl, unsigned gm);
+__device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc,
+                                                 const YawBox& yb, const YawTest& yt, double c, double sn, double level, int gl,
+                                                 unsigned gm);
 
 template <int NL = GRP>
 __device__ bool group_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c,
