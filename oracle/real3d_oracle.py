@@ -546,7 +546,8 @@ def augment_scan(task, scene_pcl5, scene_box_lines, db, counts, perms, config, *
                                                                      min_elevation)
         scene_train, scene_label = smooth_out(scene_train, scene_label)
         if ss:
-            map_arr, map_move = addjust_map_2(FreshDict(map_data), scene_pcl, transform_matrix)
+            map_arr, map_move = addjust_map_2(FreshDict(map_data), scene_pcl, transform_matrix,
+                                              config['insertion'].get('road_indexes', ROAD_INDEXES))   # the name ss/ins:209 reads
         scene_pcl_backup = scene_pcl.copy()
         orig_index_backup = orig_index.copy()
         if trace is not None:

@@ -343,3 +343,22 @@ def test_walk_profile_reports_every_scan():
     eng.close()
     assert len(cycles) == 3 and (cycles > 0).all()
     assert all(t >= len(r.inserted) for t, r in zip(tries, res))
+
+
+def test_ground_labels_of_addjust_map_2_come_from_the_config():
+    """ss/ins:209 reads a list of ground labels (`ROAD_INDEXES`) that the reference's semseg script never defines; the
+    engine takes od/fs:14's [40, 44, 48] unless the config names others (`insertion.road_indexes`, as the shipped
+    waymo.yaml does).  With another list the occupied map cells — and with them the placements — change, on the device
+    exactly as in the oracle."""
+    import copy
+    case = synth.make_case("ss", 871, shape=GOLDEN_SHAPE, counts=[1, 1, 0, 1, 1, 0], n_cars=6, obj_range=(4.0, 16.0))
+    ref0, _ = oracle_run(case)
+    case.config = copy.deepcopy(case.config)
+    case.config["insertion"]["road_indexes"] = [40]          # sidewalk / parking points now occupy their map cells
+    ref, want = oracle_run(case)
+    eng = make_engine(case)
+    assert eng.road_indexes == [40]
+    got = eng.augment_batch([scan_input_from_case(case)])[0]
+    eng.close()
+    assert_matches_oracle(case, got, ref, want)
+    assert [(n, int(r)) for n, r, _ in ref["inserted"]] != [(n, int(r)) for n, r, _ in ref0["inserted"]], "the list must matter on this case"
