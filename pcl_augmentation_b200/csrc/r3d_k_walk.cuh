@@ -23,6 +23,7 @@
 constexpr int WALK_THREADS = R3D_WALK_THREADS;
 constexpr int WALK_CTAS_PER_SM = R3D_WALK_CTAS_PER_SM;
 constexpr int WALK_W = WALK_THREADS / GRP;            // candidates per window = 8-lane groups of the CTA
+constexpr int WALK_Q = WALK_W + WALK_THREADS / 32;    // candidate records: a window's worth + the leftover of a chunk (the OD queue)
 constexpr int WALK_SEL_PTS = 1024;                    // object points / tile pixels the selection keeps in shared memory
 #ifndef R3D_WALK_SEL_TILE
 #define R3D_WALK_SEL_TILE 4096
@@ -78,22 +79,26 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     int changed;
     int cnt_lo[WALK_OCC_PAR], cnt_hi[WALK_OCC_PAR];
     int exact_cnt;
-    int wk[WALK_W];              // rotation of the window's candidates
-    unsigned char wflag[WALK_W];
-    double wlevel[WALK_W];
+    int wk[WALK_Q];              // rotation of the candidates (semseg: a window's; OD: the ring of on-map candidates)
+    unsigned char wflag[WALK_Q];
+    double wlevel[WALK_Q];
     int wfeas[WALK_W];           // window-local indices of the feasible candidates, in rotation order
     int won[WALK_W];             // window-local indices of the candidates the next sub-stage works on
     int wsub[WALK_W];            // chunk-local list (candidates of the chunk that have a road level)
     int n_sub;
     int next;                    // dynamic task counter of a sub-stage
-    double wcx[WALK_W], wcy[WALK_W];     // centre of the window's candidates (the box centre turned about the sensor)
+    double wcx[WALK_Q], wcy[WALK_Q];     // centre of the candidates (the box centre turned about the sensor)
+    int a_k[WALK_W];             // OD stage A (map test) of a window, before the on-map ones join the queue
+    unsigned char a_on[WALK_W];
+    double a_cx[WALK_W], a_cy[WALK_W];
+    int wlist[WALK_THREADS / 32];        // records of the chunk being worked on (OD)
     unsigned surf[R3D_MAX_SURFACE];      // labels the tried class may stand on (road-level search)
     int n_surf;
     double wdz[WALK_W];          // semseg fixed point: the shift candidate i was (or must be) tested under
     double wtol[WALK_W];         // ... and how far the shift may move from it without changing the verdict of the map test
     unsigned long long wtolp[WALK_W], wtolb[WALK_W];   // its parts while the map test runs: min over on-map points, max over off-map points
     int wbad[WALK_W];
-    int whit[WALK_W];            // collision found by one of the warps that share a candidate
+    int whit[WALK_Q];            // collision found by one of the warps that share a candidate
     int witness;                 // original point that made an earlier candidate of the try collide (-1: none yet)
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
@@ -655,42 +660,60 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
     const ImageGeom geom = s.geom;
     const FastGeom fgeom = make_fast_geom(geom);
     const double* smooth = e.smooth + (size_t)b * e.hw;
-    for (int base = 0; base < n_list; base += WALK_W) {
-        const int nw = min(WALK_W, n_list - base);
-        // stage A: the map test of the window's candidates -> ordered list c.won of the ones that go on.  OD: on-map test
-        // on every object point (an 8-lane group per candidate); semseg: the fixed-point walk incl. the road levels
-        int n_on;
+    // Stage A (the map test of a window of candidates) feeds a queue of on-map candidates in yaw order; stages B + C take
+    // them off the queue in CHUNKS of one candidate per warp: road level (OD) -> collision test -> occlusion count of the
+    // chunk's feasible candidates, leaving at the first candidate that keeps min_points (od/ins:530-561).  The first
+    // feasible candidates of a try are the likely winners, so the first chunk runs on whatever the first non-empty window
+    // yields; after that (OD) stage A runs ahead until a whole chunk is waiting, so that a sparse window does not cost a
+    // round of road levels / collisions / occlusion for two candidates.  Semseg keeps window-by-window chunks: its stage
+    // A already carries the road levels (the z shift walks from yaw to yaw).
+    int base = 0, q_head = 0, q_n = 0, ss_c0 = 0, ss_n = 0;
+    bool first_chunk = true;
+    for (;;) {
+        const int* chunk;
+        int nch;
         if (e.task == 0) {
-            if (g < nw) {
-                const int k = s_list[base + g];
-                const bool on = walk_onmap_od(e, b, ob, cc, ox, oy, k, gl, gm);
-                if (gl == 0) {
-                    const double ck = e.cos_k[k], sk = e.sin_k[k];
-                    c.wk[g] = k; c.wflag[g] = on ? CF_ONMAP : 0; c.wlevel[g] = 0.0;
-                    c.wcx[g] = sub(mul(ck, ob.cx), mul(sk, ob.cy)); c.wcy[g] = add(mul(sk, ob.cx), mul(ck, ob.cy));
+            while (base < n_list && (first_chunk ? q_n == 0 : q_n < WALK_NWARPS)) {
+                const int nw = min(WALK_W, n_list - base);
+                if (g < nw) {                                 // A5 + A6a on every object point, an 8-lane group per candidate
+                    const int k = s_list[base + g];
+                    const bool on = walk_onmap_od(e, b, ob, cc, ox, oy, k, gl, gm);
+                    if (gl == 0) {
+                        const double ck = e.cos_k[k], sk = e.sin_k[k];
+                        c.a_k[g] = k; c.a_on[g] = on ? 1 : 0;
+                        c.a_cx[g] = sub(mul(ck, ob.cx), mul(sk, ob.cy)); c.a_cy[g] = add(mul(sk, ob.cx), mul(ck, ob.cy));
+                    }
                 }
+                __syncthreads();
+                if (tid == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_ONMAP], (unsigned long long)(n - clk.t)); }
+                const int n_on = walk_window_list(c, nw, c.won, [&](int i) { return c.a_on[i] != 0; });
+                if (tid < n_on) {                             // append to the queue (a ring over the candidate records)
+                    const int slot = (q_head + q_n + tid) % WALK_Q, i = c.won[tid];
+                    c.wk[slot] = c.a_k[i]; c.wflag[slot] = CF_ONMAP; c.wlevel[slot] = 0.0; c.wcx[slot] = c.a_cx[i]; c.wcy[slot] = c.a_cy[i];
+                }
+                if (tid == 0) { atomicAdd(&e.stats[7], (unsigned long long)n_on); atomicAdd(&e.stats[9], 1ull); }
+                __syncthreads();
+                q_n += n_on;
+                base += WALK_W;
             }
+            if (q_n == 0) break;
+            nch = min(WALK_NWARPS, q_n);
+            if (tid < nch) c.wlist[tid] = (q_head + tid) % WALK_Q;
+            if (tid == 0) c.next = 0;
             __syncthreads();
-            if (tid == 0) { const long long n = clock64(); atomicAdd(&e.stats[WALK_T0 + WT_ONMAP], (unsigned long long)(n - clk.t)); }
-            n_on = walk_window_list(c, nw, c.won, [&](int i) { return (c.wflag[i] & CF_ONMAP) != 0; });
-            if (tid == 0) atomicAdd(&e.stats[7], (unsigned long long)n_on);
+            chunk = c.wlist;
         } else {
-            n_on = walk_window_ss(e, b, s, c, ox, oy, oz, base, nw);
+            while (ss_c0 >= ss_n && base < n_list) {
+                ss_n = walk_window_ss(e, b, s, c, ox, oy, oz, base, min(WALK_W, n_list - base));
+                ss_c0 = 0;
+                base += WALK_W;
+                if (tid == 0) atomicAdd(&e.stats[9], 1ull);
+            }
+            if (ss_c0 >= ss_n) break;
+            nch = min(WALK_NWARPS, ss_n - ss_c0);
+            chunk = c.won + ss_c0;
         }
-        if (tid == 0) atomicAdd(&e.stats[9], 1ull);
-        // stages B + C in CHUNKS of the ordered list, one candidate per warp: road level (OD) -> collision test -> occlusion
-        // count of the chunk's feasible candidates, leaving at the first candidate that keeps min_points (od/ins:530-561).
-        // The first feasible candidates of a try are the likely winners: evaluating the whole window at once spent most
-        // of its road-level / collision work on candidates that are never looked at.
-#ifndef R3D_WALK_FIRST_CHUNK
-#define R3D_WALK_FIRST_CHUNK 0                       // 0 = every chunk holds one candidate per warp
-#endif
-        for (int c0 = 0, nch = 0; c0 < n_on && c.found < 0; c0 += nch) {
-            // the very first chunk of a try may be shorter: its candidates are the likeliest winners, a full chunk spends
-            // road-level / collision work on candidates that are never looked at (the spare warps share the collisions)
-            const int cap = (R3D_WALK_FIRST_CHUNK > 0 && base == 0 && c0 == 0) ? min(R3D_WALK_FIRST_CHUNK, WALK_NWARPS) : WALK_NWARPS;
-            nch = min(cap, n_on - c0);
-            const int* chunk = c.won + c0;
+        {
             if (e.task == 0) {
                 walk_levels(e, b, c, chunk, nch);
                 __syncthreads();
@@ -758,6 +781,8 @@ __device__ R3D_WALK_FN void walk_try(const EngineDev& e, int b, ScanState& s, Wa
             clk.lap(e, WT_OCCL);
         }
         if (c.found >= 0) break;
+        if (e.task == 0) { q_head = (q_head + nch) % WALK_Q; q_n -= nch; first_chunk = false; }
+        else ss_c0 += nch;
     }
     // A11 + A12 for the chosen candidate: the first one that keeps min_points, else the last feasible one (its
     // vis_px still deletes scene points in the reference, od/ins:472-501)
