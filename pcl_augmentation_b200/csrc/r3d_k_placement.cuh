@@ -235,8 +235,11 @@ __device__ bool warp_road_level(const EngineDev& e, int b, const unsigned* __res
         for (int i = 0; i < n_surf; ++i) ok |= lab == surf[i];
         return ok;
     };
+#ifndef R3D_LEVEL_R0
+#define R3D_LEVEL_R0 1.5                            // first search radius in cells (any value gives the same result)
+#endif
     const double step = e.grid_cell;
-    double R = 1.5 * step;
+    double R = R3D_LEVEL_R0 * step;
     const int ring = e.gnear[(size_t)b * G * G + (size_t)grid_coord(e, (float)cy) * G + grid_coord(e, (float)cx)];
     if (ring >= 3) R = fmin((ring - 1) * step, 5.0);       // every cell closer than `ring` cells is empty
     double best = 1e300;
