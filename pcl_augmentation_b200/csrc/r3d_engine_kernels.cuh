@@ -25,8 +25,14 @@ __device__ __forceinline__ void set_error(ScanState& s, int code) {
 #include "r3d_k_output.cuh"
 // the per-scan walker in its two CTA shapes (see the head of r3d_k_walk.cuh)
 namespace walk_od {
-#define R3D_WALK_THREADS 384
-#define R3D_WALK_CTAS_PER_SM 3
+#ifndef R3D_WALK_OD_THREADS
+#define R3D_WALK_OD_THREADS 384
+#endif
+#ifndef R3D_WALK_OD_CTAS
+#define R3D_WALK_OD_CTAS 3
+#endif
+#define R3D_WALK_THREADS R3D_WALK_OD_THREADS
+#define R3D_WALK_CTAS_PER_SM R3D_WALK_OD_CTAS
 #include "r3d_k_walk.cuh"
 #undef R3D_WALK_THREADS
 #undef R3D_WALK_CTAS_PER_SM
