@@ -1,6 +1,9 @@
-// Kernels of the batched Real3D-Aug engine.  One "round" = one tried cut object for every unfinished scan of the
-// batch; the reference's nested Python loops (od/ins:375-614) are a per-scan state machine advanced on the device
-// (k_ctrl), so the host only launches a fixed kernel sequence per round and polls one counter.
+// Kernels of the batched Real3D-Aug engine, one header per stage.  Two execution models share them:
+//  * the per-scan walker (default; r3d_k_walk.cuh): streaming kernels once per scan (r3d_k_prepass.cuh, r3d_closefill.cuh,
+//    r3d_k_output.cuh) around ONE persistent CTA per scan that runs the reference's whole loop (od/ins:375-614);
+//  * the staged rounds of round 1 (r3d_k_ctrl / _update_project / _placement / _occlusion as kernels): one "round" = one
+//    tried cut object for every unfinished scan, the per-scan state machine advanced on the device (k_ctrl), the host
+//    launching a fixed kernel sequence per round.  Kept because it evaluates EVERY candidate of a try (debug_candidates).
 #pragma once
 #include "r3d_engine.cuh"
 #include "r3d_closefill.cuh"
