@@ -221,6 +221,55 @@ __device__ __forceinline__ void warp_visit(const int* __restrict__ cell, const f
     }
 }
 
+// ---- the same walk for the collision test of a long box: every row of cells is clipped to the columns the oriented box
+// can reach.  The box is the intersection of two slabs lo < ax x + ay y < hi (YawTest); over the y range of a row of
+// cells each slab bounds x by an interval that is linear in y, so its extremes sit at the row's edges.  A 10 m x 2.5 m
+// truck turned by 45 degrees covers ~180 of the 441 cells of its reach square.  `clip` = 6 floats per warp in shared memory
+// (A, B, S per slab: x in (A - S y, B - S y); a slab that is nearly parallel to the x axis does not bound x: A = -1e6,
+// B = 1e6, S = 0); float arithmetic with 2 cm of padding on both axes (coordinates < 200 m, |S| <= 20: errors < 1e-3 m),
+// so a point inside the box is never skipped; the exact test in `f` still decides.  Points beyond the grid extent are
+// clamped into the border cells by grid_coord, which is monotone: border ROWS are not clipped, border columns need no care.
+#ifndef R3D_CLIP_MIN_COLS
+#define R3D_CLIP_MIN_COLS 4          // rectangles narrower than this many cells take the plain walk; 0 = never clip
+#endif
+constexpr float CLIP_PAD = 0.02f;
+struct YawTest;
+__device__ __forceinline__ void make_row_clip(const YawTest& t, float* clip);
+template <class F, class S>
+__device__ __forceinline__ void warp_visit_clipped(const EngineDev& e, const int* __restrict__ cell, const float4* __restrict__ pts,
+                                                   const CellRect& rc, int lane, const float* clip, F f, S stop, int part = 0,
+                                                   int nparts = 1) {
+    const int sub = lane >> 3, sl = lane & 7, G = e.G;
+    const float cellf = (float)e.grid_cell;
+    for (int y0 = rc.y0 + 4 * part; y0 <= rc.y1; y0 += 4 * nparts) {
+        const int y = y0 + sub;
+        if (y <= rc.y1) {
+            int x0 = rc.x0, x1 = rc.x1;
+            if (y > 0 && y < G - 1) {
+                const float ylo = (float)(y - (G >> 1)) * cellf - CLIP_PAD, yhi = ylo + cellf + 2.f * CLIP_PAD;
+                const float a0 = clip[2] * ylo, b0 = clip[2] * yhi, a1 = clip[5] * ylo, b1 = clip[5] * yhi;
+                const float xmin = fmaxf(clip[0] - fmaxf(a0, b0), clip[3] - fmaxf(a1, b1)) - CLIP_PAD;
+                const float xmax = fminf(clip[1] - fminf(a0, b0), clip[4] - fminf(a1, b1)) + CLIP_PAD;
+                if (xmin > xmax) x1 = x0 - 1;
+                else { x0 = max(x0, grid_coord(e, xmin)); x1 = min(x1, grid_coord(e, xmax)); }
+            }
+            if (x0 <= x1) {
+                const int c0 = y * G + x0;
+                const int rb = c0 > 0 ? __ldg(&cell[c0 - 1]) : 0, re = __ldg(&cell[y * G + x1]);
+                for (int p = rb + sl; p < re; p += 16) {
+                    const float4 a = __ldg(&pts[p]);
+                    const bool two = p + 8 < re;
+                    float4 bq = a;
+                    if (two) bq = __ldg(&pts[p + 8]);
+                    f(a);
+                    if (two) f(bq);
+                }
+            }
+        }
+        if (stop()) return;
+    }
+}
+
 // A7 for one candidate centre, one warp (same result as group_road_level: the nearest surface point decides the radius
 // index whatever sequence of growing squares finds it).  CHECK_LABEL = false when the surface grid holds one label only (OD).
 template <bool CHECK_LABEL>
@@ -323,6 +372,19 @@ __device__ __forceinline__ bool inside_yaw(const YawTest& t, double x, double y,
     return (z < t.hi2) && (z > t.lo2);
 }
 
+// column bounds of a row of grid cells under this box (see warp_visit_clipped)
+__device__ __forceinline__ void make_row_clip(const YawTest& t, float* clip) {
+    const double ax[2] = {t.c0x, t.c1x}, ay[2] = {t.c0y, t.c0x}, lo[2] = {t.lo0, t.lo1}, hi[2] = {t.hi0, t.hi1};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float A = -1e6f, B = 1e6f, S = 0.f;
+        if (fabs(ax[k]) >= 0.05) {
+            const double inv = 1.0 / ax[k], p = lo[k] * inv, q = hi[k] * inv;
+            A = (float)fmin(p, q); B = (float)fmax(p, q); S = (float)(ay[k] * inv);
+        }
+        clip[3 * k] = A; clip[3 * k + 1] = B; clip[3 * k + 2] = S;
+    }
+}
 // rare paths of the collision test, kept out of line so the common path stays small (per-lane results):
 // obstacle points among the points of one already inserted object (its tail slice)
 template <int NL = GRP>
@@ -483,7 +545,7 @@ __device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, cons
 // try that fails never walk the grid at all.
 __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, const ObjBox& ob, const ClassCfg& cc, double c, double sn,
                               double level, int lane, int part = 0, int nparts = 1, volatile int* shared_hit = nullptr,
-                              int* witness = nullptr) {
+                              int* witness = nullptr, float* clip = nullptr) {
     const YawBox yb = make_yaw_box(ob.cx, ob.cy, ob.a, ob.b, c, sn);
     const YawTest yt = make_yaw_test(yb, level, ob.length, ob.width, ob.height);
     {
@@ -505,7 +567,7 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
         const unsigned ok_slots = e.task == 1 ? cc.ok_slots : 0u;       // OD tags carry slot 0 and no class accepts it here
         bool hit = false;
         int hit_p = -1;
-        warp_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, lane, [&](const float4& v) {
+        auto test_point = [&](const float4& v) {
             if (hit) return;
             const unsigned tag = __float_as_uint(v.w);
             if ((ok_slots >> (tag >> APT_IDX_BITS)) & 1u) return;        // semseg: ground the class may stand on (ss/fs:92-93)
@@ -515,7 +577,17 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
             if (ped && !(z >= zmin_ped)) return;
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
             if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) { hit = true; hit_p = (int)(tag & APT_IDX_MASK); }
-        }, [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && *shared_hit != 0); }, part, nparts);
+        };
+        auto stop = [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && *shared_hit != 0); };
+        if (R3D_CLIP_MIN_COLS > 0 && clip != nullptr && rc.x1 - rc.x0 + 1 >= R3D_CLIP_MIN_COLS) {     // warp-uniform
+            if (lane == 0) make_row_clip(yt, clip);
+            __syncwarp();
+            warp_visit_clipped(e, e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, rc, lane, clip, test_point, stop,
+                               part, nparts);
+            __syncwarp();                                                  // the next candidate of this warp rewrites `clip`
+        } else {
+            warp_visit(e.acell + (size_t)b * G * G, e.apts + (size_t)b * e.max_points, G, rc, lane, test_point, stop, part, nparts);
+        }
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm) {
             if (witness != nullptr && lane == __ffs(hm) - 1) *witness = hit_p;         // one word: no torn witness
