@@ -535,6 +535,14 @@ __device__ __noinline__ bool group_collides_rest(const EngineDev& e, int b, cons
     return false;
 }
 
+// A flag / hint word in shared memory that OTHER warps set while this one polls it (the shared hit flag of the warps that
+// split a candidate, the collision witness): read and written with shared-memory atomics, lane 0 reads for the warp
+// (any value is acceptable at any time, the atomics only make the accesses race-free for the memory model / racecheck)
+__device__ __forceinline__ int warp_peek(const volatile int* p, int lane) {
+    int v = 0;
+    if (lane == 0) v = atomicAdd(const_cast<int*>(p), 0);
+    return __shfl_sync(0xffffffffu, v, 0);
+}
 // A8 + A9 for one candidate, one warp: part (i) on the lean walk, the rest shared with group_collides
 // `part` of `nparts` warps work on the same candidate (the walker hands spare warps of a chunk to its candidates): the
 // rows of the obstacle grid are dealt to the parts, the tails / scene boxes are the last part's; `shared_hit` (shared
@@ -553,7 +561,7 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
         const bool ped = cc.pedestrian != 0;
         const size_t base = (size_t)b * e.P;
         if (witness != nullptr) {
-            const int wp = *(volatile int*)witness;
+            const int wp = warp_peek(witness, lane);
             if (wp >= 0) {
                 const float4 v = __ldg(&e.xyzi[(size_t)b * e.max_points + wp]);
                 const double x = v.x, yy = v.y, z = v.z;
@@ -578,7 +586,7 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
             if (!inside_yaw(yt, x, yy, z)) return;                       // exact test (cb:30-66)
             if (obstacle_point(e, b, s, cc, base, (int)(tag & APT_IDX_MASK))) { hit = true; hit_p = (int)(tag & APT_IDX_MASK); }
         };
-        auto stop = [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && *shared_hit != 0); };
+        auto stop = [&] { return __any_sync(0xffffffffu, hit) != 0 || (shared_hit != nullptr && warp_peek(shared_hit, lane) != 0); };
         if (R3D_CLIP_MIN_COLS > 0 && clip != nullptr && rc.x1 - rc.x0 + 1 >= R3D_CLIP_MIN_COLS) {     // warp-uniform
             if (lane == 0) make_row_clip(yt, clip);
             __syncwarp();
@@ -590,11 +598,11 @@ __device__ bool warp_collides(const EngineDev& e, int b, const ScanState& s, con
         }
         const unsigned hm = __ballot_sync(0xffffffffu, hit);
         if (hm) {
-            if (witness != nullptr && lane == __ffs(hm) - 1) *witness = hit_p;         // one word: no torn witness
+            if (witness != nullptr && lane == __ffs(hm) - 1) atomicExch(witness, hit_p);
             return true;
         }
     }
-    if (part != nparts - 1 || (shared_hit != nullptr && *shared_hit != 0)) return false;
+    if (part != nparts - 1 || (shared_hit != nullptr && warp_peek(shared_hit, lane) != 0)) return false;
     return group_collides_rest<32>(e, b, s, ob, cc, yb, yt, c, sn, level, lane, 0xffffffffu);
 }
 

@@ -100,12 +100,12 @@ struct WalkCtl {                 // control block of the CTA (static shared memo
     int wbad[WALK_W];
     int whit[WALK_Q];            // collision found by one of the warps that share a candidate
     int witness;                 // original point that made an earlier candidate of the try collide (-1: none yet)
-    float wclip[WALK_NWARPS][8]; // per warp: column bounds of the collision walk over a long box (make_row_clip)
     unsigned char wpass[WALK_W], wtodo[WALK_W], whok[WALK_W], whas[WALK_W];
     ObjBox ob;
     int s_warp[WALK_NWARPS];
     int upd_full, upd_patch, rect[4];
     unsigned long long el_min, el_max;
+    __align__(16) float wclip[WALK_NWARPS][8];     // per warp: column bounds of the collision walk over a long box (make_row_clip)
 };
 
 // ---- A4 on a pixel rectangle, any CTA size (the batch-wide kernel is r3d_closefill.cuh): tiles of CF_TH x CF_TW
@@ -436,7 +436,7 @@ __device__ R3D_WALK_FN void walk_collides(const EngineDev& e, int b, const ScanS
     const bool hit = warp_collides(e, b, s, ob, cc, e.cos_k[k], e.sin_k[k], c.wlevel[i], lane, part, wpc, &c.whit[i], &c.witness,
                                    c.wclip[warp]);
     if (lane == 0) {
-        if (hit) { c.whit[i] = 1; c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE); }
+        if (hit && atomicExch(&c.whit[i], 1) == 0) c.wflag[i] = (unsigned char)(CF_ONMAP | CF_HOK | CF_COLLIDE);   // the first of the warps that share it
         if (part == 0) { atomicAdd(&e.stats[WALK_T0 + WT_COLLIDE_WARP], (unsigned long long)(clock64() - t0)); atomicAdd(&e.stats[WALK_T0 + WT_N_COLLIDE], 1ull); }
     }
 }
