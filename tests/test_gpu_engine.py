@@ -291,6 +291,28 @@ def test_randomised_sweep_crowded_scenes_vs_oracle(task, counts, staged):
     assert placed >= 24
 
 
+def test_long_boxes_in_crowded_scenes_vs_oracle():
+    """Trucks (7 m x 2.5 m boxes: 16 x 16 cells of the obstacle grid under their reach circle) among 10 - 15 parked cars:
+    the collision walk clips every row of cells to the oriented box (warp_visit_clipped, od/fs:109-127 still decided by
+    the exact cut_bounding_box test), so a near miss at a box corner and a hit just inside a face must both come out as
+    in the oracle.  12 scans, three trucks and one motorcycle each; placement choices and keep-masks exact."""
+    cases = [synth.make_case("ss", 1230 + i, shape=GOLDEN_SHAPE, counts=[0, 1, 3, 0, 0, 0], obj_range=(4.0, 16.0),
+                             n_cars=10 + i % 6) for i in range(12)]
+    for c in cases[1:]:
+        c.pose, c.map_data = cases[0].pose, cases[0].map_data
+    eng = Real3DEngine("ss", cases[0].config, cases[0].db, max_scans=len(cases), max_points=max(len(c.pcl5) for c in cases),
+                       map_data=cases[0].map_data)
+    res = eng.augment_batch([scan_input_from_case(c) for c in cases])
+    stats = eng.stats()
+    eng.close()
+    placed = 0
+    for case, got in zip(cases, res):
+        ref, want = oracle_run(case)
+        assert_matches_oracle(case, got, ref, want)
+        placed += sum(1 for _, _, cls in got.inserted if int(cls) == 18)
+    assert placed >= 30 and stats["walker_detail"]["n_collide"] > 100          # trucks were placed, after many collision tests
+
+
 @pytest.mark.parametrize("task,seed,counts", [("od", 811, [2, 2]), ("ss", 812, [1, 1, 1, 0, 1, 0])])
 def test_points_next_to_bin_edges_take_the_exact_path(task, seed, counts):
     """The ingest and the occlusion counts bin with a float estimate of the angles where that is provably safe and fall
