@@ -591,6 +591,24 @@ def walk_spread(stats, clocks):
             "tries_p50": int(np.sort(tries)[len(tries) // 2]), "tries_max": int(tries.max())}
 
 
+WALK_CTAS_PER_SM = {"od": 3, "ss": 2}          # csrc/r3d_engine_kernels.cuh: walk_od 384 x 3, walk_ss 512 x 2
+
+
+def timed_mode_model(task, n_scans, table, cyc, prof_steps, clocks, ms_per_step, sm_count=None):
+    """Device time one step HOLDS when several resident batches overlap (the timed mode of `value`): a streaming kernel
+    fills the device for its serial duration, the walker holds n_scans CTA lifetimes spread over the CTA slots of the
+    device.  The two add up to about the measured step: the device is full, and the streaming kernels are the larger part."""
+    if sm_count is None:
+        import torch
+        sm_count = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    slots = sm_count * WALK_CTAS_PER_SM[task]
+    cta_ms = cyc.get("total", 0) / max(prof_steps * n_scans, 1) / ((clocks.get("sm_mhz") or 1965.0) * 1e3)
+    walker = n_scans * cta_ms / slots
+    streaming = sum(v["ms_per_step"] for k, v in table.items() if k != "scan_walk")
+    return {"walker_cta_slots": slots, "walker_slot_ms_per_step": round(walker, 4), "streaming_kernels_ms_per_step": round(streaming, 4),
+            "sum_ms": round(walker + streaming, 4), "measured_ms_per_step": round(ms_per_step, 4)}
+
+
 def measure_side_config(name, rank, world, args, barrier, max_over_ranks, sum_over_ranks, peak):
     """A short run of another BASELINE.json configuration: device-resident value, serial step + dominant kernel, e2e."""
     b = Bench(name, rank, world, args, barrier, max_over_ranks)
@@ -718,7 +736,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline_sample(name, 20.0)
-    res_depth, b_depth = b.res_depth, b.depth
+    res_depth, b_depth, b_task = b.res_depth, b.depth, b.w["task"]
     b.close()
     configs = {}
     for side in [s for s in args.side_configs.split(",") if s and s != name]:
@@ -753,6 +771,7 @@ def main():
                        "exact_occlusion_counts_per_try": stats["exact_occlusion_counts"] / max(stats["tried_objects"], 1),
                        "cta_ms_mean": round(cyc.get("total", 0) / max(prof_steps * n_scans, 1) / ((clocks.get("sm_mhz") or 1965.0) * 1e3), 4),
                        "cta_ms_percentiles": walk_spread(stats, clocks),
+                       "timed_mode_model": timed_mode_model(b_task, n_scans, table, cyc, prof_steps, clocks, dev_ms / args.steps),
                        "phase_share_of_cta_time": {k: round(v / max(cyc.get("total", 1), 1), 4) for k, v in cyc.items() if k != "total"}},
             "objects_inserted_per_scan": inserted_all / (world * n_scans),
             "configs": configs, "engine_stats": {k: v for k, v in stats.items() if k not in ("walker_cycles", "walk_profile")}})])

@@ -61,3 +61,16 @@ def test_committed_profile_records_are_consistent():
     for name in ("scan_walk", "scatter_project", "ingest_spherical", "close_fill_full", "compact_output"):
         assert n[name]["bytes_per_launch"] > 0 and n[name]["source"].startswith("profiles/r2_")
         assert os.path.exists(os.path.join(ROOT, n[name]["source"].split(" ")[0]))
+
+
+def test_timed_mode_model_adds_walker_slot_time_and_streaming_kernels():
+    """256 CTAs of 1.44 ms over 148 x 3 slots = 0.83 ms of device time next to 1.9 ms of streaming kernels."""
+    table = {"scan_walk": {"ms_per_step": 2.9}, "scatter_project": {"ms_per_step": 0.62}, "ingest_spherical": {"ms_per_step": 0.48},
+             "compact_output": {"ms_per_step": 0.30}, "close_fill_full": {"ms_per_step": 0.30}, "index_build": {"ms_per_step": 0.19}}
+    cyc = {"total": int(1.44e-3 * 1965e6) * 256 * 10}
+    m = bench.timed_mode_model("od", 256, table, cyc, 10, {"sm_mhz": 1965.0}, 2.95, sm_count=148)
+    assert m["walker_cta_slots"] == 444
+    assert abs(m["walker_slot_ms_per_step"] - 256 * 1.44 / 444) < 1e-3
+    assert abs(m["streaming_kernels_ms_per_step"] - 1.89) < 1e-9
+    assert abs(m["sum_ms"] - (m["walker_slot_ms_per_step"] + 1.89)) < 1e-3 and m["measured_ms_per_step"] == 2.95
+    assert bench.timed_mode_model("ss", 256, table, cyc, 10, {}, 13.0, sm_count=148)["walker_cta_slots"] == 296
