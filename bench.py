@@ -558,6 +558,9 @@ def kernel_table(bench, prof, steps, peak):
     return table, total / steps
 
 
+NOMINAL_HBM_GBS = 8000.0           # B200 HBM3e, nominal (B200_PROFILING.md quotes ~7.7 TB/s for this part)
+
+
 def roofline_of(name, entry, bench, peak, peak_src):
     """The JSON `roofline` object of one kernel-table entry."""
     rec = entry.get("ncu")
@@ -578,6 +581,9 @@ def roofline_of(name, entry, bench, peak, peak_src):
                    limiter={k: rec[k] for k in ("sm_throughput_pct", "issue_active_pct", "warps_active_pct") if k in rec})
     else:
         out.update(achieved=None, frac=None, bytes_source="no ncu capture committed for this kernel")
+    # both denominators — the copy bandwidth measured on this pod (`peak`) and the nominal HBM3e figure
+    out["frac_of_nominal"] = round(out["achieved"] / NOMINAL_HBM_GBS, 4) if out.get("achieved") is not None else None
+    out["nominal_peak"] = NOMINAL_HBM_GBS
     return out
 
 

@@ -33,13 +33,14 @@ def test_roofline_objects_have_the_contract_keys():
     for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic"):
         assert k in r
     assert r["frac"] <= 1.0 and r["bytes_per_launch"] == 8730240 * 256
+    assert r["nominal_peak"] == 8000.0 and abs(r["frac_of_nominal"] - 3600.0 / 8000.0) < 1e-4      # both denominators
     walker = {"ms_per_step": 2.8, "launches_per_step": 1.0, "share": 0.6, "bound": "latency / issue (no streaming model)",
               "ncu": {"bytes_per_launch": 432000000, "source": "profiles/x.csv", "sm_throughput_pct": 15.6, "issue_active_pct": 28.8,
                       "warps_active_pct": 29.7}}
     r = bench.roofline_of("scan_walk", walker, _FakeBench(), 6551.7, "measured")
     assert r["traffic"] == 432000000 and 0 < r["frac"] < 0.1 and r["limiter"]["issue_active_pct"] == 28.8
     r = bench.roofline_of("scan_walk", {k: v for k, v in walker.items() if k != "ncu"}, _FakeBench(), 6551.7, "measured")
-    assert r["achieved"] is None and r["frac"] is None and "no ncu capture" in r["bytes_source"]
+    assert r["achieved"] is None and r["frac"] is None and r["frac_of_nominal"] is None and "no ncu capture" in r["bytes_source"]
 
 
 def test_walk_spread_percentiles():
