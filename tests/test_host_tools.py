@@ -95,3 +95,67 @@ def test_reference_arm_recipe_lists_existing_reference_files():
         src = os.path.join(build_ref.SRC, rel)
         assert os.path.isfile(src), rel
         assert filecmp.cmp(src, os.path.join(build_ref.DST, rel), shallow=False), rel
+
+
+def _label_lines(n, seed):
+    from pcl_augmentation_b200 import synth
+    rng = np.random.default_rng(seed)
+    od, ss = [], []
+    for i in range(n):
+        yaw = rng.uniform(-np.pi, np.pi) if i % 7 else rng.choice([0.0, np.pi / 2, -np.pi / 2, np.pi, -np.pi, 1e-9])
+        dims, c = rng.uniform(0.4, 8, 3), rng.uniform(-60, 60, 3)
+        od.append(synth.od_label_line("Car", tuple(c), yaw, tuple(dims)) + "\n")
+        ss.append(synth.ss_label_line(18, tuple(c), yaw, tuple(dims)) + "\n")
+    return od, ss
+
+
+def test_batched_box_records_equal_the_per_line_path():
+    """read_label_line (od/fs:175-224, ss/fs:155-189) + the quaternion -> matrix step of cut_bounding_box (cb:28) for a
+    whole batch in one scipy call: every one of the 16 doubles per box bit-identical to the per-line path."""
+    from pcl_augmentation_b200 import boxes as bx
+    od, ss = _label_lines(400, 11)
+    for lines, is_ss, read in ((od, False, bx.read_label_line_od), (ss, True, bx.read_label_line_ss)):
+        want = np.array([bx.box_record(read(line)) for line in lines])
+        np.testing.assert_array_equal(bx.box_records_from_lines(lines, is_ss), want)
+        np.testing.assert_array_equal(bx.box_records_from_lines(lines[:1], is_ss), want[:1])
+    assert bx.box_records_from_lines([], False).shape == (0, 16)
+
+
+def test_stage_packs_scene_boxes_of_line_and_dictionary_scans():
+    """Real3DEngine.stage on the CPU (pageable buffers without a GPU): box offsets and records of a batch that mixes scans
+    with annotation lines, with box dictionaries and without boxes; labels as one Road bit per point for object detection."""
+    from types import SimpleNamespace
+    from pcl_augmentation_b200 import boxes as bx
+    from pcl_augmentation_b200.engine import Real3DEngine, ScanInput
+    od, _ = _label_lines(9, 12)
+    rng = np.random.default_rng(3)
+
+    def scan(n_pts, lines=None, dicts=None):
+        maps = {k: {"map": np.ones((4, 5), np.uint8), "min_x": np.array(-2), "min_y": np.array(-3)} for k in ("Road", "Sidewalk")}
+        return ScanInput(xyzi=rng.normal(size=(n_pts, 4)).astype(np.float32), labels=rng.choice([40, 1, 48], n_pts).astype(np.uint32),
+                         box_lines=lines or [], box_dicts=dicts, counts=np.array([1, 0]), perms=np.zeros((2, 2, 100), np.int32), maps=maps)
+    scans = [scan(50, od[:4]), scan(30), scan(20, dicts=[bx.read_label_line_od(l) for l in od[4:6]]), scan(10, od[6:])]
+    eng = SimpleNamespace(max_scans=8, task="od", classes=["Pedestrian", "Cyclist"], max_events=3, max_tries=100, road_label=40)
+    st = Real3DEngine.stage(eng, scans)
+    assert list(st["box_off"]) == [0, 4, 4, 6, 9] and list(st["pt_off"]) == [0, 50, 80, 100, 110]
+    np.testing.assert_array_equal(st["boxes"], np.array([bx.box_record(bx.read_label_line_od(l)) for l in od]))
+    road = np.concatenate([s.labels == 40 for s in scans])
+    np.testing.assert_array_equal(np.unpackbits(st["labels"], bitorder="little")[:110].astype(bool), road)
+    np.testing.assert_array_equal(st["xyzi"][50:80], scans[1].xyzi)
+
+
+def test_batched_placed_box_dictionaries_equal_the_per_box_path():
+    from pcl_augmentation_b200 import boxes as bx
+    rng = np.random.default_rng(2)
+    recs = []
+    for _ in range(200):
+        a = rng.uniform(-np.pi, np.pi)
+        recs.append([*rng.uniform(-50, 50, 3), np.cos(a), np.sin(a), *rng.uniform(0.5, 8, 3)])
+    for cls, ss in (("Cyclist", False), ("18", True)):
+        one = [bx.placed_box_dictionary(r, cls, ss) for r in recs]
+        many = bx.placed_box_dictionaries(recs, [cls] * len(recs), ss)
+        for a, b in zip(one, many):
+            assert a["rotation"] == b["rotation"] and a["center"] == b["center"] and a["class"] == b["class"]
+            assert (a["length"], a["width"], a["height"]) == (b["length"], b["width"], b["height"])
+            np.testing.assert_array_equal(a["_matrix"], b["_matrix"])
+    assert bx.placed_box_dictionaries([], [], False) == []
