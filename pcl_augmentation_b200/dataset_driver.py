@@ -4,7 +4,8 @@ files the reference writes (augmented cloud, ``check`` record, annotation / labe
 
 What is kept from the reference's loop: the per-frame marker file that makes concurrent runs skip frames in progress
 (od/ins:335-347) and is removed when nothing could be inserted (od/ins:616-620); ``generate_seed`` drawing the class
-counts from ``np.random`` (od/ins:171-187) and ``random.shuffle`` ordering each class's sample list (od/ins:400) — the
+counts from ``np.random`` (od/ins:171-187) and a uniform shuffle of each class's sample list per window (od/ins:400; seeded
+from ``random``, see ``_permutation_heads``) — the
 draws happen here on the host, once per frame, and are handed to the engine as tables, so a seeded ``random`` /
 ``np.random`` gives a reproducible run; ``setting.txt``; the run-folder numbering.
 """
@@ -46,20 +47,28 @@ def generate_seed(config):
     return seed
 
 
+def _permutation_heads(n_events, list_lens, tries):
+    """One uniformly shuffled order of every class's (sorted) sample list per possible window — what ``random.shuffle``
+    gives the reference at od/ins:399-402 — as an int32 table [event][class][try]; only the first ``tries`` entries of a
+    shuffle can be visited before the next one.  The reference draws its shuffles where the loop needs them, so its
+    stream cannot be reproduced by a table drawn up front anyway; what is kept is the SOURCE: one 64-bit draw from
+    ``random`` per frame seeds the generator that shuffles (a seeded ``random`` gives a reproducible run), and the
+    (events x classes) shuffles of a frame cost 0.1 ms instead of the 1 ms (6 ms for the six semseg classes) of
+    ``random.shuffle`` in a Python loop."""
+    rng = np.random.Generator(np.random.PCG64(random.getrandbits(64)))
+    perms = np.full((n_events, len(list_lens), tries), -1, dtype=np.int32)
+    for c, n in enumerate(list_lens):
+        k = min(tries, n)
+        if k > 0:
+            perms[:, c, :k] = rng.permuted(np.tile(np.arange(n, dtype=np.int32), (n_events, 1)), axis=1)[:, :k]
+    return perms
+
+
 def draw_schedule(config, list_lens, tries=MAX_NUM_TRIES):
-    """Pre-draw one frame's randomness exactly where the reference draws it: the class counts, then one
-    ``random.shuffle`` of every class's (sorted) sample list per possible window (od/ins:399-402); only the first
-    ``tries`` entries of a shuffle can be visited before the next shuffle (the rest follow in index order)."""
+    """Pre-draw one frame's randomness: the class counts (``generate_seed``, from ``np.random`` like the reference), then
+    the shuffled sample orders of every possible window (``_permutation_heads``, seeded from ``random``)."""
     counts = generate_seed(config).astype(np.int64)
-    events = int(counts.sum()) + 1
-    perms = np.full((events, len(list_lens), tries), -1, dtype=np.int32)
-    for e in range(events):
-        for c, n in enumerate(list_lens):
-            order = list(range(n))
-            random.shuffle(order)
-            k = min(tries, n)
-            perms[e, c, :k] = order[:k]
-    return counts, perms
+    return counts, _permutation_heads(int(counts.sum()) + 1, list_lens, tries)
 
 
 def _marker(out_dir, name):

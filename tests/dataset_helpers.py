@@ -15,31 +15,36 @@ def sha(a):
 
 
 class PredrawnShuffle:
-    """Stands in for ``random.shuffle`` inside ``dataset_driver.draw_schedule``: the calls of frame f walk that
-    frame's pre-drawn table in (event, class) order; each call returns the permutation head of the golden run followed
-    by the remaining indices in order.  ``perms``: one table, or a list with one table per frame."""
+    """Stands in for ``dataset_driver._permutation_heads``: frame f gets the pre-drawn table of the golden run
+    ([event][class][try]; a head shorter than a window is followed by the remaining indices in order, as a shuffled list
+    would be).  ``perms``: one table, or a list with one table per frame."""
 
     def __init__(self, perms, n_classes):
         self.tables = list(perms) if isinstance(perms, (list, tuple)) else [perms]
-        self.n_classes, self.calls, self.frame = n_classes, 0, 0
+        self.n_classes, self.frame = n_classes, 0
 
-    def __call__(self, lst):
-        table = self.tables[self.frame % len(self.tables)]
-        e, c = divmod(self.calls, self.n_classes)
-        head = [int(v) for v in table[e][c] if v >= 0]
-        hs = set(head)
-        lst[:] = head + [j for j in range(len(lst)) if j not in hs]
-        self.calls += 1
-        if self.calls == len(table) * self.n_classes:
-            self.calls, self.frame = 0, self.frame + 1
+    def __call__(self, n_events, list_lens, tries):
+        table = np.asarray(self.tables[self.frame % len(self.tables)])
+        self.frame += 1
+        assert table.shape[0] == n_events and table.shape[1] == len(list_lens) == self.n_classes
+        out = np.full((n_events, len(list_lens), tries), -1, dtype=np.int32)
+        for e in range(n_events):
+            for c, n in enumerate(list_lens):
+                head = [int(v) for v in table[e][c] if v >= 0]
+                hs = set(head)
+                order = (head + [j for j in range(n) if j not in hs])[:min(tries, n)]
+                out[e, c, :len(order)] = order
+        return out
 
     def __enter__(self):
-        self.old = random.shuffle
-        random.shuffle = self
+        from pcl_augmentation_b200 import dataset_driver as drv
+        self.old = drv._permutation_heads
+        drv._permutation_heads = self
         return self
 
     def __exit__(self, *exc):
-        random.shuffle = self.old
+        from pcl_augmentation_b200 import dataset_driver as drv
+        drv._permutation_heads = self.old
 
 
 class OracleEngine:
